@@ -1,0 +1,102 @@
+"""Deterministic synthetic phage-like genome sets.
+
+Family model, so that the prefilter is non-trivial: ``n // family`` families; each family has a uniform random
+ACGT root of length L; every member is the root with a per-member substitution rate d ~ U(0, max_div), one
+deletion and one tandem duplication of length U(0, 500), and is reverse-complemented with probability 0.5.
+Names are ``g%06d``; FASTA lines are 80 columns.
+
+The generator is pure numpy with a seeded ``default_rng`` so the same (n, L, family, seed) gives the same bytes
+here, on the GPU box and in the tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTacgtNn", b"TGCAtgcaNn"):
+    _COMP[_a] = _b
+
+BASE_SEED = 20261017
+
+
+def _member(rng: np.random.Generator, root: np.ndarray, max_div: float, indel: int) -> np.ndarray:
+    seq = root.copy()
+    d = rng.uniform(0.0, max_div)
+    n_sub = rng.binomial(seq.size, d)
+    if n_sub:
+        pos = rng.integers(0, seq.size, size=n_sub)
+        # substitute by a different base: add 1..3 mod 4 in code space
+        code = np.searchsorted(_ACGT, seq[pos])
+        seq[pos] = _ACGT[(code + rng.integers(1, 4, size=n_sub)) & 3]
+    if indel and seq.size > 4 * indel:
+        dl = int(rng.integers(0, indel + 1))
+        p = int(rng.integers(0, seq.size - dl))
+        seq = np.concatenate([seq[:p], seq[p + dl:]])
+        ul = int(rng.integers(0, indel + 1))
+        p = int(rng.integers(0, seq.size - ul))
+        seq = np.concatenate([seq[:p + ul], seq[p:]])          # tandem duplication of seq[p:p+ul]
+    if rng.random() < 0.5:
+        seq = _COMP[seq[::-1]]
+    return seq
+
+
+def make_genomes(n: int, length: int | tuple[int, int] = 40_000, family: int = 20, seed: int = BASE_SEED,
+                 max_div: float = 0.12, indel: int = 500, n_frac: float = 0.0, lower_frac: float = 0.0):
+    """Return (names, seqs) with seqs a list of uint8 ASCII arrays.
+
+    ``length`` is an int or a (lo, hi) range sampled log-uniformly per family.  ``n_frac`` of the genomes get a run
+    of 100 'N' and ``lower_frac`` get a lower-case block (exercise the symbol-coding rules of both stages).
+    """
+    rng = np.random.default_rng(seed)
+    names, seqs = [], []
+    g = 0
+    while g < n:
+        if isinstance(length, tuple):
+            L = int(np.exp(rng.uniform(np.log(length[0]), np.log(length[1]))))
+        else:
+            L = int(length)
+        root = _ACGT[rng.integers(0, 4, size=L)]
+        for _ in range(min(family, n - g)):
+            s = _member(rng, root, max_div, indel)
+            if n_frac and rng.random() < n_frac and s.size > 1000:
+                p = int(rng.integers(0, s.size - 100))
+                s[p:p + 100] = ord("N")
+            if lower_frac and rng.random() < lower_frac and s.size > 1000:
+                p = int(rng.integers(0, s.size - 500))
+                s[p:p + 500] |= 0x20
+            names.append("g%06d" % g)
+            seqs.append(s)
+            g += 1
+    return names, seqs
+
+
+def fasta_bytes(names, seqs, width: int = 80) -> bytes:
+    out = bytearray()
+    for name, s in zip(names, seqs):
+        out += b">" + name.encode() + b"\n"
+        n = s.size
+        full = (n // width) * width
+        if full:
+            body = np.empty((n // width, width + 1), dtype=np.uint8)
+            body[:, :width] = s[:full].reshape(-1, width)
+            body[:, width] = 10
+            out += body.tobytes()
+        if n > full:
+            out += s[full:].tobytes() + b"\n"
+    return bytes(out)
+
+
+def write_fasta(path, names, seqs, width: int = 80) -> None:
+    with open(path, "wb") as fh:
+        fh.write(fasta_bytes(names, seqs, width))
+
+
+# BASELINE.json configs (c2..c5) as generator arguments; c1 is example/multifasta.fna (reference fixture).
+CONFIGS = {
+    "c2": dict(n=1_000, length=40_000, family=20, seed=BASE_SEED + 2),
+    "c3": dict(n=10_000, length=40_000, family=20, seed=BASE_SEED + 3),
+    "c3_s200": dict(n=10_000, length=40_000, family=200, seed=BASE_SEED + 3),
+    "c4": dict(n=100_000, length=(5_000, 200_000), family=200, seed=BASE_SEED + 4, n_frac=0.01, lower_frac=0.01),
+    "c5": dict(n=1_000_000, length=30_000, family=20, seed=BASE_SEED + 5),
+}
