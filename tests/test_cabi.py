@@ -1,0 +1,88 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/vclust_b200.h
+declares; host-only entry points (FASTA ingest, filter read/write, number formatting) behave like the reference's."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from vclust_b200 import _lib, api, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    header = (_lib.HERE.parent / "include" / "vclust_b200.h").read_text()
+    declared = set(re.findall(r"\b(vb_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_version_and_no_device_is_an_error(lib):
+    assert "vclust-b200" in api.version()
+    if api.device_count() == 0:
+        with pytest.raises(api.VbError) as e:
+            api.Context(0)
+        assert "no CPU fallback" in str(e.value)
+
+
+def test_fasta_ingest_matches_reference_rules(lib, golden, tmp_path):
+    p = golden / "example" / "multifasta.fna.gz"
+    g = api.Genomes.load([p], True, api.FASTA_LZANI)
+    names, codes = oracle.load_genomes_lzani([p], True)
+    assert g.names() == names
+    assert [g.length(i) for i in range(len(g))] == [c.size for c in codes]
+    g2 = api.Genomes.load([p], True, api.FASTA_KMERDB)
+    recs = oracle.read_records_kmerdb(p)
+    assert g2.names() == [n for n, _ in recs]
+    assert [g2.length(i) for i in range(len(g2))] == [len(s) for _, s in recs]
+    # corner cases: CRLF, blank lines, header with description, unterminated last line, directory mode
+    fa = tmp_path / "x.fa"
+    fa.write_bytes(b">a desc here\r\nACGT\r\n\r\nNNAC\n>b\nGG\nTT")
+    g = api.Genomes.load([fa], True, api.FASTA_LZANI)
+    assert g.names() == ["a", "b"] and [g.length(i) for i in range(2)] == [8, 2]      # "TT" dropped (lz-ani quirk)
+    g = api.Genomes.load([fa], True, api.FASTA_KMERDB)
+    assert g.names() == ["a", "b"] and [g.length(i) for i in range(2)] == [8, 4]
+    g = api.Genomes.load([fa, fa], False, api.FASTA_LZANI, sep_len=40)
+    assert g.names() == ["x.fa", "x.fa"] and g.length(0) == 8 + 40 + 4
+    g = api.Genomes.load([fa], False, api.FASTA_KMERDB)
+    assert g.length(0) == 8 + 1 + 4
+
+
+def test_filter_roundtrip_and_format(lib, golden, tmp_path):
+    p = golden / "example" / "multifasta.fna.gz"
+    g = api.Genomes.load([p], True, api.FASTA_LZANI)
+    pairs = api.read_filter(golden / "example" / "fltr.txt", 0.0, g)
+    assert pairs.n_pairs == 13
+    assert list(zip(pairs.rows.tolist(), pairs.cols.tolist()))[:3] == [(1, 0), (2, 0), (2, 1)]
+    assert api.read_filter(golden / "example" / "fltr.txt", 0.99, g).n_pairs == 8
+    # names must agree (lz_matcher.cpp:43-75)
+    g_bad = api.Genomes.from_memory(["x", "y", "z"], [b"ACGT"] * 3)
+    with pytest.raises(api.VbError):
+        api.read_filter(golden / "example" / "fltr.txt", 0.0, g_bad)
+
+
+def test_number_formats_match_oracle(lib):
+    lib.vb_last_error  # noqa: B018  (library loaded)
+    import ctypes
+    so = ctypes.CDLL(str(_lib.LIB_PATH))
+    f6 = so._Z13vb_fmt_fixed6dPc
+    fr = so._Z11vb_fmt_realdiPc
+    f6.argtypes = [ctypes.c_double, ctypes.c_char_p]
+    fr.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_char_p]
+    rng = np.random.default_rng(7)
+    vals = list(rng.random(2000)) + list(rng.random(500) * 1e-4) + [0.0, 1.0, 0.5, 100.0, 0.9999996, 1e-5, 1e-4, 0.7,
+                                                                      89.28928929, 1234567.0, 0.016848, 0.01684796]
+    buf = ctypes.create_string_buffer(64)
+    for v in vals:
+        n = f6(float(v), buf)
+        assert buf.raw[:n].decode() == oracle.fixed6(float(v))
+        for prec in (4, 6):
+            n = fr(float(v), prec, buf)
+            assert buf.raw[:n].decode() == oracle.real_str(float(v), prec), v

@@ -1,0 +1,151 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the committed
+golden vectors and against the CPU oracle on seeded inputs.  Integer/byte results must be bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from vclust_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+GEN = {
+    "s60": dict(n=60, length=8000, family=6, seed=synth.BASE_SEED + 100, n_frac=0.2, lower_frac=0.2),
+    "s40_k30": dict(n=40, length=(2000, 30000), family=5, seed=synth.BASE_SEED + 101, max_div=0.2),
+    "s30_all": dict(n=30, length=(3000, 20000), family=3, seed=synth.BASE_SEED + 102, n_frac=0.3),
+}
+PRE = {
+    "s60": dict(k=25, kmers_fraction=1.0, min_kmers=20, min_ident=0.7),
+    "s60_k15": dict(k=15, kmers_fraction=1.0, min_kmers=10, min_ident=0.5),
+    "s60_f02": dict(k=25, kmers_fraction=0.2, min_kmers=4, min_ident=0.7),
+    "s40_k30": dict(k=30, kmers_fraction=1.0, min_kmers=1, min_ident=0.3),
+}
+LZP = {
+    "s60": {}, "s60_f02": {},
+    "s60_k15": dict(mal=9, msl=6, mrd=30, mqd=25, reg=30, aw=12, am=5, ar=2),
+    "s40_k30": dict(mal=13, msl=8, mrd=60, mqd=50, reg=40, aw=20, am=9, ar=4),
+    "s30_all": {},
+}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    with api.Context(0) as c:
+        yield c
+
+
+def _synth_fasta(tmp_path, case):
+    names, seqs = synth.make_genomes(**GEN["s40_k30" if case == "s40_k30" else ("s30_all" if case == "s30_all" else "s60")])
+    fa = tmp_path / (case + ".fna")
+    synth.write_fasta(fa, names, seqs)
+    return fa, names, seqs
+
+
+# ---------------------------------------------------------------- prefilter
+def test_prefilter_example_byte_exact(ctx, golden, tmp_path):
+    g = api.Genomes.load([golden / "example" / "multifasta.fna.gz"], True, api.FASTA_KMERDB)
+    pairs = api.prefilter_genomes(ctx, g)
+    assert pairs.total_kmers.tolist() == [38557, 38607, 38908, 39682, 57222, 57392, 58459, 42629, 39537, 61292, 45598, 45598]
+    got = {(int(r), int(c)): int(v) for r, c, v in zip(pairs.rows, pairs.cols, pairs.common)}
+    assert got[(1, 0)] == 35785 and got[(11, 10)] == 45550
+    out = tmp_path / "fltr.txt"
+    api.write_filter(g, pairs, out)
+    assert out.read_bytes() == (golden / "example" / "fltr.txt").read_bytes()
+
+
+@pytest.mark.parametrize("case", list(PRE))
+def test_prefilter_vs_reference_binary_outputs(ctx, golden, tmp_path, case):
+    fa, names, seqs = _synth_fasta(tmp_path, case)
+    out = tmp_path / "fltr.txt"
+    kw = PRE[case]
+    api.prefilter([fa], out, True, kmer_size=kw["k"], kmers_fraction=kw["kmers_fraction"], min_kmers=kw["min_kmers"],
+                  min_ident=kw["min_ident"])
+    assert out.read_bytes() == (golden / "ref_synth" / (case + ".fltr.txt")).read_bytes()
+
+
+@pytest.mark.parametrize("k,f", [(25, 1.0), (25, 0.2), (15, 1.0), (21, 0.5), (31, 1.0), (18, 1.0)])
+def test_prefilter_counts_vs_oracle(ctx, golden, k, f):
+    recs = oracle.read_records_kmerdb(golden / "example" / "multifasta.fna.gz")
+    sets = oracle.kmer_sets([[s] for _, s in recs], k, f)
+    rows, cols, vals = oracle.common_matrix(sets)
+    g = api.Genomes.load([golden / "example" / "multifasta.fna.gz"], True, api.FASTA_KMERDB)
+    pairs = api.prefilter_genomes(ctx, g, k=k, min_kmers=1, min_ident=0.0, kmers_fraction=f)
+    assert pairs.total_kmers.tolist() == [int(s.size) for s in sets]
+    want = {(int(r), int(c)): int(v) for r, c, v in zip(rows, cols, vals)}
+    got = {(int(r), int(c)): int(v) for r, c, v in zip(pairs.rows, pairs.cols, pairs.common)}
+    assert got == want
+
+
+def test_prefilter_edge_cases(ctx):
+    # empty genome, genome shorter than k, all-N genome, U handled as T, lower case, duplicate genomes
+    seqs = [b"", b"ACGTACGT", b"N" * 100, b"ACGU" * 30, b"acgt" * 30, b"ACGT" * 30, b"ACGTTGCAAGGCTA" * 10]
+    names = ["g%d" % i for i in range(len(seqs))]
+    g = api.Genomes.from_memory(names, seqs)
+    pairs = api.prefilter_genomes(ctx, g, k=15, min_kmers=1, min_ident=0.0)
+    sets = oracle.kmer_sets([[s] for s in seqs], 15, 1.0)
+    assert pairs.total_kmers.tolist() == [int(s.size) for s in sets]
+    rows, cols, vals = oracle.common_matrix(sets)
+    assert {(int(r), int(c)): int(v) for r, c, v in zip(pairs.rows, pairs.cols, pairs.common)} == \
+           {(int(r), int(c)): int(v) for r, c, v in zip(rows, cols, vals)}
+
+
+# ---------------------------------------------------------------- align
+def test_align_example_all_vs_all_byte_exact(ctx, golden, tmp_path):
+    out = tmp_path / "ani.tsv"
+    api.align([golden / "example" / "multifasta.fna.gz"], out, True)
+    assert (tmp_path / "ani.ids.tsv").read_bytes() == (golden / "example" / "ani.ids.tsv").read_bytes()
+    assert out.read_bytes() == (golden / "example" / "ani.tsv").read_bytes()
+
+
+def test_align_vir61_ci_gate_byte_exact(ctx, golden, tmp_path):
+    out = tmp_path / "vir61.ani.tsv"
+    cols = "qidx,ridx,query,reference,tani,gani,ani,qcov,num_alns,len_ratio".split(",")
+    api.align([golden / "vir61" / "vir61.fna.gz"], out, True, out_format=cols)
+    assert (tmp_path / "vir61.ani.ids.tsv").read_bytes() == (golden / "vir61" / "vir61.ani.ids.tsv").read_bytes()
+    assert out.read_bytes() == (golden / "vir61" / "vir61.ani.tsv").read_bytes()
+
+
+@pytest.mark.parametrize("case", list(LZP))
+def test_align_vs_reference_binary_outputs(ctx, golden, tmp_path, case):
+    fa, names, seqs = _synth_fasta(tmp_path, case)
+    out = tmp_path / "ani.tsv"
+    flt = None if case == "s30_all" else golden / "ref_synth" / (case + ".fltr.txt")
+    api.align([fa], out, True, out_format=api.ALIGN_OUTFMT["complete"], filter_file=flt, **LZP[case])
+    assert out.read_bytes() == (golden / "ref_synth" / (case + ".ani.tsv")).read_bytes()
+
+
+def test_align_pairs_vs_oracle_random(ctx):
+    names, seqs = synth.make_genomes(n=48, length=(1500, 12000), family=4, seed=99, max_div=0.25, n_frac=0.3, lower_frac=0.3)
+    # add degenerate genomes: empty, tiny, all N, a homopolymer and an exact duplicate
+    extra = [b"", b"ACG", b"N" * 300, b"A" * 2000, seqs[0].tobytes()]
+    seqs = [s.tobytes() for s in seqs] + extra
+    names = names + ["x%d" % i for i in range(len(extra))]
+    rng = np.random.default_rng(5)
+    n = len(names)
+    ref = rng.integers(0, n, size=1500)
+    qry = rng.integers(0, n, size=1500)
+    # make sure related pairs and self pairs are present
+    ref[:200] = (np.arange(200) % 48)
+    qry[:200] = (ref[:200] // 4) * 4 + rng.integers(0, 4, size=200)
+    g = api.Genomes.from_memory(names, seqs)
+    got = api.align_pairs(ctx, g, ref, qry)
+    want = oracle.run_pairs([oracle.lz_codes(s) for s in seqs], ref, qry)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, "first mismatches: %s" % [(int(ref[i]), int(qry[i]), got[i].tolist(), want[i].tolist()) for i in bad[:5]]
+
+
+@pytest.mark.parametrize("params", [
+    dict(mal=9, msl=5, mrd=20, mqd=60, reg=20, aw=8, am=3, ar=1),
+    dict(mal=16, msl=12, mrd=100, mqd=10, reg=60, aw=32, am=20, ar=6),
+    dict(mal=11, msl=7, mrd=40, mqd=40, reg=35, aw=15, am=15, ar=3),      # window rule can never fire
+])
+def test_align_pairs_vs_oracle_params(ctx, params):
+    names, seqs = synth.make_genomes(n=24, length=(2000, 9000), family=4, seed=123, max_div=0.2, n_frac=0.2)
+    seqs = [s.tobytes() for s in seqs]
+    n = len(names)
+    ref, qry = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    ref, qry = ref.ravel(), qry.ravel()
+    g = api.Genomes.from_memory(names, seqs)
+    got = api.align_pairs(ctx, g, ref, qry, api.align_params(**params))
+    want = oracle.run_pairs([oracle.lz_codes(s) for s in seqs], ref, qry, oracle.LzParams.default(**params))
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, "first mismatches: %s" % [(int(ref[i]), int(qry[i]), got[i].tolist(), want[i].tolist()) for i in bad[:5]]

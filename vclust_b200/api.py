@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+The reference's "operator API" for this path is the pair of command builders in vclust.py -- ``cmd_kmerdb_build`` /
+``cmd_kmerdb_all2all`` / ``cmd_kmerdb_distance`` (vclust.py:915-1055) and ``cmd_lzani`` (vclust.py:1058-1181) -- plus
+``run()``.  ``prefilter()`` and ``align()`` below take the same arguments with the same meaning and produce the same
+files; instead of spawning kmer-db / lz-ani they call libvclust_b200.so through ctypes.  Errors raise ``VbError``
+(the CLI maps that to ``sys.exit(1)`` exactly like vclust.py:797-805).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import AlignOut, AlignParams, Pairs, PrefilterParams, VbError, check
+
+# vclust.py:38-47
+ALIGN_OUTFMT = {
+    "lite": ["qidx", "ridx", "tani", "gani", "ani", "qcov", "rcov", "num_alns", "len_ratio"],
+    "standard": ["qidx", "ridx", "query", "reference", "tani", "gani", "ani", "qcov", "rcov", "num_alns", "len_ratio"],
+    "complete": ["qidx", "ridx", "query", "reference", "tani", "gani", "ani", "qcov", "rcov", "num_alns", "len_ratio",
+                 "qlen", "rlen", "nt_match", "nt_mismatch"],
+}
+
+FASTA_KMERDB, FASTA_LZANI = 0, 1
+
+
+def version() -> str:
+    buf = C.create_string_buffer(256)
+    check(_lib.load().vb_version(buf, 256))
+    return buf.value.decode()
+
+
+def device_count() -> int:
+    return int(_lib.load().vb_device_count())
+
+
+class Context:
+    """One CUDA device (vb_ctx).  Raises VbError when no device is usable -- there is no CPU fallback."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        check(self._L.vb_ctx_create(int(device), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._L.vb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def timing(self, key: str) -> float:
+        v = C.c_double()
+        check(self._L.vb_ctx_timing(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def timings(self, prefix: str) -> dict:
+        keys = {
+            "prefilter": ["total_ms", "upload_pack_ms", "extract_ms", "sort_ms", "segment_ms", "emit_ms", "tuples",
+                          "pair_increments", "table_slots", "candidates"],
+            "align": ["total_ms", "upload_pack_ms", "index_ms", "parse_ms", "batches", "pairs"],
+        }[prefix]
+        out = {}
+        for k in keys:
+            try:
+                out[k] = self.timing(prefix + "." + k)
+            except VbError:
+                pass
+        return out
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.vb_ctx_launches(self._h))
+
+
+class Genomes:
+    """A genome set on the host (vb_genomes)."""
+
+    def __init__(self, handle, keepalive=None):
+        self._L = _lib.load()
+        self._h = handle
+        self._keep = keepalive
+
+    @classmethod
+    def load(cls, paths: Sequence, multisample: bool, flavor: int, sep_len: int = 40) -> "Genomes":
+        L = _lib.load()
+        arr = (C.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+        h = C.c_void_p()
+        check(L.vb_genomes_load(arr, len(paths), 1 if multisample else 0, flavor, sep_len, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_memory(cls, names: Sequence[str], seqs: Sequence) -> "Genomes":
+        """seqs: bytes objects or uint8 numpy arrays of ASCII bases."""
+        L = _lib.load()
+        n = len(names)
+        arrs = [np.ascontiguousarray(np.frombuffer(s, dtype=np.uint8) if isinstance(s, (bytes, bytearray)) else s,
+                                     dtype=np.uint8) for s in seqs]
+        c_names = (C.c_char_p * n)(*[x.encode() for x in names])
+        c_seqs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        c_lens = (C.c_uint64 * n)(*[a.size for a in arrs])
+        h = C.c_void_p()
+        check(L.vb_genomes_from_memory(c_names, c_seqs, c_lens, n, C.byref(h)))
+        return cls(h)
+
+    def __len__(self):
+        return int(self._L.vb_genomes_count(self._h))
+
+    def name(self, i: int) -> str:
+        return self._L.vb_genomes_name(self._h, i).decode()
+
+    def names(self):
+        return [self.name(i) for i in range(len(self))]
+
+    def length(self, i: int) -> int:
+        return int(self._L.vb_genomes_length(self._h, i))
+
+    @property
+    def total_bases(self) -> int:
+        return int(self._L.vb_genomes_total_bases(self._h))
+
+    def close(self):
+        if self._h:
+            self._L.vb_genomes_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PairList:
+    """vb_pairs: sparse lower-triangular prefilter result (or a filter file read back)."""
+
+    def __init__(self, ptr):
+        self._L = _lib.load()
+        self._p = ptr
+
+    def _arr(self, field, n, dtype):
+        if n == 0:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(getattr(self._p.contents, field), shape=(n,)).copy()
+
+    @property
+    def n_pairs(self):
+        return int(self._p.contents.n_pairs)
+
+    @property
+    def rows(self):
+        return self._arr("row", self.n_pairs, np.uint32)
+
+    @property
+    def cols(self):
+        return self._arr("col", self.n_pairs, np.uint32)
+
+    @property
+    def common(self):
+        return self._arr("common", self.n_pairs, np.uint32)
+
+    @property
+    def ani(self):
+        return self._arr("ani", self.n_pairs, np.float64)
+
+    @property
+    def total_kmers(self):
+        return self._arr("total_kmers", int(self._p.contents.n_genomes), np.uint32)
+
+    def close(self):
+        if self._p:
+            self._L.vb_pairs_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class AlignResult:
+    def __init__(self, ptr):
+        self._L = _lib.load()
+        self._p = ptr
+
+    def _arr(self, field, n, dtype):
+        if n == 0:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(getattr(self._p.contents, field), shape=(n,)).copy()
+
+    @property
+    def n(self):
+        return int(self._p.contents.n)
+
+    @property
+    def ref(self):
+        return self._arr("ref", self.n, np.uint32)
+
+    @property
+    def qry(self):
+        return self._arr("qry", self.n, np.uint32)
+
+    @property
+    def stats(self):
+        return np.stack([self._arr("sym_in_matches", self.n, np.int32), self._arr("sym_in_literals", self.n, np.int32),
+                         self._arr("no_components", self.n, np.int32)], axis=1) if self.n else np.zeros((0, 3), np.int32)
+
+    @property
+    def order(self):
+        return self._arr("order", int(self._p.contents.n_genomes), np.uint32)
+
+    def close(self):
+        if self._p:
+            self._L.vb_align_out_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# operator-level calls
+# ----------------------------------------------------------------------------------------------------------------
+def prefilter_genomes(ctx: Context, genomes: Genomes, k: int = 25, min_kmers: int = 20, min_ident: float = 0.7,
+                      kmers_fraction: float = 1.0, max_seqs: int = 0, batch_size: int = 0) -> PairList:
+    p = PrefilterParams(k, min_kmers, min_ident, kmers_fraction, max_seqs, batch_size)
+    out = C.POINTER(Pairs)()
+    check(ctx._L.vb_prefilter(ctx._h, genomes._h, C.byref(p), C.byref(out)))
+    return PairList(out)
+
+
+def write_filter(genomes: Genomes, pairs: PairList, path) -> None:
+    check(_lib.load().vb_write_filter(genomes._h, pairs._p, str(path).encode()))
+
+
+def read_filter(path, thr: float, genomes: Genomes) -> PairList:
+    out = C.POINTER(Pairs)()
+    check(_lib.load().vb_read_filter(str(path).encode(), float(thr), genomes._h, C.byref(out)))
+    return PairList(out)
+
+
+def align_params(mal=11, msl=7, mrd=40, mqd=40, reg=35, aw=15, am=7, ar=3) -> AlignParams:
+    return AlignParams(mal, msl, mrd, mqd, reg, aw, am, ar)
+
+
+def align_genomes(ctx: Context, genomes: Genomes, pairs: PairList | None = None, params: AlignParams | None = None
+                  ) -> AlignResult:
+    params = params or align_params()
+    out = C.POINTER(AlignOut)()
+    check(ctx._L.vb_align(ctx._h, genomes._h, pairs._p if pairs is not None else None, C.byref(params), C.byref(out)))
+    return AlignResult(out)
+
+
+def align_pairs(ctx: Context, genomes: Genomes, ref: Iterable[int], qry: Iterable[int],
+                params: AlignParams | None = None) -> np.ndarray:
+    """Directed pairs in input-order ids -> (n, 3) int32 array of (sym_in_matches, sym_in_literals, no_components)."""
+    params = params or align_params()
+    r = np.ascontiguousarray(ref, dtype=np.uint32)
+    q = np.ascontiguousarray(qry, dtype=np.uint32)
+    st = np.zeros((r.size, 3), dtype=np.int32)
+    check(ctx._L.vb_align_pairs(ctx._h, genomes._h, r.ctypes.data, q.ctypes.data, r.size, C.byref(params), st.ctypes.data))
+    return st
+
+
+def write_ani(genomes: Genomes, res: AlignResult, ani_path, ids_path=None, columns: Sequence[str] | None = None,
+              out_filters: dict | None = None) -> None:
+    columns = list(columns or ALIGN_OUTFMT["standard"])
+    ani_path = Path(ani_path)
+    if ids_path is None:                      # lz_matcher.cpp:295-302
+        s = str(ani_path)
+        dot = s.rfind(".")
+        ids_path = s + ".ids" if dot < 0 else s[:dot] + ".ids" + s[dot:]
+    cols = (C.c_char_p * len(columns))(*[c.encode() for c in columns])
+    of = out_filters or {}
+    flt = (C.c_double * 5)(*[float(of.get(k, 0) or 0) for k in ("tani", "gani", "ani", "qcov", "rcov")])
+    check(_lib.load().vb_write_ani(genomes._h, res._p, str(ani_path).encode(), str(ids_path).encode(), cols,
+                                   len(columns), flt))
+
+
+def prefilter(input_paths: Sequence, output_path, is_multisample_fasta: bool, kmer_size: int = 25,
+              kmers_fraction: float = 1.0, min_kmers: int = 20, min_ident: float = 0.7, max_seqs: int = 0,
+              batch_size: int = 0, device: int = 0) -> dict:
+    """`vclust prefilter` body: cmd_kmerdb_build + cmd_kmerdb_all2all + cmd_kmerdb_distance (vclust.py:915-1055)."""
+    with Context(device) as ctx:
+        g = Genomes.load(input_paths, is_multisample_fasta, FASTA_KMERDB)
+        pairs = prefilter_genomes(ctx, g, kmer_size, min_kmers, min_ident, kmers_fraction, max_seqs, batch_size)
+        write_filter(g, pairs, output_path)
+        info = ctx.timings("prefilter")
+        info["pairs"] = pairs.n_pairs
+        pairs.close()
+        g.close()
+        return info
+
+
+def align(input_paths: Sequence, output_path, is_multisample_fasta: bool, out_format: Sequence[str] | None = None,
+          filter_file=None, filter_threshold: float = 0.0, out_filters: dict | None = None, mal=11, msl=7, mrd=40,
+          mqd=40, reg=35, aw=15, am=7, ar=3, device: int = 0) -> dict:
+    """`vclust align` body: cmd_lzani (vclust.py:1058-1181)."""
+    with Context(device) as ctx:
+        g = Genomes.load(input_paths, is_multisample_fasta, FASTA_LZANI, sep_len=mrd)
+        pairs = read_filter(filter_file, filter_threshold, g) if filter_file else None
+        res = align_genomes(ctx, g, pairs, align_params(mal, msl, mrd, mqd, reg, aw, am, ar))
+        write_ani(g, res, output_path, None, out_format or ALIGN_OUTFMT["standard"], out_filters)
+        info = ctx.timings("align")
+        res.close()
+        if pairs is not None:
+            pairs.close()
+        g.close()
+        return info

@@ -1,0 +1,690 @@
+// vb_align: the LZ-ANI pairwise parse on one B200 -- one warp per directed (reference, query) pair.
+//
+// Reference computation (paths under /root/reference/3rd_party/lz-ani/src/):
+//   reference text + indexes  CParser::prepare_reference  parser.cpp:16-34, :53-189
+//   query text                CParser::prepare_data       parser.cpp:37-50
+//   the parse                 CParser::parse              parser.cpp:482-716 (+ :192-449 helpers)
+//   per-pair statistics       CParser::calc_stats         parser.cpp:734-783
+//
+// This is a re-formulation, not a transcription (DESIGN.md "align" has the derivation):
+//   * texts are 2-bit packed with a 1-bit "not ACGT" plane; an N never matches anything (the reference gets this
+//     from code 4 in the reference text vs code 5 in the query), so every comparison is  xor | N_q | N_r  on 32 bases.
+//   * the reference's 4 MB open-addressing table of 11-mer positions becomes a per-reference table of
+//     (fingerprint, position) slots; lookups take the max over ALL entries with the same k-mer, ties to the
+//     smallest position, which is what the reference's ascending insertion + first-wins scan computes.
+//   * the short-seed CSR (4^7 buckets) is not built at all: the reference only ever searches a window of
+//     [pred - lit, pred + mrd) positions, which 32 lanes scan directly in the packed text.
+//   * no factor list: calc_stats only needs per-component sums, kept as running state.
+//   * the position-by-position search for the next seed is done 32 query positions at a time (one per lane);
+//     the approximate extension consumes 1024 bases per warp step from mismatch bit masks.
+#include <algorithm>
+#include <cmath>
+
+#include "dev_util.cuh"
+
+namespace {
+
+constexpr uint64_t HT_EMPTY = ~0ULL;
+
+struct LzParams { int mal, msl, mrd, mqd, reg, aw, am, ar; };
+
+struct RefDesc {
+    uint64_t s2_off;     // word offset of the packed text in ref_s2
+    uint64_t nv_off;     // word offset of the N plane in ref_nv
+    uint64_t ht_off;     // slot offset of the anchor table
+    uint32_t ht_mask;    // slots - 1
+    uint32_t n;          // text length: 2*len + 3*mrd
+    uint32_t len;        // genome length
+    uint32_t gid;        // genome id in the packed store
+};
+
+struct Text {
+    const uint32_t *s2;
+    const uint32_t *nv;
+    int n;
+};
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+__device__ __forceinline__ uint64_t reverse_digits(uint64_t x)
+{
+    x = __brevll(x);
+    return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k5a: reference text  R = fwd | N^mrd | N^mrd | revcomp(fwd) | N^mrd   (parser.cpp:16-34), packed
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_ref_text_kernel(const uint32_t *__restrict__ g2, const uint32_t *__restrict__ gn,
+                                                             const uint64_t *__restrict__ gofs, const RefDesc *__restrict__ refs,
+                                                             uint32_t n_refs, int mrd, uint32_t *__restrict__ ref_s2,
+                                                             uint32_t *__restrict__ ref_nv)
+{
+    for (uint32_t r = blockIdx.y; r < n_refs; r += gridDim.y) {
+        const RefDesc d = refs[r];
+        const uint64_t gbase = gofs[d.gid];
+        const uint32_t L = d.len;
+        const uint32_t rc0 = L + 2 * (uint32_t)mrd;              // first position of the reverse-complement part
+        const uint32_t n_chunks = (d.n + 31) / 32 + 4;           // + padding chunks (all N)
+        for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
+            uint32_t x0 = c * 32;
+            uint64_t w;
+            uint32_t bad;
+            if (x0 + 32 <= L) {                                   // inside the forward copy
+                w = fetch2(g2, gbase + x0);
+                bad = fetch1(gn, gbase + x0);
+            } else if (x0 >= rc0 && x0 + 32 <= rc0 + L) {         // inside the reverse complement
+                uint32_t s_lo = L - 32 - (x0 - rc0);
+                w = ~reverse_digits(fetch2(g2, gbase + s_lo));
+                bad = __brev(fetch1(gn, gbase + s_lo));
+            } else {                                              // boundary chunk: base by base
+                w = 0; bad = 0;
+                for (uint32_t j = 0; j < 32; ++j) {
+                    uint32_t x = x0 + j;
+                    uint32_t code = 0, isn = 1;
+                    if (x < L) {
+                        code = (uint32_t)(fetch2(g2, gbase + x) & 3); isn = fetch1(gn, gbase + x) & 1;
+                    } else if (x >= rc0 && x < rc0 + L) {
+                        uint32_t s = L - 1 - (x - rc0);
+                        code = 3 - (uint32_t)(fetch2(g2, gbase + s) & 3); isn = fetch1(gn, gbase + s) & 1;
+                    }
+                    if (isn) { code = 0; bad |= 1u << j; }
+                    w |= (uint64_t)code << (2 * j);
+                }
+            }
+                                                                  // N positions keep whatever 2-bit code they had:
+            ref_s2[d.s2_off + 2 * (uint64_t)c] = (uint32_t)w;     // the N plane decides every comparison
+            ref_s2[d.s2_off + 2 * (uint64_t)c + 1] = (uint32_t)(w >> 32);
+            ref_nv[d.nv_off + c] = bad;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k5b: anchor table -- every position whose mal-mer holds no N is inserted under its k-mer (parser.cpp:146-189)
+// slot = fingerprint << 32 | position
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_ref_index_kernel(const RefDesc *__restrict__ refs, uint32_t n_refs, int mal,
+                                                              const uint32_t *__restrict__ ref_s2,
+                                                              const uint32_t *__restrict__ ref_nv, uint64_t *__restrict__ ht)
+{
+    const uint64_t kmask = (~0ULL) >> (64 - 2 * mal);
+    const uint32_t nmask = (mal >= 32) ? 0xffffffffu : ((1u << mal) - 1);
+    for (uint32_t r = blockIdx.y; r < n_refs; r += gridDim.y) {
+        const RefDesc d = refs[r];
+        const uint32_t *s2 = ref_s2 + d.s2_off;
+        const uint32_t *nv = ref_nv + d.nv_off;
+        uint64_t *tab = ht + d.ht_off;
+        if (d.n < (uint32_t)mal) continue;
+        const uint32_t n_pos = d.n - mal + 1;
+        for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += gridDim.x * blockDim.x) {
+            if (fetch1(nv, p) & nmask) continue;
+            uint64_t code = fetch2(s2, p) & kmask;
+            uint64_t h = fmix64(code);
+            uint64_t val = (h & 0xffffffff00000000ULL) | p;
+            uint32_t slot = (uint32_t)h & d.ht_mask;
+            while (atomicCAS((unsigned long long *)&tab[slot], (unsigned long long)HT_EMPTY, (unsigned long long)val) != HT_EMPTY)
+                slot = (slot + 1) & d.ht_mask;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// comparison primitives
+// ---------------------------------------------------------------------------------------------------------------
+// mismatch flags of Q[qp + t] vs R[rp + t], t = 0..31; anything outside either text counts as a mismatch
+__device__ __forceinline__ uint32_t mm32(const Text &Q, int qp, const Text &R, int rp)
+{
+    int rem = min(Q.n - qp, R.n - rp);
+    if (rem <= 0 || qp < 0 || rp < 0) return 0xffffffffu;
+    uint32_t m = mismatch32(fetch2(Q.s2, (uint64_t)qp), fetch2(R.s2, (uint64_t)rp)) | fetch1(Q.nv, (uint64_t)qp) |
+                 fetch1(R.nv, (uint64_t)rp);
+    if (rem < 32) m |= 0xffffffffu << rem;
+    return m;
+}
+
+// same, for the 32 positions BEFORE (qp, rp), most recent first: bit t <-> Q[qp-1-t] vs R[rp-1-t]; t >= lim mismatch
+__device__ __forceinline__ uint32_t mm32_back(const Text &Q, int qp, const Text &R, int rp, int lim)
+{
+    if (lim <= 0) return 0xffffffffu;
+    int qs = qp - 32, rs = rp - 32;
+    int sh = 0;
+    if (qs < 0 || rs < 0) { sh = max(-qs, -rs); qs += sh; rs += sh; }      // sh < 32 because lim > 0
+    uint32_t m = mismatch32(fetch2(Q.s2, (uint64_t)qs), fetch2(R.s2, (uint64_t)rs)) | fetch1(Q.nv, (uint64_t)qs) |
+                 fetch1(R.nv, (uint64_t)rs);
+    m <<= sh;                       // ascending positions now end at bit 31 = position qp-1
+    m = __brev(m);                  // bit t = position qp-1-t
+    if (lim < 32) m |= 0xffffffffu << lim;
+    return m;
+}
+
+// parser.cpp:192-207 (one lane): length of the exact match of Q[qp..] and R[rp..], known to be >= start
+__device__ __forceinline__ int equal_len(const Text &Q, int qp, const Text &R, int rp, int start)
+{
+    int r = start;
+    for (;;) {
+        uint32_t m = mm32(Q, qp + r, R, rp + r);
+        if (m) return r + __ffs(m) - 1;
+        r += 32;
+    }
+}
+
+// number of matching positions among the first len of Q[qp..] vs R[rp..] (one lane)
+__device__ __forceinline__ int count_matches(const Text &Q, int qp, const Text &R, int rp, int len)
+{
+    int c = 0;
+    for (int o = 0; o < len; o += 32) {
+        uint32_t m = ~mm32(Q, qp + o, R, rp + o);
+        int rem = len - o;
+        if (rem < 32) m &= (1u << rem) - 1;
+        c += __popc(m);
+    }
+    return c;
+}
+
+// Sliding-window rule of try_extend_forward/backward (parser.cpp:377-441) on one lane's 32 flags.
+// x = (this lane's mismatch flags << 32) | the 32 flags before them.  Returns the flags of positions where the
+// number of mismatches among the last aw positions exceeds am (only mismatch positions can be such positions).
+__device__ __forceinline__ uint32_t window_violations(uint64_t x, int aw, int am)
+{
+    uint32_t mm = (uint32_t)(x >> 32);
+    uint32_t viol = 0;
+    if (__popcll(x >> (33 - aw)) <= am) return 0;                 // not enough mismatches in reach of this lane
+    const uint64_t wmask = (aw >= 64) ? ~0ULL : ((1ULL << aw) - 1);
+    uint32_t rest = mm;
+    while (rest) {
+        int b = __ffs(rest) - 1;
+        rest &= rest - 1;
+        if (__popcll((x >> (33 + b - aw)) & wmask) > am) viol |= 1u << b;
+    }
+    return viol;
+}
+
+// positions that END a run of >= ar consecutive matches (the run may start in the previous 32 flags)
+__device__ __forceinline__ uint32_t run_ends(uint64_t x, int ar)
+{
+    uint64_t z = ~x, acc = z;
+    for (int s = 1; s < ar; ++s) acc &= z << s;
+    return (uint32_t)(acc >> 32);
+}
+
+struct ExtResult { int len; int matches; };
+
+// parser.cpp:377-409 for the whole warp: lane l looks at offsets [base + 32 l, base + 32 l + 32).
+// Returns the extension length (end of the last run of >= ar matches before the window rule fires) and the number
+// of matching positions inside it.
+__device__ ExtResult extend_forward(const Text &Q, int qp, const Text &R, int rp, const LzParams &P, int lane)
+{
+    ExtResult res = {0, 0};
+    const int total_rem = min(Q.n - qp, R.n - rp);
+    uint32_t prev_hi = 0;           // flags of the 32 positions before this super-chunk (virtual matches at start)
+    int cum = 0;                    // matches in all earlier super-chunks
+    for (int base = 0;; base += 1024) {
+        uint32_t m = mm32(Q, qp + base + 32 * lane, R, rp + base + 32 * lane);
+        uint32_t pm = __shfl_up_sync(0xffffffffu, m, 1);
+        if (lane == 0) pm = prev_hi;
+        uint64_t x = ((uint64_t)m << 32) | pm;
+        uint32_t viol = window_violations(x, P.aw, P.am);
+        uint32_t ends = run_ends(x, P.ar);
+        unsigned vb = __ballot_sync(0xffffffffu, viol != 0);
+        int limit = 1024;
+        if (vb) {
+            int vl = __ffs(vb) - 1;
+            uint32_t v = __shfl_sync(0xffffffffu, viol, vl);
+            limit = 32 * vl + __ffs(v) - 1;
+        }
+        int my_lim = limit - 32 * lane;                         // positions of this lane that are before the stop
+        uint32_t keep = my_lim >= 32 ? 0xffffffffu : (my_lim <= 0 ? 0u : ((1u << my_lim) - 1));
+        ends &= keep;
+        unsigned eb = __ballot_sync(0xffffffffu, ends != 0);
+        if (eb) {
+            int el = 31 - __clz(eb);
+            uint32_t e = __shfl_sync(0xffffffffu, ends, el);
+            int last_local = 32 * el + (31 - __clz(e)) + 1;
+            int upto = last_local - 32 * lane;
+            uint32_t cm = upto >= 32 ? 0xffffffffu : (upto <= 0 ? 0u : ((1u << upto) - 1));
+            res.len = base + last_local;
+            res.matches = cum + __reduce_add_sync(0xffffffffu, __popc(~m & cm));
+        }
+        if (vb || base + 1024 >= total_rem) return res;           // window rule fired, or both texts are exhausted
+        cum += __reduce_add_sync(0xffffffffu, __popc(~m));
+        prev_hi = __shfl_sync(0xffffffffu, m, 31);
+    }
+}
+
+// parser.cpp:412-441 for the whole warp; offsets count backwards from (qp, rp), at most max_len of them
+__device__ ExtResult extend_backward(const Text &Q, int qp, const Text &R, int rp, int max_len, const LzParams &P, int lane)
+{
+    ExtResult res = {0, 0};
+    int lim_all = min(max_len, min(qp, rp));                      // e < max_len, qp - e > 0, rp - e > 0
+    uint32_t prev_hi = 0;
+    int cum = 0;
+    for (int base = 0;; base += 1024) {
+        int off = base + 32 * lane;
+        uint32_t m = mm32_back(Q, qp - off, R, rp - off, lim_all - off);
+        uint32_t pm = __shfl_up_sync(0xffffffffu, m, 1);
+        if (lane == 0) pm = prev_hi;
+        uint64_t x = ((uint64_t)m << 32) | pm;
+        uint32_t viol = window_violations(x, P.aw, P.am);
+        uint32_t ends = run_ends(x, P.ar);
+        // the loop also stops (without looking at the symbol) at offset lim_all
+        int stop_all = lim_all - base;                            // first offset of this super-chunk not examined
+        unsigned vb = __ballot_sync(0xffffffffu, viol != 0);
+        int limit = 1024;
+        if (vb) {
+            int vl = __ffs(vb) - 1;
+            uint32_t v = __shfl_sync(0xffffffffu, viol, vl);
+            limit = 32 * vl + __ffs(v) - 1;
+        }
+        bool done = vb != 0;
+        if (stop_all <= limit) { limit = max(stop_all, 0); done = true; }
+        int my_lim = limit - 32 * lane;
+        uint32_t keep = my_lim >= 32 ? 0xffffffffu : (my_lim <= 0 ? 0u : ((1u << my_lim) - 1));
+        ends &= keep;
+        unsigned eb = __ballot_sync(0xffffffffu, ends != 0);
+        if (eb) {
+            int el = 31 - __clz(eb);
+            uint32_t e = __shfl_sync(0xffffffffu, ends, el);
+            int last_local = 32 * el + (31 - __clz(e)) + 1;
+            int upto = last_local - 32 * lane;
+            uint32_t cm = upto >= 32 ? 0xffffffffu : (upto <= 0 ? 0u : ((1u << upto) - 1));
+            res.len = base + last_local;
+            res.matches = cum + __reduce_add_sync(0xffffffffu, __popc(~m & cm));
+        }
+        if (done) return res;
+        cum += __reduce_add_sync(0xffffffffu, __popc(~m));
+        prev_hi = __shfl_sync(0xffffffffu, m, 31);
+    }
+}
+
+// parser.h:134-188
+__device__ __forceinline__ double prob_len(int len) { return ldexp(1.0, -2 * len); }
+__device__ __forceinline__ double ipow(double base, uint32_t e)
+{
+    double r = 1.0;
+    while (e) {
+        if (e & 1) r = __dmul_rn(r, base);
+        base = __dmul_rn(base, base);
+        e >>= 1;
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// seed searches
+// ---------------------------------------------------------------------------------------------------------------
+// k-mer of `len` symbols at Q[p]; false when it holds an N or leaves the text
+__device__ __forceinline__ bool kmer_at(const Text &T, int p, int len, uint64_t &code)
+{
+    if (p < 0 || p + len > T.n) return false;
+    uint32_t nm = (len >= 32) ? 0xffffffffu : ((1u << len) - 1);
+    if (fetch1(T.nv, (uint64_t)p) & nm) return false;
+    code = fetch2(T.s2, (uint64_t)p) & ((~0ULL) >> (64 - 2 * len));
+    return true;
+}
+
+// one lane: does the anchor table hold any entry with this k-mer's fingerprint?
+__device__ __forceinline__ bool anchor_probe(const uint64_t *__restrict__ tab, uint32_t mask, uint64_t code)
+{
+    uint64_t h = fmix64(code);
+    uint32_t fp = (uint32_t)(h >> 32);
+    uint32_t slot = (uint32_t)h & mask;
+    for (;;) {
+        uint64_t s = __ldg(tab + slot);
+        if (s == HT_EMPTY) return false;
+        if ((uint32_t)(s >> 32) == fp) return true;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// whole warp, parser.cpp:514-531 / :585-602: longest exact match among all reference positions of Q's mal-mer at i
+// (>= mal), ties to the smallest position.  Lanes read 32 consecutive slots of the probe chain at a time.
+__device__ void anchor_search(const uint64_t *__restrict__ tab, uint32_t mask, const Text &Q, int i, const Text &R,
+                              const LzParams &P, int lane, int &best_len, int &best_pos)
+{
+    best_len = 0; best_pos = 0;
+    uint64_t code;
+    if (!kmer_at(Q, i, P.mal, code)) return;
+    uint64_t h = fmix64(code);
+    uint32_t fp = (uint32_t)(h >> 32);
+    uint32_t slot0 = (uint32_t)h & mask;
+    int my_len = 0, my_pos = 0x7fffffff;
+    for (uint32_t step = 0;; step += 32) {
+        uint64_t s = __ldg(tab + ((slot0 + step + lane) & mask));
+        unsigned empties = __ballot_sync(0xffffffffu, s == HT_EMPTY);
+        bool in_chain = empties == 0 || lane < (__ffs(empties) - 1);
+        if (in_chain && (uint32_t)(s >> 32) == fp) {
+            int pos = (int)(uint32_t)s;
+            int ml = equal_len(Q, i, R, pos, 0);
+            if (ml >= P.mal && (ml > my_len || (ml == my_len && pos < my_pos))) { my_len = ml; my_pos = pos; }
+        }
+        if (empties || step + 32 > mask) break;
+    }
+    int mx = __reduce_max_sync(0xffffffffu, my_len);
+    if (mx == 0) return;
+    int cand = (my_len == mx) ? my_pos : 0x7fffffff;
+    best_len = mx;
+    best_pos = __reduce_min_sync(0xffffffffu, cand);
+}
+
+// whole warp, parser.cpp:548-580: short seeds in the window [pred - lit, pred + mrd): longest continuation,
+// ties to the position closest to pred, then to the smaller position
+__device__ void close_search(const Text &Q, int i, const Text &R, int pred, int lit, const LzParams &P, int lane,
+                             int &best_len, int &best_pos)
+{
+    best_len = 0; best_pos = 0;
+    uint64_t qk;
+    if (!kmer_at(Q, i, P.msl, qk)) return;
+    const int lo = max(pred - lit, 0), hi = pred + P.mrd;
+    int my_len = 0, my_dist = 0x7fffffff, my_pos = 0x7fffffff;
+    for (int pos = lo + lane; pos < hi; pos += 32) {
+        uint64_t rk;
+        if (!kmer_at(R, pos, P.msl, rk) || rk != qk) continue;
+        int ml = equal_len(Q, i, R, pos, P.msl);
+        int dist = abs(pos - pred);
+        if (ml > my_len || (ml == my_len && dist < my_dist)) { my_len = ml; my_dist = dist; my_pos = pos; }
+    }
+    int mx = __reduce_max_sync(0xffffffffu, my_len);
+    if (mx == 0) return;
+    int d = (my_len == mx) ? my_dist : 0x7fffffff;
+    int md = __reduce_min_sync(0xffffffffu, d);
+    int c = (my_len == mx && my_dist == md) ? my_pos : 0x7fffffff;
+    best_len = mx;
+    best_pos = __reduce_min_sync(0xffffffffu, c);
+}
+
+// whole warp, parser.cpp:251-313: best number of matches when the first b gap symbols are aligned to the left
+// context and the last to_scan - b to the right context
+__device__ int gap_best_matches(const Text &Q, int d, const Text &R, int r_left, int r_end_right, int len, int lane)
+{
+    if (len <= 0) return 0;
+    int to_scan = (r_end_right < r_left) ? len : min(r_end_right - r_left, len);
+    int lim = min(to_scan, r_end_right);
+    int best = 0;
+    for (int b = lane; b <= to_scan; b += 32) {
+        int t = to_scan - b;
+        int left = count_matches(Q, d, R, r_left, b);
+        int right = (t <= lim) ? count_matches(Q, d + len - t, R, r_end_right - t, t) : 0;
+        best = max(best, left + right);
+    }
+    return __reduce_max_sync(0xffffffffu, best);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k6: the parse.  All state is warp-uniform; `lane` only selects the data a lane looks at.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void parse_pair(const Text &Q, const Text &R, const uint64_t *__restrict__ tab, uint32_t tmask, const LzParams &P,
+                           int lane, int &out_match, int &out_lit, int &out_comp)
+{
+    const int nQ = Q.n;
+    int i = 0, lit = 0, pred = 0;
+    bool lost = true;
+    int sum_match = 0, sum_lit = 0, n_comp = 0;          // components already final (calc_stats criterion applied)
+    bool comp_active = false;
+    int comp_match = 0, comp_lit = 0, comp_start = 0;    // the live component; comp_start == prev_region_start
+    int prev_end = 0;                                    // prev_region_end
+    int last_match_end = 0, saved_lme = 0;               // end of the last match factor now / before the live component
+
+    while (i + P.msl < nQ) {
+        // ---- 1. find the next query position with a seed, 32 positions per step ------------------------------
+        int steps = nQ - P.msl - i;                      // positions the main loop would still visit
+        if (!lost) steps = min(steps, P.mqd - lit + 1);  // after that many literal steps the parser is lost
+        steps = min(steps, 32);
+        bool flag = false;
+        if (lane < steps) {
+            uint64_t code;
+            if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tmask, code);
+        }
+        if (!lost) {
+            // short seeds: lane t (query position i + t) may use reference positions [lo, pred + t + mrd).  The window
+            // is shared, so its k-mers are computed once (one per lane and round) and broadcast.
+            uint64_t qk = 0;
+            const bool qv = lane < steps && !flag && kmer_at(Q, i + lane, P.msl, qk);
+            const int lo = max(pred - lit, 0);
+            const int my_w = pred + lane + P.mrd - lo;
+            const int max_w = pred + (steps - 1) + P.mrd - lo;
+            for (int j0 = 0; j0 < max_w; j0 += 32) {
+                uint64_t rk;
+                if (!kmer_at(R, lo + j0 + lane, P.msl, rk)) rk = ~0ULL;
+                for (int s = 0; s < 32; ++s) {
+                    uint64_t c = __shfl_sync(0xffffffffu, rk, s);
+                    if (qv && c == qk && j0 + s < my_w) flag = true;
+                }
+            }
+        }
+        unsigned fb = __ballot_sync(0xffffffffu, flag);
+        int adv = fb ? (__ffs(fb) - 1) : steps;
+        i += adv; lit += adv; pred += adv;
+        if (!fb) {
+            if (!lost && lit > P.mqd) lost = true;
+            continue;
+        }
+        // ---- 2. exact evaluation at i (parser.cpp:503-624) ----------------------------------------------------
+        int best_len = 0, best_pos = 0;
+        if (lost)
+            anchor_search(tab, tmask, Q, i, R, P, lane, best_len, best_pos);
+        else {
+            close_search(Q, i, R, pred, lit, P, lane, best_len, best_pos);
+            int a_len, a_pos;
+            anchor_search(tab, tmask, Q, i, R, P, lane, a_len, a_pos);
+            if (a_pos) {                                  // positions double as booleans in the reference (:604-606)
+                if (!best_pos) { best_pos = a_pos; best_len = a_len; }
+                else {
+                    double anchor_prob = ipow(1.0 - prob_len(a_len), (uint32_t)(2 * (R.n + 1 - a_len)));
+                    double close_prob = ipow(1.0 - prob_len(best_len), (uint32_t)(lit + P.mrd + 1 - best_len));
+                    if (anchor_prob > close_prob) { best_pos = a_pos; best_len = a_len; }
+                }
+            }
+        }
+        if (best_len < P.msl) {                           // fingerprint collision or the position-0 quirk
+            ++i; ++lit; ++pred;
+            if (!lost && lit > P.mqd) lost = true;
+            continue;
+        }
+        // ---- 3. account for the match (parser.cpp:626-698) ----------------------------------------------------
+        if (!lost && abs(best_pos - pred) <= P.mrd) {
+            int g = gap_best_matches(Q, i - lit, R, pred - lit, best_pos + best_len, lit, lane);
+            comp_match += g + best_len;
+            comp_lit += lit - g;
+        } else {
+            if (comp_active) {
+                if (prev_end - comp_start < P.reg) last_match_end = saved_lme;      // region deleted (:643-657)
+                else if (comp_match + comp_lit >= P.reg) { sum_match += comp_match; sum_lit += comp_lit; ++n_comp; }
+            }
+            saved_lme = last_match_end;
+            int tail = i - last_match_end;                // length of the literal run in front of the anchor
+            ExtResult back = {0, 0};
+            if (tail > 0) back = extend_backward(Q, i, R, best_pos, tail, P, lane);
+            comp_active = true;
+            comp_start = i - back.len;
+            comp_match = back.matches + best_len;
+            comp_lit = back.len - back.matches;
+        }
+        i += best_len;
+        pred = best_pos + best_len;
+        lit = 0;
+        lost = false;
+        ExtResult fw = extend_forward(Q, i, R, pred, P, lane);
+        comp_match += fw.matches;
+        comp_lit += fw.len - fw.matches;
+        i += fw.len;
+        pred += fw.len;
+        prev_end = i;
+        last_match_end = i;
+    }
+    // ---- tail (parser.cpp:710-713) ------------------------------------------------------------------------------
+    if (!lost) {
+        const int T = lit + (nQ - i);
+        const int qs = i - lit, rs = pred - lit - P.msl;
+        int mt = 0, last = -1;
+        for (int o = 32 * lane; o < T; o += 1024) {
+            uint32_t m = ~mm32(Q, qs + o, R, rs + o);
+            int rem = T - o;
+            if (rem < 32) m &= (1u << rem) - 1;
+            mt += __popc(m);
+            if (m) last = o + 31 - __clz(m);
+        }
+        mt = __reduce_add_sync(0xffffffffu, mt);
+        last = __reduce_max_sync(0xffffffffu, last);
+        if (mt > 0) { comp_match += mt; comp_lit += last + 1 - mt; }
+    }
+    if (comp_active && comp_match + comp_lit >= P.reg) { sum_match += comp_match; sum_lit += comp_lit; ++n_comp; }
+    out_match = sum_match; out_lit = sum_lit; out_comp = n_comp;
+}
+
+__global__ void __launch_bounds__(128) parse_kernel(const uint32_t *__restrict__ g2, const uint32_t *__restrict__ gn,
+                                                    const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
+                                                    const RefDesc *__restrict__ refs, const uint32_t *__restrict__ ref_s2,
+                                                    const uint32_t *__restrict__ ref_nv, const uint64_t *__restrict__ ht,
+                                                    const uint32_t *__restrict__ pair_ref, const uint32_t *__restrict__ pair_qry,
+                                                    uint32_t n_pairs, LzParams P, unsigned int *__restrict__ cursor,
+                                                    int32_t *__restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(cursor, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_pairs) return;
+        const RefDesc d = refs[pair_ref[idx]];
+        const uint32_t q = pair_qry[idx];
+        Text R = {ref_s2 + d.s2_off, ref_nv + d.nv_off, (int)d.n};
+        uint64_t qo = gofs[q];
+        Text Q = {g2 + (qo >> 4), gn + (qo >> 5), (int)glen[q] + P.mrd};
+        int m, l, c;
+        parse_pair(Q, R, ht + d.ht_off, d.ht_mask, P, lane, m, l, c);
+        if (lane == 0) { stats[3 * (uint64_t)idx] = m; stats[3 * (uint64_t)idx + 1] = l; stats[3 * (uint64_t)idx + 2] = c; }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------------------------
+void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
+                         const vb_align_params *ap, int32_t *stats)
+{
+    if (ap->mal < 4 || ap->mal > 31 || ap->msl < 2 || ap->msl > ap->mal || ap->msl > 31)
+        throw vb_error(VB_ERR_ARG, "need 2 <= msl <= mal <= 31");
+    if (ap->aw < 1 || ap->aw > 32 || ap->ar < 1 || ap->ar > 32 || ap->am < 0)
+        throw vb_error(VB_ERR_ARG, "need 1 <= aw <= 32, 1 <= ar <= 32, am >= 0");
+    if (ap->mrd < 1 || ap->mrd > 4096 || ap->mqd < 0) throw vb_error(VB_ERR_ARG, "need 1 <= mrd <= 4096, mqd >= 0");
+    if (n >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 pairs in one call");
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t ng = g->count();
+    for (uint64_t i = 0; i < n; ++i)
+        if (ref[i] >= ng || qry[i] >= ng) throw vb_error(VB_ERR_ARG, "pair id out of range");
+    LzParams P = {ap->mal, ap->msl, ap->mrd, ap->mqd, ap->reg, ap->aw, ap->am, ap->ar};
+    EventTimer t_all(st), t_up(st);
+    double ms_index = 0, ms_parse = 0;
+
+    t_all.start();
+    t_up.start();
+    DevGenomes dg;
+    vb_upload_genomes(ctx, g, /*u_is_t=*/false, dg, (uint32_t)ap->mrd + 128);
+    t_up.stop();
+
+    // pairs grouped by reference (stable), so that one reference's index is built once and stays hot in L2
+    std::vector<uint32_t> order(n);
+    for (uint64_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ref[a] < ref[b]; });
+
+    size_t free_b = 0, total_b = 0;
+    VB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget = (uint64_t)(free_b * 0.6);
+
+    DevBuf<int32_t> d_stats(3 * std::max<uint64_t>(n, 1));
+    DevBuf<uint32_t> d_pref(std::max<uint64_t>(n, 1)), d_pqry(std::max<uint64_t>(n, 1));
+    DevBuf<unsigned int> d_cursor(1);
+    std::vector<int32_t> h_stats(3 * n);
+
+    uint64_t pos = 0;
+    int n_batches = 0;
+    while (pos < n) {
+        // ---- choose a batch of references that fits the memory budget
+        std::vector<RefDesc> refs;
+        std::vector<uint32_t> b_ref, b_qry;
+        uint64_t s2_words = 0, nv_words = 0, slots = 0, bytes = 0;
+        uint64_t end = pos;
+        while (end < n) {
+            uint32_t r = ref[order[end]];
+            if (refs.empty() || refs.back().gid != r) {
+                uint64_t len = g->length(r);
+                uint64_t nR = 2 * len + 3 * (uint64_t)ap->mrd;
+                uint64_t chunks = (nR + 31) / 32 + 4;
+                uint64_t cap = 1024;
+                while (cap < 2 * nR) cap <<= 1;
+                uint64_t need = chunks * 12 + cap * 8;
+                if (!refs.empty() && bytes + need > budget) break;
+                if (refs.empty() && need > budget) throw vb_error(VB_ERR_MEM, "reference index does not fit device memory");
+                RefDesc d;
+                d.s2_off = s2_words; d.nv_off = nv_words; d.ht_off = slots;
+                d.ht_mask = (uint32_t)(cap - 1); d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = r;
+                refs.push_back(d);
+                s2_words += 2 * chunks + 4; nv_words += chunks + 4; slots += cap; bytes += need;
+            }
+            b_ref.push_back((uint32_t)refs.size() - 1);
+            b_qry.push_back(qry[order[end]]);
+            ++end;
+        }
+        const uint32_t nb = (uint32_t)(end - pos);
+        DevBuf<RefDesc> d_refs(refs.size());
+        DevBuf<uint32_t> ref_s2(s2_words + 8), ref_nv(nv_words + 8);
+        DevBuf<uint64_t> ht(slots);
+        VB_CUDA(cudaMemcpyAsync(d_refs.p, refs.data(), sizeof(RefDesc) * refs.size(), cudaMemcpyHostToDevice, st));
+        VB_CUDA(cudaMemcpyAsync(d_pref.p, b_ref.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
+        VB_CUDA(cudaMemcpyAsync(d_pqry.p, b_qry.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
+        VB_CUDA(cudaMemsetAsync(ref_nv.p, 0xff, ref_nv.bytes(), st));
+        VB_CUDA(cudaMemsetAsync(ref_s2.p, 0, ref_s2.bytes(), st));
+        VB_CUDA(cudaMemsetAsync(ht.p, 0xff, ht.bytes(), st));
+        VB_CUDA(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned int), st));
+
+        EventTimer t_idx(st), t_par(st);
+        t_idx.start();
+        dim3 grid_b(16, (unsigned)std::min<size_t>(refs.size(), 32768));
+        build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, d_refs.p, (uint32_t)refs.size(), ap->mrd,
+                                                     ref_s2.p, ref_nv.p);
+        VB_LAUNCH_CHECK(ctx);
+        build_ref_index_kernel<<<grid_b, 256, 0, st>>>(d_refs.p, (uint32_t)refs.size(), ap->mal, ref_s2.p, ref_nv.p, ht.p);
+        VB_LAUNCH_CHECK(ctx);
+        t_idx.stop();
+
+        t_par.start();
+        int per_sm = 0;
+        VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, parse_kernel, 128, 0));
+        int n_sm = 0;
+        VB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+        int blocks = std::max(1, std::min<int>(per_sm * n_sm, (int)((nb + 3) / 4)));
+        parse_kernel<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, dg.glen.p, d_refs.p, ref_s2.p, ref_nv.p, ht.p,
+                                             d_pref.p, d_pqry.p, nb, P, d_cursor.p, d_stats.p);
+        VB_LAUNCH_CHECK(ctx);
+        t_par.stop();
+        std::vector<int32_t> tmp(3 * (size_t)nb);
+        VB_CUDA(cudaMemcpyAsync(tmp.data(), d_stats.p, sizeof(int32_t) * 3 * nb, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t j = 0; j < nb; ++j) {
+            uint64_t o = order[pos + j];
+            stats[3 * o] = tmp[3 * j]; stats[3 * o + 1] = tmp[3 * j + 1]; stats[3 * o + 2] = tmp[3 * j + 2];
+        }
+        ms_index += t_idx.ms();
+        ms_parse += t_par.ms();
+        pos = end;
+        ++n_batches;
+    }
+    t_all.stop();
+    VB_CUDA(cudaStreamSynchronize(st));
+    ctx->set_timing("align.total_ms", n ? t_all.ms() : 0.0);
+    ctx->set_timing("align.upload_pack_ms", t_up.ms());
+    ctx->set_timing("align.index_ms", ms_index);
+    ctx->set_timing("align.parse_ms", ms_parse);
+    ctx->set_timing("align.batches", n_batches);
+    ctx->set_timing("align.pairs", (double)n);
+}

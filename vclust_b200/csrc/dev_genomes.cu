@@ -1,0 +1,103 @@
+// Upload of a genome set and 2-bit packing on the device (one pass over the ASCII bytes).
+#include "dev_util.cuh"
+
+namespace {
+
+// code table: 0..3 = ACGT, 4 = invalid.  Index 0: lz-ani rule (U invalid), 1: kmer-db rule (U == T).
+__constant__ uint8_t c_code[2][256];
+
+__global__ void pack_kernel(const uint8_t *__restrict__ ascii, const uint64_t *__restrict__ src_off,
+                            const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
+                            const uint32_t *__restrict__ tile_gid, uint64_t n_chunks, int rule,
+                            uint32_t *__restrict__ seq2, uint32_t *__restrict__ inv)
+{
+    // one thread per 32 base slots: two seq2 words and one inv word
+    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n_chunks;
+         c += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t slot = c * 32;
+        uint32_t gid = tile_gid[slot >> 7];
+        uint32_t w0 = 0, w1 = 0, bad = 0xffffffffu;
+        if (gid != 0xffffffffu) {
+            uint64_t local = slot - gofs[gid];
+            uint32_t len = glen[gid];
+            if (local < len) {
+                const uint8_t *src = ascii + src_off[gid] + local;
+                uint32_t m = (len - local) < 32 ? (uint32_t)(len - local) : 32u;
+                bad = 0;
+#pragma unroll 8
+                for (uint32_t j = 0; j < 32; ++j) {
+                    uint32_t code = 4;
+                    if (j < m) code = c_code[rule][src[j]];
+                    uint32_t two = code & 3;
+                    if (code > 3) { bad |= 1u << j; two = 0; }
+                    if (j < 16) w0 |= two << (2 * j);
+                    else w1 |= two << (2 * (j - 16));
+                }
+            }
+        }
+        seq2[2 * c] = w0;
+        seq2[2 * c + 1] = w1;
+        inv[c] = bad;
+    }
+}
+
+}  // namespace
+
+void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes &out, uint32_t min_pad)
+{
+    if (min_pad < 128) min_pad = 128;
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    static bool table_ready[64] = {false};
+    if (!table_ready[ctx->device & 63]) {
+        uint8_t t[2][256];
+        memset(t, 4, sizeof(t));
+        const char *acgt = "ACGT";
+        for (int r = 0; r < 2; ++r)
+            for (int i = 0; i < 4; ++i) { t[r][(uint8_t)acgt[i]] = (uint8_t)i; t[r][(uint8_t)(acgt[i] | 0x20)] = (uint8_t)i; }
+        t[1][(uint8_t)'U'] = 3; t[1][(uint8_t)'u'] = 3;
+        VB_CUDA(cudaMemcpyToSymbol(c_code, t, sizeof(t)));
+        table_ready[ctx->device & 63] = true;
+    }
+    const uint32_t n = g->count();
+    out.n = n;
+    out.h_gofs.resize(n);
+    out.h_glen.resize(n);
+    uint64_t slots = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t len = g->length(i);
+        if (len > 0x7fff0000ULL) throw vb_error(VB_ERR_ARG, "genome longer than 2^31 bases: " + g->names[i]);
+        out.h_gofs[i] = slots;
+        out.h_glen[i] = (uint32_t)len;
+        slots += ((len + min_pad + 127) / 128) * 128;  // >= min_pad invalid slots after every genome
+    }
+    slots += 128;
+    out.total_slots = slots;
+    std::vector<uint32_t> tile(slots / 128, 0xffffffffu);
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint64_t t = out.h_gofs[i] / 128; t * 128 < out.h_gofs[i] + out.h_glen[i]; ++t) tile[t] = i;
+
+    out.seq2.alloc(slots / 16 + 8);
+    out.inv.alloc(slots / 32 + 8);
+    out.gofs.alloc(n ? n : 1);
+    out.glen.alloc(n ? n : 1);
+    out.tile_gid.alloc(tile.size());
+    DevBuf<uint8_t> ascii(g->bases.size() + 64);
+    DevBuf<uint64_t> src_off(n + 1);
+    VB_CUDA(cudaMemsetAsync(out.seq2.p, 0, out.seq2.bytes(), st));
+    VB_CUDA(cudaMemsetAsync(out.inv.p, 0xff, out.inv.bytes(), st));
+    if (!g->bases.empty())
+        VB_CUDA(cudaMemcpyAsync(ascii.p, g->bases.data(), g->bases.size(), cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemcpyAsync(src_off.p, g->offset.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    if (n) {
+        VB_CUDA(cudaMemcpyAsync(out.gofs.p, out.h_gofs.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
+        VB_CUDA(cudaMemcpyAsync(out.glen.p, out.h_glen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    }
+    VB_CUDA(cudaMemcpyAsync(out.tile_gid.p, tile.data(), sizeof(uint32_t) * tile.size(), cudaMemcpyHostToDevice, st));
+    uint64_t n_chunks = slots / 32;
+    int threads = 256;
+    int blocks = (int)std::min<uint64_t>((n_chunks + threads - 1) / threads, 148 * 16);
+    pack_kernel<<<blocks, threads, 0, st>>>((const uint8_t *)ascii.p, src_off.p, out.gofs.p, out.glen.p, out.tile_gid.p,
+                                            n_chunks, u_is_t ? 1 : 0, out.seq2.p, out.inv.p);
+    VB_LAUNCH_CHECK(ctx);
+    VB_CUDA(cudaStreamSynchronize(st));     // ascii / tile vectors go out of scope
+}

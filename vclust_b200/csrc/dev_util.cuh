@@ -1,0 +1,120 @@
+// Device-side plumbing shared by the .cu files: error checks, RAII buffers, the packed genome store.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "vb_internal.h"
+
+#define VB_CUDA(expr)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            throw vb_error(VB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                            ":" + std::to_string(__LINE__) + ")");                        \
+    } while (0)
+
+#define VB_LAUNCH_CHECK(ctx)             \
+    do {                                 \
+        (ctx)->launches++;               \
+        VB_CUDA(cudaGetLastError());     \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count) {
+            cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+            if (e != cudaSuccess) {
+                p = nullptr; n = 0;
+                throw vb_error(VB_ERR_MEM, "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
+                                               cudaGetErrorString(e));
+            }
+        }
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+struct EventTimer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    explicit EventTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    void stop() { cudaEventRecord(b, s); }
+    double ms() { cudaEventSynchronize(b); float t = 0; cudaEventElapsedTime(&t, a, b); return t; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed genome store in HBM.
+//   Genome g occupies base slots [gofs[g], gofs[g] + glen[g]) of one global base axis; every genome starts at a
+//   multiple of 128 bases and is followed by at least 128 slots of padding marked invalid, so a kernel may read up
+//   to 64 bases past the end of a genome without a bounds check.
+//   seq2 : 2 bits per base, 16 bases per uint32 word, base b of a word at bits [2b, 2b+1]  (A0 C1 G2 T3)
+//   inv  : 1 bit per base, 32 bases per uint32 word, set when the base is not ACGT(U) or is padding
+//   tile_gid : genome id owning each 128-base tile (0xffffffff for none)
+// ---------------------------------------------------------------------------------------------------------------
+struct DevGenomes {
+    uint32_t n = 0;
+    uint64_t total_slots = 0;        // multiple of 128
+    DevBuf<uint32_t> seq2, inv;
+    DevBuf<uint64_t> gofs;           // n entries
+    DevBuf<uint32_t> glen;           // n entries
+    DevBuf<uint32_t> tile_gid;       // total_slots / 128
+    std::vector<uint64_t> h_gofs;
+    std::vector<uint32_t> h_glen;
+};
+
+// Upload ASCII and pack on the device.  u_is_t: kmer-db treats U/u as T; lz-ani treats it as N.
+// min_pad: invalid slots guaranteed after every genome (>= 128).
+void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes &out, uint32_t min_pad = 128);
+
+#ifdef __CUDACC__
+// 32 bases (64 bits) starting at base slot p of a 2-bit array; base p lands in bits [0,1].
+__device__ __forceinline__ uint64_t fetch2(const uint32_t *__restrict__ w, uint64_t p)
+{
+    const uint32_t *q = w + (p >> 4);
+    uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    unsigned sh = (unsigned)(p & 15) * 2;
+    uint32_t lo = __funnelshift_r(a, b, sh);
+    uint32_t hi = __funnelshift_r(b, c, sh);
+    return ((uint64_t)hi << 32) | lo;
+}
+// 32 flag bits starting at base slot p of a 1-bit array.
+__device__ __forceinline__ uint32_t fetch1(const uint32_t *__restrict__ w, uint64_t p)
+{
+    const uint32_t *q = w + (p >> 5);
+    uint32_t a = __ldg(q), b = __ldg(q + 1);
+    return __funnelshift_r(a, b, (unsigned)(p & 31));
+}
+// squeeze the even bits of a 64-bit word (one flag per 2-bit base) into 32 bits
+__device__ __forceinline__ uint32_t squeeze_even(uint64_t x)
+{
+    x &= 0x5555555555555555ULL;
+    x = (x | (x >> 1)) & 0x3333333333333333ULL;
+    x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0fULL;
+    x = (x | (x >> 4)) & 0x00ff00ff00ff00ffULL;
+    x = (x | (x >> 8)) & 0x0000ffff0000ffffULL;
+    x = (x | (x >> 16)) & 0x00000000ffffffffULL;
+    return (uint32_t)x;
+}
+// per-base mismatch flags of two 32-base words
+__device__ __forceinline__ uint32_t mismatch32(uint64_t a, uint64_t b)
+{
+    uint64_t x = a ^ b;
+    return squeeze_even(x | (x >> 1));
+}
+#endif

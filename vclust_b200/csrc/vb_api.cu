@@ -1,0 +1,225 @@
+// C ABI of libvclust_b200.so (see include/vclust_b200.h).  Everything here is glue: argument checks, exception ->
+// status translation, and the host-side bookkeeping LZ-ANI does around its matching loop (genome re-ordering,
+// filter symmetrisation: seq_reservoir.cpp:215-251, filter.cpp:80-81,253-345, lz_matcher.cpp:172-277).
+#include <algorithm>
+#include <numeric>
+
+#include "dev_util.cuh"
+
+vb_genomes *vb_genomes_load_impl(const char *const *paths, int n_paths, int multisample, vb_fasta_flavor flavor, int sep_len);
+vb_genomes *vb_genomes_from_memory_impl(const char *const *names, const char *const *seqs, const uint64_t *lens, uint32_t n);
+void vb_write_filter_impl(const vb_genomes *g, const vb_pairs *pr, const char *path);
+vb_pairs *vb_read_filter_impl(const char *path, double thr, const vb_genomes *g);
+void vb_pairs_free_impl(vb_pairs *p);
+void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char *ani_path, const char *ids_path,
+                       const char *const *columns, int n_columns, const double out_filters[5]);
+
+static thread_local std::string g_last_error;
+void vb_set_error(const std::string &msg) { g_last_error = msg; }
+
+#define VB_GUARD_BEGIN try {
+#define VB_GUARD_END                                                        \
+    }                                                                       \
+    catch (const vb_error &e) { vb_set_error(e.what()); return e.code; }    \
+    catch (const std::bad_alloc &) { vb_set_error("out of host memory"); return VB_ERR_MEM; } \
+    catch (const std::exception &e) { vb_set_error(e.what()); return VB_ERR_INTERNAL; }       \
+    return VB_OK;
+
+extern "C" {
+
+int vb_version(char *buf, size_t n)
+{
+    static const char v[] = "vclust-b200 0.1.0 (prefilter: Kmer-db 2.3.1 semantics; align: LZ-ANI 1.2.3 semantics; sm_100a)";
+    if (!buf || n == 0) return VB_ERR_ARG;
+    snprintf(buf, n, "%s", v);
+    return VB_OK;
+}
+
+int vb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *vb_last_error(void) { return g_last_error.c_str(); }
+
+int vb_ctx_create(int device, vb_ctx **out)
+{
+    VB_GUARD_BEGIN
+    if (!out) throw vb_error(VB_ERR_ARG, "vb_ctx_create: null out pointer");
+    int n = vb_device_count();
+    if (n <= 0) throw vb_error(VB_ERR_CUDA, "no CUDA device available: libvclust_b200 has no CPU fallback");
+    if (device < 0 || device >= n) throw vb_error(VB_ERR_ARG, "vb_ctx_create: device index out of range");
+    VB_CUDA(cudaSetDevice(device));
+    auto *ctx = new vb_ctx();
+    ctx->device = device;
+    cudaStream_t st;
+    VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    ctx->stream = (void *)st;
+    *out = ctx;
+    VB_GUARD_END
+}
+
+void vb_ctx_destroy(vb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy((cudaStream_t)ctx->stream);
+    delete ctx;
+}
+
+int vb_ctx_timing(const vb_ctx *ctx, const char *key, double *ms)
+{
+    if (!ctx || !key || !ms) return VB_ERR_ARG;
+    for (auto &t : ctx->timings)
+        if (t.key == key) { *ms = t.ms; return VB_OK; }
+    return VB_ERR_ARG;
+}
+
+uint64_t vb_ctx_launches(const vb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int vb_genomes_load(const char *const *paths, int n_paths, int multisample, vb_fasta_flavor flavor, int sep_len,
+                    vb_genomes **out)
+{
+    VB_GUARD_BEGIN
+    if (!paths || n_paths <= 0 || !out) throw vb_error(VB_ERR_ARG, "vb_genomes_load: bad arguments");
+    *out = vb_genomes_load_impl(paths, n_paths, multisample, flavor, sep_len);
+    VB_GUARD_END
+}
+
+int vb_genomes_from_memory(const char *const *names, const char *const *seqs, const uint64_t *lens, uint32_t n,
+                           vb_genomes **out)
+{
+    VB_GUARD_BEGIN
+    if (!names || !seqs || !lens || !out) throw vb_error(VB_ERR_ARG, "vb_genomes_from_memory: bad arguments");
+    *out = vb_genomes_from_memory_impl(names, seqs, lens, n);
+    VB_GUARD_END
+}
+
+uint32_t vb_genomes_count(const vb_genomes *g) { return g ? g->count() : 0; }
+const char *vb_genomes_name(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->names[i].c_str() : ""; }
+uint64_t vb_genomes_length(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->length(i) : 0; }
+uint64_t vb_genomes_total_bases(const vb_genomes *g) { return g ? g->bases.size() : 0; }
+void vb_genomes_free(vb_genomes *g) { delete g; }
+
+int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter: bad arguments");
+    vb_prefilter_impl(ctx, g, p, out);
+    VB_GUARD_END
+}
+
+int vb_write_filter(const vb_genomes *g, const vb_pairs *pairs, const char *path)
+{
+    VB_GUARD_BEGIN
+    if (!g || !pairs || !path) throw vb_error(VB_ERR_ARG, "vb_write_filter: bad arguments");
+    vb_write_filter_impl(g, pairs, path);
+    VB_GUARD_END
+}
+
+int vb_read_filter(const char *path, double thr, const vb_genomes *g, vb_pairs **out)
+{
+    VB_GUARD_BEGIN
+    if (!g || !path || !out) throw vb_error(VB_ERR_ARG, "vb_read_filter: bad arguments");
+    *out = vb_read_filter_impl(path, thr, g);
+    VB_GUARD_END
+}
+
+void vb_pairs_free(vb_pairs *p) { vb_pairs_free_impl(p); }
+
+int vb_align_pairs(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
+                   const vb_align_params *p, int32_t *stats)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || !g || !p || (n && (!ref || !qry || !stats))) throw vb_error(VB_ERR_ARG, "vb_align_pairs: bad arguments");
+    vb_align_pairs_impl(ctx, g, ref, qry, n, p, stats);
+    VB_GUARD_END
+}
+
+int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_align_params *p, vb_align_out **out)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_align: bad arguments");
+    const uint32_t n = g->count();
+    // LZ-ANI order: length descending, then name ascending (stable) -- seq_reservoir.cpp:229-236
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        uint32_t la = (uint32_t)g->length(a) - 2u, lb = (uint32_t)g->length(b) - 2u;   // len - 2*no_parts, unsigned (sic)
+        if (la != lb) return la > lb;
+        return g->names[a] < g->names[b];
+    });
+    std::vector<uint32_t> rank(n);
+    for (uint32_t i = 0; i < n; ++i) rank[order[i]] = i;
+
+    // directed pair list in LZ-ANI ids, grouped by reference with the queries ascending (results rows are sorted, :253)
+    std::vector<std::vector<uint32_t>> rows(n);
+    if (!pairs) {
+        for (uint32_t r = 0; r < n; ++r) {
+            rows[r].reserve(n - 1);
+            for (uint32_t q = 0; q < n; ++q) if (q != r) rows[r].push_back(q);
+        }
+    } else {
+        for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
+            uint32_t a = pairs->row[i], b = pairs->col[i];
+            if (a >= n || b >= n) throw vb_error(VB_ERR_ARG, "vb_align: pair id out of range");
+            rows[rank[a]].push_back(rank[b]);      // filter[i].push(id); filter[id].push(i)
+            rows[rank[b]].push_back(rank[a]);
+        }
+        for (auto &r : rows) std::sort(r.begin(), r.end());
+    }
+    uint64_t total = 0;
+    for (auto &r : rows) total += r.size();
+    auto *res = (vb_align_out *)calloc(1, sizeof(vb_align_out));
+    res->n = total;
+    res->n_genomes = n;
+    res->ref = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint64_t>(total, 1));
+    res->qry = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint64_t>(total, 1));
+    res->sym_in_matches = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
+    res->sym_in_literals = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
+    res->no_components = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
+    res->order = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint32_t>(n, 1));
+    std::copy(order.begin(), order.end(), res->order);
+    std::vector<uint32_t> in_ref(total), in_qry(total);
+    uint64_t w = 0;
+    for (uint32_t r = 0; r < n; ++r)
+        for (uint32_t q : rows[r]) {
+            res->ref[w] = r; res->qry[w] = q;
+            in_ref[w] = order[r]; in_qry[w] = order[q];
+            ++w;
+        }
+    std::vector<int32_t> stats(3 * std::max<uint64_t>(total, 1));
+    try {
+        vb_align_pairs_impl(ctx, g, in_ref.data(), in_qry.data(), total, p, stats.data());
+    } catch (...) {
+        vb_align_out_free(res);
+        throw;
+    }
+    for (uint64_t i = 0; i < total; ++i) {
+        res->sym_in_matches[i] = stats[3 * i];
+        res->sym_in_literals[i] = stats[3 * i + 1];
+        res->no_components[i] = stats[3 * i + 2];
+    }
+    *out = res;
+    VB_GUARD_END
+}
+
+int vb_write_ani(const vb_genomes *g, const vb_align_out *res, const char *ani_path, const char *ids_path,
+                 const char *const *columns, int n_columns, const double out_filters[5])
+{
+    VB_GUARD_BEGIN
+    if (!g || !res || !ani_path || !ids_path || (n_columns && !columns)) throw vb_error(VB_ERR_ARG, "vb_write_ani: bad arguments");
+    vb_write_ani_impl(g, res, ani_path, ids_path, columns, n_columns, out_filters);
+    VB_GUARD_END
+}
+
+void vb_align_out_free(vb_align_out *r)
+{
+    if (!r) return;
+    free(r->ref); free(r->qry); free(r->sym_in_matches); free(r->sym_in_literals); free(r->no_components); free(r->order);
+    free(r);
+}
+
+}  // extern "C"

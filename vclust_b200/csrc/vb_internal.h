@@ -1,0 +1,53 @@
+// Internal declarations shared by the translation units of libvclust_b200.so (not part of the C ABI).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vclust_b200.h"
+
+struct vb_error : std::runtime_error {
+    int code;
+    vb_error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+void vb_set_error(const std::string &msg);
+
+// Host-side genome set.  Sequences are kept as ASCII exactly as read (separators between the records of one
+// file already inserted as 'N' bytes); symbol coding happens on the device, per stage, because kmer-db and
+// lz-ani disagree on 'U' (kmer-db alphabet.h:80-85 vs lz-ani seq_reservoir.h:243-247).
+struct vb_genomes {
+    std::vector<std::string> names;
+    std::vector<uint64_t> offset;   // n+1 offsets into bases
+    std::vector<char> bases;        // concatenated ASCII
+    vb_fasta_flavor flavor = VB_FASTA_KMERDB;
+    uint32_t count() const { return (uint32_t)names.size(); }
+    uint64_t length(uint32_t i) const { return offset[i + 1] - offset[i]; }
+};
+
+// ---- text formats (host_format.cpp) ---------------------------------------------------------------------------
+int vb_fmt_fixed6(double v, char *out);                 // kmer-db conversion.h:167-219 Double2PChar(v, 6)
+int vb_fmt_real(double v, int prec, char *out);         // refresh numeric_conversions.h:229-299 real_to_pchar
+double vb_ani_shorter(uint32_t common, uint32_t cnt1, uint32_t cnt2, int k);   // kmer-db params.cpp:28-32
+
+// ---- device side (declared here, defined in the .cu files) -----------------------------------------------------
+struct vb_timing { std::string key; double ms; };
+
+struct vb_ctx {
+    int device = 0;
+    void *stream = nullptr;          // cudaStream_t
+    uint64_t launches = 0;
+    std::vector<vb_timing> timings;
+    void set_timing(const std::string &k, double ms) {
+        for (auto &t : timings) if (t.key == k) { t.ms = ms; return; }
+        timings.push_back({k, ms});
+    }
+};
+
+void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out);
+void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
+                         const vb_align_params *p, int32_t *stats);
