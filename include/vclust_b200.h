@@ -56,6 +56,10 @@ void vb_ctx_destroy(vb_ctx *ctx);
 int vb_ctx_timing(const vb_ctx *ctx, const char *key, double *ms);
 /* Number of kernel launches issued by the library on this context since creation. */
 uint64_t vb_ctx_launches(const vb_ctx *ctx);
+/* CUDA events on the context's stream, for callers that time a sequence of calls on the device:
+ * vb_ctx_mark records event `slot` (0..7); vb_ctx_elapsed_ms waits for slot_b and returns slot_a -> slot_b. */
+int vb_ctx_mark(vb_ctx *ctx, int slot);
+int vb_ctx_elapsed_ms(vb_ctx *ctx, int slot_a, int slot_b, double *ms);
 
 /* ---- genomes ------------------------------------------------------------------------------------------------ */
 /* Replaces the FASTA ingest of both tools.  paths: one multi-FASTA file (multisample != 0) or the files of a
@@ -67,6 +71,12 @@ int vb_genomes_load(const char *const *paths, int n_paths, int multisample, vb_f
 /* Same, from memory: n sequences of ASCII bases (used by the bench and the tests; no file I/O). */
 int vb_genomes_from_memory(const char *const *names, const char *const *seqs, const uint64_t *lens, uint32_t n,
                            vb_genomes **out);
+/* Keep the 2-bit packed copy of g in HBM on this context until vb_genomes_evict / vb_ctx_destroy, so that later
+ * vb_prefilter (rule VB_FASTA_KMERDB: U == T) or vb_align* (rule VB_FASTA_LZANI: U == N, padded for `mrd`) calls
+ * on the same g start with their input already on the device.  Without it every call uploads g itself.
+ * g must outlive its residency; call vb_genomes_evict(ctx, g) (g == NULL: all) before freeing it. */
+int vb_genomes_make_resident(vb_ctx *ctx, const vb_genomes *g, vb_fasta_flavor rule, int mrd);
+int vb_genomes_evict(vb_ctx *ctx, const vb_genomes *g);
 uint32_t vb_genomes_count(const vb_genomes *g);
 const char *vb_genomes_name(const vb_genomes *g, uint32_t i);
 uint64_t vb_genomes_length(const vb_genomes *g, uint32_t i);

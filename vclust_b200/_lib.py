@@ -10,7 +10,7 @@ LIB_PATH = HERE / "libvclust_b200.so"
 
 EXPORTS = [
     "vb_version", "vb_device_count", "vb_last_error", "vb_ctx_create", "vb_ctx_destroy", "vb_ctx_timing",
-    "vb_ctx_launches", "vb_genomes_load", "vb_genomes_from_memory", "vb_genomes_count", "vb_genomes_name",
+    "vb_ctx_launches", "vb_ctx_mark", "vb_ctx_elapsed_ms", "vb_genomes_make_resident", "vb_genomes_evict", "vb_genomes_load", "vb_genomes_from_memory", "vb_genomes_count", "vb_genomes_name",
     "vb_genomes_length", "vb_genomes_total_bases", "vb_genomes_free", "vb_prefilter", "vb_write_filter",
     "vb_read_filter", "vb_pairs_free", "vb_align", "vb_align_pairs", "vb_write_ani", "vb_align_out_free",
 ]
@@ -64,6 +64,10 @@ def load():
         "vb_ctx_destroy": (None, [vp]),
         "vb_ctx_timing": (i32, [vp, cp, C.POINTER(dbl)]),
         "vb_ctx_launches": (u64, [vp]),
+        "vb_ctx_mark": (i32, [vp, i32]),
+        "vb_ctx_elapsed_ms": (i32, [vp, i32, i32, C.POINTER(dbl)]),
+        "vb_genomes_make_resident": (i32, [vp, vp, i32, i32]),
+        "vb_genomes_evict": (i32, [vp, vp]),
         "vb_genomes_load": (i32, [C.POINTER(cp), i32, i32, i32, i32, C.POINTER(vp)]),
         "vb_genomes_from_memory": (i32, [C.POINTER(cp), C.POINTER(vp), C.POINTER(u64), u32, C.POINTER(vp)]),
         "vb_genomes_count": (u32, [vp]),

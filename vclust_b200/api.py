@@ -86,6 +86,20 @@ class Context:
     def launches(self) -> int:
         return int(self._L.vb_ctx_launches(self._h))
 
+    def mark(self, slot: int) -> None:
+        check(self._L.vb_ctx_mark(self._h, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        v = C.c_double()
+        check(self._L.vb_ctx_elapsed_ms(self._h, a, b, C.byref(v)))
+        return v.value
+
+    def make_resident(self, genomes: "Genomes", rule: int, mrd: int = 40) -> None:
+        check(self._L.vb_genomes_make_resident(self._h, genomes._h, rule, mrd))
+
+    def evict(self, genomes: "Genomes | None" = None) -> None:
+        check(self._L.vb_genomes_evict(self._h, genomes._h if genomes is not None else None))
+
 
 class Genomes:
     """A genome set on the host (vb_genomes)."""

@@ -588,8 +588,8 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
 
     t_all.start();
     t_up.start();
-    DevGenomes dg;
-    vb_upload_genomes(ctx, g, /*u_is_t=*/false, dg, (uint32_t)ap->mrd + 128);
+    DevGenomes dg_scratch;
+    const DevGenomes &dg = vb_get_dev_genomes(ctx, g, /*u_is_t=*/false, (uint32_t)ap->mrd + 128, dg_scratch);
     t_up.stop();
 
     // pairs grouped by reference (stable), so that one reference's index is built once and stays hot in L2

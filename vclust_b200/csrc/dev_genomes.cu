@@ -81,6 +81,11 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes
     out.gofs.alloc(n ? n : 1);
     out.glen.alloc(n ? n : 1);
     out.tile_gid.alloc(tile.size());
+    if (!g->pinned && !g->bases.empty()) {
+        // page-lock the host copy once so that H2D runs at full PCIe rate (and truly asynchronously)
+        if (cudaHostRegister((void *)g->bases.data(), g->bases.size(), cudaHostRegisterDefault) == cudaSuccess) g->pinned = true;
+        else cudaGetLastError();
+    }
     DevBuf<uint8_t> ascii(g->bases.size() + 64);
     DevBuf<uint64_t> src_off(n + 1);
     VB_CUDA(cudaMemsetAsync(out.seq2.p, 0, out.seq2.bytes(), st));
@@ -100,4 +105,39 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes
                                             n_chunks, u_is_t ? 1 : 0, out.seq2.p, out.inv.p);
     VB_LAUNCH_CHECK(ctx);
     VB_CUDA(cudaStreamSynchronize(st));     // ascii / tile vectors go out of scope
+}
+
+const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32_t min_pad, DevGenomes &scratch,
+                                     bool *was_resident)
+{
+    for (auto &r : ctx->resident)
+        if (r.g == g && r.u_is_t == (int)u_is_t && r.min_pad >= min_pad) {
+            if (was_resident) *was_resident = true;
+            return *r.dev;
+        }
+    if (was_resident) *was_resident = false;
+    vb_upload_genomes(ctx, g, u_is_t, scratch, min_pad);
+    return scratch;
+}
+
+void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32_t min_pad)
+{
+    for (auto &r : ctx->resident)
+        if (r.g == g && r.u_is_t == (int)u_is_t && r.min_pad >= min_pad) return;
+    auto *d = new DevGenomes();
+    try { vb_upload_genomes(ctx, g, u_is_t, *d, min_pad); } catch (...) { delete d; throw; }
+    ctx->resident.push_back({g, (int)u_is_t, min_pad < 128 ? 128u : min_pad, d});
+}
+
+void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g)
+{
+    for (size_t i = 0; i < ctx->resident.size();) {
+        if (g == nullptr || ctx->resident[i].g == g) { delete ctx->resident[i].dev; ctx->resident.erase(ctx->resident.begin() + i); }
+        else ++i;
+    }
+}
+
+void vb_unpin_genomes(const vb_genomes *g)
+{
+    if (g->pinned) { cudaHostUnregister((void *)g->bases.data()); g->pinned = false; }
 }

@@ -82,6 +82,11 @@ struct DevGenomes {
 // min_pad: invalid slots guaranteed after every genome (>= 128).
 void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes &out, uint32_t min_pad = 128);
 
+// Returns the packed copy of g for this rule: the resident one when vb_genomes_make_resident was called for it
+// (no transfer), otherwise uploads into `scratch` and returns that.
+const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32_t min_pad, DevGenomes &scratch,
+                                     bool *was_resident = nullptr);
+
 #ifdef __CUDACC__
 // 32 bases (64 bits) starting at base slot p of a 2-bit array; base p lands in bits [0,1].
 __device__ __forceinline__ uint64_t fetch2(const uint32_t *__restrict__ w, uint64_t p)

@@ -235,8 +235,8 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
 
     t_all.start();
     t_up.start();
-    DevGenomes dg;
-    vb_upload_genomes(ctx, g, /*u_is_t=*/true, dg);
+    DevGenomes dg_scratch;
+    const DevGenomes &dg = vb_get_dev_genomes(ctx, g, /*u_is_t=*/true, 128, dg_scratch);
     t_up.stop();
 
     // ---- k1

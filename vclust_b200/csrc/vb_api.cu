@@ -14,6 +14,10 @@ void vb_pairs_free_impl(vb_pairs *p);
 void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char *ani_path, const char *ids_path,
                        const char *const *columns, int n_columns, const double out_filters[5]);
 
+void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32_t min_pad);
+void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g);
+void vb_unpin_genomes(const vb_genomes *g);
+
 static thread_local std::string g_last_error;
 void vb_set_error(const std::string &msg) { g_last_error = msg; }
 
@@ -65,8 +69,50 @@ void vb_ctx_destroy(vb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    vb_evict_impl(ctx, nullptr);
+    for (auto &e : ctx->events) if (e) cudaEventDestroy((cudaEvent_t)e);
     if (ctx->stream) cudaStreamDestroy((cudaStream_t)ctx->stream);
     delete ctx;
+}
+
+int vb_ctx_mark(vb_ctx *ctx, int slot)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || slot < 0 || slot >= 8) throw vb_error(VB_ERR_ARG, "vb_ctx_mark: slot must be 0..7");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->events[slot]) { cudaEvent_t e; VB_CUDA(cudaEventCreate(&e)); ctx->events[slot] = (void *)e; }
+    VB_CUDA(cudaEventRecord((cudaEvent_t)ctx->events[slot], (cudaStream_t)ctx->stream));
+    VB_GUARD_END
+}
+
+int vb_ctx_elapsed_ms(vb_ctx *ctx, int slot_a, int slot_b, double *ms)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || !ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || !ctx->events[slot_a] || !ctx->events[slot_b])
+        throw vb_error(VB_ERR_ARG, "vb_ctx_elapsed_ms: unknown slot");
+    VB_CUDA(cudaEventSynchronize((cudaEvent_t)ctx->events[slot_b]));
+    float t = 0;
+    VB_CUDA(cudaEventElapsedTime(&t, (cudaEvent_t)ctx->events[slot_a], (cudaEvent_t)ctx->events[slot_b]));
+    *ms = t;
+    VB_GUARD_END
+}
+
+int vb_genomes_make_resident(vb_ctx *ctx, const vb_genomes *g, vb_fasta_flavor rule, int mrd)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || !g) throw vb_error(VB_ERR_ARG, "vb_genomes_make_resident: bad arguments");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_make_resident_impl(ctx, g, rule == VB_FASTA_KMERDB, rule == VB_FASTA_KMERDB ? 128u : (uint32_t)std::max(mrd, 0) + 128u);
+    VB_GUARD_END
+}
+
+int vb_genomes_evict(vb_ctx *ctx, const vb_genomes *g)
+{
+    VB_GUARD_BEGIN
+    if (!ctx) throw vb_error(VB_ERR_ARG, "vb_genomes_evict: bad arguments");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_evict_impl(ctx, g);
+    VB_GUARD_END
 }
 
 int vb_ctx_timing(const vb_ctx *ctx, const char *key, double *ms)
@@ -101,7 +147,7 @@ uint32_t vb_genomes_count(const vb_genomes *g) { return g ? g->count() : 0; }
 const char *vb_genomes_name(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->names[i].c_str() : ""; }
 uint64_t vb_genomes_length(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->length(i) : 0; }
 uint64_t vb_genomes_total_bases(const vb_genomes *g) { return g ? g->bases.size() : 0; }
-void vb_genomes_free(vb_genomes *g) { delete g; }
+void vb_genomes_free(vb_genomes *g) { if (g) { vb_unpin_genomes(g); delete g; } }
 
 int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out)
 {

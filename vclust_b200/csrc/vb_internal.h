@@ -25,6 +25,7 @@ struct vb_genomes {
     std::vector<uint64_t> offset;   // n+1 offsets into bases
     std::vector<char> bases;        // concatenated ASCII
     vb_fasta_flavor flavor = VB_FASTA_KMERDB;
+    mutable bool pinned = false;    // bases page-locked with cudaHostRegister (done lazily by the first upload)
     uint32_t count() const { return (uint32_t)names.size(); }
     uint64_t length(uint32_t i) const { return offset[i + 1] - offset[i]; }
 };
@@ -37,10 +38,20 @@ double vb_ani_shorter(uint32_t common, uint32_t cnt1, uint32_t cnt2, int k);   /
 // ---- device side (declared here, defined in the .cu files) -----------------------------------------------------
 struct vb_timing { std::string key; double ms; };
 
+struct DevGenomes;
+struct vb_resident {                 // a genome set kept packed in HBM across calls (vb_genomes_make_resident)
+    const vb_genomes *g;
+    int u_is_t;
+    uint32_t min_pad;
+    DevGenomes *dev;
+};
+
 struct vb_ctx {
     int device = 0;
     void *stream = nullptr;          // cudaStream_t
+    void *events[8] = {nullptr};     // cudaEvent_t, vb_ctx_mark / vb_ctx_elapsed_ms
     uint64_t launches = 0;
+    std::vector<vb_resident> resident;
     std::vector<vb_timing> timings;
     void set_timing(const std::string &k, double ms) {
         for (auto &t : timings) if (t.key == k) { t.ms = ms; return; }
