@@ -252,10 +252,13 @@ def main_ours(args, rank: int, world: int, local_rank: int):
     clocks = sampler.stop()
     # ---- end-to-end measurement: host buffers, H2D inside every step
     ctx.evict()
-    step()
-    barrier()
-    e_ev, e_wall, e_infos = timed(args.steps)
-    barrier()
+    if args.quick:
+        e_wall = wall_ms
+    else:
+        step()
+        barrier()
+        e_ev, e_wall, e_infos = timed(args.steps)
+        barrier()
 
     step_ms = float(np.mean(wall_ms))          # wall of the synchronous calls == device events + host glue
     e2e_ms = float(np.mean(e_wall))
@@ -327,8 +330,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling run: 1 warm-up, no e2e leg, no CPU baseline (never a bench value)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.quick:
+        args.warmup, args.no_cpu_baseline = 1, True
+    elif args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

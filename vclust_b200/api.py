@@ -72,7 +72,7 @@ class Context:
         keys = {
             "prefilter": ["total_ms", "upload_pack_ms", "extract_ms", "sort_ms", "segment_ms", "emit_ms", "tuples",
                           "pair_increments", "table_slots", "candidates"],
-            "align": ["total_ms", "upload_pack_ms", "index_ms", "parse_ms", "batches", "pairs"],
+            "align": ["total_ms", "upload_pack_ms", "index_ms", "parse_ms", "host_prep_ms", "host_post_ms", "batches", "pairs"],
         }[prefix]
         out = {}
         for k in keys:

@@ -18,13 +18,14 @@
 //   * the position-by-position search for the next seed is done 32 query positions at a time (one per lane);
 //     the approximate extension consumes 1024 bases per warp step from mismatch bit masks.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 #include "dev_util.cuh"
 
 namespace {
 
-constexpr uint64_t HT_EMPTY = ~0ULL;
+constexpr uint32_t HT_EMPTY = 0xffffffffu;
 
 struct LzParams { int mal, msl, mrd, mqd, reg, aw, am, ar; };
 
@@ -33,6 +34,7 @@ struct RefDesc {
     uint64_t nv_off;     // word offset of the N plane in ref_nv
     uint64_t ht_off;     // slot offset of the anchor table
     uint32_t ht_mask;    // slots - 1
+    uint32_t pos_bits;   // a slot is fingerprint << pos_bits | position, 2^pos_bits > n
     uint32_t n;          // text length: 2*len + 3*mrd
     uint32_t len;        // genome length
     uint32_t gid;        // genome id in the packed store
@@ -108,11 +110,11 @@ __global__ void __launch_bounds__(256) build_ref_text_kernel(const uint32_t *__r
 
 // ---------------------------------------------------------------------------------------------------------------
 // k5b: anchor table -- every position whose mal-mer holds no N is inserted under its k-mer (parser.cpp:146-189)
-// slot = fingerprint << 32 | position
+// slot (32 bit) = fingerprint << pos_bits | position; the fingerprint is the top 32 - pos_bits bits of the k-mer hash
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_ref_index_kernel(const RefDesc *__restrict__ refs, uint32_t n_refs, int mal,
                                                               const uint32_t *__restrict__ ref_s2,
-                                                              const uint32_t *__restrict__ ref_nv, uint64_t *__restrict__ ht)
+                                                              const uint32_t *__restrict__ ref_nv, uint32_t *__restrict__ ht)
 {
     const uint64_t kmask = (~0ULL) >> (64 - 2 * mal);
     const uint32_t nmask = (mal >= 32) ? 0xffffffffu : ((1u << mal) - 1);
@@ -120,17 +122,16 @@ __global__ void __launch_bounds__(256) build_ref_index_kernel(const RefDesc *__r
         const RefDesc d = refs[r];
         const uint32_t *s2 = ref_s2 + d.s2_off;
         const uint32_t *nv = ref_nv + d.nv_off;
-        uint64_t *tab = ht + d.ht_off;
+        uint32_t *tab = ht + d.ht_off;
         if (d.n < (uint32_t)mal) continue;
         const uint32_t n_pos = d.n - mal + 1;
         for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += gridDim.x * blockDim.x) {
             if (fetch1(nv, p) & nmask) continue;
             uint64_t code = fetch2(s2, p) & kmask;
             uint64_t h = fmix64(code);
-            uint64_t val = (h & 0xffffffff00000000ULL) | p;
+            uint32_t val = ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | p;
             uint32_t slot = (uint32_t)h & d.ht_mask;
-            while (atomicCAS((unsigned long long *)&tab[slot], (unsigned long long)HT_EMPTY, (unsigned long long)val) != HT_EMPTY)
-                slot = (slot + 1) & d.ht_mask;
+            while (atomicCAS(&tab[slot], HT_EMPTY, val) != HT_EMPTY) slot = (slot + 1) & d.ht_mask;
         }
     }
 }
@@ -330,37 +331,38 @@ __device__ __forceinline__ bool kmer_at(const Text &T, int p, int len, uint64_t 
 }
 
 // one lane: does the anchor table hold any entry with this k-mer's fingerprint?
-__device__ __forceinline__ bool anchor_probe(const uint64_t *__restrict__ tab, uint32_t mask, uint64_t code)
+__device__ __forceinline__ bool anchor_probe(const uint32_t *__restrict__ tab, uint32_t mask, uint32_t pos_bits, uint64_t code)
 {
     uint64_t h = fmix64(code);
-    uint32_t fp = (uint32_t)(h >> 32);
+    uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
     uint32_t slot = (uint32_t)h & mask;
     for (;;) {
-        uint64_t s = __ldg(tab + slot);
+        uint32_t s = __ldg(tab + slot);
         if (s == HT_EMPTY) return false;
-        if ((uint32_t)(s >> 32) == fp) return true;
+        if ((s >> pos_bits) == fp) return true;
         slot = (slot + 1) & mask;
     }
 }
 
 // whole warp, parser.cpp:514-531 / :585-602: longest exact match among all reference positions of Q's mal-mer at i
 // (>= mal), ties to the smallest position.  Lanes read 32 consecutive slots of the probe chain at a time.
-__device__ void anchor_search(const uint64_t *__restrict__ tab, uint32_t mask, const Text &Q, int i, const Text &R,
-                              const LzParams &P, int lane, int &best_len, int &best_pos)
+__device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t mask, uint32_t pos_bits, const Text &Q, int i,
+                              const Text &R, const LzParams &P, int lane, int &best_len, int &best_pos)
 {
     best_len = 0; best_pos = 0;
     uint64_t code;
     if (!kmer_at(Q, i, P.mal, code)) return;
     uint64_t h = fmix64(code);
-    uint32_t fp = (uint32_t)(h >> 32);
+    uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
     uint32_t slot0 = (uint32_t)h & mask;
+    const uint32_t pmask = (1u << pos_bits) - 1;
     int my_len = 0, my_pos = 0x7fffffff;
     for (uint32_t step = 0;; step += 32) {
-        uint64_t s = __ldg(tab + ((slot0 + step + lane) & mask));
+        uint32_t s = __ldg(tab + ((slot0 + step + lane) & mask));
         unsigned empties = __ballot_sync(0xffffffffu, s == HT_EMPTY);
         bool in_chain = empties == 0 || lane < (__ffs(empties) - 1);
-        if (in_chain && (uint32_t)(s >> 32) == fp) {
-            int pos = (int)(uint32_t)s;
+        if (in_chain && (s >> pos_bits) == fp) {
+            int pos = (int)(s & pmask);
             int ml = equal_len(Q, i, R, pos, 0);
             if (ml >= P.mal && (ml > my_len || (ml == my_len && pos < my_pos))) { my_len = ml; my_pos = pos; }
         }
@@ -419,8 +421,8 @@ __device__ int gap_best_matches(const Text &Q, int d, const Text &R, int r_left,
 // ---------------------------------------------------------------------------------------------------------------
 // k6: the parse.  All state is warp-uniform; `lane` only selects the data a lane looks at.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void parse_pair(const Text &Q, const Text &R, const uint64_t *__restrict__ tab, uint32_t tmask, const LzParams &P,
-                           int lane, int &out_match, int &out_lit, int &out_comp)
+__device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restrict__ tab, uint32_t tmask, uint32_t pos_bits,
+                           const LzParams &P, int lane, int &out_match, int &out_lit, int &out_comp)
 {
     const int nQ = Q.n;
     int i = 0, lit = 0, pred = 0;
@@ -439,7 +441,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint64_t *__restr
         bool flag = false;
         if (lane < steps) {
             uint64_t code;
-            if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tmask, code);
+            if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tmask, pos_bits, code);
         }
         if (!lost) {
             // short seeds: lane t (query position i + t) may use reference positions [lo, pred + t + mrd).  The window
@@ -468,11 +470,11 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint64_t *__restr
         // ---- 2. exact evaluation at i (parser.cpp:503-624) ----------------------------------------------------
         int best_len = 0, best_pos = 0;
         if (lost)
-            anchor_search(tab, tmask, Q, i, R, P, lane, best_len, best_pos);
+            anchor_search(tab, tmask, pos_bits, Q, i, R, P, lane, best_len, best_pos);
         else {
             close_search(Q, i, R, pred, lit, P, lane, best_len, best_pos);
             int a_len, a_pos;
-            anchor_search(tab, tmask, Q, i, R, P, lane, a_len, a_pos);
+            anchor_search(tab, tmask, pos_bits, Q, i, R, P, lane, a_len, a_pos);
             if (a_pos) {                                  // positions double as booleans in the reference (:604-606)
                 if (!best_pos) { best_pos = a_pos; best_len = a_len; }
                 else {
@@ -541,7 +543,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint64_t *__restr
 __global__ void __launch_bounds__(128) parse_kernel(const uint32_t *__restrict__ g2, const uint32_t *__restrict__ gn,
                                                     const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
                                                     const RefDesc *__restrict__ refs, const uint32_t *__restrict__ ref_s2,
-                                                    const uint32_t *__restrict__ ref_nv, const uint64_t *__restrict__ ht,
+                                                    const uint32_t *__restrict__ ref_nv, const uint32_t *__restrict__ ht,
                                                     const uint32_t *__restrict__ pair_ref, const uint32_t *__restrict__ pair_qry,
                                                     uint32_t n_pairs, LzParams P, unsigned int *__restrict__ cursor,
                                                     int32_t *__restrict__ stats)
@@ -558,7 +560,7 @@ __global__ void __launch_bounds__(128) parse_kernel(const uint32_t *__restrict__
         uint64_t qo = gofs[q];
         Text Q = {g2 + (qo >> 4), gn + (qo >> 5), (int)glen[q] + P.mrd};
         int m, l, c;
-        parse_pair(Q, R, ht + d.ht_off, d.ht_mask, P, lane, m, l, c);
+        parse_pair(Q, R, ht + d.ht_off, d.ht_mask, d.pos_bits, P, lane, m, l, c);
         if (lane == 0) { stats[3 * (uint64_t)idx] = m; stats[3 * (uint64_t)idx + 1] = l; stats[3 * (uint64_t)idx + 2] = c; }
     }
 }
@@ -583,6 +585,8 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
     for (uint64_t i = 0; i < n; ++i)
         if (ref[i] >= ng || qry[i] >= ng) throw vb_error(VB_ERR_ARG, "pair id out of range");
     LzParams P = {ap->mal, ap->msl, ap->mrd, ap->mqd, ap->reg, ap->aw, ap->am, ap->ar};
+    const auto h0 = std::chrono::steady_clock::now();
+    double host_prep_ms = 0, host_post_ms = 0;
     EventTimer t_all(st), t_up(st);
     double ms_index = 0, ms_parse = 0;
 
@@ -597,9 +601,8 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
     for (uint64_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ref[a] < ref[b]; });
 
-    size_t free_b = 0, total_b = 0;
-    VB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t budget = (uint64_t)(free_b * 0.6);
+    // reference texts + anchor tables of one batch may take up to 40 % of the device (no per-call memory query)
+    const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
 
     DevBuf<int32_t> d_stats(3 * std::max<uint64_t>(n, 1));
     DevBuf<uint32_t> d_pref(std::max<uint64_t>(n, 1)), d_pqry(std::max<uint64_t>(n, 1));
@@ -622,12 +625,14 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
                 uint64_t chunks = (nR + 31) / 32 + 4;
                 uint64_t cap = 1024;
                 while (cap < 2 * nR) cap <<= 1;
-                uint64_t need = chunks * 12 + cap * 8;
+                uint64_t need = chunks * 12 + cap * 4;
+                uint32_t pos_bits = 1;
+                while ((1ULL << pos_bits) <= nR) ++pos_bits;
                 if (!refs.empty() && bytes + need > budget) break;
                 if (refs.empty() && need > budget) throw vb_error(VB_ERR_MEM, "reference index does not fit device memory");
                 RefDesc d;
                 d.s2_off = s2_words; d.nv_off = nv_words; d.ht_off = slots;
-                d.ht_mask = (uint32_t)(cap - 1); d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = r;
+                d.ht_mask = (uint32_t)(cap - 1); d.pos_bits = pos_bits; d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = r;
                 refs.push_back(d);
                 s2_words += 2 * chunks + 4; nv_words += chunks + 4; slots += cap; bytes += need;
             }
@@ -638,7 +643,7 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
         const uint32_t nb = (uint32_t)(end - pos);
         DevBuf<RefDesc> d_refs(refs.size());
         DevBuf<uint32_t> ref_s2(s2_words + 8), ref_nv(nv_words + 8);
-        DevBuf<uint64_t> ht(slots);
+        DevBuf<uint32_t> ht(slots);
         VB_CUDA(cudaMemcpyAsync(d_refs.p, refs.data(), sizeof(RefDesc) * refs.size(), cudaMemcpyHostToDevice, st));
         VB_CUDA(cudaMemcpyAsync(d_pref.p, b_ref.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
         VB_CUDA(cudaMemcpyAsync(d_pqry.p, b_qry.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
@@ -647,6 +652,7 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
         VB_CUDA(cudaMemsetAsync(ht.p, 0xff, ht.bytes(), st));
         VB_CUDA(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned int), st));
 
+        if (n_batches == 0) host_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         EventTimer t_idx(st), t_par(st);
         t_idx.start();
         dim3 grid_b(16, (unsigned)std::min<size_t>(refs.size(), 32768));
@@ -670,12 +676,14 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
         std::vector<int32_t> tmp(3 * (size_t)nb);
         VB_CUDA(cudaMemcpyAsync(tmp.data(), d_stats.p, sizeof(int32_t) * 3 * nb, cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaStreamSynchronize(st));
+        const auto h1 = std::chrono::steady_clock::now();
         for (uint32_t j = 0; j < nb; ++j) {
             uint64_t o = order[pos + j];
             stats[3 * o] = tmp[3 * j]; stats[3 * o + 1] = tmp[3 * j + 1]; stats[3 * o + 2] = tmp[3 * j + 2];
         }
         ms_index += t_idx.ms();
         ms_parse += t_par.ms();
+        host_post_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h1).count();
         pos = end;
         ++n_batches;
     }
@@ -685,6 +693,8 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
     ctx->set_timing("align.upload_pack_ms", t_up.ms());
     ctx->set_timing("align.index_ms", ms_index);
     ctx->set_timing("align.parse_ms", ms_parse);
+    ctx->set_timing("align.host_prep_ms", host_prep_ms);
+    ctx->set_timing("align.host_post_ms", host_post_ms);
     ctx->set_timing("align.batches", n_batches);
     ctx->set_timing("align.pairs", (double)n);
 }

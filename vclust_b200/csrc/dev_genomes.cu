@@ -141,3 +141,16 @@ void vb_unpin_genomes(const vb_genomes *g)
 {
     if (g->pinned) { cudaHostUnregister((void *)g->bases.data()); g->pinned = false; }
 }
+
+uint64_t vb_device_available(vb_ctx *ctx)
+{
+    size_t free_b = 0, total_b = 0;
+    VB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    cudaMemPool_t pool;
+    uint64_t reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    }
+    return (uint64_t)free_b + (reserved > used ? reserved - used : 0);
+}

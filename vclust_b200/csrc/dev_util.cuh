@@ -20,6 +20,11 @@
         VB_CUDA(cudaGetLastError());     \
     } while (0)
 
+// All device memory comes from the device's default stream-ordered pool (release threshold = never), on the
+// stream of the context the calling thread is working for: after the first call no cudaMalloc / cudaFree (and
+// none of their implicit device synchronisations) happens on the hot path.
+extern thread_local cudaStream_t vb_tls_stream;
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;
@@ -36,17 +41,21 @@ struct DevBuf {
         release();
         n = count;
         if (count) {
-            cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+            cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), vb_tls_stream);
             if (e != cudaSuccess) {
                 p = nullptr; n = 0;
-                throw vb_error(VB_ERR_MEM, "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
+                cudaGetLastError();
+                throw vb_error(VB_ERR_MEM, "cudaMallocAsync of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
                                                cudaGetErrorString(e));
             }
         }
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, vb_tls_stream); p = nullptr; n = 0; }
     size_t bytes() const { return n * sizeof(T); }
 };
+
+// bytes this context could still allocate: free device memory + what the pool holds but is not using
+uint64_t vb_device_available(vb_ctx *ctx);
 
 struct EventTimer {
     cudaEvent_t a, b;

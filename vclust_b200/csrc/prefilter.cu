@@ -92,10 +92,9 @@ __global__ void __launch_bounds__(256) extract_kernel(const uint32_t *__restrict
     }
 }
 
-// k3a: duplicates per genome + number of pair increments (sum over k-mer runs of m*(m-1)/2)
+// k3a (only for very large N): number of pair increments (sum over k-mer runs of m*(m-1)/2), to size the table
 __global__ void __launch_bounds__(256) segment_count_kernel(const uint64_t *__restrict__ keys,
                                                             const uint32_t *__restrict__ vals, uint64_t n,
-                                                            uint32_t *__restrict__ dup_cnt,
                                                             unsigned long long *__restrict__ n_inc)
 {
     unsigned long long local = 0;
@@ -103,7 +102,7 @@ __global__ void __launch_bounds__(256) segment_count_kernel(const uint64_t *__re
         uint64_t key = keys[i];
         if (key == KEY_SENTINEL) continue;
         uint32_t g = vals[i];
-        if (i > 0 && keys[i - 1] == key && vals[i - 1] == g) { atomicAdd(&dup_cnt[g], 1u); continue; }
+        if (i > 0 && keys[i - 1] == key && vals[i - 1] == g) continue;
         // rank of this genome inside the run = number of distinct genomes before it
         uint32_t prev = g;
         for (uint64_t j = i; j-- > 0 && keys[j] == key;) {
@@ -131,18 +130,19 @@ __device__ __forceinline__ void table_add(uint64_t *__restrict__ tkeys, uint32_t
     *overflow = 1;
 }
 
-// k3b: every distinct (k-mer, genome) occurrence pairs with the distinct genomes before it in the run;
+// k3b: duplicates per genome; every distinct (k-mer, genome) occurrence pairs with the distinct genomes before it in the run;
 // row = the later (larger) genome id, col = the earlier one -- the lower triangle of all2all_sp.
 __global__ void __launch_bounds__(256) segment_pairs_kernel(const uint64_t *__restrict__ keys,
                                                             const uint32_t *__restrict__ vals, uint64_t n,
-                                                            uint64_t *__restrict__ tkeys, uint32_t *__restrict__ tvals,
-                                                            uint64_t cap_mask, int *__restrict__ overflow)
+                                                            uint32_t *__restrict__ dup_cnt, uint64_t *__restrict__ tkeys,
+                                                            uint32_t *__restrict__ tvals, uint64_t cap_mask,
+                                                            int *__restrict__ overflow)
 {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t key = keys[i];
         if (key == KEY_SENTINEL) continue;
         uint32_t g = vals[i];
-        if (i > 0 && keys[i - 1] == key && vals[i - 1] == g) continue;
+        if (i > 0 && keys[i - 1] == key && vals[i - 1] == g) { atomicAdd(&dup_cnt[g], 1u); continue; }   // same k-mer twice in g
         uint32_t prev = g;
         for (uint64_t j = i; j-- > 0 && keys[j] == key;) {
             uint32_t gj = vals[j];
@@ -273,12 +273,15 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     t_seg.start();
     DevBuf<unsigned long long> scalars(4);
     VB_CUDA(cudaMemsetAsync(scalars.p, 0, scalars.bytes(), st));
-    segment_count_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, dup_cnt, scalars.p);
-    VB_LAUNCH_CHECK(ctx);
-    unsigned long long n_inc = 0;
-    VB_CUDA(cudaMemcpyAsync(&n_inc, scalars.p, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
-    VB_CUDA(cudaStreamSynchronize(st));
     unsigned long long max_pairs = (unsigned long long)n * (n > 0 ? n - 1 : 0) / 2;
+    unsigned long long n_inc = max_pairs;
+    const bool count_first = max_pairs > (1ULL << 26);      // otherwise the dense bound N(N-1)/2 sizes the table
+    if (count_first) {
+        segment_count_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, scalars.p);
+        VB_LAUNCH_CHECK(ctx);
+        VB_CUDA(cudaMemcpyAsync(&n_inc, scalars.p, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+    }
     unsigned long long distinct_bound = std::min(n_inc, max_pairs);
     uint64_t cap = 1024;
     while (cap < 2 * distinct_bound) cap <<= 1;
@@ -286,14 +289,11 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     DevBuf<uint64_t> tkeys(cap);
     DevBuf<uint32_t> tvals(cap);
     DevBuf<int> overflow(1);
-    fill_u64_kernel<<<grid_for(cap), 256, 0, st>>>(tkeys.p, cap, SLOT_EMPTY);
-    VB_LAUNCH_CHECK(ctx);
+    VB_CUDA(cudaMemsetAsync(tkeys.p, 0xff, tkeys.bytes(), st));       // SLOT_EMPTY
     VB_CUDA(cudaMemsetAsync(tvals.p, 0, tvals.bytes(), st));
     VB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st));
-    if (n_inc) {
-        segment_pairs_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, tkeys.p, tvals.p, cap - 1, overflow.p);
-        VB_LAUNCH_CHECK(ctx);
-    }
+    segment_pairs_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, dup_cnt, tkeys.p, tvals.p, cap - 1, overflow.p);
+    VB_LAUNCH_CHECK(ctx);
     totals_kernel<<<(n + 255) / 256 + 1, 256, 0, st>>>(valid_cnt, dup_cnt, n, totals);
     VB_LAUNCH_CHECK(ctx);
     t_seg.stop();

@@ -18,6 +18,7 @@ void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32
 void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g);
 void vb_unpin_genomes(const vb_genomes *g);
 
+thread_local cudaStream_t vb_tls_stream = nullptr;
 static thread_local std::string g_last_error;
 void vb_set_error(const std::string &msg) { g_last_error = msg; }
 
@@ -61,6 +62,13 @@ int vb_ctx_create(int device, vb_ctx **out)
     cudaStream_t st;
     VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     ctx->stream = (void *)st;
+    cudaMemPool_t pool;
+    VB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t never = UINT64_MAX;
+    VB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+    size_t free_b = 0, total_b = 0;
+    VB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    ctx->mem_total = total_b;
     *out = ctx;
     VB_GUARD_END
 }
@@ -69,7 +77,9 @@ void vb_ctx_destroy(vb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    vb_tls_stream = (cudaStream_t)ctx->stream;
     vb_evict_impl(ctx, nullptr);
+    cudaStreamSynchronize((cudaStream_t)ctx->stream);
     for (auto &e : ctx->events) if (e) cudaEventDestroy((cudaEvent_t)e);
     if (ctx->stream) cudaStreamDestroy((cudaStream_t)ctx->stream);
     delete ctx;
@@ -102,6 +112,7 @@ int vb_genomes_make_resident(vb_ctx *ctx, const vb_genomes *g, vb_fasta_flavor r
     VB_GUARD_BEGIN
     if (!ctx || !g) throw vb_error(VB_ERR_ARG, "vb_genomes_make_resident: bad arguments");
     VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tls_stream = (cudaStream_t)ctx->stream;
     vb_make_resident_impl(ctx, g, rule == VB_FASTA_KMERDB, rule == VB_FASTA_KMERDB ? 128u : (uint32_t)std::max(mrd, 0) + 128u);
     VB_GUARD_END
 }
@@ -111,6 +122,7 @@ int vb_genomes_evict(vb_ctx *ctx, const vb_genomes *g)
     VB_GUARD_BEGIN
     if (!ctx) throw vb_error(VB_ERR_ARG, "vb_genomes_evict: bad arguments");
     VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tls_stream = (cudaStream_t)ctx->stream;
     vb_evict_impl(ctx, g);
     VB_GUARD_END
 }
@@ -153,6 +165,8 @@ int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p,
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter: bad arguments");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tls_stream = (cudaStream_t)ctx->stream;
     vb_prefilter_impl(ctx, g, p, out);
     VB_GUARD_END
 }
@@ -180,6 +194,8 @@ int vb_align_pairs(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const 
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || (n && (!ref || !qry || !stats))) throw vb_error(VB_ERR_ARG, "vb_align_pairs: bad arguments");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tls_stream = (cudaStream_t)ctx->stream;
     vb_align_pairs_impl(ctx, g, ref, qry, n, p, stats);
     VB_GUARD_END
 }
@@ -188,6 +204,8 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_align: bad arguments");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tls_stream = (cudaStream_t)ctx->stream;
     const uint32_t n = g->count();
     // LZ-ANI order: length descending, then name ascending (stable) -- seq_reservoir.cpp:229-236
     std::vector<uint32_t> order(n);

@@ -51,6 +51,7 @@ struct vb_ctx {
     void *stream = nullptr;          // cudaStream_t
     void *events[8] = {nullptr};     // cudaEvent_t, vb_ctx_mark / vb_ctx_elapsed_ms
     uint64_t launches = 0;
+    uint64_t mem_total = 0;          // device memory, queried once (cudaMemGetInfo is slow and synchronising)
     std::vector<vb_resident> resident;
     std::vector<vb_timing> timings;
     void set_timing(const std::string &k, double ms) {
