@@ -112,6 +112,16 @@ typedef struct vb_pairs {
 /* Replaces: kmer-db build [-multisample-fasta] -k K -f F  +  kmer-db all2all-sp -sparse -min num-kmers:X
  *           -min ani-shorter:Y [-sample-rows ani-shorter:N]   (console_build.cpp:33, similarity_calculator.cpp:442). */
 int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out);
+/* Multi-GPU building blocks (no reference counterpart; the reference is single-process):
+ * vb_prefilter_partial counts only the k-mers of one hash shard (fmix64(kmer) % shard_count == shard_index) and
+ * returns EVERY pair with a non-zero partial count (no thresholds, ani = 0) plus the shard's part of total_kmers;
+ * summing the parts of all shards gives exactly vb_prefilter's integers.  vb_pairs_merge does that sum for a
+ * concatenation of partial triples (any order, duplicates allowed), applies the two -min filters with the exact
+ * double metric and returns the same vb_pairs vb_prefilter would. */
+int vb_prefilter_partial(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, uint32_t shard_index,
+                         uint32_t shard_count, vb_pairs **out);
+int vb_pairs_merge(const uint32_t *row, const uint32_t *col, const uint32_t *common, uint64_t n,
+                   const uint32_t *total_kmers, uint32_t n_genomes, const vb_prefilter_params *p, vb_pairs **out);
 /* Replaces: kmer-db distance ani-shorter -sparse -min Y (console_distance.cpp:7-213): writes the filter text. */
 int vb_write_filter(const vb_genomes *g, const vb_pairs *pairs, const char *path);
 /* Replaces: CFilter::load_filter (lz-ani filter.cpp:20-298): reads a filter text, keeps entries >= thr, checks
@@ -147,6 +157,10 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
  * stats[3*i..] = (sym_in_matches, sym_in_literals, no_components) of pair i. */
 int vb_align_pairs(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
                    const vb_align_params *p, int32_t *stats);
+/* Assemble the result object of vb_align [LZ-ANI ids, sorted by (ref, qry)] from directed pairs in INPUT-order ids and their
+ * 3-int statistics, e.g. gathered from several GPUs. */
+int vb_align_out_from_pairs(const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, const int32_t *stats, uint64_t n,
+                            vb_align_out **out);
 /* Replaces: CLZMatcher::store_results (lz_matcher.cpp:280-579): writes <ani_path> and <ids_path>.
  * columns: the --out-format list (vclust.py:38-47); out_filters: minimum tani, gani, ani, qcov, rcov (0 = off). */
 int vb_write_ani(const vb_genomes *g, const vb_align_out *res, const char *ani_path, const char *ids_path,

@@ -149,3 +149,34 @@ def test_align_pairs_vs_oracle_params(ctx, params):
     want = oracle.run_pairs([oracle.lz_codes(s) for s in seqs], ref, qry, oracle.LzParams.default(**params))
     bad = np.nonzero((got != want).any(axis=1))[0]
     assert bad.size == 0, "first mismatches: %s" % [(int(ref[i]), int(qry[i]), got[i].tolist(), want[i].tolist()) for i in bad[:5]]
+
+
+# ---------------------------------------------------------------- multi-GPU building blocks (on one GPU)
+@pytest.mark.parametrize("world", [2, 3])
+def test_prefilter_partial_shards_sum_to_full(ctx, golden, world):
+    g = api.Genomes.load([golden / "example" / "multifasta.fna.gz"], True, api.FASTA_KMERDB)
+    full = api.prefilter_genomes(ctx, g, k=25, min_kmers=20, min_ident=0.7)
+    rows, cols, vals, totals = [], [], [], np.zeros(len(g), dtype=np.int64)
+    for r in range(world):
+        part = api.prefilter_partial(ctx, g, r, world, k=25)
+        rows.append(part.rows); cols.append(part.cols); vals.append(part.common)
+        totals += part.total_kmers
+    assert totals.tolist() == full.total_kmers.tolist()
+    m = api.merge_pairs(np.concatenate(rows), np.concatenate(cols), np.concatenate(vals), totals.astype(np.uint32),
+                        k=25, min_kmers=20, min_ident=0.7)
+    assert list(zip(m.rows.tolist(), m.cols.tolist(), m.common.tolist())) == \
+           list(zip(full.rows.tolist(), full.cols.tolist(), full.common.tolist()))
+    assert np.array_equal(m.ani, full.ani)
+
+
+def test_align_result_assembly_matches_vb_align(ctx, golden, tmp_path):
+    p = golden / "example" / "multifasta.fna.gz"
+    g = api.Genomes.load([p], True, api.FASTA_LZANI)
+    pairs = api.read_filter(golden / "example" / "fltr.txt", 0.0, g)
+    ref = np.concatenate([pairs.rows, pairs.cols]); qry = np.concatenate([pairs.cols, pairs.rows])
+    st = api.align_pairs(ctx, g, ref, qry)
+    res = api.align_result_from_pairs(g, ref, qry, st)
+    api.write_ani(g, res, tmp_path / "a.tsv")
+    api.align([p], tmp_path / "b.tsv", True, filter_file=golden / "example" / "fltr.txt")
+    assert (tmp_path / "a.tsv").read_bytes() == (tmp_path / "b.tsv").read_bytes()
+    assert (tmp_path / "a.ids.tsv").read_bytes() == (tmp_path / "b.ids.tsv").read_bytes()

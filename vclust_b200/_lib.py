@@ -12,7 +12,7 @@ EXPORTS = [
     "vb_version", "vb_device_count", "vb_last_error", "vb_ctx_create", "vb_ctx_destroy", "vb_ctx_timing",
     "vb_ctx_launches", "vb_ctx_mark", "vb_ctx_elapsed_ms", "vb_genomes_make_resident", "vb_genomes_evict", "vb_genomes_load", "vb_genomes_from_memory", "vb_genomes_count", "vb_genomes_name",
     "vb_genomes_length", "vb_genomes_total_bases", "vb_genomes_free", "vb_prefilter", "vb_write_filter",
-    "vb_read_filter", "vb_pairs_free", "vb_align", "vb_align_pairs", "vb_write_ani", "vb_align_out_free",
+    "vb_read_filter", "vb_pairs_free", "vb_prefilter_partial", "vb_pairs_merge", "vb_align_out_from_pairs", "vb_align", "vb_align_pairs", "vb_write_ani", "vb_align_out_free",
 ]
 
 
@@ -76,6 +76,9 @@ def load():
         "vb_genomes_total_bases": (u64, [vp]),
         "vb_genomes_free": (None, [vp]),
         "vb_prefilter": (i32, [vp, vp, C.POINTER(PrefilterParams), C.POINTER(C.POINTER(Pairs))]),
+        "vb_prefilter_partial": (i32, [vp, vp, C.POINTER(PrefilterParams), u32, u32, C.POINTER(C.POINTER(Pairs))]),
+        "vb_pairs_merge": (i32, [vp, vp, vp, u64, vp, u32, C.POINTER(PrefilterParams), C.POINTER(C.POINTER(Pairs))]),
+        "vb_align_out_from_pairs": (i32, [vp, vp, vp, vp, u64, C.POINTER(C.POINTER(AlignOut))]),
         "vb_write_filter": (i32, [vp, C.POINTER(Pairs), cp]),
         "vb_read_filter": (i32, [cp, dbl, vp, C.POINTER(C.POINTER(Pairs))]),
         "vb_pairs_free": (None, [C.POINTER(Pairs)]),

@@ -261,6 +261,39 @@ def prefilter_genomes(ctx: Context, genomes: Genomes, k: int = 25, min_kmers: in
     return PairList(out)
 
 
+def prefilter_partial(ctx: Context, genomes: Genomes, shard_index: int, shard_count: int, k: int = 25,
+                      kmers_fraction: float = 1.0) -> PairList:
+    """Partial counts of one k-mer hash shard (multi-GPU building block): no thresholds applied."""
+    p = PrefilterParams(k, 0, 0.0, kmers_fraction, 0, 0)
+    out = C.POINTER(Pairs)()
+    check(ctx._L.vb_prefilter_partial(ctx._h, genomes._h, C.byref(p), shard_index, shard_count, C.byref(out)))
+    return PairList(out)
+
+
+def merge_pairs(rows, cols, common, total_kmers, k: int = 25, min_kmers: int = 20, min_ident: float = 0.7,
+                kmers_fraction: float = 1.0) -> PairList:
+    """Sum partial (row, col, common) triples, apply the two -min filters exactly; host only."""
+    r = np.ascontiguousarray(rows, dtype=np.uint32)
+    c = np.ascontiguousarray(cols, dtype=np.uint32)
+    v = np.ascontiguousarray(common, dtype=np.uint32)
+    t = np.ascontiguousarray(total_kmers, dtype=np.uint32)
+    p = PrefilterParams(k, min_kmers, min_ident, kmers_fraction, 0, 0)
+    out = C.POINTER(Pairs)()
+    check(_lib.load().vb_pairs_merge(r.ctypes.data, c.ctypes.data, v.ctypes.data, r.size, t.ctypes.data, t.size,
+                                     C.byref(p), C.byref(out)))
+    return PairList(out)
+
+
+def align_result_from_pairs(genomes: Genomes, ref, qry, stats) -> AlignResult:
+    r = np.ascontiguousarray(ref, dtype=np.uint32)
+    q = np.ascontiguousarray(qry, dtype=np.uint32)
+    st = np.ascontiguousarray(stats, dtype=np.int32)
+    out = C.POINTER(AlignOut)()
+    check(_lib.load().vb_align_out_from_pairs(genomes._h, r.ctypes.data, q.ctypes.data, st.ctypes.data, r.size,
+                                              C.byref(out)))
+    return AlignResult(out)
+
+
 def write_filter(genomes: Genomes, pairs: PairList, path) -> None:
     check(_lib.load().vb_write_filter(genomes._h, pairs._p, str(path).encode()))
 

@@ -58,6 +58,8 @@ struct ExtractParams {
     int use_filter;
     uint64_t max_thr;       // filter.h:42-43
     uint64_t c;             // ceil(k/4)
+    uint32_t shard_index;   // multi-GPU: this rank keeps the k-mers with fmix64(kmer) % shard_count == shard_index
+    uint32_t shard_count;
 };
 
 // k1: one thread per base slot; a warp covers 32 consecutive slots of one 128-slot tile (= one genome).
@@ -81,7 +83,9 @@ __global__ void __launch_bounds__(256) extract_kernel(const uint32_t *__restrict
                 uint64_t fw = reverse_digits(w) >> (64 - 2 * k); // == reference's kmer_str (first base most significant)
                 uint64_t can = fw < rc ? fw : rc;
                 can = (can << ep.shift) | (can & ep.tail_mask);
-                if (!ep.use_filter || minhash64(can, ep.c) < ep.max_thr) key = can;
+                bool keep = !ep.use_filter || minhash64(can, ep.c) < ep.max_thr;
+                if (keep && ep.shard_count > 1) keep = (fmix64(can) % ep.shard_count) == ep.shard_index;
+                if (keep) key = can;
             }
         }
         keys[p] = key;
@@ -223,8 +227,12 @@ int grid_for(uint64_t n, int threads = 256, int max_blocks = 148 * 16)
 
 vb_pairs *vb_pairs_alloc(uint64_t n, uint32_t n_genomes);
 
-void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out_pairs)
+// shard_count > 1: partial result of one k-mer shard -- no thresholds, ani = 0, total_kmers = this shard's part
+void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, uint32_t shard_index,
+                       uint32_t shard_count, vb_pairs **out_pairs)
 {
+    const bool partial = shard_count > 1;
+    if (shard_count == 0 || shard_index >= shard_count) throw vb_error(VB_ERR_ARG, "bad k-mer shard");
     if (p->k < 10 || p->k > 31) throw vb_error(VB_ERR_ARG, "k must be in [10, 31]");
     if (!(p->kmers_fraction > 0)) throw vb_error(VB_ERR_ARG, "kmers_fraction must be > 0");
     if (p->max_seqs > 0) throw vb_error(VB_ERR_ARG, "--max-seqs is not implemented on the GPU path yet");
@@ -255,6 +263,8 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     ep.use_filter = p->kmers_fraction < 1.0;
     ep.max_thr = (uint64_t)((double)UINT64_MAX * (0.0 + p->kmers_fraction));
     ep.c = (uint64_t)std::ceil((double)p->k / 4);
+    ep.shard_index = shard_index;
+    ep.shard_count = shard_count;
     extract_kernel<<<grid_for(n_pad), 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_pad, ep, keys_a.p,
                                                    vals_a.p, valid_cnt);
     VB_LAUNCH_CHECK(ctx);
@@ -301,8 +311,8 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     // ---- k4
     t_emit.start();
     EmitParams em;
-    em.min_kmers = (uint32_t)std::max(p->min_kmers, 0);
-    em.min_ident_slack = p->min_ident - 1e-7;
+    em.min_kmers = partial ? 1u : (uint32_t)std::max(p->min_kmers, 0);
+    em.min_ident_slack = partial ? -1e300 : p->min_ident - 1e-7;
     em.k = p->k;
     em.gbits = 1;
     while ((1ULL << em.gbits) < n) em.gbits++;
@@ -341,6 +351,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     const uint64_t cmask = (1ULL << em.gbits) - 1;
     for (uint64_t i = 0; i < n_emit; ++i) {
         uint32_t r = (uint32_t)(h_keys[i] >> em.gbits), c = (uint32_t)(h_keys[i] & cmask);
+        if (partial) { ani[i] = 0; keep.push_back(i); continue; }
         ani[i] = vb_ani_shorter(h_vals[i], h_tot[r], h_tot[c], p->k);
         if (ani[i] >= p->min_ident) keep.push_back(i);
     }

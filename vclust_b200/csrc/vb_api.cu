@@ -30,6 +30,35 @@ void vb_set_error(const std::string &msg) { g_last_error = msg; }
     catch (const std::exception &e) { vb_set_error(e.what()); return VB_ERR_INTERNAL; }       \
     return VB_OK;
 
+vb_pairs *vb_pairs_alloc(uint64_t n, uint32_t n_genomes);
+
+// LZ-ANI order: length descending, then name ascending (stable) -- seq_reservoir.cpp:229-236
+static std::vector<uint32_t> vb_lz_order(const vb_genomes *g)
+{
+    std::vector<uint32_t> order(g->count());
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        uint32_t la = (uint32_t)g->length(a) - 2u, lb = (uint32_t)g->length(b) - 2u;   // len - 2*no_parts, unsigned (sic)
+        if (la != lb) return la > lb;
+        return g->names[a] < g->names[b];
+    });
+    return order;
+}
+
+static vb_align_out *vb_align_out_alloc(uint64_t total, uint32_t n)
+{
+    auto *res = (vb_align_out *)calloc(1, sizeof(vb_align_out));
+    res->n = total;
+    res->n_genomes = n;
+    res->ref = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint64_t>(total, 1));
+    res->qry = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint64_t>(total, 1));
+    res->sym_in_matches = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
+    res->sym_in_literals = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
+    res->no_components = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
+    res->order = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint32_t>(n, 1));
+    return res;
+}
+
 extern "C" {
 
 int vb_version(char *buf, size_t n)
@@ -167,7 +196,79 @@ int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p,
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter: bad arguments");
     VB_CUDA(cudaSetDevice(ctx->device));
     vb_tls_stream = (cudaStream_t)ctx->stream;
-    vb_prefilter_impl(ctx, g, p, out);
+    vb_prefilter_impl(ctx, g, p, 0, 1, out);
+    VB_GUARD_END
+}
+
+int vb_prefilter_partial(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, uint32_t shard_index,
+                         uint32_t shard_count, vb_pairs **out)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter_partial: bad arguments");
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_prefilter_impl(ctx, g, p, shard_index, shard_count, out);
+    VB_GUARD_END
+}
+
+int vb_pairs_merge(const uint32_t *row, const uint32_t *col, const uint32_t *common, uint64_t n,
+                   const uint32_t *total_kmers, uint32_t n_genomes, const vb_prefilter_params *p, vb_pairs **out)
+{
+    VB_GUARD_BEGIN
+    if (!p || !out || !total_kmers || (n && (!row || !col || !common))) throw vb_error(VB_ERR_ARG, "vb_pairs_merge: bad arguments");
+    std::vector<uint64_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0ULL);
+    std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) {
+        return row[a] != row[b] ? row[a] < row[b] : col[a] < col[b];
+    });
+    std::vector<uint32_t> r, c, v;
+    std::vector<double> a;
+    for (uint64_t i = 0; i < n;) {
+        uint64_t j = i;
+        uint64_t sum = 0;
+        while (j < n && row[idx[j]] == row[idx[i]] && col[idx[j]] == col[idx[i]]) sum += common[idx[j++]];
+        uint32_t rr = row[idx[i]], cc = col[idx[i]];
+        if (rr >= n_genomes || cc >= n_genomes) throw vb_error(VB_ERR_ARG, "vb_pairs_merge: id out of range");
+        if (sum > 0 && sum >= (uint64_t)std::max(p->min_kmers, 0)) {           // sparse_filters.h:49-61
+            double ani = vb_ani_shorter((uint32_t)sum, total_kmers[rr], total_kmers[cc], p->k);
+            if (ani >= p->min_ident) { r.push_back(rr); c.push_back(cc); v.push_back((uint32_t)sum); a.push_back(ani); }
+        }
+        i = j;
+    }
+    vb_pairs *res = vb_pairs_alloc(r.size(), n_genomes);
+    for (size_t i = 0; i < r.size(); ++i) { res->row[i] = r[i]; res->col[i] = c[i]; res->common[i] = v[i]; res->ani[i] = a[i]; }
+    for (uint32_t i = 0; i < n_genomes; ++i) res->total_kmers[i] = total_kmers[i];
+    res->k = p->k;
+    res->kmers_fraction = p->kmers_fraction;
+    *out = res;
+    VB_GUARD_END
+}
+
+int vb_align_out_from_pairs(const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, const int32_t *stats, uint64_t n,
+                            vb_align_out **out)
+{
+    VB_GUARD_BEGIN
+    if (!g || !out || (n && (!ref || !qry || !stats))) throw vb_error(VB_ERR_ARG, "vb_align_out_from_pairs: bad arguments");
+    const uint32_t ng = g->count();
+    std::vector<uint32_t> order = vb_lz_order(g);
+    std::vector<uint32_t> rank(ng);
+    for (uint32_t i = 0; i < ng; ++i) rank[order[i]] = i;
+    std::vector<uint64_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0ULL);
+    for (uint64_t i = 0; i < n; ++i)
+        if (ref[i] >= ng || qry[i] >= ng) throw vb_error(VB_ERR_ARG, "vb_align_out_from_pairs: id out of range");
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) {
+        uint32_t ra = rank[ref[a]], rb = rank[ref[b]];
+        return ra != rb ? ra < rb : rank[qry[a]] < rank[qry[b]];
+    });
+    vb_align_out *res = vb_align_out_alloc(n, ng);
+    std::copy(order.begin(), order.end(), res->order);
+    for (uint64_t o = 0; o < n; ++o) {
+        uint64_t i = idx[o];
+        res->ref[o] = rank[ref[i]]; res->qry[o] = rank[qry[i]];
+        res->sym_in_matches[o] = stats[3 * i]; res->sym_in_literals[o] = stats[3 * i + 1]; res->no_components[o] = stats[3 * i + 2];
+    }
+    *out = res;
     VB_GUARD_END
 }
 
@@ -207,14 +308,7 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
     VB_CUDA(cudaSetDevice(ctx->device));
     vb_tls_stream = (cudaStream_t)ctx->stream;
     const uint32_t n = g->count();
-    // LZ-ANI order: length descending, then name ascending (stable) -- seq_reservoir.cpp:229-236
-    std::vector<uint32_t> order(n);
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        uint32_t la = (uint32_t)g->length(a) - 2u, lb = (uint32_t)g->length(b) - 2u;   // len - 2*no_parts, unsigned (sic)
-        if (la != lb) return la > lb;
-        return g->names[a] < g->names[b];
-    });
+    std::vector<uint32_t> order = vb_lz_order(g);
     std::vector<uint32_t> rank(n);
     for (uint32_t i = 0; i < n; ++i) rank[order[i]] = i;
 
@@ -236,15 +330,7 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
     }
     uint64_t total = 0;
     for (auto &r : rows) total += r.size();
-    auto *res = (vb_align_out *)calloc(1, sizeof(vb_align_out));
-    res->n = total;
-    res->n_genomes = n;
-    res->ref = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint64_t>(total, 1));
-    res->qry = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint64_t>(total, 1));
-    res->sym_in_matches = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
-    res->sym_in_literals = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
-    res->no_components = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
-    res->order = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint32_t>(n, 1));
+    vb_align_out *res = vb_align_out_alloc(total, n);
     std::copy(order.begin(), order.end(), res->order);
     std::vector<uint32_t> in_ref(total), in_qry(total);
     uint64_t w = 0;

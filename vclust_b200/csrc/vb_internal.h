@@ -60,6 +60,7 @@ struct vb_ctx {
     }
 };
 
-void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out);
+void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, uint32_t shard_index,
+                       uint32_t shard_count, vb_pairs **out);
 void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
                          const vb_align_params *p, int32_t *stats);
