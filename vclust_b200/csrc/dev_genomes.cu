@@ -125,14 +125,21 @@ void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32
     for (auto &r : ctx->resident)
         if (r.g == g && r.u_is_t == (int)u_is_t && r.min_pad >= min_pad) return;
     auto *d = new DevGenomes();
-    try { vb_upload_genomes(ctx, g, u_is_t, *d, min_pad); } catch (...) { delete d; throw; }
+    vb_arena *saved = vb_tls_arena;
+    vb_tls_arena = nullptr;                       // resident buffers outlive the call: plain cudaMalloc
+    try { vb_upload_genomes(ctx, g, u_is_t, *d, min_pad); } catch (...) { vb_tls_arena = saved; delete d; throw; }
+    vb_tls_arena = saved;
     ctx->resident.push_back({g, (int)u_is_t, min_pad < 128 ? 128u : min_pad, d});
 }
 
 void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g)
 {
     for (size_t i = 0; i < ctx->resident.size();) {
-        if (g == nullptr || ctx->resident[i].g == g) { delete ctx->resident[i].dev; ctx->resident.erase(ctx->resident.begin() + i); }
+        if (g == nullptr || ctx->resident[i].g == g) {
+            cudaStreamSynchronize((cudaStream_t)ctx->stream);
+            delete ctx->resident[i].dev;
+            ctx->resident.erase(ctx->resident.begin() + i);
+        }
         else ++i;
     }
 }
@@ -141,6 +148,8 @@ void vb_unpin_genomes(const vb_genomes *g)
 {
     if (g->pinned) { cudaHostUnregister((void *)g->bases.data()); g->pinned = false; }
 }
+
+thread_local vb_arena *vb_tls_arena = nullptr;
 
 uint64_t vb_device_available(vb_ctx *ctx)
 {
@@ -153,4 +162,70 @@ uint64_t vb_device_available(vb_ctx *ctx)
         cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
     }
     return (uint64_t)free_b + (reserved > used ? reserved - used : 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// arena
+// ---------------------------------------------------------------------------------------------------------------
+static size_t arena_round(size_t b) { return (b + 511) & ~(size_t)511; }
+
+void *vb_arena::alloc(size_t bytes)
+{
+    bytes = arena_round(bytes);
+    if (slabs.empty() || slabs.back().off + bytes > slabs.back().cap) {
+        // grow: a new slab at least as large as everything so far (only during warm-up; reset() merges the slabs)
+        size_t total = 0;
+        for (auto &s : slabs) total += s.cap;
+        size_t cap = std::max(bytes, std::max<size_t>(total, (size_t)256 << 20));
+        char *base = nullptr;
+        cudaError_t e = cudaMalloc((void **)&base, cap);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cap = bytes;
+            e = cudaMalloc((void **)&base, cap);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                throw vb_error(VB_ERR_MEM, "cudaMalloc of " + std::to_string(cap) + " bytes failed: " + cudaGetErrorString(e));
+            }
+        }
+        slabs.push_back({base, cap, 0});
+    }
+    Slab &s = slabs.back();
+    void *p = s.base + s.off;
+    s.off += bytes;
+    live += bytes;
+    peak = std::max(peak, live);
+    return p;
+}
+
+void vb_arena::pop(void *p, size_t bytes)
+{
+    bytes = arena_round(bytes);
+    live -= std::min(live, bytes);
+    for (size_t i = slabs.size(); i-- > 0;) {
+        Slab &s = slabs[i];
+        if ((char *)p + bytes == s.base + s.off) { s.off -= bytes; return; }     // top of this slab's stack
+        if (s.off != 0) return;                                                  // not LIFO: space returns at reset()
+    }
+}
+
+void vb_arena::reset(cudaStream_t st)
+{
+    if (slabs.size() > 1) {
+        cudaStreamSynchronize(st);
+        for (auto &s : slabs) cudaFree(s.base);
+        slabs.clear();
+        size_t want = std::max(arena_round(peak + peak / 8), (size_t)256 << 20);
+        char *base = nullptr;
+        if (cudaMalloc((void **)&base, want) == cudaSuccess) slabs.push_back({base, want, 0});
+        else cudaGetLastError();
+    }
+    for (auto &s : slabs) s.off = 0;
+    live = 0;
+}
+
+void vb_arena::destroy()
+{
+    for (auto &s : slabs) cudaFree(s.base);
+    slabs.clear();
 }

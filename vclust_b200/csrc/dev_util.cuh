@@ -20,37 +20,59 @@
         VB_CUDA(cudaGetLastError());     \
     } while (0)
 
-// All device memory comes from the device's default stream-ordered pool (release threshold = never), on the
-// stream of the context the calling thread is working for: after the first call no cudaMalloc / cudaFree (and
-// none of their implicit device synchronisations) happens on the hot path.
+// Device memory for call-scoped temporaries comes from a per-context ARENA: one slab that only grows, handed out by
+// bumping a pointer and popped in LIFO order (C++ scopes destroy DevBufs in reverse order), reset at the start of
+// every top-level call.  After warm-up there is no cudaMalloc / cudaFree (and none of their implicit device
+// synchronisations or page mapping) on the hot path.  Buffers that outlive a call (resident genomes) are allocated
+// while vb_tls_arena == nullptr and use plain cudaMalloc.
+struct vb_arena {
+    struct Slab { char *base; size_t cap; size_t off; };
+    std::vector<Slab> slabs;
+    size_t peak = 0, live = 0;
+    void *alloc(size_t bytes);
+    void pop(void *p, size_t bytes);
+    void reset(cudaStream_t st);          // call with no arena buffer alive
+    void destroy();
+};
+extern thread_local vb_arena *vb_tls_arena;
 extern thread_local cudaStream_t vb_tls_stream;
 
 template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    vb_arena *arena = nullptr;
     DevBuf() = default;
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), arena(o.arena) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept
+    {
+        if (this != &o) { release(); p = o.p; n = o.n; arena = o.arena; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
     ~DevBuf() { release(); }
     void alloc(size_t count)
     {
         release();
         n = count;
-        if (count) {
-            cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), vb_tls_stream);
-            if (e != cudaSuccess) {
-                p = nullptr; n = 0;
-                cudaGetLastError();
-                throw vb_error(VB_ERR_MEM, "cudaMallocAsync of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
-                                               cudaGetErrorString(e));
-            }
+        if (!count) return;
+        arena = vb_tls_arena;
+        if (arena) { p = (T *)arena->alloc(count * sizeof(T)); return; }
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr; n = 0;
+            cudaGetLastError();
+            throw vb_error(VB_ERR_MEM, "cudaMalloc of " + std::to_string(count * sizeof(T)) + " bytes failed: " +
+                                           cudaGetErrorString(e));
         }
     }
-    void release() { if (p) cudaFreeAsync(p, vb_tls_stream); p = nullptr; n = 0; }
+    void release()
+    {
+        if (p) { if (arena) arena->pop(p, n * sizeof(T)); else cudaFree(p); }
+        p = nullptr; n = 0;
+    }
     size_t bytes() const { return n * sizeof(T); }
 };
 

@@ -158,6 +158,411 @@ __global__ void __launch_bounds__(256) segment_pairs_kernel(const uint64_t *__re
     }
 }
 
+
+// ===============================================================================================================
+// MSD path (default): group equal k-mers WITHOUT a full sort.
+//   Only the grouping of equal k-mers matters, not their numeric order, so tuples are keyed by h = fmix64(k-mer)
+//   (a bijection on 64 bits): the top b1 + b2 bits of h select one of B1*B2 buckets of ~1000 tuples; a bucket is then
+//   grouped entirely in shared memory (hash table keyed by h) and the pairs are emitted from there.
+//     count_kernel   genomes -> bucket histogram (+ valid k-mers per genome)                       0.375 B/base read
+//     scan_kernel    exclusive scan -> bucket offsets, write cursors, tile map
+//     part_kernel<A> genomes -> level-1 buckets (extraction fused, coalesced runs via smem staging)  12 B/tuple written
+//     part_kernel<B> level-1 -> level-2 buckets                                                     12 B read + 12 B written
+//     bucket_kernel  level-2 bucket -> smem grouping -> duplicates per genome + pair increments      12 B read
+//   = 48 B of HBM traffic per tuple instead of 7 radix passes x 32 B.
+// ===============================================================================================================
+constexpr int PART_THREADS = 256;
+constexpr int PART_ITEMS = 16;
+constexpr int PART_TILE = PART_THREADS * PART_ITEMS;      // 4096 tuples per block
+constexpr int MAX_BUCKET_BITS = 9;                        // per level
+constexpr int BUCKET_CAP = 2048;                          // tuples a bucket may hold to be grouped in shared memory
+constexpr int BUCKET_SLOTS = 4096;                        // hash slots per bucket (load <= 0.5)
+constexpr int BUCKET_TARGET = 1280;                       // planned mean bucket size (CAP is 20 sigma above it)
+constexpr int SMALL_GROUP = 32;                           // groups up to this size are sorted by one thread
+
+struct MsdPlan {
+    int b1, b2;              // bucket bits of level 1 and level 2 (b2 == 0: one level)
+    uint32_t B1, B2, NB;     // 1 << b1, 1 << b2, B1 * B2
+};
+
+__device__ __forceinline__ bool extract_at(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
+                                           const uint32_t *__restrict__ tile_gid, uint64_t p, uint64_t n_slots,
+                                           const ExtractParams &ep, uint64_t kmask, uint32_t wmask, uint64_t &h, uint32_t &gid)
+{
+    if (p >= n_slots) return false;
+    gid = tile_gid[p >> 7];
+    if (gid == 0xffffffffu || (fetch1(inv, p) & wmask) != 0) return false;
+    uint64_t w = fetch2(seq2, p) & kmask;
+    uint64_t rc = (~w) & kmask;
+    uint64_t fw = reverse_digits(w) >> (64 - 2 * ep.k);
+    uint64_t can = fw < rc ? fw : rc;
+    can = (can << ep.shift) | (can & ep.tail_mask);
+    if (ep.use_filter && !(minhash64(can, ep.c) < ep.max_thr)) return false;
+    h = fmix64(can);
+    if (ep.shard_count > 1 && (h % ep.shard_count) != ep.shard_index) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) count_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
+                                                    const uint32_t *__restrict__ tile_gid, uint64_t n_slots, uint64_t n_iter,
+                                                    ExtractParams ep, int total_bits, uint32_t *__restrict__ hist,
+                                                    uint32_t *__restrict__ valid_cnt)
+{
+    const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
+    const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n_iter; p += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t h; uint32_t gid = 0;
+        bool ok = extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, h, gid);
+        if (ok) atomicAdd(&hist[total_bits ? (uint32_t)(h >> (64 - total_bits)) : 0u], 1u);
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m && (threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(&valid_cnt[gid], (uint32_t)__popc(m));
+    }
+}
+
+// one block: off[i] = exclusive prefix of hist (NB + 1 entries); cursor2 = off; cursor1[b] = off[b * B2];
+// tile_start[b] = number of PART_TILE tiles in level-1 buckets < b (B1 + 1 entries)
+__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *__restrict__ hist, MsdPlan pl, uint32_t *__restrict__ off,
+                                                    uint32_t *__restrict__ cursor1, uint32_t *__restrict__ cursor2,
+                                                    uint32_t *__restrict__ tile_start)
+{
+    __shared__ uint32_t part[1024];
+    __shared__ uint32_t s_total;
+    const uint32_t per = (pl.NB + 1023) / 1024;
+    const uint32_t lo = min(threadIdx.x * per, pl.NB), hi = min(lo + per, pl.NB);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += hist[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 1024; ++i) { uint32_t t = part[i]; part[i] = run; run += t; }
+        s_total = run;
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; ++i) { off[i] = run; cursor2[i] = run; run += hist[i]; }
+    if (threadIdx.x == 0) off[pl.NB] = s_total;
+    __syncthreads();                    // block-wide visibility of the off[] writes (same block reads them below)
+    if (threadIdx.x == 0) {
+        uint32_t tiles = 0;
+        for (uint32_t b = 0; b < pl.B1; ++b) {
+            uint32_t beg = off[b * pl.B2], end = off[(b + 1) * pl.B2];
+            cursor1[b] = beg;
+            tile_start[b] = tiles;
+            tiles += (end - beg + PART_TILE - 1) / PART_TILE;
+        }
+        tile_start[pl.B1] = tiles;
+    }
+}
+
+// Partition one tile of tuples into buckets.  LEVEL 1: tuples come from the genomes (extraction fused), bucket = top b1
+// bits of h.  LEVEL 2: tuples come from a level-1 bucket, bucket = next b2 bits.  Inside the block the tile is first
+// grouped by bucket in shared memory, so that every bucket receives one contiguous run per tile.
+template <int LEVEL>
+__global__ void __launch_bounds__(PART_THREADS) part_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
+                                                            const uint32_t *__restrict__ tile_gid, uint64_t n_slots,
+                                                            ExtractParams ep, MsdPlan pl, const uint64_t *__restrict__ in_keys,
+                                                            const uint32_t *__restrict__ in_vals, const uint32_t *__restrict__ off,
+                                                            const uint32_t *__restrict__ tile_start, uint32_t n_tiles,
+                                                            uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys,
+                                                            uint32_t *__restrict__ out_vals)
+{
+    extern __shared__ unsigned char smem_raw[];
+    uint64_t *st_keys = (uint64_t *)smem_raw;                          // PART_TILE
+    uint32_t *st_vals = (uint32_t *)(st_keys + PART_TILE);              // PART_TILE
+    uint32_t *s_cnt = st_vals + PART_TILE;                              // 512 each
+    uint32_t *s_start = s_cnt + 512;
+    uint32_t *s_fill = s_start + 512;
+    uint32_t *s_gbase = s_fill + 512;
+    __shared__ uint32_t s_total, s_bucket, s_tile_lo;
+    const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
+    const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
+    const uint32_t NBK = (LEVEL == 1) ? pl.B1 : pl.B2;
+    const int shift = (LEVEL == 1) ? (64 - pl.b1) : (64 - pl.b1 - pl.b2);
+
+    if (LEVEL == 2) n_tiles = tile_start[pl.B1];
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t b = threadIdx.x; b < NBK; b += PART_THREADS) { s_cnt[b] = 0; s_fill[b] = 0; }
+        uint64_t src_lo = 0, src_hi = 0;
+        uint32_t parent = 0;
+        if (LEVEL == 2) {
+            if (threadIdx.x == 0) {                                     // which level-1 bucket does this tile belong to?
+                uint32_t lo = 0, hi = pl.B1;
+                while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (tile_start[mid] <= tile) lo = mid; else hi = mid; }
+                s_bucket = lo; s_tile_lo = tile_start[lo];
+            }
+        }
+        __syncthreads();
+        if (LEVEL == 2) {
+            parent = s_bucket;
+            uint64_t beg = off[parent * pl.B2], end = off[(parent + 1) * pl.B2];
+            src_lo = beg + (uint64_t)(tile - s_tile_lo) * PART_TILE;
+            src_hi = min(src_lo + PART_TILE, end);
+        } else {
+            src_lo = (uint64_t)tile * PART_TILE;
+            src_hi = src_lo + PART_TILE;                                // extract_at checks n_slots
+        }
+        uint64_t key[PART_ITEMS];
+        uint32_t val[PART_ITEMS];
+        uint32_t bk[PART_ITEMS];
+#pragma unroll
+        for (int r = 0; r < PART_ITEMS; ++r) {
+            uint64_t p = src_lo + (uint64_t)r * PART_THREADS + threadIdx.x;
+            bool ok;
+            if (LEVEL == 1) ok = extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, key[r], val[r]);
+            else {
+                ok = p < src_hi;
+                if (ok) { key[r] = in_keys[p]; val[r] = in_vals[p]; }
+            }
+            bk[r] = 0xffffffffu;
+            if (ok) {
+                bk[r] = (NBK > 1) ? (uint32_t)((key[r] >> shift) & (NBK - 1)) : 0u;
+                atomicAdd(&s_cnt[bk[r]], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of s_cnt (NBK <= 512) + one global reservation per non-empty bucket
+        if (threadIdx.x < 32) {
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < NBK; base += 32) {
+                uint32_t b = base + threadIdx.x;
+                uint32_t v = b < NBK ? s_cnt[b] : 0, x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (threadIdx.x >= o) x += y; }
+                if (b < NBK) s_start[b] = carry + x - v;
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (threadIdx.x == 0) s_total = carry;
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < NBK; b += PART_THREADS) {
+            uint32_t c = s_cnt[b];
+            if (c) s_gbase[b] = atomicAdd(&cursor[(LEVEL == 1) ? b : parent * pl.B2 + b], c);
+        }
+#pragma unroll
+        for (int r = 0; r < PART_ITEMS; ++r) {
+            if (bk[r] != 0xffffffffu) {
+                uint32_t pos = s_start[bk[r]] + atomicAdd(&s_fill[bk[r]], 1u);
+                st_keys[pos] = key[r];
+                st_vals[pos] = val[r];
+            }
+        }
+        __syncthreads();
+        const uint32_t total = s_total;
+        for (uint32_t s = threadIdx.x; s < total; s += PART_THREADS) {
+            uint64_t k = st_keys[s];
+            uint32_t b = (NBK > 1) ? (uint32_t)((k >> shift) & (NBK - 1)) : 0u;
+            uint32_t dst = s_gbase[b] + (s - s_start[b]);
+            out_keys[dst] = k;
+            out_vals[dst] = st_vals[s];
+        }
+        __syncthreads();
+    }
+}
+
+// shared-memory layout of bucket_kernel (dynamic)
+struct BucketSmem {
+    uint64_t keys[BUCKET_CAP];
+    uint32_t gids[BUCKET_CAP];
+    uint32_t table[BUCKET_SLOTS];      // slot -> index of the first tuple with that key (0xffffffff = empty)
+    uint32_t cnt[BUCKET_SLOTS];        // tuples per slot, then exclusive start
+    uint32_t grp[BUCKET_CAP];          // genome ids regrouped by slot
+    uint16_t grp_slot[BUCKET_CAP];     // slot of every regrouped element
+    uint32_t large[64];                // slots whose group is larger than SMALL_GROUP
+    uint32_t n_large;
+    uint32_t warp_sum[8];
+};
+
+__device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, int count_only, unsigned long long &local_inc,
+                                          uint64_t *__restrict__ tkeys, uint32_t *__restrict__ tvals, uint64_t cap_mask,
+                                          int *__restrict__ overflow)
+{
+    if (count_only) { ++local_inc; return; }
+    uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
+    table_add(tkeys, tvals, cap_mask, ((uint64_t)hi << 32) | lo, 1u, overflow);
+}
+
+// One block per final bucket: group equal k-mers in shared memory, count duplicates per genome, emit pair increments.
+// count_only: only sum the number of pair increments (sizing pass for very large N).
+__global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                     const uint32_t *__restrict__ off, uint32_t n_buckets, int count_only,
+                                                     uint32_t *__restrict__ dup_cnt, uint64_t *__restrict__ tkeys,
+                                                     uint32_t *__restrict__ tvals, uint64_t cap_mask, int *__restrict__ overflow,
+                                                     uint32_t *__restrict__ big_list, uint32_t *__restrict__ n_big,
+                                                     unsigned long long *__restrict__ n_inc)
+{
+    extern __shared__ unsigned char smem_raw[];
+    BucketSmem &S = *(BucketSmem *)smem_raw;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned long long local_inc = 0;
+    for (uint32_t bkt = blockIdx.x; bkt < n_buckets; bkt += gridDim.x) {
+        const uint32_t beg = off[bkt], size = off[bkt + 1] - beg;
+        if (size < 2) continue;                                              // uniform for the block
+        if (size > BUCKET_CAP) {                                             // too big for shared memory: generic path
+            if (tid == 0) big_list[atomicAdd(n_big, 1u)] = bkt;
+            continue;
+        }
+        for (int s = tid; s < BUCKET_SLOTS; s += 256) { S.table[s] = 0xffffffffu; S.cnt[s] = 0; }
+        for (uint32_t i = tid; i < size; i += 256) { S.keys[i] = keys[beg + i]; S.gids[i] = vals[beg + i]; }
+        if (tid == 0) S.n_large = 0;
+        __syncthreads();
+        // ---- insert: every tuple finds the slot of its key
+        uint32_t my_slot[BUCKET_CAP / 256], my_rank[BUCKET_CAP / 256];
+#pragma unroll
+        for (int r = 0; r < BUCKET_CAP / 256; ++r) {
+            uint32_t i = tid + r * 256;
+            my_slot[r] = 0xffffffffu;
+            if (i < size) {
+                uint64_t k = S.keys[i];
+                uint32_t s = (uint32_t)k & (BUCKET_SLOTS - 1);                // low bits: independent of the bucket bits
+                for (;;) {
+                    uint32_t cur = S.table[s];
+                    if (cur == 0xffffffffu) {
+                        cur = atomicCAS(&S.table[s], 0xffffffffu, i);
+                        if (cur == 0xffffffffu) cur = i;
+                    }
+                    if (S.keys[cur] == k) break;
+                    s = (s + 1) & (BUCKET_SLOTS - 1);
+                }
+                my_slot[r] = s;
+                my_rank[r] = atomicAdd(&S.cnt[s], 1u);
+            }
+        }
+        __syncthreads();
+        // ---- exclusive scan of cnt over the slots (16 per thread)
+        {
+            constexpr int PER = BUCKET_SLOTS / 256;
+            uint32_t loc[PER], sum = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { loc[j] = S.cnt[tid * PER + j]; sum += loc[j]; }
+            uint32_t x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) S.warp_sum[wid] = x;
+            __syncthreads();
+            uint32_t pre = x - sum;
+            for (int j = 0; j < wid; ++j) pre += S.warp_sum[j];
+            // keep the group size in the upper half of the word: start (low 16 bits... sizes up to 2048 need 12 bits)
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { uint32_t c = loc[j]; S.cnt[tid * PER + j] = (c << 16) | pre; pre += c; }
+        }
+        __syncthreads();
+        // ---- regroup genome ids by slot
+#pragma unroll
+        for (int r = 0; r < BUCKET_CAP / 256; ++r) {
+            if (my_slot[r] != 0xffffffffu) {
+                uint32_t pos = (S.cnt[my_slot[r]] & 0xffffu) + my_rank[r];
+                S.grp[pos] = S.gids[tid + r * 256];
+                S.grp_slot[pos] = (uint16_t)my_slot[r];
+            }
+        }
+        __syncthreads();
+        // ---- sort every group by genome id: small groups by one thread, large ones by the whole block
+        for (int s = tid; s < BUCKET_SLOTS; s += 256) {
+            uint32_t c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
+            if (c < 2) continue;
+            if (c > SMALL_GROUP) { uint32_t q = atomicAdd(&S.n_large, 1u); if (q < 64) S.large[q] = s; continue; }
+            for (uint32_t a = 1; a < c; ++a) {                                // insertion sort
+                uint32_t v = S.grp[st0 + a];
+                uint32_t b = a;
+                while (b > 0 && S.grp[st0 + b - 1] > v) { S.grp[st0 + b] = S.grp[st0 + b - 1]; --b; }
+                S.grp[st0 + b] = v;
+            }
+        }
+        __syncthreads();
+        const uint32_t n_large = min(S.n_large, 64u);
+        if (S.n_large > 64) {                                                // pathological: leave it to the generic path
+            if (tid == 0) big_list[atomicAdd(n_big, 1u)] = bkt;
+            __syncthreads();
+            continue;
+        }
+        for (uint32_t q = 0; q < n_large; ++q) {                             // block-wide bitonic sort (all-ascending form)
+            const uint32_t s = S.large[q], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
+            uint32_t n2 = 1; while (n2 < c) n2 <<= 1;
+            for (uint32_t k = 2; k <= n2; k <<= 1) {
+                for (uint32_t i = tid; i < n2; i += 256) {
+                    uint32_t l = i ^ (k - 1);
+                    if (l > i && l < c) { uint32_t a = S.grp[st0 + i], b = S.grp[st0 + l]; if (a > b) { S.grp[st0 + i] = b; S.grp[st0 + l] = a; } }
+                }
+                __syncthreads();
+                for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                    for (uint32_t i = tid; i < n2; i += 256) {
+                        uint32_t l = i ^ j;
+                        if (l > i && l < c) { uint32_t a = S.grp[st0 + i], b = S.grp[st0 + l]; if (a > b) { S.grp[st0 + i] = b; S.grp[st0 + l] = a; } }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        // ---- every element pairs with the distinct genomes before it in its (now sorted) group
+        for (uint32_t e = tid; e < size; e += 256) {
+            const uint32_t s = S.grp_slot[e], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
+            if (c < 2) continue;
+            const uint32_t g = S.grp[e];
+            if (e > st0 && S.grp[e - 1] == g) { if (!count_only) atomicAdd(&dup_cnt[g], 1u); continue; }
+            uint32_t prev = g;
+            for (uint32_t j = e; j-- > st0;) {
+                uint32_t gj = S.grp[j];
+                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, tkeys, tvals, cap_mask, overflow); prev = gj; }
+            }
+        }
+        __syncthreads();
+    }
+    if (count_only) {
+        for (int o = 16; o; o >>= 1) local_inc += __shfl_down_sync(0xffffffffu, local_inc, o);
+        if (lane == 0 && local_inc) atomicAdd(n_inc, local_inc);
+    }
+}
+
+// Generic path for buckets that do not fit shared memory (a k-mer shared by thousands of genomes lands here): the
+// block sorts the bucket in place in global memory by (h, genome) with the all-ascending bitonic network, then runs
+// the same run scan as the LSD path.
+__global__ void __launch_bounds__(1024) big_bucket_kernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                                          const uint32_t *__restrict__ off, const uint32_t *__restrict__ big_list,
+                                                          const uint32_t *__restrict__ n_big, int count_only,
+                                                          uint32_t *__restrict__ dup_cnt, uint64_t *__restrict__ tkeys,
+                                                          uint32_t *__restrict__ tvals, uint64_t cap_mask, int *__restrict__ overflow,
+                                                          unsigned long long *__restrict__ n_inc)
+{
+    const uint32_t nb = *n_big;
+    unsigned long long local_inc = 0;
+    for (uint32_t q = blockIdx.x; q < nb; q += gridDim.x) {
+        const uint32_t bkt = big_list[q];
+        const uint32_t beg = off[bkt], c = off[bkt + 1] - beg;
+        uint64_t *K = keys + beg;
+        uint32_t *V = vals + beg;
+        uint32_t n2 = 1; while (n2 < c) n2 <<= 1;
+        auto cmpx = [&](uint32_t i, uint32_t l) {
+            uint64_t ka = K[i], kb = K[l];
+            uint32_t va = V[i], vb = V[l];
+            if (ka > kb || (ka == kb && va > vb)) { K[i] = kb; K[l] = ka; V[i] = vb; V[l] = va; }
+        };
+        for (uint32_t k = 2; k <= n2; k <<= 1) {
+            for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) { uint32_t l = i ^ (k - 1); if (l > i && l < c) cmpx(i, l); }
+            __syncthreads();
+            for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) { uint32_t l = i ^ j; if (l > i && l < c) cmpx(i, l); }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+            uint64_t key = K[i];
+            uint32_t g = V[i];
+            if (i > 0 && K[i - 1] == key && V[i - 1] == g) { if (!count_only) atomicAdd(&dup_cnt[g], 1u); continue; }
+            uint32_t prev = g;
+            for (uint32_t j = i; j-- > 0 && K[j] == key;) {
+                uint32_t gj = V[j];
+                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, tkeys, tvals, cap_mask, overflow); prev = gj; }
+            }
+        }
+        __syncthreads();
+    }
+    if (count_only) {
+        for (int o = 16; o; o >>= 1) local_inc += __shfl_down_sync(0xffffffffu, local_inc, o);
+        if ((threadIdx.x & 31) == 0 && local_inc) atomicAdd(n_inc, local_inc);
+    }
+}
+
 __global__ void totals_kernel(const uint32_t *__restrict__ valid_cnt, const uint32_t *__restrict__ dup_cnt, uint32_t n,
                               uint32_t *__restrict__ totals)
 {
@@ -247,12 +652,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     const DevGenomes &dg = vb_get_dev_genomes(ctx, g, /*u_is_t=*/true, 128, dg_scratch);
     t_up.stop();
 
-    // ---- k1
-    t_ext.start();
     const uint64_t n_slots = dg.total_slots;
-    const uint64_t n_pad = ((n_slots + rsort::TILE - 1) / rsort::TILE) * rsort::TILE;
-    DevBuf<uint64_t> keys_a(n_pad), keys_b(n_pad);
-    DevBuf<uint32_t> vals_a(n_pad), vals_b(n_pad);
     DevBuf<uint32_t> counters(3 * (size_t)std::max<uint32_t>(n, 1));        // valid | dup | totals
     uint32_t *valid_cnt = counters.p, *dup_cnt = counters.p + n, *totals = counters.p + 2 * (size_t)n;
     VB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
@@ -265,45 +665,128 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     ep.c = (uint64_t)std::ceil((double)p->k / 4);
     ep.shard_index = shard_index;
     ep.shard_count = shard_count;
-    extract_kernel<<<grid_for(n_pad), 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_pad, ep, keys_a.p,
-                                                   vals_a.p, valid_cnt);
-    VB_LAUNCH_CHECK(ctx);
-    t_ext.stop();
 
-    // ---- k2 (bit 2k+shift is set only in the sentinel, so it sorts last)
-    t_sort.start();
-    rsort::Workspace ws;
-    const int key_bits = 2 * p->k + ep.shift + 1;
-    bool in_b = rsort::sort_kv<8>(ctx, keys_a.p, vals_a.p, keys_b.p, vals_b.p, n_pad, key_bits, ws);
-    const uint64_t *skeys = in_b ? keys_b.p : keys_a.p;
-    const uint32_t *svals = in_b ? vals_b.p : vals_a.p;
-    t_sort.stop();
-
-    // ---- k3
-    t_seg.start();
     DevBuf<unsigned long long> scalars(4);
     VB_CUDA(cudaMemsetAsync(scalars.p, 0, scalars.bytes(), st));
-    unsigned long long max_pairs = (unsigned long long)n * (n > 0 ? n - 1 : 0) / 2;
+    const unsigned long long max_pairs = (unsigned long long)n * (n > 0 ? n - 1 : 0) / 2;
     unsigned long long n_inc = max_pairs;
     const bool count_first = max_pairs > (1ULL << 26);      // otherwise the dense bound N(N-1)/2 sizes the table
-    if (count_first) {
-        segment_count_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, scalars.p);
-        VB_LAUNCH_CHECK(ctx);
+    DevBuf<uint64_t> tkeys;
+    DevBuf<uint32_t> tvals;
+    DevBuf<int> overflow(1);
+    uint64_t cap = 0;
+    auto alloc_table = [&]() {
+        unsigned long long distinct_bound = std::min(n_inc, max_pairs);
+        cap = 1024;
+        while (cap < 2 * distinct_bound) cap <<= 1;
+        if (cap > (1ULL << 32)) throw vb_error(VB_ERR_MEM, "pair table would exceed 2^32 slots; split the input (--batch-size)");
+        tkeys.alloc(cap);
+        tvals.alloc(cap);
+        VB_CUDA(cudaMemsetAsync(tkeys.p, 0xff, tkeys.bytes(), st));       // SLOT_EMPTY
+        VB_CUDA(cudaMemsetAsync(tvals.p, 0, tvals.bytes(), st));
+        VB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st));
+    };
+    auto read_n_inc = [&]() {
         VB_CUDA(cudaMemcpyAsync(&n_inc, scalars.p, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaStreamSynchronize(st));
+    };
+    rsort::Workspace ws;
+    static const bool use_lsd = getenv("VB_PREFILTER_LSD") != nullptr;      // A/B switch: the round-1 LSD radix path
+
+    if (use_lsd) {
+        // ---- k1 + k2 + k3, LSD flavour: full stable sort of (k-mer, genome) tuples, then a run scan
+        t_ext.start();
+        const uint64_t n_pad = ((n_slots + rsort::TILE - 1) / rsort::TILE) * rsort::TILE;
+        DevBuf<uint64_t> keys_a(n_pad), keys_b(n_pad);
+        DevBuf<uint32_t> vals_a(n_pad), vals_b(n_pad);
+        extract_kernel<<<grid_for(n_pad), 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_pad, ep, keys_a.p,
+                                                       vals_a.p, valid_cnt);
+        VB_LAUNCH_CHECK(ctx);
+        t_ext.stop();
+        t_sort.start();                                     // bit 2k+shift is set only in the sentinel: it sorts last
+        const int key_bits = 2 * p->k + ep.shift + 1;
+        bool in_b = rsort::sort_kv<8>(ctx, keys_a.p, vals_a.p, keys_b.p, vals_b.p, n_pad, key_bits, ws);
+        const uint64_t *skeys = in_b ? keys_b.p : keys_a.p;
+        const uint32_t *svals = in_b ? vals_b.p : vals_a.p;
+        t_sort.stop();
+        t_seg.start();
+        if (count_first) {
+            segment_count_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, scalars.p);
+            VB_LAUNCH_CHECK(ctx);
+            read_n_inc();
+        }
+        alloc_table();
+        segment_pairs_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, dup_cnt, tkeys.p, tvals.p, cap - 1, overflow.p);
+        VB_LAUNCH_CHECK(ctx);
+    } else {
+        // ---- k1 + k2 + k3, MSD flavour: hash-bucket partition + shared-memory grouping
+        t_ext.start();
+        MsdPlan pl;
+        {
+            double est = (double)n_slots * std::min(1.0, p->kmers_fraction) / shard_count;
+            int bits = 0;
+            while (est / (double)(1ULL << bits) > BUCKET_TARGET && bits < 2 * MAX_BUCKET_BITS) ++bits;
+            pl.b1 = (bits + 1) / 2; pl.b2 = bits - pl.b1;
+            pl.B1 = 1u << pl.b1; pl.B2 = 1u << pl.b2; pl.NB = pl.B1 * pl.B2;
+        }
+        if (n_slots >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 base slots in one prefilter call");
+        DevBuf<uint32_t> hist(pl.NB), off(pl.NB + 1), cursor1(pl.B1), cursor2(pl.NB), tile_start(pl.B1 + 1), big_list(pl.NB + 1);
+        DevBuf<uint32_t> n_big(1);
+        VB_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
+        VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
+        const uint64_t n_iter = (n_slots + 31) / 32 * 32;
+        count_kernel<<<grid_for(n_iter), 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep, pl.b1 + pl.b2,
+                                                      hist.p, valid_cnt);
+        VB_LAUNCH_CHECK(ctx);
+        scan_kernel<<<1, 1024, 0, st>>>(hist.p, pl, off.p, cursor1.p, cursor2.p, tile_start.p);
+        VB_LAUNCH_CHECK(ctx);
+        t_ext.stop();
+        t_sort.start();
+        DevBuf<uint64_t> keys1(n_slots + 64), keys2(pl.b2 ? n_slots + 64 : 1);
+        DevBuf<uint32_t> vals1(n_slots + 64), vals2(pl.b2 ? n_slots + 64 : 1);
+        const size_t part_smem = PART_TILE * 12 + 4 * 512 * sizeof(uint32_t);
+        static bool attr_done = false;
+        if (!attr_done) {
+            VB_CUDA(cudaFuncSetAttribute(part_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            VB_CUDA(cudaFuncSetAttribute(part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            VB_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
+            attr_done = true;
+        }
+        const uint32_t tiles1 = (uint32_t)((n_slots + PART_TILE - 1) / PART_TILE);
+        part_kernel<1><<<std::min<uint32_t>(tiles1, 148 * 8), PART_THREADS, part_smem, st>>>(
+            dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, ep, pl, nullptr, nullptr, off.p, tile_start.p, tiles1, cursor1.p,
+            keys1.p, vals1.p);
+        VB_LAUNCH_CHECK(ctx);
+        uint64_t *fkeys = keys1.p;
+        uint32_t *fvals = vals1.p;
+        if (pl.b2) {
+            part_kernel<2><<<std::min<uint32_t>(tiles1 + pl.B1, 148 * 8), PART_THREADS, part_smem, st>>>(
+                dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, ep, pl, keys1.p, vals1.p, off.p, tile_start.p, 0, cursor2.p,
+                keys2.p, vals2.p);
+            VB_LAUNCH_CHECK(ctx);
+            fkeys = keys2.p; fvals = vals2.p;
+        }
+        t_sort.stop();
+        t_seg.start();
+        const int bgrid = (int)std::min<uint32_t>(pl.NB, 148 * 12);
+        if (count_first) {
+            bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(fkeys, fvals, off.p, pl.NB, 1, dup_cnt, nullptr, nullptr, 0,
+                                                                  overflow.p, big_list.p, n_big.p, scalars.p);
+            VB_LAUNCH_CHECK(ctx);
+            big_bucket_kernel<<<64, 1024, 0, st>>>(fkeys, fvals, off.p, big_list.p, n_big.p, 1, dup_cnt, nullptr, nullptr, 0,
+                                                   overflow.p, scalars.p);
+            VB_LAUNCH_CHECK(ctx);
+            read_n_inc();
+            VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
+        }
+        alloc_table();
+        bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(fkeys, fvals, off.p, pl.NB, 0, dup_cnt, tkeys.p, tvals.p, cap - 1,
+                                                              overflow.p, big_list.p, n_big.p, scalars.p);
+        VB_LAUNCH_CHECK(ctx);
+        big_bucket_kernel<<<64, 1024, 0, st>>>(fkeys, fvals, off.p, big_list.p, n_big.p, 0, dup_cnt, tkeys.p, tvals.p, cap - 1,
+                                               overflow.p, scalars.p);
+        VB_LAUNCH_CHECK(ctx);
     }
-    unsigned long long distinct_bound = std::min(n_inc, max_pairs);
-    uint64_t cap = 1024;
-    while (cap < 2 * distinct_bound) cap <<= 1;
-    if (cap > (1ULL << 32)) throw vb_error(VB_ERR_MEM, "pair table would exceed 2^32 slots; split the input (--batch-size)");
-    DevBuf<uint64_t> tkeys(cap);
-    DevBuf<uint32_t> tvals(cap);
-    DevBuf<int> overflow(1);
-    VB_CUDA(cudaMemsetAsync(tkeys.p, 0xff, tkeys.bytes(), st));       // SLOT_EMPTY
-    VB_CUDA(cudaMemsetAsync(tvals.p, 0, tvals.bytes(), st));
-    VB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st));
-    segment_pairs_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, dup_cnt, tkeys.p, tvals.p, cap - 1, overflow.p);
-    VB_LAUNCH_CHECK(ctx);
     totals_kernel<<<(n + 255) / 256 + 1, 256, 0, st>>>(valid_cnt, dup_cnt, n, totals);
     VB_LAUNCH_CHECK(ctx);
     t_seg.stop();
@@ -374,7 +857,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     ctx->set_timing("prefilter.sort_ms", t_sort.ms());
     ctx->set_timing("prefilter.segment_ms", t_seg.ms());
     ctx->set_timing("prefilter.emit_ms", t_emit.ms());
-    ctx->set_timing("prefilter.tuples", (double)n_slots);
+    ctx->set_timing("prefilter.tuples", (double)dg.total_slots);
     ctx->set_timing("prefilter.pair_increments", (double)n_inc);
     ctx->set_timing("prefilter.table_slots", (double)cap);
     ctx->set_timing("prefilter.candidates", (double)n_emit);

@@ -32,6 +32,16 @@ void vb_set_error(const std::string &msg) { g_last_error = msg; }
 
 vb_pairs *vb_pairs_alloc(uint64_t n, uint32_t n_genomes);
 
+// every device-touching entry point: select the device, bind this thread to the context's stream and arena, and
+// start with an empty arena (all temporaries of the previous call are dead by now)
+static void vb_enter(vb_ctx *ctx)
+{
+    VB_CUDA(cudaSetDevice(ctx->device));
+    vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_tls_arena = ctx->arena;
+    ctx->arena->reset((cudaStream_t)ctx->stream);
+}
+
 // LZ-ANI order: length descending, then name ascending (stable) -- seq_reservoir.cpp:229-236
 static std::vector<uint32_t> vb_lz_order(const vb_genomes *g)
 {
@@ -91,10 +101,7 @@ int vb_ctx_create(int device, vb_ctx **out)
     cudaStream_t st;
     VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     ctx->stream = (void *)st;
-    cudaMemPool_t pool;
-    VB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t never = UINT64_MAX;
-    VB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+    ctx->arena = new vb_arena();
     size_t free_b = 0, total_b = 0;
     VB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     ctx->mem_total = total_b;
@@ -107,8 +114,10 @@ void vb_ctx_destroy(vb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_tls_arena = nullptr;
     vb_evict_impl(ctx, nullptr);
     cudaStreamSynchronize((cudaStream_t)ctx->stream);
+    if (ctx->arena) { ctx->arena->destroy(); delete ctx->arena; }
     for (auto &e : ctx->events) if (e) cudaEventDestroy((cudaEvent_t)e);
     if (ctx->stream) cudaStreamDestroy((cudaStream_t)ctx->stream);
     delete ctx;
@@ -140,8 +149,7 @@ int vb_genomes_make_resident(vb_ctx *ctx, const vb_genomes *g, vb_fasta_flavor r
 {
     VB_GUARD_BEGIN
     if (!ctx || !g) throw vb_error(VB_ERR_ARG, "vb_genomes_make_resident: bad arguments");
-    VB_CUDA(cudaSetDevice(ctx->device));
-    vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_enter(ctx);
     vb_make_resident_impl(ctx, g, rule == VB_FASTA_KMERDB, rule == VB_FASTA_KMERDB ? 128u : (uint32_t)std::max(mrd, 0) + 128u);
     VB_GUARD_END
 }
@@ -150,8 +158,7 @@ int vb_genomes_evict(vb_ctx *ctx, const vb_genomes *g)
 {
     VB_GUARD_BEGIN
     if (!ctx) throw vb_error(VB_ERR_ARG, "vb_genomes_evict: bad arguments");
-    VB_CUDA(cudaSetDevice(ctx->device));
-    vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_enter(ctx);
     vb_evict_impl(ctx, g);
     VB_GUARD_END
 }
@@ -194,8 +201,7 @@ int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p,
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter: bad arguments");
-    VB_CUDA(cudaSetDevice(ctx->device));
-    vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_enter(ctx);
     vb_prefilter_impl(ctx, g, p, 0, 1, out);
     VB_GUARD_END
 }
@@ -205,8 +211,7 @@ int vb_prefilter_partial(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_pa
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter_partial: bad arguments");
-    VB_CUDA(cudaSetDevice(ctx->device));
-    vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_enter(ctx);
     vb_prefilter_impl(ctx, g, p, shard_index, shard_count, out);
     VB_GUARD_END
 }
@@ -295,8 +300,7 @@ int vb_align_pairs(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const 
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || (n && (!ref || !qry || !stats))) throw vb_error(VB_ERR_ARG, "vb_align_pairs: bad arguments");
-    VB_CUDA(cudaSetDevice(ctx->device));
-    vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_enter(ctx);
     vb_align_pairs_impl(ctx, g, ref, qry, n, p, stats);
     VB_GUARD_END
 }
@@ -305,8 +309,7 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_align: bad arguments");
-    VB_CUDA(cudaSetDevice(ctx->device));
-    vb_tls_stream = (cudaStream_t)ctx->stream;
+    vb_enter(ctx);
     const uint32_t n = g->count();
     std::vector<uint32_t> order = vb_lz_order(g);
     std::vector<uint32_t> rank(n);

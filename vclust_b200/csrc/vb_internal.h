@@ -39,6 +39,7 @@ double vb_ani_shorter(uint32_t common, uint32_t cnt1, uint32_t cnt2, int k);   /
 struct vb_timing { std::string key; double ms; };
 
 struct DevGenomes;
+struct vb_arena;
 struct vb_resident {                 // a genome set kept packed in HBM across calls (vb_genomes_make_resident)
     const vb_genomes *g;
     int u_is_t;
@@ -51,6 +52,7 @@ struct vb_ctx {
     void *stream = nullptr;          // cudaStream_t
     void *events[8] = {nullptr};     // cudaEvent_t, vb_ctx_mark / vb_ctx_elapsed_ms
     uint64_t launches = 0;
+    vb_arena *arena = nullptr;       // call-scoped device temporaries (dev_util.cuh)
     uint64_t mem_total = 0;          // device memory, queried once (cudaMemGetInfo is slow and synchronising)
     std::vector<vb_resident> resident;
     std::vector<vb_timing> timings;
