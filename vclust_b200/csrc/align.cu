@@ -207,6 +207,37 @@ __device__ __forceinline__ uint32_t window_violations(uint64_t x, int aw, int am
     return viol;
 }
 
+// The same rule for the default parameters (aw = 15, am = 7), branch-free: the 15 shifted copies of the flags are
+// summed per position with a carry-save adder tree (13 adders); "more than 7" is bit 3 of the 4-bit count.
+__device__ __forceinline__ uint32_t window_violations_15_7(uint64_t x)
+{
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+#define VB_Y(s) __funnelshift_l(lo, hi, s)                         /* bit b = flag of position b - s */
+#define VB_FA(a, b, c, sum, car) { uint32_t _a = (a), _b = (b), _c = (c); sum = _a ^ _b ^ _c; car = (_a & _b) | (_c & (_a ^ _b)); }
+    uint32_t s0, s1, s2, s3, s4, c0, c1, c2, c3, c4;
+    VB_FA(hi, VB_Y(1), VB_Y(2), s0, c0)
+    VB_FA(VB_Y(3), VB_Y(4), VB_Y(5), s1, c1)
+    VB_FA(VB_Y(6), VB_Y(7), VB_Y(8), s2, c2)
+    VB_FA(VB_Y(9), VB_Y(10), VB_Y(11), s3, c3)
+    VB_FA(VB_Y(12), VB_Y(13), VB_Y(14), s4, c4)
+    uint32_t t0, d0, t1, d1, u0, d2;
+    VB_FA(s0, s1, s2, t0, d0)
+    t1 = s3 ^ s4; d1 = s3 & s4;
+    u0 = t0 ^ t1; d2 = t0 & t1;                                    // u0 = bit 0 of the count (unused)
+    (void)u0;
+    uint32_t e0, f0, e1, f1, e2, f2, f3;
+    VB_FA(c0, c1, c2, e0, f0)
+    VB_FA(c3, c4, d0, e1, f1)
+    VB_FA(d1, d2, e0, e2, f2)
+    f3 = e1 & e2;                                                  // (e1 ^ e2 = bit 1 of the count, unused)
+    uint32_t g0, h0;
+    VB_FA(f0, f1, f2, g0, h0)
+    uint32_t h1 = g0 & f3;                                         // (g0 ^ f3 = bit 2)
+    return h0 | h1;                                                // bit 3: count >= 8
+#undef VB_Y
+#undef VB_FA
+}
+
 // positions that END a run of >= ar consecutive matches (the run may start in the previous 32 flags)
 __device__ __forceinline__ uint32_t run_ends(uint64_t x, int ar)
 {
@@ -231,7 +262,7 @@ __device__ ExtResult extend_forward(const Text &Q, int qp, const Text &R, int rp
         uint32_t pm = __shfl_up_sync(0xffffffffu, m, 1);
         if (lane == 0) pm = prev_hi;
         uint64_t x = ((uint64_t)m << 32) | pm;
-        uint32_t viol = window_violations(x, P.aw, P.am);
+        uint32_t viol = (P.aw == 15 && P.am == 7) ? window_violations_15_7(x) : window_violations(x, P.aw, P.am);
         uint32_t ends = run_ends(x, P.ar);
         unsigned vb = __ballot_sync(0xffffffffu, viol != 0);
         int limit = 1024;
@@ -272,7 +303,7 @@ __device__ ExtResult extend_backward(const Text &Q, int qp, const Text &R, int r
         uint32_t pm = __shfl_up_sync(0xffffffffu, m, 1);
         if (lane == 0) pm = prev_hi;
         uint64_t x = ((uint64_t)m << 32) | pm;
-        uint32_t viol = window_violations(x, P.aw, P.am);
+        uint32_t viol = (P.aw == 15 && P.am == 7) ? window_violations_15_7(x) : window_violations(x, P.aw, P.am);
         uint32_t ends = run_ends(x, P.ar);
         // the loop also stops (without looking at the symbol) at offset lim_all
         int stop_all = lim_all - base;                            // first offset of this super-chunk not examined
@@ -421,8 +452,11 @@ __device__ int gap_best_matches(const Text &Q, int d, const Text &R, int r_left,
 // ---------------------------------------------------------------------------------------------------------------
 // k6: the parse.  All state is warp-uniform; `lane` only selects the data a lane looks at.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int SEED_WORDS = 6;         // seed windows of up to 192 reference positions use the Shift-And path
+
 __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restrict__ tab, uint32_t tmask, uint32_t pos_bits,
-                           const LzParams &P, int lane, int &out_match, int &out_lit, int &out_comp)
+                           const LzParams &P, int lane, uint32_t (*seed_masks)[4][SEED_WORDS + 1], int &out_match, int &out_lit,
+                           int &out_comp)
 {
     const int nQ = Q.n;
     int i = 0, lit = 0, pred = 0;
@@ -444,19 +478,65 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
             if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tmask, pos_bits, code);
         }
         if (!lost) {
-            // short seeds: lane t (query position i + t) may use reference positions [lo, pred + t + mrd).  The window
-            // is shared, so its k-mers are computed once (one per lane and round) and broadcast.
+            // short seeds: lane t (query position i + t) may use reference positions [lo, pred + t + mrd).  The window is
+            // shared by all lanes, so it is turned once into four position bit masks E_c ("symbol at window position w is
+            // c", an N sets no bit); lane t then ANDs E_{q_j} >> j over the msl symbols of its k-mer (Shift-And).
             uint64_t qk = 0;
             const bool qv = lane < steps && !flag && kmer_at(Q, i + lane, P.msl, qk);
             const int lo = max(pred - lit, 0);
             const int my_w = pred + lane + P.mrd - lo;
             const int max_w = pred + (steps - 1) + P.mrd - lo;
-            for (int j0 = 0; j0 < max_w; j0 += 32) {
-                uint64_t rk;
-                if (!kmer_at(R, lo + j0 + lane, P.msl, rk)) rk = ~0ULL;
-                for (int s = 0; s < 32; ++s) {
-                    uint64_t c = __shfl_sync(0xffffffffu, rk, s);
-                    if (qv && c == qk && j0 + s < my_w) flag = true;
+            const int nw = (max_w + P.msl - 1 + 31) >> 5;
+            if (nw <= SEED_WORDS) {
+                uint32_t(*E)[SEED_WORDS + 1] = seed_masks[threadIdx.x >> 5];
+                for (int k = 0; k < nw; ++k) {
+                    const int pos = lo + 32 * k + lane;
+                    uint32_t sym = 4;
+                    if (pos < R.n) {
+                        sym = (__ldg(R.s2 + (pos >> 4)) >> ((pos & 15) * 2)) & 3;
+                        if ((__ldg(R.nv + (pos >> 5)) >> (pos & 31)) & 1) sym = 4;
+                    }
+                    uint32_t b0 = __ballot_sync(0xffffffffu, sym == 0), b1 = __ballot_sync(0xffffffffu, sym == 1);
+                    uint32_t b2 = __ballot_sync(0xffffffffu, sym == 2), b3 = __ballot_sync(0xffffffffu, sym == 3);
+                    if (lane < 4) E[lane][k] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+                }
+                if (lane < 4) E[lane][nw] = 0;
+                __syncwarp();
+                if (qv) {
+                    uint32_t acc[SEED_WORDS];
+#pragma unroll
+                    for (int k = 0; k < SEED_WORDS; ++k) acc[k] = 0xffffffffu;
+                    for (int j = 0; j < P.msl; ++j) {
+                        const uint32_t *e = E[(qk >> (2 * j)) & 3];
+                        uint32_t cur = e[0];
+#pragma unroll
+                        for (int k = 0; k < SEED_WORDS; ++k) {
+                            if (k < nw) {
+                                uint32_t nxt = e[k + 1];
+                                acc[k] &= __funnelshift_r(cur, nxt, j);
+                                cur = nxt;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < SEED_WORDS; ++k) {
+                        if (k < nw) {
+                            int rem = my_w - 32 * k;
+                            uint32_t keep = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1));
+                            if (acc[k] & keep) flag = true;
+                        }
+                    }
+                }
+                __syncwarp();
+            } else {
+                // very wide windows (non-default mqd/mrd): k-mers computed once per round and broadcast with shuffles
+                for (int j0 = 0; j0 < max_w; j0 += 32) {
+                    uint64_t rk;
+                    if (!kmer_at(R, lo + j0 + lane, P.msl, rk)) rk = ~0ULL;
+                    for (int s = 0; s < 32; ++s) {
+                        uint64_t c = __shfl_sync(0xffffffffu, rk, s);
+                        if (qv && c == qk && j0 + s < my_w) flag = true;
+                    }
                 }
             }
         }
@@ -549,6 +629,7 @@ __global__ void __launch_bounds__(128) parse_kernel(const uint32_t *__restrict__
                                                     int32_t *__restrict__ stats)
 {
     const int lane = threadIdx.x & 31;
+    __shared__ uint32_t seed_masks[4][4][SEED_WORDS + 1];       // per warp: 4 symbol masks of the seed window
     for (;;) {
         uint32_t idx = 0;
         if (lane == 0) idx = atomicAdd(cursor, 1u);
@@ -560,7 +641,7 @@ __global__ void __launch_bounds__(128) parse_kernel(const uint32_t *__restrict__
         uint64_t qo = gofs[q];
         Text Q = {g2 + (qo >> 4), gn + (qo >> 5), (int)glen[q] + P.mrd};
         int m, l, c;
-        parse_pair(Q, R, ht + d.ht_off, d.ht_mask, d.pos_bits, P, lane, m, l, c);
+        parse_pair(Q, R, ht + d.ht_off, d.ht_mask, d.pos_bits, P, lane, seed_masks, m, l, c);
         if (lane == 0) { stats[3 * (uint64_t)idx] = m; stats[3 * (uint64_t)idx + 1] = l; stats[3 * (uint64_t)idx + 2] = c; }
     }
 }
