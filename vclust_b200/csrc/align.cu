@@ -60,6 +60,13 @@ __device__ __forceinline__ uint64_t reverse_digits(uint64_t x)
     return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
 }
 
+// min(K, reverse complement of K) for a k-mer of `len` 2-bit digits
+__device__ __forceinline__ uint64_t canonical_kmer(uint64_t code, int len, uint64_t kmask)
+{
+    uint64_t rc = reverse_digits((~code) & kmask) >> (64 - 2 * len);
+    return code < rc ? code : rc;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k5a: reference text  R = fwd | N^mrd | N^mrd | revcomp(fwd) | N^mrd   (parser.cpp:16-34), packed
 // ---------------------------------------------------------------------------------------------------------------
@@ -109,8 +116,11 @@ __global__ void __launch_bounds__(256) build_ref_text_kernel(const uint32_t *__r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k5b: anchor table -- every position whose mal-mer holds no N is inserted under its k-mer (parser.cpp:146-189)
-// slot (32 bit) = fingerprint << pos_bits | position; the fingerprint is the top 32 - pos_bits bits of the k-mer hash
+// k5b: anchor table (parser.cpp:146-189).  The reference text holds every mal-mer of the genome twice -- at forward
+// position p and, reverse-complemented, at rc0 + (len - mal - p) -- so only FORWARD positions are stored, under the
+// canonical k-mer min(K, revcomp K); a lookup canonicalises the query k-mer and tries both text positions of every
+// hit.  Half the inserts and half the table for the same candidate set.
+// slot (32 bit) = fingerprint << pos_bits | forward position; fingerprint = top 32 - pos_bits bits of the hash
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_ref_index_kernel(const RefDesc *__restrict__ refs, uint32_t n_refs, int mal,
                                                               const uint32_t *__restrict__ ref_s2,
@@ -123,12 +133,12 @@ __global__ void __launch_bounds__(256) build_ref_index_kernel(const RefDesc *__r
         const uint32_t *s2 = ref_s2 + d.s2_off;
         const uint32_t *nv = ref_nv + d.nv_off;
         uint32_t *tab = ht + d.ht_off;
-        if (d.n < (uint32_t)mal) continue;
-        const uint32_t n_pos = d.n - mal + 1;
+        if (d.len < (uint32_t)mal) continue;
+        const uint32_t n_pos = d.len - mal + 1;
         for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += gridDim.x * blockDim.x) {
             if (fetch1(nv, p) & nmask) continue;
             uint64_t code = fetch2(s2, p) & kmask;
-            uint64_t h = fmix64(code);
+            uint64_t h = fmix64(canonical_kmer(code, mal, kmask));
             uint32_t val = ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | p;
             uint32_t slot = (uint32_t)h & d.ht_mask;
             while (atomicCAS(&tab[slot], HT_EMPTY, val) != HT_EMPTY) slot = (slot + 1) & d.ht_mask;
@@ -362,9 +372,10 @@ __device__ __forceinline__ bool kmer_at(const Text &T, int p, int len, uint64_t 
 }
 
 // one lane: does the anchor table hold any entry with this k-mer's fingerprint?
-__device__ __forceinline__ bool anchor_probe(const uint32_t *__restrict__ tab, uint32_t mask, uint32_t pos_bits, uint64_t code)
+__device__ __forceinline__ bool anchor_probe(const uint32_t *__restrict__ tab, uint32_t mask, uint32_t pos_bits, uint64_t code,
+                                             int mal)
 {
-    uint64_t h = fmix64(code);
+    uint64_t h = fmix64(canonical_kmer(code, mal, (~0ULL) >> (64 - 2 * mal)));
     uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
     uint32_t slot = (uint32_t)h & mask;
     for (;;) {
@@ -383,19 +394,25 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t mask, u
     best_len = 0; best_pos = 0;
     uint64_t code;
     if (!kmer_at(Q, i, P.mal, code)) return;
-    uint64_t h = fmix64(code);
+    uint64_t h = fmix64(canonical_kmer(code, P.mal, (~0ULL) >> (64 - 2 * P.mal)));
     uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
     uint32_t slot0 = (uint32_t)h & mask;
     const uint32_t pmask = (1u << pos_bits) - 1;
+    const int len = (R.n - 3 * P.mrd) / 2;                  // genome length; the reverse complement starts at rc0
+    const int rc0 = len + 2 * P.mrd;
     int my_len = 0, my_pos = 0x7fffffff;
     for (uint32_t step = 0;; step += 32) {
         uint32_t s = __ldg(tab + ((slot0 + step + lane) & mask));
         unsigned empties = __ballot_sync(0xffffffffu, s == HT_EMPTY);
         bool in_chain = empties == 0 || lane < (__ffs(empties) - 1);
         if (in_chain && (s >> pos_bits) == fp) {
-            int pos = (int)(s & pmask);
-            int ml = equal_len(Q, i, R, pos, 0);
-            if (ml >= P.mal && (ml > my_len || (ml == my_len && pos < my_pos))) { my_len = ml; my_pos = pos; }
+            const int pf = (int)(s & pmask);
+#pragma unroll
+            for (int strand = 0; strand < 2; ++strand) {    // forward occurrence, reverse-complement occurrence
+                const int pos = strand ? rc0 + (len - P.mal - pf) : pf;
+                int ml = equal_len(Q, i, R, pos, 0);
+                if (ml >= P.mal && (ml > my_len || (ml == my_len && pos < my_pos))) { my_len = ml; my_pos = pos; }
+            }
         }
         if (empties || step + 32 > mask) break;
     }
@@ -475,7 +492,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         bool flag = false;
         if (lane < steps) {
             uint64_t code;
-            if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tmask, pos_bits, code);
+            if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tmask, pos_bits, code, P.mal);
         }
         if (!lost) {
             // short seeds: lane t (query position i + t) may use reference positions [lo, pred + t + mrd).  The window is
@@ -705,7 +722,7 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
                 uint64_t nR = 2 * len + 3 * (uint64_t)ap->mrd;
                 uint64_t chunks = (nR + 31) / 32 + 4;
                 uint64_t cap = 1024;
-                while (cap < 2 * nR) cap <<= 1;
+                while (cap < 2 * (len + 1)) cap <<= 1;                 // forward positions only, load <= 0.5
                 uint64_t need = chunks * 12 + cap * 4;
                 uint32_t pos_bits = 1;
                 while ((1ULL << pos_bits) <= nR) ++pos_bits;
@@ -715,7 +732,7 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
                 d.s2_off = s2_words; d.nv_off = nv_words; d.ht_off = slots;
                 d.ht_mask = (uint32_t)(cap - 1); d.pos_bits = pos_bits; d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = r;
                 refs.push_back(d);
-                s2_words += 2 * chunks + 4; nv_words += chunks + 4; slots += cap; bytes += need;
+                s2_words += 2 * chunks + 4; nv_words += chunks + 4; slots += cap; bytes += need;    // cap is a multiple of 1024: 16-byte aligned tables
             }
             b_ref.push_back((uint32_t)refs.size() - 1);
             b_qry.push_back(qry[order[end]]);
@@ -728,8 +745,6 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
         VB_CUDA(cudaMemcpyAsync(d_refs.p, refs.data(), sizeof(RefDesc) * refs.size(), cudaMemcpyHostToDevice, st));
         VB_CUDA(cudaMemcpyAsync(d_pref.p, b_ref.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
         VB_CUDA(cudaMemcpyAsync(d_pqry.p, b_qry.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
-        VB_CUDA(cudaMemsetAsync(ref_nv.p, 0xff, ref_nv.bytes(), st));
-        VB_CUDA(cudaMemsetAsync(ref_s2.p, 0, ref_s2.bytes(), st));
         VB_CUDA(cudaMemsetAsync(ht.p, 0xff, ht.bytes(), st));
         VB_CUDA(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned int), st));
 

@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(256) segment_pairs_kernel(const uint64_t *__re
 //     bucket_kernel  level-2 bucket -> smem grouping -> duplicates per genome + pair increments      12 B read
 //   = 48 B of HBM traffic per tuple instead of 7 radix passes x 32 B.
 // ===============================================================================================================
-constexpr int PART_THREADS = 256;
-constexpr int PART_ITEMS = 16;
+constexpr int PART_THREADS = 512;
+constexpr int PART_ITEMS = 8;
 constexpr int PART_TILE = PART_THREADS * PART_ITEMS;      // 4096 tuples per block
 constexpr int MAX_BUCKET_BITS = 9;                        // per level
 constexpr int BUCKET_CAP = 2048;                          // tuples a bucket may hold to be grouped in shared memory
@@ -210,13 +210,82 @@ __global__ void __launch_bounds__(256) count_kernel(const uint32_t *__restrict__
 {
     const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
     const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n_iter; p += (uint64_t)gridDim.x * blockDim.x) {
+    // each block owns a contiguous range of slots, so a warp stays inside one genome for many iterations and can
+    // keep the genome's valid-k-mer count in a register (one atomic per genome change instead of one per 32 slots)
+    const uint64_t per_block = ((n_iter + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const uint64_t p_end = min(n_iter, (blockIdx.x + 1) * per_block);
+    uint32_t acc_gid = 0xffffffffu, acc = 0;
+    for (uint64_t p = blockIdx.x * per_block + threadIdx.x; p < p_end; p += blockDim.x) {
         uint64_t h; uint32_t gid = 0;
         bool ok = extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, h, gid);
         if (ok) atomicAdd(&hist[total_bits ? (uint32_t)(h >> (64 - total_bits)) : 0u], 1u);
         unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (m && (threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd(&valid_cnt[gid], (uint32_t)__popc(m));
+        if (m) {
+            uint32_t g = __shfl_sync(0xffffffffu, gid, __ffs(m) - 1);       // a warp's 32 slots share the genome
+            if (g != acc_gid) {
+                if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
+                acc_gid = g; acc = 0;
+            }
+            acc += (uint32_t)__popc(m);
+        }
     }
+    if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
+}
+
+// exclusive scan of one value per thread over a 1024-thread block; returns the prefix, *total gets the sum
+__device__ __forceinline__ uint32_t block_exscan_1024(uint32_t v, uint32_t *warp_tot /* [32] shared */, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = warp_tot[lane], z = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+        warp_tot[lane] = z - t;
+        if (lane == 31) *total = z;
+    }
+    __syncthreads();
+    uint32_t pre = warp_tot[w] + x - v;
+    __syncthreads();
+    return pre;
+}
+
+// same, with the bucket histogram privatised in shared memory (NB <= 32768 bins = 128 KB): one block per SM, the
+// 40 M atomics stay on chip and only 148 x NB flush atomics reach L2
+__global__ void __launch_bounds__(1024) count_smem_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
+                                                          const uint32_t *__restrict__ tile_gid, uint64_t n_slots, uint64_t n_iter,
+                                                          ExtractParams ep, int total_bits, uint32_t nb,
+                                                          uint32_t *__restrict__ hist, uint32_t *__restrict__ valid_cnt)
+{
+    extern __shared__ uint32_t s_hist[];
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+    const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
+    const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
+    const uint64_t per_block = ((n_iter + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
+    const uint64_t p_end = min(n_iter, (blockIdx.x + 1) * per_block);
+    uint32_t acc_gid = 0xffffffffu, acc = 0;
+    for (uint64_t p = blockIdx.x * per_block + threadIdx.x; p < p_end; p += blockDim.x) {
+        uint64_t h; uint32_t gid = 0;
+        bool ok = extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, h, gid);
+        if (ok) atomicAdd(&s_hist[total_bits ? (uint32_t)(h >> (64 - total_bits)) : 0u], 1u);
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+            uint32_t g = __shfl_sync(0xffffffffu, gid, __ffs(m) - 1);
+            if (g != acc_gid) {
+                if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
+                acc_gid = g; acc = 0;
+            }
+            acc += (uint32_t)__popc(m);
+        }
+    }
+    if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) { uint32_t c = s_hist[b]; if (c) atomicAdd(&hist[b], c); }
 }
 
 // one block: off[i] = exclusive prefix of hist (NB + 1 entries); cursor2 = off; cursor1[b] = off[b * B2];
@@ -225,34 +294,25 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *__restrict__
                                                     uint32_t *__restrict__ cursor1, uint32_t *__restrict__ cursor2,
                                                     uint32_t *__restrict__ tile_start)
 {
-    __shared__ uint32_t part[1024];
+    __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_total;
     const uint32_t per = (pl.NB + 1023) / 1024;
     const uint32_t lo = min(threadIdx.x * per, pl.NB), hi = min(lo + per, pl.NB);
     uint32_t sum = 0;
     for (uint32_t i = lo; i < hi; ++i) sum += hist[i];
-    part[threadIdx.x] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int i = 0; i < 1024; ++i) { uint32_t t = part[i]; part[i] = run; run += t; }
-        s_total = run;
-    }
-    __syncthreads();
-    uint32_t run = part[threadIdx.x];
+    uint32_t run = block_exscan_1024(sum, warp_tot, &s_total);
     for (uint32_t i = lo; i < hi; ++i) { off[i] = run; cursor2[i] = run; run += hist[i]; }
     if (threadIdx.x == 0) off[pl.NB] = s_total;
-    __syncthreads();                    // block-wide visibility of the off[] writes (same block reads them below)
-    if (threadIdx.x == 0) {
-        uint32_t tiles = 0;
-        for (uint32_t b = 0; b < pl.B1; ++b) {
-            uint32_t beg = off[b * pl.B2], end = off[(b + 1) * pl.B2];
-            cursor1[b] = beg;
-            tile_start[b] = tiles;
-            tiles += (end - beg + PART_TILE - 1) / PART_TILE;
-        }
-        tile_start[pl.B1] = tiles;
+    __syncthreads();                    // block-wide visibility of the off[] writes (the same block reads them below)
+    uint32_t tiles = 0, beg = 0;
+    if (threadIdx.x < pl.B1) {          // B1 <= 512
+        beg = off[threadIdx.x * pl.B2];
+        uint32_t end = off[(threadIdx.x + 1) * pl.B2];
+        tiles = (end - beg + PART_TILE - 1) / PART_TILE;
     }
+    uint32_t tpre = block_exscan_1024(tiles, warp_tot, &s_total);
+    if (threadIdx.x < pl.B1) { cursor1[threadIdx.x] = beg; tile_start[threadIdx.x] = tpre; }
+    if (threadIdx.x == 0) tile_start[pl.B1] = s_total;
 }
 
 // Partition one tile of tuples into buckets.  LEVEL 1: tuples come from the genomes (extraction fused), bucket = top b1
@@ -360,15 +420,20 @@ __global__ void __launch_bounds__(PART_THREADS) part_kernel(const uint32_t *__re
     }
 }
 
-// shared-memory layout of bucket_kernel (dynamic)
+// shared-memory layout of bucket_kernel (dynamic, 48.6 KB -> 4 blocks per SM).  Regions are reused once dead:
+//   keys  -> (after the insert phase) grp + sorted          table -> (after the insert phase) grp_slot
 struct BucketSmem {
-    uint64_t keys[BUCKET_CAP];
+    union {
+        uint64_t keys[BUCKET_CAP];                                 // h of every tuple (insert phase)
+        struct { uint32_t grp[BUCKET_CAP]; uint32_t sorted[BUCKET_CAP]; } g;   // genome ids grouped by slot / sorted
+    } a;
     uint32_t gids[BUCKET_CAP];
-    uint32_t table[BUCKET_SLOTS];      // slot -> index of the first tuple with that key (0xffffffff = empty)
-    uint32_t cnt[BUCKET_SLOTS];        // tuples per slot, then exclusive start
-    uint32_t grp[BUCKET_CAP];          // genome ids regrouped by slot
-    uint16_t grp_slot[BUCKET_CAP];     // slot of every regrouped element
-    uint32_t large[64];                // slots whose group is larger than SMALL_GROUP
+    union {
+        uint16_t table[BUCKET_SLOTS];      // slot -> index of the first tuple with that key (0xffff = empty)
+        uint16_t grp_slot[BUCKET_CAP];     // slot of every regrouped element
+    } t;
+    uint32_t cnt[BUCKET_SLOTS];            // tuples per slot, then (count << 16 | start)
+    uint32_t large[64];                    // slots whose group is larger than SMALL_GROUP
     uint32_t n_large;
     uint32_t warp_sum[8];
 };
@@ -381,6 +446,35 @@ __device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, int count_only
     uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
     table_add(tkeys, tvals, cap_mask, ((uint64_t)hi << 32) | lo, 1u, overflow);
 }
+
+// up to 4 pair increments at once: the four table probes are issued before any of them is consumed
+struct PairBatch {
+    uint64_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+    int n = 0;
+    __device__ __forceinline__ void flush(uint64_t *__restrict__ tkeys, uint32_t *__restrict__ tvals, uint64_t cap_mask,
+                                          int *__restrict__ overflow)
+    {
+        const uint64_t h0 = fmix64(k0) & cap_mask, h1 = fmix64(k1) & cap_mask, h2 = fmix64(k2) & cap_mask, h3 = fmix64(k3) & cap_mask;
+        uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (n > 0) c0 = tkeys[h0];
+        if (n > 1) c1 = tkeys[h1];
+        if (n > 2) c2 = tkeys[h2];
+        if (n > 3) c3 = tkeys[h3];
+        if (n > 0) { if (c0 == k0) atomicAdd(&tvals[h0], 1u); else table_add(tkeys, tvals, cap_mask, k0, 1u, overflow); }
+        if (n > 1) { if (c1 == k1) atomicAdd(&tvals[h1], 1u); else table_add(tkeys, tvals, cap_mask, k1, 1u, overflow); }
+        if (n > 2) { if (c2 == k2) atomicAdd(&tvals[h2], 1u); else table_add(tkeys, tvals, cap_mask, k2, 1u, overflow); }
+        if (n > 3) { if (c3 == k3) atomicAdd(&tvals[h3], 1u); else table_add(tkeys, tvals, cap_mask, k3, 1u, overflow); }
+        n = 0;
+    }
+    __device__ __forceinline__ void add(uint32_t a, uint32_t b, uint64_t *__restrict__ tkeys, uint32_t *__restrict__ tvals,
+                                        uint64_t cap_mask, int *__restrict__ overflow)
+    {
+        const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
+        const uint64_t key = ((uint64_t)hi << 32) | lo;
+        if (n == 0) k0 = key; else if (n == 1) k1 = key; else if (n == 2) k2 = key; else k3 = key;
+        if (++n == 4) flush(tkeys, tvals, cap_mask, overflow);
+    }
+};
 
 // One block per final bucket: group equal k-mers in shared memory, count duplicates per genome, emit pair increments.
 // count_only: only sum the number of pair increments (sizing pass for very large N).
@@ -402,8 +496,8 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             if (tid == 0) big_list[atomicAdd(n_big, 1u)] = bkt;
             continue;
         }
-        for (int s = tid; s < BUCKET_SLOTS; s += 256) { S.table[s] = 0xffffffffu; S.cnt[s] = 0; }
-        for (uint32_t i = tid; i < size; i += 256) { S.keys[i] = keys[beg + i]; S.gids[i] = vals[beg + i]; }
+        for (int s = tid; s < BUCKET_SLOTS; s += 256) { S.t.table[s] = 0xffffu; S.cnt[s] = 0; }
+        for (uint32_t i = tid; i < size; i += 256) { S.a.keys[i] = keys[beg + i]; S.gids[i] = vals[beg + i]; }
         if (tid == 0) S.n_large = 0;
         __syncthreads();
         // ---- insert: every tuple finds the slot of its key
@@ -413,15 +507,15 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             uint32_t i = tid + r * 256;
             my_slot[r] = 0xffffffffu;
             if (i < size) {
-                uint64_t k = S.keys[i];
+                uint64_t k = S.a.keys[i];
                 uint32_t s = (uint32_t)k & (BUCKET_SLOTS - 1);                // low bits: independent of the bucket bits
                 for (;;) {
-                    uint32_t cur = S.table[s];
-                    if (cur == 0xffffffffu) {
-                        cur = atomicCAS(&S.table[s], 0xffffffffu, i);
-                        if (cur == 0xffffffffu) cur = i;
+                    uint32_t cur = S.t.table[s];
+                    if (cur == 0xffffu) {
+                        cur = atomicCAS(&S.t.table[s], (unsigned short)0xffffu, (unsigned short)i);
+                        if (cur == 0xffffu) cur = i;
                     }
-                    if (S.keys[cur] == k) break;
+                    if (S.a.keys[cur] == k) break;
                     s = (s + 1) & (BUCKET_SLOTS - 1);
                 }
                 my_slot[r] = s;
@@ -429,7 +523,7 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             }
         }
         __syncthreads();
-        // ---- exclusive scan of cnt over the slots (16 per thread)
+        // ---- exclusive scan of cnt over the slots (16 per thread); cnt becomes count << 16 | start
         {
             constexpr int PER = BUCKET_SLOTS / 256;
             uint32_t loc[PER], sum = 0;
@@ -442,70 +536,79 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             __syncthreads();
             uint32_t pre = x - sum;
             for (int j = 0; j < wid; ++j) pre += S.warp_sum[j];
-            // keep the group size in the upper half of the word: start (low 16 bits... sizes up to 2048 need 12 bits)
 #pragma unroll
             for (int j = 0; j < PER; ++j) { uint32_t c = loc[j]; S.cnt[tid * PER + j] = (c << 16) | pre; pre += c; }
         }
         __syncthreads();
-        // ---- regroup genome ids by slot
+        // ---- regroup genome ids by slot (keys and table are dead from here on)
 #pragma unroll
         for (int r = 0; r < BUCKET_CAP / 256; ++r) {
             if (my_slot[r] != 0xffffffffu) {
                 uint32_t pos = (S.cnt[my_slot[r]] & 0xffffu) + my_rank[r];
-                S.grp[pos] = S.gids[tid + r * 256];
-                S.grp_slot[pos] = (uint16_t)my_slot[r];
+                S.a.g.grp[pos] = S.gids[tid + r * 256];
+                S.t.grp_slot[pos] = (uint16_t)my_slot[r];
             }
         }
         __syncthreads();
-        // ---- sort every group by genome id: small groups by one thread, large ones by the whole block
-        for (int s = tid; s < BUCKET_SLOTS; s += 256) {
-            uint32_t c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
-            if (c < 2) continue;
-            if (c > SMALL_GROUP) { uint32_t q = atomicAdd(&S.n_large, 1u); if (q < 64) S.large[q] = s; continue; }
-            for (uint32_t a = 1; a < c; ++a) {                                // insertion sort
-                uint32_t v = S.grp[st0 + a];
-                uint32_t b = a;
-                while (b > 0 && S.grp[st0 + b - 1] > v) { S.grp[st0 + b] = S.grp[st0 + b - 1]; --b; }
-                S.grp[st0 + b] = v;
+        // ---- sort every group by genome id: rank sort, one thread per element (groups are small)
+        for (uint32_t e = tid; e < size; e += 256) {
+            const uint32_t s = S.t.grp_slot[e], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
+            const uint32_t g = S.a.g.grp[e];
+            if (c > SMALL_GROUP) {
+                S.a.g.sorted[e] = g;
+                if (e == st0) { uint32_t q = atomicAdd(&S.n_large, 1u); if (q < 64) S.large[q] = s; }
+                continue;
             }
+            uint32_t rank = 0;
+            for (uint32_t x = st0; x < st0 + c; ++x) {
+                uint32_t gx = S.a.g.grp[x];
+                rank += (gx < g) || (gx == g && x < e);
+            }
+            S.a.g.sorted[st0 + rank] = g;
         }
         __syncthreads();
-        const uint32_t n_large = min(S.n_large, 64u);
         if (S.n_large > 64) {                                                // pathological: leave it to the generic path
             if (tid == 0) big_list[atomicAdd(n_big, 1u)] = bkt;
             __syncthreads();
             continue;
         }
+        const uint32_t n_large = S.n_large;
         for (uint32_t q = 0; q < n_large; ++q) {                             // block-wide bitonic sort (all-ascending form)
             const uint32_t s = S.large[q], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
+            uint32_t *G = S.a.g.sorted + st0;
             uint32_t n2 = 1; while (n2 < c) n2 <<= 1;
             for (uint32_t k = 2; k <= n2; k <<= 1) {
                 for (uint32_t i = tid; i < n2; i += 256) {
                     uint32_t l = i ^ (k - 1);
-                    if (l > i && l < c) { uint32_t a = S.grp[st0 + i], b = S.grp[st0 + l]; if (a > b) { S.grp[st0 + i] = b; S.grp[st0 + l] = a; } }
+                    if (l > i && l < c) { uint32_t a = G[i], b = G[l]; if (a > b) { G[i] = b; G[l] = a; } }
                 }
                 __syncthreads();
                 for (uint32_t j = k >> 2; j > 0; j >>= 1) {
                     for (uint32_t i = tid; i < n2; i += 256) {
                         uint32_t l = i ^ j;
-                        if (l > i && l < c) { uint32_t a = S.grp[st0 + i], b = S.grp[st0 + l]; if (a > b) { S.grp[st0 + i] = b; S.grp[st0 + l] = a; } }
+                        if (l > i && l < c) { uint32_t a = G[i], b = G[l]; if (a > b) { G[i] = b; G[l] = a; } }
                     }
                     __syncthreads();
                 }
             }
         }
         // ---- every element pairs with the distinct genomes before it in its (now sorted) group
+        PairBatch batch;
         for (uint32_t e = tid; e < size; e += 256) {
-            const uint32_t s = S.grp_slot[e], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
-            if (c < 2) continue;
-            const uint32_t g = S.grp[e];
-            if (e > st0 && S.grp[e - 1] == g) { if (!count_only) atomicAdd(&dup_cnt[g], 1u); continue; }
-            uint32_t prev = g;
-            for (uint32_t j = e; j-- > st0;) {
-                uint32_t gj = S.grp[j];
-                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, tkeys, tvals, cap_mask, overflow); prev = gj; }
+            const uint32_t s = S.t.grp_slot[e], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
+            if (c < 2 || e == st0) continue;
+            const uint32_t g = S.a.g.sorted[e];
+            if (S.a.g.sorted[e - 1] == g) { if (!count_only) atomicAdd(&dup_cnt[g], 1u); continue; }
+            uint32_t prev = 0xffffffffu;
+            for (uint32_t j = st0; j < e; ++j) {
+                uint32_t gj = S.a.g.sorted[j];
+                if (gj != prev) {
+                    if (count_only) ++local_inc; else batch.add(g, gj, tkeys, tvals, cap_mask, overflow);
+                    prev = gj;
+                }
             }
         }
+        if (batch.n) batch.flush(tkeys, tvals, cap_mask, overflow);
         __syncthreads();
     }
     if (count_only) {
@@ -735,8 +838,16 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         VB_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
         VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
         const uint64_t n_iter = (n_slots + 31) / 32 * 32;
-        count_kernel<<<grid_for(n_iter), 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep, pl.b1 + pl.b2,
-                                                      hist.p, valid_cnt);
+        if (pl.NB <= 32768) {
+            static bool cattr = false;
+            if (!cattr) { VB_CUDA(cudaFuncSetAttribute(count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4)); cattr = true; }
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+            count_smem_kernel<<<n_sm, 1024, pl.NB * sizeof(uint32_t), st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep,
+                                                                           pl.b1 + pl.b2, pl.NB, hist.p, valid_cnt);
+        } else
+            count_kernel<<<grid_for(n_iter), 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep, pl.b1 + pl.b2,
+                                                          hist.p, valid_cnt);
         VB_LAUNCH_CHECK(ctx);
         scan_kernel<<<1, 1024, 0, st>>>(hist.p, pl, off.p, cursor1.p, cursor2.p, tile_start.p);
         VB_LAUNCH_CHECK(ctx);
