@@ -637,7 +637,8 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
     out_match = sum_match; out_lit = sum_lit; out_comp = n_comp;
 }
 
-__global__ void __launch_bounds__(128) parse_kernel(const uint32_t *__restrict__ g2, const uint32_t *__restrict__ gn,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) parse_kernel(const uint32_t *__restrict__ g2, const uint32_t *__restrict__ gn,
                                                     const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
                                                     const RefDesc *__restrict__ refs, const uint32_t *__restrict__ ref_s2,
                                                     const uint32_t *__restrict__ ref_nv, const uint32_t *__restrict__ ht,
@@ -697,7 +698,13 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
     // pairs grouped by reference (stable), so that one reference's index is built once and stays hot in L2
     std::vector<uint32_t> order(n);
     for (uint64_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ref[a] < ref[b]; });
+    {   // already grouped (every reference in one contiguous run, as vb_align delivers it)?  then keep the order
+        std::vector<uint8_t> seen(ng, 0);
+        bool grouped = true;
+        for (uint64_t i = 0; i < n && grouped; ++i)
+            if (i == 0 || ref[i] != ref[i - 1]) { if (seen[ref[i]]) grouped = false; seen[ref[i]] = 1; }
+        if (!grouped) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ref[a] < ref[b]; });
+    }
 
     // reference texts + anchor tables of one batch may take up to 40 % of the device (no per-call memory query)
     const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
@@ -761,11 +768,13 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
 
         t_par.start();
         int per_sm = 0;
-        VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, parse_kernel, 128, 0));
+        static const int minb = getenv("VB_PARSE_MINB") ? atoi(getenv("VB_PARSE_MINB")) : 6;
+        auto kern = minb >= 8 ? parse_kernel<8> : (minb == 7 ? parse_kernel<7> : (minb == 6 ? parse_kernel<6> : parse_kernel<5>));
+        VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
         int n_sm = 0;
         VB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
         int blocks = std::max(1, std::min<int>(per_sm * n_sm, (int)((nb + 3) / 4)));
-        parse_kernel<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, dg.glen.p, d_refs.p, ref_s2.p, ref_nv.p, ht.p,
+        kern<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, dg.glen.p, d_refs.p, ref_s2.p, ref_nv.p, ht.p,
                                              d_pref.p, d_pqry.p, nb, P, d_cursor.p, d_stats.p);
         VB_LAUNCH_CHECK(ctx);
         t_par.stop();

@@ -12,6 +12,7 @@
 //   k4 emit kernels     table -> (row, col, common) passing the integer filter and a conservative ani test
 // The exact IEEE-double ani-shorter test and the text formatting run on the host (libm log() must match glibc's).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 #include "dev_util.cuh"
@@ -178,7 +179,8 @@ constexpr int MAX_BUCKET_BITS = 9;                        // per level
 constexpr int BUCKET_CAP = 2048;                          // tuples a bucket may hold to be grouped in shared memory
 constexpr int BUCKET_SLOTS = 4096;                        // hash slots per bucket (load <= 0.5)
 constexpr int BUCKET_TARGET = 1280;                       // planned mean bucket size (CAP is 20 sigma above it)
-constexpr int SMALL_GROUP = 32;                           // groups up to this size are sorted by one thread
+constexpr int SMALL_GROUP = 32;                           // larger groups are sorted by the whole block
+constexpr uint32_t GROUP_HAS_DUP = 0x80000000u;            // flag in BucketSmem::cnt (count << 16 | start)
 
 struct MsdPlan {
     int b1, b2;              // bucket bits of level 1 and level 2 (b2 == 0: one level)
@@ -435,6 +437,7 @@ struct BucketSmem {
     uint32_t cnt[BUCKET_SLOTS];            // tuples per slot, then (count << 16 | start)
     uint32_t large[64];                    // slots whose group is larger than SMALL_GROUP
     uint32_t n_large;
+    uint32_t n_pairs;
     uint32_t warp_sum[8];
 };
 
@@ -446,35 +449,6 @@ __device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, int count_only
     uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
     table_add(tkeys, tvals, cap_mask, ((uint64_t)hi << 32) | lo, 1u, overflow);
 }
-
-// up to 4 pair increments at once: the four table probes are issued before any of them is consumed
-struct PairBatch {
-    uint64_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
-    int n = 0;
-    __device__ __forceinline__ void flush(uint64_t *__restrict__ tkeys, uint32_t *__restrict__ tvals, uint64_t cap_mask,
-                                          int *__restrict__ overflow)
-    {
-        const uint64_t h0 = fmix64(k0) & cap_mask, h1 = fmix64(k1) & cap_mask, h2 = fmix64(k2) & cap_mask, h3 = fmix64(k3) & cap_mask;
-        uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        if (n > 0) c0 = tkeys[h0];
-        if (n > 1) c1 = tkeys[h1];
-        if (n > 2) c2 = tkeys[h2];
-        if (n > 3) c3 = tkeys[h3];
-        if (n > 0) { if (c0 == k0) atomicAdd(&tvals[h0], 1u); else table_add(tkeys, tvals, cap_mask, k0, 1u, overflow); }
-        if (n > 1) { if (c1 == k1) atomicAdd(&tvals[h1], 1u); else table_add(tkeys, tvals, cap_mask, k1, 1u, overflow); }
-        if (n > 2) { if (c2 == k2) atomicAdd(&tvals[h2], 1u); else table_add(tkeys, tvals, cap_mask, k2, 1u, overflow); }
-        if (n > 3) { if (c3 == k3) atomicAdd(&tvals[h3], 1u); else table_add(tkeys, tvals, cap_mask, k3, 1u, overflow); }
-        n = 0;
-    }
-    __device__ __forceinline__ void add(uint32_t a, uint32_t b, uint64_t *__restrict__ tkeys, uint32_t *__restrict__ tvals,
-                                        uint64_t cap_mask, int *__restrict__ overflow)
-    {
-        const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
-        const uint64_t key = ((uint64_t)hi << 32) | lo;
-        if (n == 0) k0 = key; else if (n == 1) k1 = key; else if (n == 2) k2 = key; else k3 = key;
-        if (++n == 4) flush(tkeys, tvals, cap_mask, overflow);
-    }
-};
 
 // One block per final bucket: group equal k-mers in shared memory, count duplicates per genome, emit pair increments.
 // count_only: only sum the number of pair increments (sizing pass for very large N).
@@ -552,19 +526,21 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
         __syncthreads();
         // ---- sort every group by genome id: rank sort, one thread per element (groups are small)
         for (uint32_t e = tid; e < size; e += 256) {
-            const uint32_t s = S.t.grp_slot[e], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
+            const uint32_t s = S.t.grp_slot[e], c = (S.cnt[s] >> 16) & 0x7fffu, st0 = S.cnt[s] & 0xffffu;
             const uint32_t g = S.a.g.grp[e];
             if (c > SMALL_GROUP) {
                 S.a.g.sorted[e] = g;
-                if (e == st0) { uint32_t q = atomicAdd(&S.n_large, 1u); if (q < 64) S.large[q] = s; }
+                if (e == st0) { uint32_t q = atomicAdd(&S.n_large, 1u); if (q < 64) S.large[q] = s; atomicOr(&S.cnt[s], GROUP_HAS_DUP); }
                 continue;
             }
-            uint32_t rank = 0;
+            uint32_t rank = 0, same = 0;
             for (uint32_t x = st0; x < st0 + c; ++x) {
                 uint32_t gx = S.a.g.grp[x];
                 rank += (gx < g) || (gx == g && x < e);
+                same += gx == g;
             }
             S.a.g.sorted[st0 + rank] = g;
+            if (same > 1) atomicOr(&S.cnt[s], GROUP_HAS_DUP);      // a genome holds this k-mer more than once
         }
         __syncthreads();
         if (S.n_large > 64) {                                                // pathological: leave it to the generic path
@@ -574,7 +550,7 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
         }
         const uint32_t n_large = S.n_large;
         for (uint32_t q = 0; q < n_large; ++q) {                             // block-wide bitonic sort (all-ascending form)
-            const uint32_t s = S.large[q], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
+            const uint32_t s = S.large[q], c = (S.cnt[s] >> 16) & 0x7fffu, st0 = S.cnt[s] & 0xffffu;
             uint32_t *G = S.a.g.sorted + st0;
             uint32_t n2 = 1; while (n2 < c) n2 <<= 1;
             for (uint32_t k = 2; k <= n2; k <<= 1) {
@@ -592,23 +568,77 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
                 }
             }
         }
-        // ---- every element pairs with the distinct genomes before it in its (now sorted) group
-        PairBatch batch;
+        // ---- pair increments.  Element e of a duplicate-free group pairs with the e - st0 elements before it; these
+        // pairs are numbered across the whole bucket (prefix sum) and dealt out evenly to the threads, four per thread
+        // and round so that the four table probes are in flight together.
+        uint32_t *pfx = S.gids;                                              // gids is dead: reuse for the prefix sums
+        __syncthreads();
+        {
+            constexpr int PER = BUCKET_CAP / 256;
+            uint32_t w[PER], sum = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                uint32_t e = tid * PER + j;
+                w[j] = 0;
+                if (e < size) {
+                    uint32_t cs = S.cnt[S.t.grp_slot[e]];
+                    if (!(cs & GROUP_HAS_DUP)) w[j] = e - (cs & 0xffffu);
+                }
+                sum += w[j];
+            }
+            uint32_t x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) S.warp_sum[wid] = x;
+            __syncthreads();
+            uint32_t pre = x - sum;
+            for (int j = 0; j < wid; ++j) pre += S.warp_sum[j];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { uint32_t e = tid * PER + j; if (e < size) pfx[e] = pre; pre += w[j]; }
+            if (tid == 255) S.n_pairs = pre;
+        }
+        __syncthreads();
+        const uint32_t n_pairs = S.n_pairs;
+        if (count_only) { if (tid == 0) local_inc += n_pairs; }
+        else {
+            for (uint32_t base = tid; base < n_pairs; base += 4 * 256) {
+                uint64_t key[4], h[4], cur[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t idx = base + q * 256;
+                    key[q] = SLOT_EMPTY;
+                    if (idx < n_pairs) {
+                        uint32_t lo = 0, hi = size;                          // last e with pfx[e] <= idx
+                        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (pfx[mid] <= idx) lo = mid; else hi = mid; }
+                        const uint32_t st0 = S.cnt[S.t.grp_slot[lo]] & 0xffffu;
+                        const uint32_t a = S.a.g.sorted[lo], b = S.a.g.sorted[st0 + (idx - pfx[lo])];      // a > b
+                        key[q] = ((uint64_t)a << 32) | b;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (key[q] != SLOT_EMPTY) { h[q] = fmix64(key[q]) & cap_mask; cur[q] = tkeys[h[q]]; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (key[q] != SLOT_EMPTY) {
+                        if (cur[q] == key[q]) atomicAdd(&tvals[h[q]], 1u);
+                        else table_add(tkeys, tvals, cap_mask, key[q], 1u, overflow);
+                    }
+            }
+        }
+        // groups with duplicates (and block-sorted large groups): element by element, skipping repeated genome ids
         for (uint32_t e = tid; e < size; e += 256) {
-            const uint32_t s = S.t.grp_slot[e], c = S.cnt[s] >> 16, st0 = S.cnt[s] & 0xffffu;
-            if (c < 2 || e == st0) continue;
+            const uint32_t cs = S.cnt[S.t.grp_slot[e]];
+            if (!(cs & GROUP_HAS_DUP)) continue;
+            const uint32_t st0 = cs & 0xffffu;
+            if (e == st0) continue;
             const uint32_t g = S.a.g.sorted[e];
             if (S.a.g.sorted[e - 1] == g) { if (!count_only) atomicAdd(&dup_cnt[g], 1u); continue; }
             uint32_t prev = 0xffffffffu;
             for (uint32_t j = st0; j < e; ++j) {
                 uint32_t gj = S.a.g.sorted[j];
-                if (gj != prev) {
-                    if (count_only) ++local_inc; else batch.add(g, gj, tkeys, tvals, cap_mask, overflow);
-                    prev = gj;
-                }
+                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, tkeys, tvals, cap_mask, overflow); prev = gj; }
             }
         }
-        if (batch.n) batch.flush(tkeys, tvals, cap_mask, overflow);
         __syncthreads();
     }
     if (count_only) {
@@ -939,6 +969,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     VB_CUDA(cudaStreamSynchronize(st));
 
     // ---- host: exact IEEE-double metric (params.cpp:28-32) and the two -min filters (sparse_filters.h:49-61)
+    const auto hp0 = std::chrono::steady_clock::now();
     std::vector<uint64_t> keep;
     keep.reserve(n_emit);
     std::vector<double> ani(n_emit);
@@ -961,6 +992,8 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     res->k = p->k;
     res->kmers_fraction = p->kmers_fraction;
     *out_pairs = res;
+    ctx->set_timing("prefilter.host_post_ms",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hp0).count());
 
     ctx->set_timing("prefilter.total_ms", t_all.ms());
     ctx->set_timing("prefilter.upload_pack_ms", t_up.ms());

@@ -2,6 +2,7 @@
 // status translation, and the host-side bookkeeping LZ-ANI does around its matching loop (genome re-ordering,
 // filter symmetrisation: seq_reservoir.cpp:215-251, filter.cpp:80-81,253-345, lz_matcher.cpp:172-277).
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 
 #include "dev_util.cuh"
@@ -310,42 +311,52 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_align: bad arguments");
     vb_enter(ctx);
+    const auto h0 = std::chrono::steady_clock::now();
     const uint32_t n = g->count();
     std::vector<uint32_t> order = vb_lz_order(g);
     std::vector<uint32_t> rank(n);
     for (uint32_t i = 0; i < n; ++i) rank[order[i]] = i;
 
-    // directed pair list in LZ-ANI ids, grouped by reference with the queries ascending (results rows are sorted, :253)
-    std::vector<std::vector<uint32_t>> rows(n);
+    // directed pair list in LZ-ANI ids, grouped by reference with the queries ascending (results rows are sorted, :253);
+    // built as a CSR (count, prefix, fill, sort each row)
+    std::vector<uint64_t> start(n + 1, 0);
     if (!pairs) {
-        for (uint32_t r = 0; r < n; ++r) {
-            rows[r].reserve(n - 1);
-            for (uint32_t q = 0; q < n; ++q) if (q != r) rows[r].push_back(q);
-        }
+        for (uint32_t r = 0; r < n; ++r) start[r + 1] = start[r] + (n - 1);
     } else {
         for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
             uint32_t a = pairs->row[i], b = pairs->col[i];
             if (a >= n || b >= n) throw vb_error(VB_ERR_ARG, "vb_align: pair id out of range");
-            rows[rank[a]].push_back(rank[b]);      // filter[i].push(id); filter[id].push(i)
-            rows[rank[b]].push_back(rank[a]);
+            start[rank[a] + 1]++;                    // filter[i].push(id); filter[id].push(i)
+            start[rank[b] + 1]++;
         }
-        for (auto &r : rows) std::sort(r.begin(), r.end());
+        for (uint32_t r = 0; r < n; ++r) start[r + 1] += start[r];
     }
-    uint64_t total = 0;
-    for (auto &r : rows) total += r.size();
+    const uint64_t total = start[n];
     vb_align_out *res = vb_align_out_alloc(total, n);
     std::copy(order.begin(), order.end(), res->order);
-    std::vector<uint32_t> in_ref(total), in_qry(total);
-    uint64_t w = 0;
-    for (uint32_t r = 0; r < n; ++r)
-        for (uint32_t q : rows[r]) {
-            res->ref[w] = r; res->qry[w] = q;
-            in_ref[w] = order[r]; in_qry[w] = order[q];
-            ++w;
+    if (!pairs) {
+        uint64_t w = 0;
+        for (uint32_t r = 0; r < n; ++r)
+            for (uint32_t q = 0; q < n; ++q) if (q != r) { res->ref[w] = r; res->qry[w] = q; ++w; }
+    } else {
+        std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+        for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
+            uint32_t a = rank[pairs->row[i]], b = rank[pairs->col[i]];
+            res->qry[fill[a]++] = b;
+            res->qry[fill[b]++] = a;
         }
+        for (uint32_t r = 0; r < n; ++r) {
+            std::sort(res->qry + start[r], res->qry + start[r + 1]);
+            std::fill(res->ref + start[r], res->ref + start[r + 1], r);
+        }
+    }
+    std::vector<uint32_t> in_ref(total), in_qry(total);
+    for (uint64_t w = 0; w < total; ++w) { in_ref[w] = order[res->ref[w]]; in_qry[w] = order[res->qry[w]]; }
     std::vector<int32_t> stats(3 * std::max<uint64_t>(total, 1));
+    const double api_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
     try {
         vb_align_pairs_impl(ctx, g, in_ref.data(), in_qry.data(), total, p, stats.data());
+        ctx->set_timing("align.api_prep_ms", api_prep_ms);
     } catch (...) {
         vb_align_out_free(res);
         throw;
