@@ -119,29 +119,45 @@ __global__ void __launch_bounds__(256) segment_count_kernel(const uint64_t *__re
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_inc, local);
 }
 
-__device__ __forceinline__ void table_add(uint64_t *__restrict__ tkeys, uint32_t *__restrict__ tvals, uint64_t cap_mask,
-                                          uint64_t key, uint32_t inc, int *__restrict__ overflow)
+// Accumulator of pair increments.  Two layouts:
+//   dense  (N(N-1)/2 <= 2^26): one uint32 counter per pair at index row*(row-1)/2 + col -- an increment is a single
+//          fire-and-forget atomic, and an ordered scan of the array yields the pairs already sorted by (row, col);
+//   hashed (larger N): open addressing, uint64 key (row << 32 | col) + uint32 count.
+struct PairAcc {
+    uint32_t *dense;        // non-null selects the dense layout
+    uint64_t *tkeys;
+    uint32_t *tvals;
+    uint64_t cap_mask;
+    int *overflow;
+};
+
+__device__ __forceinline__ void table_add(const PairAcc &A, uint64_t key, uint32_t inc)
 {
-    uint64_t h = fmix64(key) & cap_mask;
-    for (uint64_t probes = 0; probes <= cap_mask; ++probes) {
-        uint64_t cur = tkeys[h];
+    uint64_t h = fmix64(key) & A.cap_mask;
+    for (uint64_t probes = 0; probes <= A.cap_mask; ++probes) {
+        uint64_t cur = A.tkeys[h];
         if (cur == SLOT_EMPTY) {
-            cur = atomicCAS((unsigned long long *)&tkeys[h], (unsigned long long)SLOT_EMPTY, (unsigned long long)key);
+            cur = atomicCAS((unsigned long long *)&A.tkeys[h], (unsigned long long)SLOT_EMPTY, (unsigned long long)key);
             if (cur == SLOT_EMPTY) cur = key;
         }
-        if (cur == key) { atomicAdd(&tvals[h], inc); return; }
-        h = (h + 1) & cap_mask;
+        if (cur == key) { atomicAdd(&A.tvals[h], inc); return; }
+        h = (h + 1) & A.cap_mask;
     }
-    *overflow = 1;
+    *A.overflow = 1;
+}
+
+// one increment for the pair (hi, lo), hi > lo
+__device__ __forceinline__ void pair_add(const PairAcc &A, uint32_t hi, uint32_t lo)
+{
+    if (A.dense) atomicAdd(&A.dense[(uint64_t)hi * (hi - 1) / 2 + lo], 1u);
+    else table_add(A, ((uint64_t)hi << 32) | lo, 1u);
 }
 
 // k3b: duplicates per genome; every distinct (k-mer, genome) occurrence pairs with the distinct genomes before it in the run;
 // row = the later (larger) genome id, col = the earlier one -- the lower triangle of all2all_sp.
 __global__ void __launch_bounds__(256) segment_pairs_kernel(const uint64_t *__restrict__ keys,
                                                             const uint32_t *__restrict__ vals, uint64_t n,
-                                                            uint32_t *__restrict__ dup_cnt, uint64_t *__restrict__ tkeys,
-                                                            uint32_t *__restrict__ tvals, uint64_t cap_mask,
-                                                            int *__restrict__ overflow)
+                                                            uint32_t *__restrict__ dup_cnt, PairAcc A)
 {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t key = keys[i];
@@ -152,7 +168,7 @@ __global__ void __launch_bounds__(256) segment_pairs_kernel(const uint64_t *__re
         for (uint64_t j = i; j-- > 0 && keys[j] == key;) {
             uint32_t gj = vals[j];
             if (gj != prev) {
-                table_add(tkeys, tvals, cap_mask, ((uint64_t)g << 32) | gj, 1u, overflow);
+                pair_add(A, g, gj);
                 prev = gj;
             }
         }
@@ -441,21 +457,17 @@ struct BucketSmem {
     uint32_t warp_sum[8];
 };
 
-__device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, int count_only, unsigned long long &local_inc,
-                                          uint64_t *__restrict__ tkeys, uint32_t *__restrict__ tvals, uint64_t cap_mask,
-                                          int *__restrict__ overflow)
+__device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, int count_only, unsigned long long &local_inc, const PairAcc &A)
 {
     if (count_only) { ++local_inc; return; }
-    uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
-    table_add(tkeys, tvals, cap_mask, ((uint64_t)hi << 32) | lo, 1u, overflow);
+    pair_add(A, a > b ? a : b, a > b ? b : a);
 }
 
 // One block per final bucket: group equal k-mers in shared memory, count duplicates per genome, emit pair increments.
 // count_only: only sum the number of pair increments (sizing pass for very large N).
 __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                      const uint32_t *__restrict__ off, uint32_t n_buckets, int count_only,
-                                                     uint32_t *__restrict__ dup_cnt, uint64_t *__restrict__ tkeys,
-                                                     uint32_t *__restrict__ tvals, uint64_t cap_mask, int *__restrict__ overflow,
+                                                     uint32_t *__restrict__ dup_cnt, PairAcc A,
                                                      uint32_t *__restrict__ big_list, uint32_t *__restrict__ n_big,
                                                      unsigned long long *__restrict__ n_inc)
 {
@@ -615,14 +627,23 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
                         key[q] = ((uint64_t)a << 32) | b;
                     }
                 }
+                if (A.dense) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if (key[q] != SLOT_EMPTY) { h[q] = fmix64(key[q]) & cap_mask; cur[q] = tkeys[h[q]]; }
+                    for (int q = 0; q < 4; ++q)
+                        if (key[q] != SLOT_EMPTY) {
+                            const uint32_t a = (uint32_t)(key[q] >> 32), b = (uint32_t)key[q];
+                            atomicAdd(&A.dense[(uint64_t)a * (a - 1) / 2 + b], 1u);
+                        }
+                } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (key[q] != SLOT_EMPTY) {
-                        if (cur[q] == key[q]) atomicAdd(&tvals[h[q]], 1u);
-                        else table_add(tkeys, tvals, cap_mask, key[q], 1u, overflow);
-                    }
+                    for (int q = 0; q < 4; ++q) if (key[q] != SLOT_EMPTY) { h[q] = fmix64(key[q]) & A.cap_mask; cur[q] = A.tkeys[h[q]]; }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (key[q] != SLOT_EMPTY) {
+                            if (cur[q] == key[q]) atomicAdd(&A.tvals[h[q]], 1u);
+                            else table_add(A, key[q], 1u);
+                        }
+                }
             }
         }
         // groups with duplicates (and block-sorted large groups): element by element, skipping repeated genome ids
@@ -636,7 +657,7 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             uint32_t prev = 0xffffffffu;
             for (uint32_t j = st0; j < e; ++j) {
                 uint32_t gj = S.a.g.sorted[j];
-                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, tkeys, tvals, cap_mask, overflow); prev = gj; }
+                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, A); prev = gj; }
             }
         }
         __syncthreads();
@@ -653,8 +674,7 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
 __global__ void __launch_bounds__(1024) big_bucket_kernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                                           const uint32_t *__restrict__ off, const uint32_t *__restrict__ big_list,
                                                           const uint32_t *__restrict__ n_big, int count_only,
-                                                          uint32_t *__restrict__ dup_cnt, uint64_t *__restrict__ tkeys,
-                                                          uint32_t *__restrict__ tvals, uint64_t cap_mask, int *__restrict__ overflow,
+                                                          uint32_t *__restrict__ dup_cnt, PairAcc A,
                                                           unsigned long long *__restrict__ n_inc)
 {
     const uint32_t nb = *n_big;
@@ -685,7 +705,7 @@ __global__ void __launch_bounds__(1024) big_bucket_kernel(uint64_t *__restrict__
             uint32_t prev = g;
             for (uint32_t j = i; j-- > 0 && K[j] == key;) {
                 uint32_t gj = V[j];
-                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, tkeys, tvals, cap_mask, overflow); prev = gj; }
+                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, A); prev = gj; }
             }
         }
         __syncthreads();
@@ -751,6 +771,71 @@ __global__ void __launch_bounds__(256) emit_kernel(const uint64_t *__restrict__ 
     }
 }
 
+
+// k4 (dense layout): ordered compaction of the triangular counter array.  pass 0: passing entries per block;
+// pass 1 (after a scan of the block counts): write them in index order = sorted by (row, col).
+__device__ __forceinline__ void tri_decode(uint64_t t, uint32_t &row, uint32_t &col)
+{
+    uint32_t r = (uint32_t)((1.0 + sqrt(1.0 + 8.0 * (double)t)) * 0.5);
+    while ((uint64_t)r * (r - 1) / 2 > t) --r;
+    while ((uint64_t)(r + 1) * r / 2 <= t) ++r;
+    row = r; col = (uint32_t)(t - (uint64_t)r * (r - 1) / 2);
+}
+
+__global__ void __launch_bounds__(256) dense_emit_kernel(const uint32_t *__restrict__ dense, uint64_t n_entries, uint64_t per_block,
+                                                         const uint32_t *__restrict__ totals, EmitParams ep, int write,
+                                                         uint32_t *__restrict__ block_cnt, uint64_t *__restrict__ out_keys,
+                                                         uint32_t *__restrict__ out_vals)
+{
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ uint32_t s_run;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t lo = blockIdx.x * per_block, hi = min(n_entries, lo + per_block);
+    if (threadIdx.x == 0) s_run = write ? block_cnt[blockIdx.x] : 0;        // pass 1: block_cnt holds the exclusive offsets
+    __syncthreads();
+    for (uint64_t base = lo; base < hi; base += 256) {
+        const uint64_t t = base + threadIdx.x;
+        bool ok = false;
+        uint32_t v = 0, row = 0, col = 0;
+        if (t < hi) {
+            v = dense[t];
+            if (v >= ep.min_kmers && v > 0) {
+                tri_decode(t, row, col);
+                ok = emit_pass(((uint64_t)row << 32) | col, v, totals, ep);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) warp_cnt[wid] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { uint32_t c = warp_cnt[j]; if (j < wid) before += c; all += c; }
+        if (ok && write) {
+            const uint32_t o = s_run + before + __popc(m & ((1u << lane) - 1));
+            out_keys[o] = ((uint64_t)row << ep.gbits) | col;
+            out_vals[o] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += all;
+        __syncthreads();
+    }
+    if (!write && threadIdx.x == 0) block_cnt[blockIdx.x] = s_run;
+}
+
+// exclusive scan of up to 4096 block counts in one block; total -> *total
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *__restrict__ cnt, uint32_t n, unsigned long long *__restrict__ total)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_total;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { uint32_t i = threadIdx.x * 4 + j; v[j] = i < n ? cnt[i] : 0; sum += v[j]; }
+    uint32_t pre = block_exscan_1024(sum, warp_tot, &s_total);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { uint32_t i = threadIdx.x * 4 + j; if (i < n) cnt[i] = pre; pre += v[j]; }
+    if (threadIdx.x == 0) *total = s_total;
+}
+
 __global__ void fill_u64_kernel(uint64_t *p, uint64_t n, uint64_t v)
 {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
@@ -803,12 +888,22 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     VB_CUDA(cudaMemsetAsync(scalars.p, 0, scalars.bytes(), st));
     const unsigned long long max_pairs = (unsigned long long)n * (n > 0 ? n - 1 : 0) / 2;
     unsigned long long n_inc = max_pairs;
-    const bool count_first = max_pairs > (1ULL << 26);      // otherwise the dense bound N(N-1)/2 sizes the table
+    static const bool force_hash = getenv("VB_PREFILTER_HASH") != nullptr;   // test hook: exercise the large-N layout
+    const bool count_first = force_hash || max_pairs > (1ULL << 26);   // large N: hashed pair table sized by a counting pass
     DevBuf<uint64_t> tkeys;
-    DevBuf<uint32_t> tvals;
+    DevBuf<uint32_t> tvals, dense;
     DevBuf<int> overflow(1);
     uint64_t cap = 0;
+    PairAcc acc = {nullptr, nullptr, nullptr, 0, overflow.p};
     auto alloc_table = [&]() {
+        VB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st));
+        if (!count_first) {                                  // dense triangular counters
+            dense.alloc(std::max<unsigned long long>(max_pairs, 1));
+            VB_CUDA(cudaMemsetAsync(dense.p, 0, dense.bytes(), st));
+            acc.dense = dense.p;
+            cap = max_pairs;
+            return;
+        }
         unsigned long long distinct_bound = std::min(n_inc, max_pairs);
         cap = 1024;
         while (cap < 2 * distinct_bound) cap <<= 1;
@@ -817,7 +912,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         tvals.alloc(cap);
         VB_CUDA(cudaMemsetAsync(tkeys.p, 0xff, tkeys.bytes(), st));       // SLOT_EMPTY
         VB_CUDA(cudaMemsetAsync(tvals.p, 0, tvals.bytes(), st));
-        VB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st));
+        acc.tkeys = tkeys.p; acc.tvals = tvals.p; acc.cap_mask = cap - 1;
     };
     auto read_n_inc = [&]() {
         VB_CUDA(cudaMemcpyAsync(&n_inc, scalars.p, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
@@ -849,7 +944,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
             read_n_inc();
         }
         alloc_table();
-        segment_pairs_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, dup_cnt, tkeys.p, tvals.p, cap - 1, overflow.p);
+        segment_pairs_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, dup_cnt, acc);
         VB_LAUNCH_CHECK(ctx);
     } else {
         // ---- k1 + k2 + k3, MSD flavour: hash-bucket partition + shared-memory grouping
@@ -911,21 +1006,19 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         t_seg.start();
         const int bgrid = (int)std::min<uint32_t>(pl.NB, 148 * 12);
         if (count_first) {
-            bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(fkeys, fvals, off.p, pl.NB, 1, dup_cnt, nullptr, nullptr, 0,
-                                                                  overflow.p, big_list.p, n_big.p, scalars.p);
+            bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(fkeys, fvals, off.p, pl.NB, 1, dup_cnt, acc, big_list.p, n_big.p,
+                                                                  scalars.p);
             VB_LAUNCH_CHECK(ctx);
-            big_bucket_kernel<<<64, 1024, 0, st>>>(fkeys, fvals, off.p, big_list.p, n_big.p, 1, dup_cnt, nullptr, nullptr, 0,
-                                                   overflow.p, scalars.p);
+            big_bucket_kernel<<<64, 1024, 0, st>>>(fkeys, fvals, off.p, big_list.p, n_big.p, 1, dup_cnt, acc, scalars.p);
             VB_LAUNCH_CHECK(ctx);
             read_n_inc();
             VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
         }
         alloc_table();
-        bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(fkeys, fvals, off.p, pl.NB, 0, dup_cnt, tkeys.p, tvals.p, cap - 1,
-                                                              overflow.p, big_list.p, n_big.p, scalars.p);
+        bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(fkeys, fvals, off.p, pl.NB, 0, dup_cnt, acc, big_list.p, n_big.p,
+                                                              scalars.p);
         VB_LAUNCH_CHECK(ctx);
-        big_bucket_kernel<<<64, 1024, 0, st>>>(fkeys, fvals, off.p, big_list.p, n_big.p, 0, dup_cnt, tkeys.p, tvals.p, cap - 1,
-                                               overflow.p, scalars.p);
+        big_bucket_kernel<<<64, 1024, 0, st>>>(fkeys, fvals, off.p, big_list.p, n_big.p, 0, dup_cnt, acc, scalars.p);
         VB_LAUNCH_CHECK(ctx);
     }
     totals_kernel<<<(n + 255) / 256 + 1, 256, 0, st>>>(valid_cnt, dup_cnt, n, totals);
@@ -940,27 +1033,52 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     em.k = p->k;
     em.gbits = 1;
     while ((1ULL << em.gbits) < n) em.gbits++;
-    emit_kernel<<<grid_for(cap), 256, 0, st>>>(tkeys.p, tvals.p, cap, totals, em, 0, scalars.p + 1, nullptr, nullptr);
-    VB_LAUNCH_CHECK(ctx);
     unsigned long long n_emit = 0;
     int h_overflow = 0;
-    VB_CUDA(cudaMemcpyAsync(&n_emit, scalars.p + 1, sizeof(n_emit), cudaMemcpyDeviceToHost, st));
-    VB_CUDA(cudaMemcpyAsync(&h_overflow, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VB_CUDA(cudaStreamSynchronize(st));
-    if (h_overflow) throw vb_error(VB_ERR_INTERNAL, "pair table overflow");
-    const uint64_t e_pad = ((n_emit + rsort::TILE - 1) / rsort::TILE) * rsort::TILE;
-    std::vector<uint64_t> h_keys(n_emit);
-    std::vector<uint32_t> h_vals(n_emit);
-    if (n_emit) {
-        DevBuf<uint64_t> ek_a(e_pad), ek_b(e_pad);
-        DevBuf<uint32_t> ev_a(e_pad), ev_b(e_pad);
-        fill_u64_kernel<<<grid_for(e_pad), 256, 0, st>>>(ek_a.p, e_pad, KEY_SENTINEL);
+    std::vector<uint64_t> h_keys;
+    std::vector<uint32_t> h_vals;
+    if (acc.dense) {
+        // dense layout: ordered compaction, the output is born sorted by (row, col)
+        const uint32_t n_blocks = (uint32_t)std::min<uint64_t>(4096, (max_pairs + 255) / 256 + 1);
+        const uint64_t per_block = ((max_pairs + n_blocks - 1) / n_blocks + 255) / 256 * 256;
+        DevBuf<uint32_t> block_cnt(4096);
+        dense_emit_kernel<<<n_blocks, 256, 0, st>>>(dense.p, max_pairs, per_block, totals, em, 0, block_cnt.p, nullptr, nullptr);
         VB_LAUNCH_CHECK(ctx);
-        emit_kernel<<<grid_for(cap), 256, 0, st>>>(tkeys.p, tvals.p, cap, totals, em, 1, scalars.p + 2, ek_a.p, ev_a.p);
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(block_cnt.p, n_blocks, scalars.p + 1);
         VB_LAUNCH_CHECK(ctx);
-        bool eb = rsort::sort_kv<8>(ctx, ek_a.p, ev_a.p, ek_b.p, ev_b.p, e_pad, 2 * em.gbits + 1, ws);
-        VB_CUDA(cudaMemcpyAsync(h_keys.data(), eb ? ek_b.p : ek_a.p, sizeof(uint64_t) * n_emit, cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaMemcpyAsync(h_vals.data(), eb ? ev_b.p : ev_a.p, sizeof(uint32_t) * n_emit, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaMemcpyAsync(&n_emit, scalars.p + 1, sizeof(n_emit), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        h_keys.resize(n_emit); h_vals.resize(n_emit);
+        if (n_emit) {
+            DevBuf<uint64_t> ek(n_emit);
+            DevBuf<uint32_t> ev(n_emit);
+            dense_emit_kernel<<<n_blocks, 256, 0, st>>>(dense.p, max_pairs, per_block, totals, em, 1, block_cnt.p, ek.p, ev.p);
+            VB_LAUNCH_CHECK(ctx);
+            VB_CUDA(cudaMemcpyAsync(h_keys.data(), ek.p, sizeof(uint64_t) * n_emit, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(h_vals.data(), ev.p, sizeof(uint32_t) * n_emit, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+        }
+    } else {
+        emit_kernel<<<grid_for(cap), 256, 0, st>>>(tkeys.p, tvals.p, cap, totals, em, 0, scalars.p + 1, nullptr, nullptr);
+        VB_LAUNCH_CHECK(ctx);
+        VB_CUDA(cudaMemcpyAsync(&n_emit, scalars.p + 1, sizeof(n_emit), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaMemcpyAsync(&h_overflow, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        if (h_overflow) throw vb_error(VB_ERR_INTERNAL, "pair table overflow");
+        const uint64_t e_pad = ((n_emit + rsort::TILE - 1) / rsort::TILE) * rsort::TILE;
+        h_keys.resize(n_emit); h_vals.resize(n_emit);
+        if (n_emit) {
+            DevBuf<uint64_t> ek_a(e_pad), ek_b(e_pad);
+            DevBuf<uint32_t> ev_a(e_pad), ev_b(e_pad);
+            fill_u64_kernel<<<grid_for(e_pad), 256, 0, st>>>(ek_a.p, e_pad, KEY_SENTINEL);
+            VB_LAUNCH_CHECK(ctx);
+            emit_kernel<<<grid_for(cap), 256, 0, st>>>(tkeys.p, tvals.p, cap, totals, em, 1, scalars.p + 2, ek_a.p, ev_a.p);
+            VB_LAUNCH_CHECK(ctx);
+            bool eb = rsort::sort_kv<8>(ctx, ek_a.p, ev_a.p, ek_b.p, ev_b.p, e_pad, 2 * em.gbits + 1, ws);
+            VB_CUDA(cudaMemcpyAsync(h_keys.data(), eb ? ek_b.p : ek_a.p, sizeof(uint64_t) * n_emit, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(h_vals.data(), eb ? ev_b.p : ev_a.p, sizeof(uint32_t) * n_emit, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+        }
     }
     std::vector<uint32_t> h_tot(n);
     if (n) VB_CUDA(cudaMemcpyAsync(h_tot.data(), totals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
