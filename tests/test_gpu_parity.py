@@ -180,3 +180,37 @@ def test_align_result_assembly_matches_vb_align(ctx, golden, tmp_path):
     api.align([p], tmp_path / "b.tsv", True, filter_file=golden / "example" / "fltr.txt")
     assert (tmp_path / "a.tsv").read_bytes() == (tmp_path / "b.tsv").read_bytes()
     assert (tmp_path / "a.ids.tsv").read_bytes() == (tmp_path / "b.ids.tsv").read_bytes()
+
+
+# ---------------------------------------------------------------- full-size configuration (BASELINE configs[1] = c2)
+def test_c2_full_size_vs_reference_binaries(ctx, tmp_path):
+    """1000 x 40 kb genomes: filter file and ani.tsv must be byte-identical to the unmodified reference tools
+    (oracle/_ref, run here on the host cores).  Skipped when the binaries did not travel."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref binaries not present")
+    names, seqs = synth.make_genomes(**synth.CONFIGS["c2"])
+    fa = tmp_path / "c2.fna"
+    synth.write_fasta(fa, names, seqs)
+    api.prefilter([fa], tmp_path / "fltr.txt", True)
+    oracle.ref_prefilter([fa], tmp_path / "ref_fltr.txt", tmp_path / "p")
+    assert (tmp_path / "fltr.txt").read_bytes() == (tmp_path / "ref_fltr.txt").read_bytes()
+    api.align([fa], tmp_path / "ani.tsv", True, filter_file=tmp_path / "fltr.txt", out_format=api.ALIGN_OUTFMT["complete"])
+    oracle.ref_align([fa], tmp_path / "ref_ani.tsv", tmp_path / "a", filter_path=tmp_path / "ref_fltr.txt",
+                     columns=api.ALIGN_OUTFMT["complete"])
+    assert (tmp_path / "ani.tsv").read_bytes() == (tmp_path / "ref_ani.tsv").read_bytes()
+    assert (tmp_path / "ani.ids.tsv").read_bytes() == (tmp_path / "ref_ani.ids.tsv").read_bytes()
+
+
+def test_c2_unrelated_pairs_sample_vs_oracle(ctx):
+    """All-vs-all slice of c2 (mostly unrelated pairs: the lost-mode / spurious-anchor regime) against the C oracle."""
+    names, seqs = synth.make_genomes(**synth.CONFIGS["c2"])
+    raw = [s.tobytes() for s in seqs]
+    rng = np.random.default_rng(11)
+    ref = rng.integers(0, len(raw), size=600)
+    qry = rng.integers(0, len(raw), size=600)
+    g = api.Genomes.from_memory(names, raw)
+    got = api.align_pairs(ctx, g, ref, qry)
+    sub = sorted(set(ref.tolist()) | set(qry.tolist()))
+    remap = {x: i for i, x in enumerate(sub)}
+    want = oracle.run_pairs([oracle.lz_codes(raw[x]) for x in sub], [remap[x] for x in ref], [remap[x] for x in qry])
+    assert np.array_equal(got, want)
