@@ -71,7 +71,7 @@ class Context:
     def timings(self, prefix: str) -> dict:
         keys = {
             "prefilter": ["total_ms", "upload_pack_ms", "extract_ms", "sort_ms", "segment_ms", "emit_ms", "host_post_ms", "tuples",
-                          "pair_increments", "table_slots", "candidates"],
+                          "survivors", "pair_increments", "table_slots", "candidates"],
             "align": ["total_ms", "upload_pack_ms", "index_ms", "parse_ms", "api_prep_ms", "host_prep_ms", "host_post_ms", "batches", "pairs"],
         }[prefix]
         out = {}

@@ -33,7 +33,7 @@ struct RefDesc {
     uint64_t s2_off;     // word offset of the packed text in ref_s2
     uint64_t nv_off;     // word offset of the N plane in ref_nv
     uint64_t ht_off;     // slot offset of the anchor table
-    uint32_t ht_mask;    // slots - 1
+    uint32_t ht_cap;     // slots (any size >= 2 * forward positions; range reduction by multiply-shift)
     uint32_t pos_bits;   // a slot is fingerprint << pos_bits | position, 2^pos_bits > n
     uint32_t n;          // text length: 2*len + 3*mrd
     uint32_t len;        // genome length
@@ -59,6 +59,9 @@ __device__ __forceinline__ uint64_t reverse_digits(uint64_t x)
     x = __brevll(x);
     return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
 }
+
+// home slot of a hash in a table of `cap` slots (low 32 bits; the fingerprint comes from the high 32)
+__device__ __forceinline__ uint32_t ht_slot(uint64_t h, uint32_t cap) { return __umulhi((uint32_t)h, cap); }
 
 // min(K, reverse complement of K) for a k-mer of `len` 2-bit digits
 __device__ __forceinline__ uint64_t canonical_kmer(uint64_t code, int len, uint64_t kmask)
@@ -140,8 +143,8 @@ __global__ void __launch_bounds__(256) build_ref_index_kernel(const RefDesc *__r
             uint64_t code = fetch2(s2, p) & kmask;
             uint64_t h = fmix64(canonical_kmer(code, mal, kmask));
             uint32_t val = ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | p;
-            uint32_t slot = (uint32_t)h & d.ht_mask;
-            while (atomicCAS(&tab[slot], HT_EMPTY, val) != HT_EMPTY) slot = (slot + 1) & d.ht_mask;
+            uint32_t slot = ht_slot(h, d.ht_cap);
+            while (atomicCAS(&tab[slot], HT_EMPTY, val) != HT_EMPTY) slot = (slot + 1 == d.ht_cap) ? 0u : slot + 1;
         }
     }
 }
@@ -372,23 +375,23 @@ __device__ __forceinline__ bool kmer_at(const Text &T, int p, int len, uint64_t 
 }
 
 // one lane: does the anchor table hold any entry with this k-mer's fingerprint?
-__device__ __forceinline__ bool anchor_probe(const uint32_t *__restrict__ tab, uint32_t mask, uint32_t pos_bits, uint64_t code,
+__device__ __forceinline__ bool anchor_probe(const uint32_t *__restrict__ tab, uint32_t cap, uint32_t pos_bits, uint64_t code,
                                              int mal)
 {
     uint64_t h = fmix64(canonical_kmer(code, mal, (~0ULL) >> (64 - 2 * mal)));
     uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
-    uint32_t slot = (uint32_t)h & mask;
+    uint32_t slot = ht_slot(h, cap);
     for (;;) {
         uint32_t s = __ldg(tab + slot);
         if (s == HT_EMPTY) return false;
         if ((s >> pos_bits) == fp) return true;
-        slot = (slot + 1) & mask;
+        slot = (slot + 1 == cap) ? 0u : slot + 1;
     }
 }
 
 // whole warp, parser.cpp:514-531 / :585-602: longest exact match among all reference positions of Q's mal-mer at i
 // (>= mal), ties to the smallest position.  Lanes read 32 consecutive slots of the probe chain at a time.
-__device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t mask, uint32_t pos_bits, const Text &Q, int i,
+__device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, uint32_t pos_bits, const Text &Q, int i,
                               const Text &R, const LzParams &P, int lane, int &best_len, int &best_pos)
 {
     best_len = 0; best_pos = 0;
@@ -396,13 +399,16 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t mask, u
     if (!kmer_at(Q, i, P.mal, code)) return;
     uint64_t h = fmix64(canonical_kmer(code, P.mal, (~0ULL) >> (64 - 2 * P.mal)));
     uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
-    uint32_t slot0 = (uint32_t)h & mask;
+    uint32_t slot0 = ht_slot(h, cap);
     const uint32_t pmask = (1u << pos_bits) - 1;
     const int len = (R.n - 3 * P.mrd) / 2;                  // genome length; the reverse complement starts at rc0
     const int rc0 = len + 2 * P.mrd;
     int my_len = 0, my_pos = 0x7fffffff;
     for (uint32_t step = 0;; step += 32) {
-        uint32_t s = __ldg(tab + ((slot0 + step + lane) & mask));
+        uint32_t at = slot0 + step + lane;                  // slot0 < cap and step < cap: at most two wraps
+        if (at >= cap) at -= cap;
+        if (at >= cap) at -= cap;
+        uint32_t s = __ldg(tab + at);
         unsigned empties = __ballot_sync(0xffffffffu, s == HT_EMPTY);
         bool in_chain = empties == 0 || lane < (__ffs(empties) - 1);
         if (in_chain && (s >> pos_bits) == fp) {
@@ -414,7 +420,7 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t mask, u
                 if (ml >= P.mal && (ml > my_len || (ml == my_len && pos < my_pos))) { my_len = ml; my_pos = pos; }
             }
         }
-        if (empties || step + 32 > mask) break;
+        if (empties || step + 32 >= cap) break;             // an empty slot ends the chain; else the whole table was seen
     }
     int mx = __reduce_max_sync(0xffffffffu, my_len);
     if (mx == 0) return;
@@ -471,7 +477,7 @@ __device__ int gap_best_matches(const Text &Q, int d, const Text &R, int r_left,
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SEED_WORDS = 6;         // seed windows of up to 192 reference positions use the Shift-And path
 
-__device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restrict__ tab, uint32_t tmask, uint32_t pos_bits,
+__device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restrict__ tab, uint32_t tcap, uint32_t pos_bits,
                            const LzParams &P, int lane, uint32_t (*seed_masks)[4][SEED_WORDS + 1], int &out_match, int &out_lit,
                            int &out_comp)
 {
@@ -492,7 +498,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         bool flag = false;
         if (lane < steps) {
             uint64_t code;
-            if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tmask, pos_bits, code, P.mal);
+            if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tcap, pos_bits, code, P.mal);
         }
         if (!lost) {
             // short seeds: lane t (query position i + t) may use reference positions [lo, pred + t + mrd).  The window is
@@ -567,11 +573,11 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         // ---- 2. exact evaluation at i (parser.cpp:503-624) ----------------------------------------------------
         int best_len = 0, best_pos = 0;
         if (lost)
-            anchor_search(tab, tmask, pos_bits, Q, i, R, P, lane, best_len, best_pos);
+            anchor_search(tab, tcap, pos_bits, Q, i, R, P, lane, best_len, best_pos);
         else {
             close_search(Q, i, R, pred, lit, P, lane, best_len, best_pos);
             int a_len, a_pos;
-            anchor_search(tab, tmask, pos_bits, Q, i, R, P, lane, a_len, a_pos);
+            anchor_search(tab, tcap, pos_bits, Q, i, R, P, lane, a_len, a_pos);
             if (a_pos) {                                  // positions double as booleans in the reference (:604-606)
                 if (!best_pos) { best_pos = a_pos; best_len = a_len; }
                 else {
@@ -659,7 +665,7 @@ __global__ void __launch_bounds__(128, MINB) parse_kernel(const uint32_t *__rest
         uint64_t qo = gofs[q];
         Text Q = {g2 + (qo >> 4), gn + (qo >> 5), (int)glen[q] + P.mrd};
         int m, l, c;
-        parse_pair(Q, R, ht + d.ht_off, d.ht_mask, d.pos_bits, P, lane, seed_masks, m, l, c);
+        parse_pair(Q, R, ht + d.ht_off, d.ht_cap, d.pos_bits, P, lane, seed_masks, m, l, c);
         if (lane == 0) { stats[3 * (uint64_t)idx] = m; stats[3 * (uint64_t)idx + 1] = l; stats[3 * (uint64_t)idx + 2] = c; }
     }
 }
@@ -669,31 +675,144 @@ __global__ void __launch_bounds__(128, MINB) parse_kernel(const uint32_t *__rest
 // ---------------------------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------------------------
-void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
-                         const vb_align_params *ap, int32_t *stats)
+// The reference side (texts + anchor tables) depends only on WHICH genomes are references, so it is launched first and
+// the host builds and sorts the pair list while the GPU works on it (vb_align_job_begin ... vb_align_job_run).
+struct RefBatch {
+    std::vector<RefDesc> refs;
+    uint64_t s2_words = 0, nv_words = 0, slots = 0, bytes = 0;
+    DevBuf<RefDesc> d_refs;
+    DevBuf<uint32_t> ref_s2, ref_nv, ht;
+};
+
+static uint64_t ref_table_slots(uint64_t len)
+{
+    // forward positions only (canonical k-mers); a multiple of 1024 keeps every table 16-byte aligned
+    static const int quarter_slots = getenv("VB_ALIGN_TABLE_Q") ? atoi(getenv("VB_ALIGN_TABLE_Q")) : 16;  // slots per position * 4 (load 0.25 measured best)
+    return std::max<uint64_t>(1024, ((uint64_t)quarter_slots * (len + 1) / 4 + 1023) / 1024 * 1024);
+}
+
+static uint64_t ref_bytes(uint64_t len, int mrd)
+{
+    const uint64_t chunks = (2 * len + 3 * (uint64_t)mrd + 31) / 32 + 4;
+    return chunks * 12 + ref_table_slots(len) * 4;
+}
+
+static void ref_batch_add(RefBatch &b, const vb_genomes *g, uint32_t gid, int mrd)
+{
+    const uint64_t len = g->length(gid);
+    const uint64_t nR = 2 * len + 3 * (uint64_t)mrd;
+    const uint64_t chunks = (nR + 31) / 32 + 4;
+    const uint64_t cap = ref_table_slots(len);
+    if (cap >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "genome too long for the anchor table");
+    uint32_t pos_bits = 1;
+    while ((1ULL << pos_bits) <= nR) ++pos_bits;
+    RefDesc d;
+    d.s2_off = b.s2_words; d.nv_off = b.nv_words; d.ht_off = b.slots;
+    d.ht_cap = (uint32_t)cap; d.pos_bits = pos_bits; d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = gid;
+    b.refs.push_back(d);
+    b.s2_words += 2 * chunks + 4; b.nv_words += chunks + 4; b.slots += cap; b.bytes += chunks * 12 + cap * 4;
+}
+
+// allocate, upload the descriptors, clear the tables, build texts and anchor tables (all asynchronous)
+static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, const vb_align_params *ap, cudaStream_t st)
+{
+    b.d_refs.alloc(b.refs.size());
+    b.ref_s2.alloc(b.s2_words + 8);
+    b.ref_nv.alloc(b.nv_words + 8);
+    b.ht.alloc(b.slots);
+    VB_CUDA(cudaMemcpyAsync(b.d_refs.p, b.refs.data(), sizeof(RefDesc) * b.refs.size(), cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemsetAsync(b.ht.p, 0xff, b.ht.bytes(), st));
+    dim3 grid_b(16, (unsigned)std::min<size_t>(b.refs.size(), 32768));
+    build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, b.d_refs.p, (uint32_t)b.refs.size(), ap->mrd,
+                                                 b.ref_s2.p, b.ref_nv.p);
+    VB_LAUNCH_CHECK(ctx);
+    build_ref_index_kernel<<<grid_b, 256, 0, st>>>(b.d_refs.p, (uint32_t)b.refs.size(), ap->mal, b.ref_s2.p, b.ref_nv.p, b.ht.p);
+    VB_LAUNCH_CHECK(ctx);
+}
+
+static void parse_launch(vb_ctx *ctx, const DevGenomes &dg, const RefBatch &b, const uint32_t *d_pref, const uint32_t *d_pqry,
+                         uint32_t nb, const LzParams &P, unsigned int *d_cursor, int32_t *d_stats, cudaStream_t st)
+{
+    int per_sm = 0;
+    static const int minb = getenv("VB_PARSE_MINB") ? atoi(getenv("VB_PARSE_MINB")) : 6;
+    auto kern = minb >= 8 ? parse_kernel<8> : (minb == 7 ? parse_kernel<7> : (minb == 6 ? parse_kernel<6> : parse_kernel<5>));
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+    int n_sm = 0;
+    VB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+    int blocks = std::max(1, std::min<int>(per_sm * n_sm, (int)((nb + 3) / 4)));
+    kern<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, dg.glen.p, b.d_refs.p, b.ref_s2.p, b.ref_nv.p, b.ht.p, d_pref,
+                                 d_pqry, nb, P, d_cursor, d_stats);
+    VB_LAUNCH_CHECK(ctx);
+}
+
+struct vb_align_job {
+    vb_ctx *ctx;
+    const vb_genomes *g;
+    vb_align_params ap;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point h0;
+    EventTimer t_all, t_up, t_idx;
+    DevGenomes dg_scratch;
+    const DevGenomes *dg = nullptr;
+    bool prebuilt = false;               // all references of the call fit one batch and are being indexed already
+    std::vector<int32_t> slot_of_gid;    // prebuilt: index of a genome's RefDesc, -1 if it is not a reference
+    RefBatch all;
+    vb_align_job(vb_ctx *c, const vb_genomes *gg, const vb_align_params *p)
+        : ctx(c), g(gg), ap(*p), st((cudaStream_t)c->stream), t_all(st), t_up(st), t_idx(st) {}
+};
+
+vb_align_job *vb_align_job_begin(vb_ctx *ctx, const vb_genomes *g, const vb_align_params *ap, const uint8_t *is_ref)
 {
     if (ap->mal < 4 || ap->mal > 31 || ap->msl < 2 || ap->msl > ap->mal || ap->msl > 31)
         throw vb_error(VB_ERR_ARG, "need 2 <= msl <= mal <= 31");
     if (ap->aw < 1 || ap->aw > 32 || ap->ar < 1 || ap->ar > 32 || ap->am < 0)
         throw vb_error(VB_ERR_ARG, "need 1 <= aw <= 32, 1 <= ar <= 32, am >= 0");
     if (ap->mrd < 1 || ap->mrd > 4096 || ap->mqd < 0) throw vb_error(VB_ERR_ARG, "need 1 <= mrd <= 4096, mqd >= 0");
-    if (n >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 pairs in one call");
-    cudaStream_t st = (cudaStream_t)ctx->stream;
     VB_CUDA(cudaSetDevice(ctx->device));
+    vb_align_job *job = new vb_align_job(ctx, g, ap);
+    try {
+        job->h0 = std::chrono::steady_clock::now();
+        job->t_all.start();
+        job->t_up.start();
+        job->dg = &vb_get_dev_genomes(ctx, g, /*u_is_t=*/false, (uint32_t)ap->mrd + 128, job->dg_scratch);
+        job->t_up.stop();
+        // reference texts + anchor tables of one batch may take up to 40 % of the device (no per-call memory query)
+        const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
+        const uint32_t ng = g->count();
+        uint64_t need = 0;
+        uint32_t n_refs = 0;
+        for (uint32_t i = 0; i < ng; ++i) if (is_ref[i]) { need += ref_bytes(g->length(i), ap->mrd); ++n_refs; }
+        job->t_idx.start();
+        if (n_refs && need <= budget) {
+            job->slot_of_gid.assign(ng, -1);
+            for (uint32_t i = 0; i < ng; ++i) if (is_ref[i]) { job->slot_of_gid[i] = (int32_t)job->all.refs.size(); ref_batch_add(job->all, g, i, ap->mrd); }
+            ref_batch_launch(ctx, job->all, *job->dg, ap, job->st);
+            job->prebuilt = true;
+        }
+        job->t_idx.stop();
+    } catch (...) {
+        delete job;
+        throw;
+    }
+    return job;
+}
+
+void vb_align_job_end(vb_align_job *job) { delete job; }
+
+void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qry, uint64_t n, int32_t *stats)
+{
+    vb_ctx *ctx = job->ctx;
+    const vb_genomes *g = job->g;
+    const vb_align_params *ap = &job->ap;
+    cudaStream_t st = job->st;
+    const DevGenomes &dg = *job->dg;
+    if (n >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 pairs in one call");
     const uint32_t ng = g->count();
     for (uint64_t i = 0; i < n; ++i)
         if (ref[i] >= ng || qry[i] >= ng) throw vb_error(VB_ERR_ARG, "pair id out of range");
     LzParams P = {ap->mal, ap->msl, ap->mrd, ap->mqd, ap->reg, ap->aw, ap->am, ap->ar};
-    const auto h0 = std::chrono::steady_clock::now();
     double host_prep_ms = 0, host_post_ms = 0;
-    EventTimer t_all(st), t_up(st);
     double ms_index = 0, ms_parse = 0;
-
-    t_all.start();
-    t_up.start();
-    DevGenomes dg_scratch;
-    const DevGenomes &dg = vb_get_dev_genomes(ctx, g, /*u_is_t=*/false, (uint32_t)ap->mrd + 128, dg_scratch);
-    t_up.stop();
 
     // pairs grouped by reference (stable), so that one reference's index is built once and stays hot in L2
     std::vector<uint32_t> order(n);
@@ -705,78 +824,55 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
             if (i == 0 || ref[i] != ref[i - 1]) { if (seen[ref[i]]) grouped = false; seen[ref[i]] = 1; }
         if (!grouped) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ref[a] < ref[b]; });
     }
-
-    // reference texts + anchor tables of one batch may take up to 40 % of the device (no per-call memory query)
     const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
 
     DevBuf<int32_t> d_stats(3 * std::max<uint64_t>(n, 1));
     DevBuf<uint32_t> d_pref(std::max<uint64_t>(n, 1)), d_pqry(std::max<uint64_t>(n, 1));
     DevBuf<unsigned int> d_cursor(1);
-    std::vector<int32_t> h_stats(3 * n);
 
     uint64_t pos = 0;
     int n_batches = 0;
     while (pos < n) {
-        // ---- choose a batch of references that fits the memory budget
-        std::vector<RefDesc> refs;
+        // ---- the references of this batch: all of them (already launched), or as many as fit the memory budget
+        RefBatch local;
+        RefBatch &rb = job->prebuilt ? job->all : local;
         std::vector<uint32_t> b_ref, b_qry;
-        uint64_t s2_words = 0, nv_words = 0, slots = 0, bytes = 0;
         uint64_t end = pos;
-        while (end < n) {
-            uint32_t r = ref[order[end]];
-            if (refs.empty() || refs.back().gid != r) {
-                uint64_t len = g->length(r);
-                uint64_t nR = 2 * len + 3 * (uint64_t)ap->mrd;
-                uint64_t chunks = (nR + 31) / 32 + 4;
-                uint64_t cap = 1024;
-                while (cap < 2 * (len + 1)) cap <<= 1;                 // forward positions only, load <= 0.5
-                uint64_t need = chunks * 12 + cap * 4;
-                uint32_t pos_bits = 1;
-                while ((1ULL << pos_bits) <= nR) ++pos_bits;
-                if (!refs.empty() && bytes + need > budget) break;
-                if (refs.empty() && need > budget) throw vb_error(VB_ERR_MEM, "reference index does not fit device memory");
-                RefDesc d;
-                d.s2_off = s2_words; d.nv_off = nv_words; d.ht_off = slots;
-                d.ht_mask = (uint32_t)(cap - 1); d.pos_bits = pos_bits; d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = r;
-                refs.push_back(d);
-                s2_words += 2 * chunks + 4; nv_words += chunks + 4; slots += cap; bytes += need;    // cap is a multiple of 1024: 16-byte aligned tables
+        if (job->prebuilt) {
+            b_ref.resize(n); b_qry.resize(n);
+            for (uint64_t i = 0; i < n; ++i) {
+                const int32_t slot = job->slot_of_gid[ref[order[i]]];
+                if (slot < 0) throw vb_error(VB_ERR_INTERNAL, "reference was not announced to vb_align_job_begin");
+                b_ref[i] = (uint32_t)slot; b_qry[i] = qry[order[i]];
             }
-            b_ref.push_back((uint32_t)refs.size() - 1);
-            b_qry.push_back(qry[order[end]]);
-            ++end;
+            end = n;
+        } else {
+            while (end < n) {
+                uint32_t r = ref[order[end]];
+                if (local.refs.empty() || local.refs.back().gid != r) {
+                    const uint64_t need = ref_bytes(g->length(r), ap->mrd);
+                    if (!local.refs.empty() && local.bytes + need > budget) break;
+                    if (local.refs.empty() && need > budget) throw vb_error(VB_ERR_MEM, "reference index does not fit device memory");
+                    ref_batch_add(local, g, r, ap->mrd);
+                }
+                b_ref.push_back((uint32_t)local.refs.size() - 1);
+                b_qry.push_back(qry[order[end]]);
+                ++end;
+            }
         }
         const uint32_t nb = (uint32_t)(end - pos);
-        DevBuf<RefDesc> d_refs(refs.size());
-        DevBuf<uint32_t> ref_s2(s2_words + 8), ref_nv(nv_words + 8);
-        DevBuf<uint32_t> ht(slots);
-        VB_CUDA(cudaMemcpyAsync(d_refs.p, refs.data(), sizeof(RefDesc) * refs.size(), cudaMemcpyHostToDevice, st));
+        EventTimer t_idx(st), t_par(st);
+        if (!job->prebuilt) {
+            t_idx.start();
+            ref_batch_launch(ctx, local, dg, ap, st);
+            t_idx.stop();
+        }
         VB_CUDA(cudaMemcpyAsync(d_pref.p, b_ref.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
         VB_CUDA(cudaMemcpyAsync(d_pqry.p, b_qry.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
-        VB_CUDA(cudaMemsetAsync(ht.p, 0xff, ht.bytes(), st));
         VB_CUDA(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned int), st));
-
-        if (n_batches == 0) host_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
-        EventTimer t_idx(st), t_par(st);
-        t_idx.start();
-        dim3 grid_b(16, (unsigned)std::min<size_t>(refs.size(), 32768));
-        build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, d_refs.p, (uint32_t)refs.size(), ap->mrd,
-                                                     ref_s2.p, ref_nv.p);
-        VB_LAUNCH_CHECK(ctx);
-        build_ref_index_kernel<<<grid_b, 256, 0, st>>>(d_refs.p, (uint32_t)refs.size(), ap->mal, ref_s2.p, ref_nv.p, ht.p);
-        VB_LAUNCH_CHECK(ctx);
-        t_idx.stop();
-
+        if (n_batches == 0) host_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - job->h0).count();
         t_par.start();
-        int per_sm = 0;
-        static const int minb = getenv("VB_PARSE_MINB") ? atoi(getenv("VB_PARSE_MINB")) : 6;
-        auto kern = minb >= 8 ? parse_kernel<8> : (minb == 7 ? parse_kernel<7> : (minb == 6 ? parse_kernel<6> : parse_kernel<5>));
-        VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
-        int n_sm = 0;
-        VB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-        int blocks = std::max(1, std::min<int>(per_sm * n_sm, (int)((nb + 3) / 4)));
-        kern<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, dg.glen.p, d_refs.p, ref_s2.p, ref_nv.p, ht.p,
-                                             d_pref.p, d_pqry.p, nb, P, d_cursor.p, d_stats.p);
-        VB_LAUNCH_CHECK(ctx);
+        parse_launch(ctx, dg, rb, d_pref.p, d_pqry.p, nb, P, d_cursor.p, d_stats.p, st);
         t_par.stop();
         std::vector<int32_t> tmp(3 * (size_t)nb);
         VB_CUDA(cudaMemcpyAsync(tmp.data(), d_stats.p, sizeof(int32_t) * 3 * nb, cudaMemcpyDeviceToHost, st));
@@ -786,20 +882,39 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
             uint64_t o = order[pos + j];
             stats[3 * o] = tmp[3 * j]; stats[3 * o + 1] = tmp[3 * j + 1]; stats[3 * o + 2] = tmp[3 * j + 2];
         }
-        ms_index += t_idx.ms();
+        ms_index += job->prebuilt ? job->t_idx.ms() : t_idx.ms();
         ms_parse += t_par.ms();
         host_post_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h1).count();
         pos = end;
         ++n_batches;
     }
-    t_all.stop();
+    job->t_all.stop();
     VB_CUDA(cudaStreamSynchronize(st));
-    ctx->set_timing("align.total_ms", n ? t_all.ms() : 0.0);
-    ctx->set_timing("align.upload_pack_ms", t_up.ms());
+    ctx->set_timing("align.total_ms", n ? job->t_all.ms() : 0.0);
+    ctx->set_timing("align.upload_pack_ms", job->t_up.ms());
     ctx->set_timing("align.index_ms", ms_index);
     ctx->set_timing("align.parse_ms", ms_parse);
     ctx->set_timing("align.host_prep_ms", host_prep_ms);
     ctx->set_timing("align.host_post_ms", host_post_ms);
     ctx->set_timing("align.batches", n_batches);
     ctx->set_timing("align.pairs", (double)n);
+}
+
+void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
+                         const vb_align_params *ap, int32_t *stats)
+{
+    const uint32_t ng = g->count();
+    std::vector<uint8_t> is_ref(ng, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (ref[i] >= ng || qry[i] >= ng) throw vb_error(VB_ERR_ARG, "pair id out of range");
+        is_ref[ref[i]] = 1;
+    }
+    vb_align_job *job = vb_align_job_begin(ctx, g, ap, is_ref.data());
+    try {
+        vb_align_job_run(job, ref, qry, n, stats);
+    } catch (...) {
+        vb_align_job_end(job);
+        throw;
+    }
+    vb_align_job_end(job);
 }

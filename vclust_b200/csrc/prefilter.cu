@@ -195,8 +195,6 @@ constexpr int MAX_BUCKET_BITS = 9;                        // per level
 constexpr int BUCKET_CAP = 2048;                          // tuples a bucket may hold to be grouped in shared memory
 constexpr int BUCKET_SLOTS = 4096;                        // hash slots per bucket (load <= 0.5)
 constexpr int BUCKET_TARGET = 1280;                       // planned mean bucket size (CAP is 20 sigma above it)
-constexpr int SMALL_GROUP = 32;                           // larger groups are sorted by the whole block
-constexpr uint32_t GROUP_HAS_DUP = 0x80000000u;            // flag in BucketSmem::cnt (count << 16 | start)
 
 struct MsdPlan {
     int b1, b2;              // bucket bits of level 1 and level 2 (b2 == 0: one level)
@@ -221,33 +219,177 @@ __device__ __forceinline__ bool extract_at(const uint32_t *__restrict__ seq2, co
     return true;
 }
 
-__global__ void __launch_bounds__(256) count_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
-                                                    const uint32_t *__restrict__ tile_gid, uint64_t n_slots, uint64_t n_iter,
-                                                    ExtractParams ep, int total_bits, uint32_t *__restrict__ hist,
-                                                    uint32_t *__restrict__ valid_cnt)
+// Singleton screen.  A k-mer that occurs once in the whole input shares nothing and is the common case (92 % of the
+// distinct k-mers of c2), so it is dropped before the partition: a table of 2-bit slots indexed by hash bits records
+// "seen" (bit 0) and "seen again" (bit 1); only tuples whose slot has bit 1 go on.  Every occurrence of a k-mer maps to
+// the same slot, so a k-mer with two or more occurrences (in any genomes, or twice in one genome) always survives;
+// a singleton survives only when it collides with another k-mer (harmless).  The table is sized to stay L2-resident.
+struct SeenTable {
+    uint32_t *words;        // nullptr: screen disabled, everything survives
+    uint64_t slot_mask;     // slots - 1 (power of two); 16 slots per word
+};
+
+__device__ __forceinline__ bool seen_twice(const SeenTable &T, uint64_t h)
 {
+    if (!T.words) return true;
+    const uint64_t s = (h >> 16) & T.slot_mask;
+    return (__ldg(T.words + (s >> 4)) >> (2 * (uint32_t)(s & 15) + 1)) & 1u;
+}
+
+constexpr int FINE_BITS = 2 * MAX_BUCKET_BITS;          // resolution of the survivor histogram taken during compaction
+
+// Append this block's surviving tuples (up to ITEMS per thread) to the compact list -- order is irrelevant, tuples are
+// grouped by hash later -- and count them in the fine histogram.  One global cursor atomic per call and block.  All
+// threads of the block must call; s_warp is [2][33] shared words, `phase` alternates 0/1 between successive calls so that
+// a call never overwrites prefixes another warp is still reading (two barriers per call instead of three).
+template <int ITEMS>
+__device__ __forceinline__ void block_append(const bool (&keep)[ITEMS], const uint64_t (&h)[ITEMS], const uint32_t (&gid)[ITEMS],
+                                             uint32_t (*s_warp)[33], int phase, unsigned long long *__restrict__ cursor,
+                                             uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
+                                             uint32_t *__restrict__ fine_hist)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t *sw = s_warp[phase];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) cnt += keep[r];
+    uint32_t x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) sw[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = lane < nw ? sw[lane] : 0, z = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+        const uint32_t total = __shfl_sync(0xffffffffu, z, 31);
+        unsigned long long base = 0;
+        if (lane == 0 && total) base = atomicAdd(cursor, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < nw) sw[lane] = (uint32_t)base + z - v;      // fewer than 2^32 slots per call, so the low word is enough
+    }
+    __syncthreads();
+    uint32_t o = sw[wid] + x - cnt;
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r)
+        if (keep[r]) {
+            out_keys[o] = h[r];
+            out_vals[o] = gid[r];
+            ++o;
+            atomicAdd(&fine_hist[(uint32_t)(h[r] >> (64 - FINE_BITS))], 1u);
+        }
+}
+
+
+// k1: one thread per base slot: h = fmix64(canonical k-mer) (a bijection; the preimage of ~0 is >= 2^63, not a k-mer, so
+// KEY_SENTINEL marks "no k-mer here"); valid k-mers per genome.  Each block owns a contiguous range of slots, so a warp
+// stays inside one genome for many iterations and keeps that genome's count in a register (one atomic per genome change).
+//   SCREEN: hbuf[p] = h, the seen table is updated, *n_again counts tuples that found their slot already marked;
+//           compact_kernel then picks the survivors.
+//   !SCREEN: every valid tuple survives and is appended to the compact list right here.
+template <bool SCREEN>
+__global__ void __launch_bounds__(512) hash_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
+                                                   const uint32_t *__restrict__ tile_gid, uint64_t n_slots, uint64_t n_iter,
+                                                   ExtractParams ep, uint64_t *__restrict__ hbuf, SeenTable T,
+                                                   uint32_t *__restrict__ valid_cnt, unsigned long long *__restrict__ n_again,
+                                                   unsigned long long *__restrict__ cursor, uint64_t *__restrict__ out_keys,
+                                                   uint32_t *__restrict__ out_vals, uint32_t *__restrict__ fine_hist)
+{
+    constexpr int HASH_ITEMS = SCREEN ? 1 : 4;             // the append amortises its barriers and cursor atomic over 4
+    __shared__ uint32_t s_warp[2][33];
     const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
     const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
-    // each block owns a contiguous range of slots, so a warp stays inside one genome for many iterations and can
-    // keep the genome's valid-k-mer count in a register (one atomic per genome change instead of one per 32 slots)
-    const uint64_t per_block = ((n_iter + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
-    const uint64_t p_end = min(n_iter, (blockIdx.x + 1) * per_block);
-    uint32_t acc_gid = 0xffffffffu, acc = 0;
-    for (uint64_t p = blockIdx.x * per_block + threadIdx.x; p < p_end; p += blockDim.x) {
-        uint64_t h; uint32_t gid = 0;
-        bool ok = extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, h, gid);
-        if (ok) atomicAdd(&hist[total_bits ? (uint32_t)(h >> (64 - total_bits)) : 0u], 1u);
-        unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (m) {
-            uint32_t g = __shfl_sync(0xffffffffu, gid, __ffs(m) - 1);       // a warp's 32 slots share the genome
-            if (g != acc_gid) {
-                if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
-                acc_gid = g; acc = 0;
+    const uint64_t chunk = (uint64_t)blockDim.x * HASH_ITEMS;
+    const uint64_t per_block = ((n_iter + gridDim.x - 1) / gridDim.x + chunk - 1) / chunk * chunk;
+    const uint64_t p_beg = min(n_iter, blockIdx.x * per_block), p_end = min(n_iter, p_beg + per_block);
+    uint32_t acc_gid = 0xffffffffu, acc = 0, again = 0;
+    int phase = 0;
+    for (uint64_t base = p_beg; base < p_end; base += chunk, phase ^= 1) {  // uniform trip count: block_append synchronises
+        bool ok[HASH_ITEMS];
+        uint64_t h[HASH_ITEMS];
+        uint32_t gid[HASH_ITEMS];
+#pragma unroll
+        for (int r = 0; r < HASH_ITEMS; ++r) {
+            const uint64_t p = base + (uint64_t)r * blockDim.x + threadIdx.x;       // whole warps are inside or outside
+            h[r] = KEY_SENTINEL; gid[r] = 0;
+            ok[r] = p < p_end && extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, h[r], gid[r]);
+            if (SCREEN) {
+                if (p < p_end) hbuf[p] = ok[r] ? h[r] : KEY_SENTINEL;
+                if (ok[r]) {
+                    const uint64_t s = (h[r] >> 16) & T.slot_mask;
+                    uint32_t *w = T.words + (s >> 4);
+                    const uint32_t b0 = 1u << (2 * (uint32_t)(s & 15));
+                    if (atomicOr(w, b0) & b0) { atomicOr(w, b0 << 1); ++again; }
+                }
             }
-            acc += (uint32_t)__popc(m);
+        }
+        if (!SCREEN) block_append<HASH_ITEMS>(ok, h, gid, s_warp, phase, cursor, out_keys, out_vals, fine_hist);
+#pragma unroll
+        for (int r = 0; r < HASH_ITEMS; ++r) {
+            unsigned m = __ballot_sync(0xffffffffu, ok[r]);
+            if (m) {
+                uint32_t g = __shfl_sync(0xffffffffu, gid[r], __ffs(m) - 1);    // a warp's 32 slots share the genome
+                if (g != acc_gid) {
+                    if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
+                    acc_gid = g; acc = 0;
+                }
+                acc += (uint32_t)__popc(m);
+            }
         }
     }
     if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
+    if (SCREEN) {
+        again = __reduce_add_sync(0xffffffffu, again);
+        if ((threadIdx.x & 31) == 0 && again) atomicAdd(n_again, (unsigned long long)again);
+    }
+}
+
+// SCREEN path: hbuf + seen table -> compact list of survivors + fine histogram
+constexpr int COMPACT_ITEMS = 8;
+__global__ void __launch_bounds__(256) compact_kernel(const uint64_t *__restrict__ hbuf, uint64_t n_iter, SeenTable T,
+                                                      const uint32_t *__restrict__ tile_gid,
+                                                      unsigned long long *__restrict__ cursor, uint64_t *__restrict__ out_keys,
+                                                      uint32_t *__restrict__ out_vals, uint32_t *__restrict__ fine_hist)
+{
+    __shared__ uint32_t s_warp[2][33];
+    const uint64_t chunk = 256ull * COMPACT_ITEMS;
+    int phase = 0;
+    for (uint64_t base = blockIdx.x * chunk; base < n_iter; base += (uint64_t)gridDim.x * chunk, phase ^= 1) {
+        bool keep[COMPACT_ITEMS];
+        uint64_t h[COMPACT_ITEMS];
+        uint32_t gid[COMPACT_ITEMS];
+#pragma unroll
+        for (int r = 0; r < COMPACT_ITEMS; ++r) {
+            const uint64_t p = base + r * 256 + threadIdx.x;
+            h[r] = p < n_iter ? hbuf[p] : KEY_SENTINEL;
+        }
+#pragma unroll
+        for (int r = 0; r < COMPACT_ITEMS; ++r) {
+            keep[r] = h[r] != KEY_SENTINEL && seen_twice(T, h[r]);
+            gid[r] = keep[r] ? tile_gid[(base + r * 256 + threadIdx.x) >> 7] : 0u;
+        }
+        block_append<COMPACT_ITEMS>(keep, h, gid, s_warp, phase, cursor, out_keys, out_vals, fine_hist);
+    }
+}
+
+// coarse bucket histogram (NB = 2^total_bits bins) from the fine one
+__global__ void __launch_bounds__(256) coarsen_kernel(const uint32_t *__restrict__ fine_hist, int total_bits, uint32_t *__restrict__ hist)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << FINE_BITS)) return;
+    const uint32_t c = fine_hist[i];
+    if (c) atomicAdd(&hist[total_bits ? (i >> (FINE_BITS - total_bits)) : 0u], c);
+}
+
+// number of slots with bit 1 set (= distinct slots that hold a repeated k-mer); survivors = *n_again + that number
+__global__ void __launch_bounds__(256) seen_popc_kernel(const uint32_t *__restrict__ words, uint64_t n_words,
+                                                        unsigned long long *__restrict__ n_slots_again)
+{
+    uint32_t c = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x)
+        c += __popc(words[i] & 0xaaaaaaaau);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_slots_again, (unsigned long long)c);
 }
 
 // exclusive scan of one value per thread over a 1024-thread block; returns the prefix, *total gets the sum
@@ -270,40 +412,6 @@ __device__ __forceinline__ uint32_t block_exscan_1024(uint32_t v, uint32_t *warp
     uint32_t pre = warp_tot[w] + x - v;
     __syncthreads();
     return pre;
-}
-
-// same, with the bucket histogram privatised in shared memory (NB <= 32768 bins = 128 KB): one block per SM, the
-// 40 M atomics stay on chip and only 148 x NB flush atomics reach L2
-__global__ void __launch_bounds__(1024) count_smem_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
-                                                          const uint32_t *__restrict__ tile_gid, uint64_t n_slots, uint64_t n_iter,
-                                                          ExtractParams ep, int total_bits, uint32_t nb,
-                                                          uint32_t *__restrict__ hist, uint32_t *__restrict__ valid_cnt)
-{
-    extern __shared__ uint32_t s_hist[];
-    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) s_hist[b] = 0;
-    __syncthreads();
-    const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
-    const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
-    const uint64_t per_block = ((n_iter + gridDim.x - 1) / gridDim.x + blockDim.x - 1) / blockDim.x * blockDim.x;
-    const uint64_t p_end = min(n_iter, (blockIdx.x + 1) * per_block);
-    uint32_t acc_gid = 0xffffffffu, acc = 0;
-    for (uint64_t p = blockIdx.x * per_block + threadIdx.x; p < p_end; p += blockDim.x) {
-        uint64_t h; uint32_t gid = 0;
-        bool ok = extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, h, gid);
-        if (ok) atomicAdd(&s_hist[total_bits ? (uint32_t)(h >> (64 - total_bits)) : 0u], 1u);
-        unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (m) {
-            uint32_t g = __shfl_sync(0xffffffffu, gid, __ffs(m) - 1);
-            if (g != acc_gid) {
-                if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
-                acc_gid = g; acc = 0;
-            }
-            acc += (uint32_t)__popc(m);
-        }
-    }
-    if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) { uint32_t c = s_hist[b]; if (c) atomicAdd(&hist[b], c); }
 }
 
 // one block: off[i] = exclusive prefix of hist (NB + 1 entries); cursor2 = off; cursor1[b] = off[b * B2];
@@ -333,13 +441,11 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *__restrict__
     if (threadIdx.x == 0) tile_start[pl.B1] = s_total;
 }
 
-// Partition one tile of tuples into buckets.  LEVEL 1: tuples come from the genomes (extraction fused), bucket = top b1
+// Partition one tile of tuples into buckets.  LEVEL 1: tuples come from the compact survivor list, bucket = top b1
 // bits of h.  LEVEL 2: tuples come from a level-1 bucket, bucket = next b2 bits.  Inside the block the tile is first
 // grouped by bucket in shared memory, so that every bucket receives one contiguous run per tile.
 template <int LEVEL>
-__global__ void __launch_bounds__(PART_THREADS) part_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
-                                                            const uint32_t *__restrict__ tile_gid, uint64_t n_slots,
-                                                            ExtractParams ep, MsdPlan pl, const uint64_t *__restrict__ in_keys,
+__global__ void __launch_bounds__(PART_THREADS) part_kernel(uint64_t n_in, MsdPlan pl, const uint64_t *__restrict__ in_keys,
                                                             const uint32_t *__restrict__ in_vals, const uint32_t *__restrict__ off,
                                                             const uint32_t *__restrict__ tile_start, uint32_t n_tiles,
                                                             uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys,
@@ -353,8 +459,6 @@ __global__ void __launch_bounds__(PART_THREADS) part_kernel(const uint32_t *__re
     uint32_t *s_fill = s_start + 512;
     uint32_t *s_gbase = s_fill + 512;
     __shared__ uint32_t s_total, s_bucket, s_tile_lo;
-    const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
-    const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
     const uint32_t NBK = (LEVEL == 1) ? pl.B1 : pl.B2;
     const int shift = (LEVEL == 1) ? (64 - pl.b1) : (64 - pl.b1 - pl.b2);
 
@@ -378,7 +482,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_kernel(const uint32_t *__re
             src_hi = min(src_lo + PART_TILE, end);
         } else {
             src_lo = (uint64_t)tile * PART_TILE;
-            src_hi = src_lo + PART_TILE;                                // extract_at checks n_slots
+            src_hi = min(src_lo + PART_TILE, n_in);
         }
         uint64_t key[PART_ITEMS];
         uint32_t val[PART_ITEMS];
@@ -386,12 +490,8 @@ __global__ void __launch_bounds__(PART_THREADS) part_kernel(const uint32_t *__re
 #pragma unroll
         for (int r = 0; r < PART_ITEMS; ++r) {
             uint64_t p = src_lo + (uint64_t)r * PART_THREADS + threadIdx.x;
-            bool ok;
-            if (LEVEL == 1) ok = extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, key[r], val[r]);
-            else {
-                ok = p < src_hi;
-                if (ok) { key[r] = in_keys[p]; val[r] = in_vals[p]; }
-            }
+            const bool ok = p < src_hi;
+            if (ok) { key[r] = in_keys[p]; val[r] = in_vals[p]; }
             bk[r] = 0xffffffffu;
             if (ok) {
                 bk[r] = (NBK > 1) ? (uint32_t)((key[r] >> shift) & (NBK - 1)) : 0u;
@@ -438,23 +538,14 @@ __global__ void __launch_bounds__(PART_THREADS) part_kernel(const uint32_t *__re
     }
 }
 
-// shared-memory layout of bucket_kernel (dynamic, 48.6 KB -> 4 blocks per SM).  Regions are reused once dead:
-//   keys  -> (after the insert phase) grp + sorted          table -> (after the insert phase) grp_slot
+// shared-memory layout of bucket_kernel (dynamic, 44 KB -> 5 blocks per SM)
+constexpr uint32_t CHAIN_END = 0x7fffu;        // prev[]: low 15 bits = previous tuple with the same k-mer
+constexpr uint32_t CHAIN_DUP = 0x8000u;        // prev[]: this tuple repeats a genome that is already in its chain
 struct BucketSmem {
-    union {
-        uint64_t keys[BUCKET_CAP];                                 // h of every tuple (insert phase)
-        struct { uint32_t grp[BUCKET_CAP]; uint32_t sorted[BUCKET_CAP]; } g;   // genome ids grouped by slot / sorted
-    } a;
+    uint64_t keys[BUCKET_CAP];                 // h of every tuple
     uint32_t gids[BUCKET_CAP];
-    union {
-        uint16_t table[BUCKET_SLOTS];      // slot -> index of the first tuple with that key (0xffff = empty)
-        uint16_t grp_slot[BUCKET_CAP];     // slot of every regrouped element
-    } t;
-    uint32_t cnt[BUCKET_SLOTS];            // tuples per slot, then (count << 16 | start)
-    uint32_t large[64];                    // slots whose group is larger than SMALL_GROUP
-    uint32_t n_large;
-    uint32_t n_pairs;
-    uint32_t warp_sum[8];
+    uint32_t table[BUCKET_SLOTS];              // slot -> the most recently inserted tuple with the slot's key
+    uint16_t prev[BUCKET_CAP];
 };
 
 __device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, int count_only, unsigned long long &local_inc, const PairAcc &A)
@@ -463,7 +554,11 @@ __device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, int count_only
     pair_add(A, a > b ? a : b, a > b ? b : a);
 }
 
-// One block per final bucket: group equal k-mers in shared memory, count duplicates per genome, emit pair increments.
+// One block per final bucket.  Equal k-mers are linked into chains through a shared-memory hash table: a tuple finds the
+// slot of its key and swaps itself in as the slot's newest member, keeping the previous one as its predecessor.  A
+// tuple's chain is then exactly the set of tuples with the same k-mer inserted before it, so walking it enumerates every
+// unordered pair of the group once -- no sort, no regrouping.  A tuple whose genome already occurs in its chain is a
+// within-genome duplicate (counted in dup_cnt, skipped by everybody else).
 // count_only: only sum the number of pair increments (sizing pass for very large N).
 __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                      const uint32_t *__restrict__ off, uint32_t n_buckets, int count_only,
@@ -473,7 +568,7 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
 {
     extern __shared__ unsigned char smem_raw[];
     BucketSmem &S = *(BucketSmem *)smem_raw;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     unsigned long long local_inc = 0;
     for (uint32_t bkt = blockIdx.x; bkt < n_buckets; bkt += gridDim.x) {
         const uint32_t beg = off[bkt], size = off[bkt + 1] - beg;
@@ -482,182 +577,50 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             if (tid == 0) big_list[atomicAdd(n_big, 1u)] = bkt;
             continue;
         }
-        for (int s = tid; s < BUCKET_SLOTS; s += 256) { S.t.table[s] = 0xffffu; S.cnt[s] = 0; }
-        for (uint32_t i = tid; i < size; i += 256) { S.a.keys[i] = keys[beg + i]; S.gids[i] = vals[beg + i]; }
-        if (tid == 0) S.n_large = 0;
+        for (int s = tid; s < BUCKET_SLOTS; s += 256) S.table[s] = 0xffffffffu;
+        for (uint32_t i = tid; i < size; i += 256) { S.keys[i] = keys[beg + i]; S.gids[i] = vals[beg + i]; }
         __syncthreads();
-        // ---- insert: every tuple finds the slot of its key
-        uint32_t my_slot[BUCKET_CAP / 256], my_rank[BUCKET_CAP / 256];
-#pragma unroll
-        for (int r = 0; r < BUCKET_CAP / 256; ++r) {
-            uint32_t i = tid + r * 256;
-            my_slot[r] = 0xffffffffu;
-            if (i < size) {
-                uint64_t k = S.a.keys[i];
-                uint32_t s = (uint32_t)k & (BUCKET_SLOTS - 1);                // low bits: independent of the bucket bits
-                for (;;) {
-                    uint32_t cur = S.t.table[s];
-                    if (cur == 0xffffu) {
-                        cur = atomicCAS(&S.t.table[s], (unsigned short)0xffffu, (unsigned short)i);
-                        if (cur == 0xffffu) cur = i;
-                    }
-                    if (S.a.keys[cur] == k) break;
-                    s = (s + 1) & (BUCKET_SLOTS - 1);
+        // ---- insert: chain every tuple to the earlier tuples with the same key
+        for (uint32_t i = tid; i < size; i += 256) {
+            const uint64_t k = S.keys[i];
+            uint32_t s = (uint32_t)k & (BUCKET_SLOTS - 1);                    // low bits: independent of the bucket bits
+            uint32_t pv = CHAIN_END;
+            for (;;) {
+                uint32_t cur = S.table[s];
+                if (cur == 0xffffffffu) {
+                    cur = atomicCAS(&S.table[s], 0xffffffffu, i);
+                    if (cur == 0xffffffffu) break;                            // first tuple with this key
                 }
-                my_slot[r] = s;
-                my_rank[r] = atomicAdd(&S.cnt[s], 1u);
+                if (S.keys[cur] == k) { pv = atomicExch(&S.table[s], i); break; }
+                s = (s + 1) & (BUCKET_SLOTS - 1);
             }
+            S.prev[i] = (uint16_t)pv;
         }
         __syncthreads();
-        // ---- exclusive scan of cnt over the slots (16 per thread); cnt becomes count << 16 | start
-        {
-            constexpr int PER = BUCKET_SLOTS / 256;
-            uint32_t loc[PER], sum = 0;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) { loc[j] = S.cnt[tid * PER + j]; sum += loc[j]; }
-            uint32_t x = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            if (lane == 31) S.warp_sum[wid] = x;
-            __syncthreads();
-            uint32_t pre = x - sum;
-            for (int j = 0; j < wid; ++j) pre += S.warp_sum[j];
-#pragma unroll
-            for (int j = 0; j < PER; ++j) { uint32_t c = loc[j]; S.cnt[tid * PER + j] = (c << 16) | pre; pre += c; }
-        }
-        __syncthreads();
-        // ---- regroup genome ids by slot (keys and table are dead from here on)
-#pragma unroll
-        for (int r = 0; r < BUCKET_CAP / 256; ++r) {
-            if (my_slot[r] != 0xffffffffu) {
-                uint32_t pos = (S.cnt[my_slot[r]] & 0xffffu) + my_rank[r];
-                S.a.g.grp[pos] = S.gids[tid + r * 256];
-                S.t.grp_slot[pos] = (uint16_t)my_slot[r];
-            }
-        }
-        __syncthreads();
-        // ---- sort every group by genome id: rank sort, one thread per element (groups are small)
-        for (uint32_t e = tid; e < size; e += 256) {
-            const uint32_t s = S.t.grp_slot[e], c = (S.cnt[s] >> 16) & 0x7fffu, st0 = S.cnt[s] & 0xffffu;
-            const uint32_t g = S.a.g.grp[e];
-            if (c > SMALL_GROUP) {
-                S.a.g.sorted[e] = g;
-                if (e == st0) { uint32_t q = atomicAdd(&S.n_large, 1u); if (q < 64) S.large[q] = s; atomicOr(&S.cnt[s], GROUP_HAS_DUP); }
-                continue;
-            }
-            uint32_t rank = 0, same = 0;
-            for (uint32_t x = st0; x < st0 + c; ++x) {
-                uint32_t gx = S.a.g.grp[x];
-                rank += (gx < g) || (gx == g && x < e);
-                same += gx == g;
-            }
-            S.a.g.sorted[st0 + rank] = g;
-            if (same > 1) atomicOr(&S.cnt[s], GROUP_HAS_DUP);      // a genome holds this k-mer more than once
-        }
-        __syncthreads();
-        if (S.n_large > 64) {                                                // pathological: leave it to the generic path
-            if (tid == 0) big_list[atomicAdd(n_big, 1u)] = bkt;
-            __syncthreads();
-            continue;
-        }
-        const uint32_t n_large = S.n_large;
-        for (uint32_t q = 0; q < n_large; ++q) {                             // block-wide bitonic sort (all-ascending form)
-            const uint32_t s = S.large[q], c = (S.cnt[s] >> 16) & 0x7fffu, st0 = S.cnt[s] & 0xffffu;
-            uint32_t *G = S.a.g.sorted + st0;
-            uint32_t n2 = 1; while (n2 < c) n2 <<= 1;
-            for (uint32_t k = 2; k <= n2; k <<= 1) {
-                for (uint32_t i = tid; i < n2; i += 256) {
-                    uint32_t l = i ^ (k - 1);
-                    if (l > i && l < c) { uint32_t a = G[i], b = G[l]; if (a > b) { G[i] = b; G[l] = a; } }
+        // ---- duplicates: same genome earlier in the chain
+        for (uint32_t i = tid; i < size; i += 256) {
+            const uint32_t g = S.gids[i];
+            uint32_t j = S.prev[i];                                           // no flag set yet in the own entry
+            while (j != CHAIN_END) {
+                if (S.gids[j] == g) {
+                    S.prev[i] = (uint16_t)(S.prev[i] | CHAIN_DUP);
+                    if (!count_only) atomicAdd(&dup_cnt[g], 1u);
+                    break;
                 }
-                __syncthreads();
-                for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-                    for (uint32_t i = tid; i < n2; i += 256) {
-                        uint32_t l = i ^ j;
-                        if (l > i && l < c) { uint32_t a = G[i], b = G[l]; if (a > b) { G[i] = b; G[l] = a; } }
-                    }
-                    __syncthreads();
-                }
+                j = S.prev[j] & CHAIN_END;
             }
-        }
-        // ---- pair increments.  Element e of a duplicate-free group pairs with the e - st0 elements before it; these
-        // pairs are numbered across the whole bucket (prefix sum) and dealt out evenly to the threads, four per thread
-        // and round so that the four table probes are in flight together.
-        uint32_t *pfx = S.gids;                                              // gids is dead: reuse for the prefix sums
-        __syncthreads();
-        {
-            constexpr int PER = BUCKET_CAP / 256;
-            uint32_t w[PER], sum = 0;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                uint32_t e = tid * PER + j;
-                w[j] = 0;
-                if (e < size) {
-                    uint32_t cs = S.cnt[S.t.grp_slot[e]];
-                    if (!(cs & GROUP_HAS_DUP)) w[j] = e - (cs & 0xffffu);
-                }
-                sum += w[j];
-            }
-            uint32_t x = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            if (lane == 31) S.warp_sum[wid] = x;
-            __syncthreads();
-            uint32_t pre = x - sum;
-            for (int j = 0; j < wid; ++j) pre += S.warp_sum[j];
-#pragma unroll
-            for (int j = 0; j < PER; ++j) { uint32_t e = tid * PER + j; if (e < size) pfx[e] = pre; pre += w[j]; }
-            if (tid == 255) S.n_pairs = pre;
         }
         __syncthreads();
-        const uint32_t n_pairs = S.n_pairs;
-        if (count_only) { if (tid == 0) local_inc += n_pairs; }
-        else {
-            for (uint32_t base = tid; base < n_pairs; base += 4 * 256) {
-                uint64_t key[4], h[4], cur[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t idx = base + q * 256;
-                    key[q] = SLOT_EMPTY;
-                    if (idx < n_pairs) {
-                        uint32_t lo = 0, hi = size;                          // last e with pfx[e] <= idx
-                        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (pfx[mid] <= idx) lo = mid; else hi = mid; }
-                        const uint32_t st0 = S.cnt[S.t.grp_slot[lo]] & 0xffffu;
-                        const uint32_t a = S.a.g.sorted[lo], b = S.a.g.sorted[st0 + (idx - pfx[lo])];      // a > b
-                        key[q] = ((uint64_t)a << 32) | b;
-                    }
-                }
-                if (A.dense) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (key[q] != SLOT_EMPTY) {
-                            const uint32_t a = (uint32_t)(key[q] >> 32), b = (uint32_t)key[q];
-                            atomicAdd(&A.dense[(uint64_t)a * (a - 1) / 2 + b], 1u);
-                        }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) if (key[q] != SLOT_EMPTY) { h[q] = fmix64(key[q]) & A.cap_mask; cur[q] = A.tkeys[h[q]]; }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (key[q] != SLOT_EMPTY) {
-                            if (cur[q] == key[q]) atomicAdd(&A.tvals[h[q]], 1u);
-                            else table_add(A, key[q], 1u);
-                        }
-                }
-            }
-        }
-        // groups with duplicates (and block-sorted large groups): element by element, skipping repeated genome ids
-        for (uint32_t e = tid; e < size; e += 256) {
-            const uint32_t cs = S.cnt[S.t.grp_slot[e]];
-            if (!(cs & GROUP_HAS_DUP)) continue;
-            const uint32_t st0 = cs & 0xffffu;
-            if (e == st0) continue;
-            const uint32_t g = S.a.g.sorted[e];
-            if (S.a.g.sorted[e - 1] == g) { if (!count_only) atomicAdd(&dup_cnt[g], 1u); continue; }
-            uint32_t prev = 0xffffffffu;
-            for (uint32_t j = st0; j < e; ++j) {
-                uint32_t gj = S.a.g.sorted[j];
-                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, A); prev = gj; }
+        // ---- pair increments: every non-duplicate tuple with every non-duplicate tuple before it in its chain
+        for (uint32_t i = tid; i < size; i += 256) {
+            const uint32_t pi = S.prev[i];
+            if (pi & CHAIN_DUP) continue;
+            const uint32_t g = S.gids[i];
+            uint32_t j = pi;
+            while (j != CHAIN_END) {
+                const uint32_t pj = S.prev[j];
+                if (!(pj & CHAIN_DUP)) emit_pair(g, S.gids[j], count_only, local_inc, A);
+                j = pj & CHAIN_END;
             }
         }
         __syncthreads();
@@ -884,7 +847,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     ep.shard_index = shard_index;
     ep.shard_count = shard_count;
 
-    DevBuf<unsigned long long> scalars(4);
+    DevBuf<unsigned long long> scalars(8);
     VB_CUDA(cudaMemsetAsync(scalars.p, 0, scalars.bytes(), st));
     const unsigned long long max_pairs = (unsigned long long)n * (n > 0 ? n - 1 : 0) / 2;
     unsigned long long n_inc = max_pairs;
@@ -919,6 +882,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         VB_CUDA(cudaStreamSynchronize(st));
     };
     rsort::Workspace ws;
+    unsigned long long n_survivors = 0;
     static const bool use_lsd = getenv("VB_PREFILTER_LSD") != nullptr;      // A/B switch: the round-1 LSD radix path
 
     if (use_lsd) {
@@ -947,39 +911,63 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         segment_pairs_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, dup_cnt, acc);
         VB_LAUNCH_CHECK(ctx);
     } else {
-        // ---- k1 + k2 + k3, MSD flavour: hash-bucket partition + shared-memory grouping
+        // ---- k1 + k2 + k3, MSD flavour: hash once, screen out singletons, hash-bucket partition, shared-memory grouping
         t_ext.start();
+        if (n_slots >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 base slots in one prefilter call");
+        const uint64_t n_iter = (n_slots + 31) / 32 * 32;
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+        // seen table: >= 4 slots per expected k-mer, at most 2^28 slots (64 MB, stays in the 126 MB L2); for inputs
+        // beyond ~2^27 k-mers the collision rate would let most singletons through, so the screen is switched off
+        static const char *seen_env = getenv("VB_PREFILTER_SEEN");          // "0": off, "N": force 2^N slots
+        const double est_all = (double)n_slots * std::min(1.0, p->kmers_fraction) / shard_count;
+        int seen_bits = 20;
+        while ((double)(1ULL << seen_bits) < 4.0 * est_all && seen_bits < 28) ++seen_bits;
+        bool use_seen = est_all <= (double)(1ULL << 27);
+        if (seen_env) { int v = atoi(seen_env); use_seen = v > 0; if (v >= 10 && v <= 34) seen_bits = v; }
+        DevBuf<uint32_t> fine_hist(1u << FINE_BITS);
+        VB_CUDA(cudaMemsetAsync(fine_hist.p, 0, fine_hist.bytes(), st));
+        DevBuf<uint64_t> keys0(n_iter + 64);                 // compact list of surviving (hash, genome) tuples
+        DevBuf<uint32_t> vals0(n_iter + 64);
+        unsigned long long *d_cursor = scalars.p + 6;
+        if (use_seen) {
+            DevBuf<uint64_t> hbuf(n_iter);
+            DevBuf<uint32_t> seen_words((1ULL << seen_bits) / 16);
+            VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
+            SeenTable seen = {seen_words.p, (1ULL << seen_bits) - 1};
+            hash_kernel<true><<<n_sm * 4, 512, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep, hbuf.p, seen,
+                                                        valid_cnt, scalars.p + 4, d_cursor, keys0.p, vals0.p, fine_hist.p);
+            VB_LAUNCH_CHECK(ctx);
+            compact_kernel<<<n_sm * 8, 256, 0, st>>>(hbuf.p, n_iter, seen, dg.tile_gid.p, d_cursor, keys0.p, vals0.p, fine_hist.p);
+            VB_LAUNCH_CHECK(ctx);
+        } else {
+            SeenTable seen = {nullptr, 0};
+            hash_kernel<false><<<n_sm * 4, 512, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep, nullptr, seen,
+                                                         valid_cnt, scalars.p + 4, d_cursor, keys0.p, vals0.p, fine_hist.p);
+            VB_LAUNCH_CHECK(ctx);
+        }
+        VB_CUDA(cudaMemcpyAsync(&n_survivors, d_cursor, sizeof(n_survivors), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));                  // the bucket plan and the grids below depend on the count
+        const uint64_t n_keep = n_survivors;
         MsdPlan pl;
         {
-            double est = (double)n_slots * std::min(1.0, p->kmers_fraction) / shard_count;
             int bits = 0;
-            while (est / (double)(1ULL << bits) > BUCKET_TARGET && bits < 2 * MAX_BUCKET_BITS) ++bits;
+            while ((double)n_keep / (double)(1ULL << bits) > BUCKET_TARGET && bits < FINE_BITS) ++bits;
             pl.b1 = (bits + 1) / 2; pl.b2 = bits - pl.b1;
             pl.B1 = 1u << pl.b1; pl.B2 = 1u << pl.b2; pl.NB = pl.B1 * pl.B2;
         }
-        if (n_slots >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 base slots in one prefilter call");
         DevBuf<uint32_t> hist(pl.NB), off(pl.NB + 1), cursor1(pl.B1), cursor2(pl.NB), tile_start(pl.B1 + 1), big_list(pl.NB + 1);
         DevBuf<uint32_t> n_big(1);
         VB_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
         VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
-        const uint64_t n_iter = (n_slots + 31) / 32 * 32;
-        if (pl.NB <= 32768) {
-            static bool cattr = false;
-            if (!cattr) { VB_CUDA(cudaFuncSetAttribute(count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4)); cattr = true; }
-            int n_sm = 148;
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-            count_smem_kernel<<<n_sm, 1024, pl.NB * sizeof(uint32_t), st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep,
-                                                                           pl.b1 + pl.b2, pl.NB, hist.p, valid_cnt);
-        } else
-            count_kernel<<<grid_for(n_iter), 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep, pl.b1 + pl.b2,
-                                                          hist.p, valid_cnt);
+        coarsen_kernel<<<(1u << FINE_BITS) / 256, 256, 0, st>>>(fine_hist.p, pl.b1 + pl.b2, hist.p);
         VB_LAUNCH_CHECK(ctx);
         scan_kernel<<<1, 1024, 0, st>>>(hist.p, pl, off.p, cursor1.p, cursor2.p, tile_start.p);
         VB_LAUNCH_CHECK(ctx);
         t_ext.stop();
         t_sort.start();
-        DevBuf<uint64_t> keys1(n_slots + 64), keys2(pl.b2 ? n_slots + 64 : 1);
-        DevBuf<uint32_t> vals1(n_slots + 64), vals2(pl.b2 ? n_slots + 64 : 1);
+        DevBuf<uint64_t> keys1(n_keep + 64), keys2(pl.b2 ? n_keep + 64 : 1);
+        DevBuf<uint32_t> vals1(n_keep + 64), vals2(pl.b2 ? n_keep + 64 : 1);
         const size_t part_smem = PART_TILE * 12 + 4 * 512 * sizeof(uint32_t);
         static bool attr_done = false;
         if (!attr_done) {
@@ -988,17 +976,17 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
             VB_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
             attr_done = true;
         }
-        const uint32_t tiles1 = (uint32_t)((n_slots + PART_TILE - 1) / PART_TILE);
-        part_kernel<1><<<std::min<uint32_t>(tiles1, 148 * 8), PART_THREADS, part_smem, st>>>(
-            dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, ep, pl, nullptr, nullptr, off.p, tile_start.p, tiles1, cursor1.p,
-            keys1.p, vals1.p);
-        VB_LAUNCH_CHECK(ctx);
+        const uint32_t tiles1 = (uint32_t)((n_keep + PART_TILE - 1) / PART_TILE);
         uint64_t *fkeys = keys1.p;
         uint32_t *fvals = vals1.p;
+        if (tiles1) {
+            part_kernel<1><<<std::min<uint32_t>(tiles1, 148 * 8), PART_THREADS, part_smem, st>>>(
+                n_keep, pl, keys0.p, vals0.p, off.p, tile_start.p, tiles1, cursor1.p, keys1.p, vals1.p);
+            VB_LAUNCH_CHECK(ctx);
+        }
         if (pl.b2) {
             part_kernel<2><<<std::min<uint32_t>(tiles1 + pl.B1, 148 * 8), PART_THREADS, part_smem, st>>>(
-                dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, ep, pl, keys1.p, vals1.p, off.p, tile_start.p, 0, cursor2.p,
-                keys2.p, vals2.p);
+                n_keep, pl, keys1.p, vals1.p, off.p, tile_start.p, 0, cursor2.p, keys2.p, vals2.p);
             VB_LAUNCH_CHECK(ctx);
             fkeys = keys2.p; fvals = vals2.p;
         }
@@ -1120,6 +1108,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     ctx->set_timing("prefilter.segment_ms", t_seg.ms());
     ctx->set_timing("prefilter.emit_ms", t_emit.ms());
     ctx->set_timing("prefilter.tuples", (double)dg.total_slots);
+    ctx->set_timing("prefilter.survivors", (double)n_survivors);
     ctx->set_timing("prefilter.pair_increments", (double)n_inc);
     ctx->set_timing("prefilter.table_slots", (double)cap);
     ctx->set_timing("prefilter.candidates", (double)n_emit);

@@ -313,59 +313,70 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
     vb_enter(ctx);
     const auto h0 = std::chrono::steady_clock::now();
     const uint32_t n = g->count();
-    std::vector<uint32_t> order = vb_lz_order(g);
-    std::vector<uint32_t> rank(n);
-    for (uint32_t i = 0; i < n; ++i) rank[order[i]] = i;
-
-    // directed pair list in LZ-ANI ids, grouped by reference with the queries ascending (results rows are sorted, :253);
-    // built as a CSR (count, prefix, fill, sort each row)
-    std::vector<uint64_t> start(n + 1, 0);
-    if (!pairs) {
-        for (uint32_t r = 0; r < n; ++r) start[r + 1] = start[r] + (n - 1);
-    } else {
+    // which genomes are references?  (every genome that occurs in a pair: the list is symmetrised)  The reference side
+    // of the work is launched now; the pair list is built on the host while the GPU indexes the references.
+    std::vector<uint8_t> is_ref(n, pairs ? 0 : 1);
+    if (pairs)
         for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
             uint32_t a = pairs->row[i], b = pairs->col[i];
             if (a >= n || b >= n) throw vb_error(VB_ERR_ARG, "vb_align: pair id out of range");
-            start[rank[a] + 1]++;                    // filter[i].push(id); filter[id].push(i)
-            start[rank[b] + 1]++;
+            is_ref[a] = 1; is_ref[b] = 1;
         }
-        for (uint32_t r = 0; r < n; ++r) start[r + 1] += start[r];
-    }
-    const uint64_t total = start[n];
-    vb_align_out *res = vb_align_out_alloc(total, n);
-    std::copy(order.begin(), order.end(), res->order);
-    if (!pairs) {
-        uint64_t w = 0;
-        for (uint32_t r = 0; r < n; ++r)
-            for (uint32_t q = 0; q < n; ++q) if (q != r) { res->ref[w] = r; res->qry[w] = q; ++w; }
-    } else {
-        std::vector<uint64_t> fill(start.begin(), start.end() - 1);
-        for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
-            uint32_t a = rank[pairs->row[i]], b = rank[pairs->col[i]];
-            res->qry[fill[a]++] = b;
-            res->qry[fill[b]++] = a;
-        }
-        for (uint32_t r = 0; r < n; ++r) {
-            std::sort(res->qry + start[r], res->qry + start[r + 1]);
-            std::fill(res->ref + start[r], res->ref + start[r + 1], r);
-        }
-    }
-    std::vector<uint32_t> in_ref(total), in_qry(total);
-    for (uint64_t w = 0; w < total; ++w) { in_ref[w] = order[res->ref[w]]; in_qry[w] = order[res->qry[w]]; }
-    std::vector<int32_t> stats(3 * std::max<uint64_t>(total, 1));
-    const double api_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    if (!pairs && n < 2) std::fill(is_ref.begin(), is_ref.end(), 0);
+    vb_align_job *job = vb_align_job_begin(ctx, g, p, is_ref.data());
+    vb_align_out *res = nullptr;
     try {
-        vb_align_pairs_impl(ctx, g, in_ref.data(), in_qry.data(), total, p, stats.data());
+        std::vector<uint32_t> order = vb_lz_order(g);
+        std::vector<uint32_t> rank(n);
+        for (uint32_t i = 0; i < n; ++i) rank[order[i]] = i;
+        // directed pair list in LZ-ANI ids, grouped by reference with the queries ascending (results rows are sorted,
+        // :253); built as a CSR (count, prefix, fill, sort each row)
+        std::vector<uint64_t> start(n + 1, 0);
+        if (!pairs) {
+            for (uint32_t r = 0; r < n; ++r) start[r + 1] = start[r] + (n - 1);
+        } else {
+            for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
+                start[rank[pairs->row[i]] + 1]++;        // filter[i].push(id); filter[id].push(i)
+                start[rank[pairs->col[i]] + 1]++;
+            }
+            for (uint32_t r = 0; r < n; ++r) start[r + 1] += start[r];
+        }
+        const uint64_t total = start[n];
+        res = vb_align_out_alloc(total, n);
+        std::copy(order.begin(), order.end(), res->order);
+        if (!pairs) {
+            uint64_t w = 0;
+            for (uint32_t r = 0; r < n; ++r)
+                for (uint32_t q = 0; q < n; ++q) if (q != r) { res->ref[w] = r; res->qry[w] = q; ++w; }
+        } else {
+            std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+            for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
+                uint32_t a = rank[pairs->row[i]], b = rank[pairs->col[i]];
+                res->qry[fill[a]++] = b;
+                res->qry[fill[b]++] = a;
+            }
+            for (uint32_t r = 0; r < n; ++r) {
+                std::sort(res->qry + start[r], res->qry + start[r + 1]);
+                std::fill(res->ref + start[r], res->ref + start[r + 1], r);
+            }
+        }
+        std::vector<uint32_t> in_ref(total), in_qry(total);
+        for (uint64_t w = 0; w < total; ++w) { in_ref[w] = order[res->ref[w]]; in_qry[w] = order[res->qry[w]]; }
+        std::vector<int32_t> stats(3 * std::max<uint64_t>(total, 1));
+        const double api_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+        vb_align_job_run(job, in_ref.data(), in_qry.data(), total, stats.data());
         ctx->set_timing("align.api_prep_ms", api_prep_ms);
+        for (uint64_t i = 0; i < total; ++i) {
+            res->sym_in_matches[i] = stats[3 * i];
+            res->sym_in_literals[i] = stats[3 * i + 1];
+            res->no_components[i] = stats[3 * i + 2];
+        }
     } catch (...) {
-        vb_align_out_free(res);
+        vb_align_job_end(job);
+        if (res) vb_align_out_free(res);
         throw;
     }
-    for (uint64_t i = 0; i < total; ++i) {
-        res->sym_in_matches[i] = stats[3 * i];
-        res->sym_in_literals[i] = stats[3 * i + 1];
-        res->no_components[i] = stats[3 * i + 2];
-    }
+    vb_align_job_end(job);
     *out = res;
     VB_GUARD_END
 }

@@ -64,5 +64,12 @@ struct vb_ctx {
 
 void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, uint32_t shard_index,
                        uint32_t shard_count, vb_pairs **out);
+// vb_align in two steps: _begin uploads the genomes and launches the reference texts + anchor tables of the genomes
+// flagged in is_ref[n_genomes] (asynchronously); _run takes the directed pairs (every reference must have been
+// flagged) and returns the statistics; _end releases the device buffers (LIFO after everything _run allocated).
+struct vb_align_job;
+vb_align_job *vb_align_job_begin(vb_ctx *ctx, const vb_genomes *g, const vb_align_params *p, const uint8_t *is_ref);
+void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qry, uint64_t n, int32_t *stats);
+void vb_align_job_end(vb_align_job *job);
 void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
                          const vb_align_params *p, int32_t *stats);
