@@ -167,6 +167,32 @@ int vb_write_ani(const vb_genomes *g, const vb_align_out *res, const char *ani_p
                  const char *const *columns, int n_columns, const double out_filters[5]);
 void vb_align_out_free(vb_align_out *r);
 
+/* ---- alignment regions (vclust align --out-aln -> lz-ani --out-alignment) ------------------------------------ */
+/* One row per local alignment (a component of the parse at least `reg` symbols long; parser.cpp:786-837 calc_regions).
+ * ref / qry are INPUT-order genome ids; coordinates are 0-based half-open: [q_start, q_end) in the query and
+ * [r_start, r_end) in the reference TEXT (forward genome, 2*mrd separators, reverse complement), exactly the
+ * region_t fields of lz-ani defs.h:67-142.  Rows are grouped by directed pair (in the order of the call's result),
+ * inside a pair sorted like calc_regions: longer first, then smaller q_start. */
+typedef struct vb_regions {
+    uint64_t n;
+    uint32_t *ref;
+    uint32_t *qry;
+    int32_t *q_start, *q_end, *r_start, *r_end, *matches, *mismatches;
+    int32_t mrd;            /* needed to map reverse-strand coordinates (lz_matcher.cpp:113,158-162) */
+} vb_regions;
+
+/* vb_align that also returns the regions of every directed pair (either out pointer may be NULL). */
+int vb_align_regions(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_align_params *p, vb_align_out **out,
+                     vb_regions **regions);
+/* vb_align_pairs that also returns the regions (explicit directed pairs, INPUT-order ids). */
+int vb_align_pairs_regions(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
+                           const vb_align_params *p, int32_t *stats, vb_regions **regions);
+/* Replaces: CLZMatcher::store_alignment (lz_matcher.cpp:102-169): writes the alignment TSV (header lz_matcher.h:68).
+ * out_filters as in vb_write_ani; only gani, ani and qcov apply here, computed per directed pair from its regions.
+ * The reference writes the pairs in thread-completion order; this writer uses the deterministic order of `regions`. */
+int vb_write_aln(const vb_genomes *g, const vb_regions *regions, const char *path, const double out_filters[5]);
+void vb_regions_free(vb_regions *r);
+
 #ifdef __cplusplus
 }
 #endif

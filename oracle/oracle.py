@@ -325,6 +325,75 @@ def run_pairs(codes, pair_ref, pair_qry, params: LzParams | None = None) -> np.n
     return st
 
 
+class LzRegion(C.Structure):                     # lzo_region in lz_oracle.c (region_t, lz-ani defs.h:67-142)
+    _fields_ = [(k, C.c_int) for k in ("ref_start", "ref_end", "seq_start", "seq_end", "num_matches", "num_mismatches")]
+
+
+def run_pairs_regions(codes, pair_ref, pair_qry, params: LzParams | None = None):
+    """Like run_pairs, plus the regions of every pair (calc_regions order): list of (n_i, 6) int arrays
+    [ref_start, ref_end, seq_start, seq_end, matches, mismatches]."""
+    L = lib()
+    params = params or LzParams.default()
+    L.lzo_create.restype = C.c_void_p
+    L.lzo_create.argtypes = [C.POINTER(LzParams)]
+    L.lzo_destroy.argtypes = [C.c_void_p]
+    L.lzo_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.lzo_parse_query.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.lzo_last_regions.argtypes = [C.c_void_p, C.POINTER(LzRegion), C.c_int]
+    L.lzo_last_regions.restype = C.c_int
+    ctx = L.lzo_create(C.byref(params))
+    stats = np.zeros((len(pair_ref), 3), dtype=np.int32)
+    regions = []
+    cap = 1 << 16
+    buf = (LzRegion * cap)()
+    st = (C.c_int * 3)()
+    cur = None
+    try:
+        for k in np.argsort(np.asarray(pair_ref), kind="stable"):
+            r, q = int(pair_ref[k]), int(pair_qry[k])
+            if r != cur:
+                ref = np.ascontiguousarray(codes[r], dtype=np.uint8)
+                L.lzo_set_reference(ctx, ref.ctypes.data, ref.size)
+                cur = r
+            qc = np.ascontiguousarray(codes[q], dtype=np.uint8)
+            L.lzo_parse_query(ctx, qc.ctypes.data, qc.size, st)
+            stats[k] = list(st)
+            n = L.lzo_last_regions(ctx, buf, cap)
+            regions.append((int(k), np.array([[b.ref_start, b.ref_end, b.seq_start, b.seq_end, b.num_matches, b.num_mismatches]
+                                              for b in buf[:n]], dtype=np.int64).reshape(n, 6)))
+    finally:
+        L.lzo_destroy(ctx)
+    regions.sort(key=lambda t: t[0])
+    return stats, [r for _, r in regions]
+
+
+def aln_lines(names, codes, pair_ref, pair_qry, params: LzParams | None = None, out_filters=None):
+    """lz-ani --out-alignment rows (without the header) for directed pairs in INPUT ids, as a list of strings:
+    CLZMatcher::store_alignment, L/lz_matcher.cpp:102-169.  The reference writes them in thread-completion order, so
+    callers compare sorted lists."""
+    params = params or LzParams.default()
+    flt = {k: float(v) for k, v in (out_filters or {}).items() if v}
+    _, regs = run_pairs_regions(codes, pair_ref, pair_qry, params)
+    out = []
+    for k, rg in enumerate(regs):
+        r, q = int(pair_ref[k]), int(pair_qry[k])
+        len1, len2 = int(codes[r].size), int(codes[q].size)
+        rc_corr = 2 * len1 + 2 * params.mrd + 1
+        if flt:
+            m, l = int(rg[:, 4].sum()), int(rg[:, 5].sum())
+            if m / len2 < flt.get("gani", 0) or (m / (m + l) if m + l else 0.0) < flt.get("ani", 0) or (m + l) / len2 < flt.get("qcov", 0):
+                continue
+        for rs, re_, ss, se, nm, nmm in rg.tolist():
+            ln = se - ss
+            if rs < len1:
+                a, b = 1 + rs, re_
+            else:
+                a, b = rc_corr - (1 + rs), rc_corr - re_
+            out.append("\t".join([names[q], names[r], real_str(100.0 * nm / ln, 6), str(ln), str(1 + ss), str(se), str(a), str(b),
+                                   str(nm), str(nmm)]))
+    return out
+
+
 def real_str(val: float, prec: int) -> str:
     """refresh::real_to_pchar (lz-ani/libs/refresh/conversions/lib/numeric_conversions.h:229-299,342-390):
     shortest round-trip decimal, then round-half-up to `prec` significant digits, no zero padding."""

@@ -151,6 +151,47 @@ def test_align_pairs_vs_oracle_params(ctx, params):
     assert bad.size == 0, "first mismatches: %s" % [(int(ref[i]), int(qry[i]), got[i].tolist(), want[i].tolist()) for i in bad[:5]]
 
 
+# ---------------------------------------------------------------- --out-aln (alignment regions)
+def test_out_aln_example_vs_golden(ctx, golden, tmp_path):
+    import gzip
+    api.align([golden / "example" / "multifasta.fna.gz"], tmp_path / "ani.tsv", True, out_aln=tmp_path / "ani.aln.tsv")
+    assert (tmp_path / "ani.tsv").read_bytes() == (golden / "example" / "ani.tsv").read_bytes()
+    got = (tmp_path / "ani.aln.tsv").read_text().splitlines()
+    want = gzip.open(golden / "example" / "ani.aln.tsv.gz", "rt").read().splitlines()
+    assert got[0] == want[0]
+    assert sorted(got[1:]) == sorted(want[1:])
+
+
+@pytest.mark.parametrize("params", [
+    {},
+    dict(mal=9, msl=5, mrd=20, mqd=60, reg=20, aw=8, am=3, ar=1),
+    dict(mal=13, msl=8, mrd=60, mqd=50, reg=40, aw=20, am=9, ar=4),
+])
+def test_regions_vs_oracle(ctx, params):
+    names, seqs = synth.make_genomes(n=32, length=(1500, 12000), family=4, seed=321, max_div=0.25, n_frac=0.3, lower_frac=0.2)
+    seqs = [s.tobytes() for s in seqs] + [b"", b"ACGTTGCA" * 40, b"N" * 200]
+    names = names + ["e0", "e1", "e2"]
+    n = len(names)
+    rng = np.random.default_rng(17)
+    ref = rng.integers(0, n, size=700)
+    qry = rng.integers(0, n, size=700)
+    ref[:300] = np.arange(300) % 32
+    qry[:300] = (ref[:300] // 4) * 4 + rng.integers(0, 4, size=300)
+    g = api.Genomes.from_memory(names, seqs)
+    st, regions = api.align_pairs_regions(ctx, g, ref, qry, api.align_params(**params))
+    codes = [oracle.lz_codes(s) for s in seqs]
+    want_st, want_regs = oracle.run_pairs_regions(codes, ref, qry, oracle.LzParams.default(**params))
+    assert np.array_equal(st, want_st)
+    assert np.array_equal(st, api.align_pairs(ctx, g, ref, qry, api.align_params(**params)))    # both kernel variants agree
+    tab = regions.table()
+    want_rows = []
+    for k, rg in enumerate(want_regs):                       # oracle columns: ref_start, ref_end, seq_start, seq_end, m, mm
+        for rs, re_, ss, se, m, mm in rg.tolist():
+            want_rows.append((int(ref[k]), int(qry[k]), ss, se, rs, re_, m, mm))
+    # duplicates of a (ref, qry) pair in the input list produce duplicate regions on both sides; compare as multisets
+    assert sorted(map(tuple, tab.tolist())) == sorted(want_rows)
+
+
 # ---------------------------------------------------------------- multi-GPU building blocks (on one GPU)
 @pytest.mark.parametrize("world", [2, 3])
 def test_prefilter_partial_shards_sum_to_full(ctx, golden, world):

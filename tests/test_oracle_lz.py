@@ -65,3 +65,16 @@ def test_against_reference_binary_outputs(golden, tmp_path, case):
     ani, _, _ = oracle.align_text(names, codes, adj=adj, params=oracle.LzParams.default(**LZP[case]),
                                   columns=oracle.OUTFMT["complete"])
     assert ani.encode() == (golden / "ref_synth" / (case + ".ani.tsv")).read_bytes()
+
+
+def test_example_alignment_regions_vs_golden(golden):
+    """calc_regions / store_alignment restatement against example/output/ani.aln.tsv (row order in the reference depends
+    on thread timing, so the rows are compared as a sorted list)."""
+    names, codes = oracle.load_genomes_lzani([golden / "example" / "multifasta.fna.gz"], True)
+    n = len(names)
+    pr = [r for r in range(n) for q in range(n) if q != r]
+    pq = [q for r in range(n) for q in range(n) if q != r]
+    got = sorted(oracle.aln_lines(names, codes, pr, pq))
+    want = gzip.open(golden / "example" / "ani.aln.tsv.gz", "rt").read().splitlines()
+    assert want[0] == "query\treference\tpident\talnlen\tqstart\tqend\trstart\trend\tnt_match\tnt_mismatch"
+    assert got == sorted(want[1:])

@@ -13,6 +13,7 @@ EXPORTS = [
     "vb_ctx_launches", "vb_ctx_mark", "vb_ctx_elapsed_ms", "vb_genomes_make_resident", "vb_genomes_evict", "vb_genomes_load", "vb_genomes_from_memory", "vb_genomes_count", "vb_genomes_name",
     "vb_genomes_length", "vb_genomes_total_bases", "vb_genomes_free", "vb_prefilter", "vb_write_filter",
     "vb_read_filter", "vb_pairs_free", "vb_prefilter_partial", "vb_pairs_merge", "vb_align_out_from_pairs", "vb_align", "vb_align_pairs", "vb_write_ani", "vb_align_out_free",
+    "vb_align_regions", "vb_align_pairs_regions", "vb_write_aln", "vb_regions_free",
 ]
 
 
@@ -41,6 +42,12 @@ class AlignOut(C.Structure):
     _fields_ = [("n", C.c_uint64), ("ref", C.POINTER(C.c_uint32)), ("qry", C.POINTER(C.c_uint32)),
                 ("sym_in_matches", C.POINTER(C.c_int32)), ("sym_in_literals", C.POINTER(C.c_int32)),
                 ("no_components", C.POINTER(C.c_int32)), ("n_genomes", C.c_uint32), ("order", C.POINTER(C.c_uint32))]
+
+
+class Regions(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("ref", C.POINTER(C.c_uint32)), ("qry", C.POINTER(C.c_uint32))] + \
+               [(k, C.POINTER(C.c_int32)) for k in ("q_start", "q_end", "r_start", "r_end", "matches", "mismatches")] + \
+               [("mrd", C.c_int32)]
 
 
 _lib = None
@@ -86,6 +93,11 @@ def load():
         "vb_align_pairs": (i32, [vp, vp, vp, vp, u64, C.POINTER(AlignParams), vp]),
         "vb_write_ani": (i32, [vp, C.POINTER(AlignOut), cp, cp, C.POINTER(cp), i32, C.POINTER(dbl)]),
         "vb_align_out_free": (None, [C.POINTER(AlignOut)]),
+        "vb_align_regions": (i32, [vp, vp, C.POINTER(Pairs), C.POINTER(AlignParams), C.POINTER(C.POINTER(AlignOut)),
+                                   C.POINTER(C.POINTER(Regions))]),
+        "vb_align_pairs_regions": (i32, [vp, vp, vp, vp, u64, C.POINTER(AlignParams), vp, C.POINTER(C.POINTER(Regions))]),
+        "vb_write_aln": (i32, [vp, C.POINTER(Regions), cp, C.POINTER(dbl)]),
+        "vb_regions_free": (None, [C.POINTER(Regions)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

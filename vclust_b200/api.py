@@ -327,6 +327,66 @@ def align_pairs(ctx: Context, genomes: Genomes, ref: Iterable[int], qry: Iterabl
     return st
 
 
+class RegionList:
+    """Alignment regions (vb_regions): one row per local alignment, grouped by directed pair."""
+
+    def __init__(self, ptr):
+        self._p = ptr
+        self._L = _lib.load()
+
+    @property
+    def n(self) -> int:
+        return int(self._p.contents.n)
+
+    def _arr(self, name, dtype):
+        return np.ctypeslib.as_array(getattr(self._p.contents, name), shape=(self.n,)).astype(dtype) if self.n else np.zeros(0, dtype)
+
+    def table(self) -> np.ndarray:
+        """(n, 8) int64: ref, qry (input-order ids), q_start, q_end, r_start, r_end, matches, mismatches."""
+        cols = [self._arr("ref", np.int64), self._arr("qry", np.int64)] + \
+               [self._arr(k, np.int64) for k in ("q_start", "q_end", "r_start", "r_end", "matches", "mismatches")]
+        return np.stack(cols, axis=1) if self.n else np.zeros((0, 8), np.int64)
+
+    def close(self):
+        if self._p:
+            self._L.vb_regions_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def align_genomes_regions(ctx: Context, genomes: Genomes, pairs: PairList | None = None, params: AlignParams | None = None):
+    """vb_align_regions: the statistics of vb_align plus the alignment regions of every directed pair."""
+    params = params or align_params()
+    out = C.POINTER(AlignOut)()
+    reg = C.POINTER(_lib.Regions)()
+    check(ctx._L.vb_align_regions(ctx._h, genomes._h, pairs._p if pairs is not None else None, C.byref(params),
+                                  C.byref(out), C.byref(reg)))
+    return AlignResult(out), RegionList(reg)
+
+
+def align_pairs_regions(ctx: Context, genomes: Genomes, ref: Iterable[int], qry: Iterable[int],
+                        params: AlignParams | None = None):
+    params = params or align_params()
+    r = np.ascontiguousarray(ref, dtype=np.uint32)
+    q = np.ascontiguousarray(qry, dtype=np.uint32)
+    st = np.zeros((r.size, 3), dtype=np.int32)
+    reg = C.POINTER(_lib.Regions)()
+    check(ctx._L.vb_align_pairs_regions(ctx._h, genomes._h, r.ctypes.data, q.ctypes.data, r.size, C.byref(params),
+                                        st.ctypes.data, C.byref(reg)))
+    return st, RegionList(reg)
+
+
+def write_aln(genomes: Genomes, regions: RegionList, path, out_filters: dict | None = None) -> None:
+    of = out_filters or {}
+    flt = (C.c_double * 5)(*[float(of.get(k, 0) or 0) for k in ("tani", "gani", "ani", "qcov", "rcov")])
+    check(_lib.load().vb_write_aln(genomes._h, regions._p, str(path).encode(), flt))
+
+
 def write_ani(genomes: Genomes, res: AlignResult, ani_path, ids_path=None, columns: Sequence[str] | None = None,
               out_filters: dict | None = None) -> None:
     columns = list(columns or ALIGN_OUTFMT["standard"])
@@ -359,12 +419,17 @@ def prefilter(input_paths: Sequence, output_path, is_multisample_fasta: bool, km
 
 def align(input_paths: Sequence, output_path, is_multisample_fasta: bool, out_format: Sequence[str] | None = None,
           filter_file=None, filter_threshold: float = 0.0, out_filters: dict | None = None, mal=11, msl=7, mrd=40,
-          mqd=40, reg=35, aw=15, am=7, ar=3, device: int = 0) -> dict:
-    """`vclust align` body: cmd_lzani (vclust.py:1058-1181)."""
+          mqd=40, reg=35, aw=15, am=7, ar=3, device: int = 0, out_aln=None) -> dict:
+    """`vclust align` body: cmd_lzani (vclust.py:1058-1181); out_aln = --out-aln (lz-ani --out-alignment)."""
     with Context(device) as ctx:
         g = Genomes.load(input_paths, is_multisample_fasta, FASTA_LZANI, sep_len=mrd)
         pairs = read_filter(filter_file, filter_threshold, g) if filter_file else None
-        res = align_genomes(ctx, g, pairs, align_params(mal, msl, mrd, mqd, reg, aw, am, ar))
+        if out_aln:
+            res, regions = align_genomes_regions(ctx, g, pairs, align_params(mal, msl, mrd, mqd, reg, aw, am, ar))
+            write_aln(g, regions, out_aln, out_filters)
+            regions.close()
+        else:
+            res = align_genomes(ctx, g, pairs, align_params(mal, msl, mrd, mqd, reg, aw, am, ar))
         write_ani(g, res, output_path, None, out_format or ALIGN_OUTFMT["standard"], out_filters)
         info = ctx.timings("align")
         res.close()

@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in SOURCES:
         obj = obj_dir / (src + ".o")
         objs.append(str(obj))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("VB_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

@@ -100,16 +100,13 @@ def handle_prefilter(args, parser, logger) -> None:
 
 def handle_align(args, parser, logger) -> None:
     args = _fasta_inputs(args, parser)
-    if args.aln_path:
-        logger.error("--out-aln is not available on the GPU path yet (SURVEY 8(f) rank 1); use the reference lz-ani for it")
-        sys.exit(1)
     try:
         info = api.align(args.fasta_paths, args.output_path, args.is_multifasta,
                          out_format=api.ALIGN_OUTFMT[args.outfmt], filter_file=args.filter_path,
                          filter_threshold=args.filter_threshold,
                          out_filters=dict(tani=args.tani, gani=args.gani, ani=args.ani, qcov=args.qcov, rcov=args.rcov),
                          mal=args.mal, msl=args.msl, mrd=args.mrd, mqd=args.mqd, reg=args.reg, aw=args.aw, am=args.am,
-                         ar=args.ar, device=args.device)
+                         ar=args.ar, device=args.device, out_aln=args.aln_path)
     except (api.VbError, ImportError) as e:
         logger.error(f"align failed with message: {e}")
         sys.exit(1)

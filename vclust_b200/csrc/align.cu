@@ -472,15 +472,82 @@ __device__ int gap_best_matches(const Text &Q, int d, const Text &R, int r_left,
     return __reduce_max_sync(0xffffffffu, best);
 }
 
+// ---- region output (lz-ani --out-alignment; parser.cpp:786-837 calc_regions) --------------------------------------
+// A region is a component seen through its match factors: query span [first match, end of last match), reference span
+// [min offset of a match factor, ref_end), where ref_end follows region_t::extend_region / update_ref_end
+// (defs.h:114-142): for every match factor  ref_end = max(ref_end + literals since the previous match, offset + len).
+// For a run of factors on ONE diagonal this collapses to  ref_end = max(ref_end + G, end of the last match), G = the
+// literals in front of that last match, so the kernel only needs, per collinear part, the first and last matching
+// position and the match count -- still no factor list.
+struct RegionSink {
+    int32_t *rec;                      // 7 ints per region: pair, q_start, q_end, r_start, r_end, matches, mismatches
+    unsigned long long *count;         // regions produced (may exceed cap: the host then re-runs with a larger buffer)
+    unsigned long long cap;
+};
+
+// whole warp: among positions [0, len) of Q[qp..] vs R[rp..]: first and last matching offset (-1: none) and the count
+__device__ void match_extent(const Text &Q, int qp, const Text &R, int rp, int len, int lane, int &first, int &last, int &cnt)
+{
+    int f = 0x7fffffff, l = -1, c = 0;
+    for (int o = 32 * lane; o < len; o += 1024) {
+        uint32_t m = ~mm32(Q, qp + o, R, rp + o);
+        int rem = len - o;
+        if (rem < 32) m &= (1u << rem) - 1;
+        if (m) { f = min(f, o + __ffs(m) - 1); l = o + 31 - __clz(m); c += __popc(m); }
+    }
+    f = __reduce_min_sync(0xffffffffu, f);
+    first = f == 0x7fffffff ? -1 : f;
+    last = __reduce_max_sync(0xffffffffu, l);
+    cnt = __reduce_add_sync(0xffffffffu, c);
+}
+
+// compare_ranges_both_ways (parser.cpp:251-374) as seen by a region: the chosen split (ties -> the largest, :308) and the
+// match extents of the part aligned to the left context and of the part aligned to the right context
+struct GapParts { int best, split, to_scan, lf, ll, ml, rv0, rf, rl, mr; };
+__device__ GapParts gap_parts(const Text &Q, int d, const Text &R, int r_left, int r_end_right, int len, int lane)
+{
+    GapParts g = {0, 0, 0, -1, -1, 0, 0, -1, -1, 0};
+    if (len <= 0) return g;
+    const int to_scan = (r_end_right < r_left) ? len : min(r_end_right - r_left, len);
+    const int lim = min(to_scan, r_end_right);
+    int best = -1, bsplit = 0;
+    for (int b = lane; b <= to_scan; b += 32) {
+        int t = to_scan - b;
+        int left = count_matches(Q, d, R, r_left, b);
+        int right = (t <= lim) ? count_matches(Q, d + len - t, R, r_end_right - t, t) : 0;
+        if (left + right >= best) { best = left + right; bsplit = b; }
+    }
+    const int mx = __reduce_max_sync(0xffffffffu, best);
+    const int sp = __reduce_max_sync(0xffffffffu, best == mx ? bsplit : -1);
+    g.best = mx; g.split = sp; g.to_scan = to_scan;
+    match_extent(Q, d, R, r_left, sp, lane, g.lf, g.ll, g.ml);
+    const int from_right = to_scan - sp;                 // right part: v = 0 .. from_right - 1, i = from_right - v <= lim
+    g.rv0 = max(0, from_right - lim);
+    match_extent(Q, d + len - from_right + g.rv0, R, r_end_right - from_right + g.rv0, from_right - g.rv0, lane, g.rf, g.rl, g.mr);
+    if (g.rf >= 0) { g.rf += g.rv0; g.rl += g.rv0; }
+    return g;
+}
+
+__device__ __forceinline__ void region_emit(const RegionSink &S, uint32_t pair, int qs, int qe, int rs, int re, int m, int mm, int lane)
+{
+    if (lane != 0) return;
+    unsigned long long at = atomicAdd(S.count, 1ULL);
+    if (at >= S.cap) return;
+    int32_t *o = S.rec + 7 * at;
+    o[0] = (int32_t)pair; o[1] = qs; o[2] = qe; o[3] = rs; o[4] = re; o[5] = m; o[6] = mm;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k6: the parse.  All state is warp-uniform; `lane` only selects the data a lane looks at.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SEED_WORDS = 6;         // seed windows of up to 192 reference positions use the Shift-And path
 
+template <bool REGIONS>
 __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restrict__ tab, uint32_t tcap, uint32_t pos_bits,
                            const LzParams &P, int lane, uint32_t (*seed_masks)[4][SEED_WORDS + 1], int &out_match, int &out_lit,
-                           int &out_comp)
+                           int &out_comp, const RegionSink &sink, uint32_t pair_idx)
 {
+    int reg_rs = 0, reg_re = 0;                          // REGIONS: reference span of the live component
     const int nQ = Q.n;
     int i = 0, lit = 0, pred = 0;
     bool lost = true;
@@ -593,15 +660,40 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
             continue;
         }
         // ---- 3. account for the match (parser.cpp:626-698) ----------------------------------------------------
+        int reg_buf = 0;                                  // REGIONS: literals pending in front of the anchor factor
+        bool reg_fresh = false;
         if (!lost && abs(best_pos - pred) <= P.mrd) {
-            int g = gap_best_matches(Q, i - lit, R, pred - lit, best_pos + best_len, lit, lane);
+            int g;
+            if (REGIONS) {
+                const int r_left = pred - lit, r_end_right = best_pos + best_len;
+                const GapParts gp = gap_parts(Q, i - lit, R, r_left, r_end_right, lit, lane);
+                g = gp.best;
+                if (gp.ml > 0) {
+                    reg_rs = min(reg_rs, r_left + gp.lf);
+                    reg_re = max(reg_re + (gp.ll + 1 - gp.ml), r_left + gp.ll + 1);
+                    reg_buf = gp.split - 1 - gp.ll;
+                } else reg_buf = gp.split;
+                reg_buf += lit - gp.to_scan;
+                const int from_right = gp.to_scan - gp.split;
+                if (gp.mr > 0) {
+                    const int rbase = r_end_right - from_right;
+                    reg_rs = min(reg_rs, rbase + gp.rf);
+                    reg_re = max(reg_re + reg_buf + (gp.rl + 1 - gp.mr), rbase + gp.rl + 1);
+                    reg_buf = from_right - 1 - gp.rl;
+                } else reg_buf += from_right;
+            } else
+                g = gap_best_matches(Q, i - lit, R, pred - lit, best_pos + best_len, lit, lane);
             comp_match += g + best_len;
             comp_lit += lit - g;
         } else {
             if (comp_active) {
                 if (prev_end - comp_start < P.reg) last_match_end = saved_lme;      // region deleted (:643-657)
-                else if (comp_match + comp_lit >= P.reg) { sum_match += comp_match; sum_lit += comp_lit; ++n_comp; }
+                else if (comp_match + comp_lit >= P.reg) {
+                    sum_match += comp_match; sum_lit += comp_lit; ++n_comp;
+                    if (REGIONS) region_emit(sink, pair_idx, comp_start, comp_start + comp_match + comp_lit, reg_rs, reg_re, comp_match, comp_lit, lane);
+                }
             }
+            reg_fresh = true;
             saved_lme = last_match_end;
             int tail = i - last_match_end;                // length of the literal run in front of the anchor
             ExtResult back = {0, 0};
@@ -618,6 +710,10 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         ExtResult fw = extend_forward(Q, i, R, pred, P, lane);
         comp_match += fw.matches;
         comp_lit += fw.len - fw.matches;
+        if (REGIONS) {
+            if (reg_fresh) { reg_rs = best_pos - (i - best_len - comp_start); reg_re = pred + fw.len; }    // i - best_len - comp_start = backward extension
+            else { reg_rs = min(reg_rs, best_pos); reg_re = max(reg_re + reg_buf + (fw.len - fw.matches), pred + fw.len); }
+        }
         i += fw.len;
         pred += fw.len;
         prev_end = i;
@@ -627,30 +723,40 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
     if (!lost) {
         const int T = lit + (nQ - i);
         const int qs = i - lit, rs = pred - lit - P.msl;
-        int mt = 0, last = -1;
+        int mt = 0, last = -1, first = 0x7fffffff;
         for (int o = 32 * lane; o < T; o += 1024) {
             uint32_t m = ~mm32(Q, qs + o, R, rs + o);
             int rem = T - o;
             if (rem < 32) m &= (1u << rem) - 1;
             mt += __popc(m);
-            if (m) last = o + 31 - __clz(m);
+            if (m) { last = o + 31 - __clz(m); if (REGIONS) first = min(first, o + __ffs(m) - 1); }
         }
         mt = __reduce_add_sync(0xffffffffu, mt);
         last = __reduce_max_sync(0xffffffffu, last);
-        if (mt > 0) { comp_match += mt; comp_lit += last + 1 - mt; }
+        if (mt > 0) {
+            comp_match += mt; comp_lit += last + 1 - mt;
+            if (REGIONS) {
+                first = __reduce_min_sync(0xffffffffu, first);
+                reg_rs = min(reg_rs, rs + first);
+                reg_re = max(reg_re + (last + 1 - mt), rs + last + 1);
+            }
+        }
     }
-    if (comp_active && comp_match + comp_lit >= P.reg) { sum_match += comp_match; sum_lit += comp_lit; ++n_comp; }
+    if (comp_active && comp_match + comp_lit >= P.reg) {
+        sum_match += comp_match; sum_lit += comp_lit; ++n_comp;
+        if (REGIONS) region_emit(sink, pair_idx, comp_start, comp_start + comp_match + comp_lit, reg_rs, reg_re, comp_match, comp_lit, lane);
+    }
     out_match = sum_match; out_lit = sum_lit; out_comp = n_comp;
 }
 
-template <int MINB>
+template <int MINB, bool REGIONS>
 __global__ void __launch_bounds__(128, MINB) parse_kernel(const uint32_t *__restrict__ g2, const uint32_t *__restrict__ gn,
                                                     const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
                                                     const RefDesc *__restrict__ refs, const uint32_t *__restrict__ ref_s2,
                                                     const uint32_t *__restrict__ ref_nv, const uint32_t *__restrict__ ht,
                                                     const uint32_t *__restrict__ pair_ref, const uint32_t *__restrict__ pair_qry,
                                                     uint32_t n_pairs, LzParams P, unsigned int *__restrict__ cursor,
-                                                    int32_t *__restrict__ stats)
+                                                    int32_t *__restrict__ stats, RegionSink sink, uint32_t pair_base)
 {
     const int lane = threadIdx.x & 31;
     __shared__ uint32_t seed_masks[4][4][SEED_WORDS + 1];       // per warp: 4 symbol masks of the seed window
@@ -665,7 +771,7 @@ __global__ void __launch_bounds__(128, MINB) parse_kernel(const uint32_t *__rest
         uint64_t qo = gofs[q];
         Text Q = {g2 + (qo >> 4), gn + (qo >> 5), (int)glen[q] + P.mrd};
         int m, l, c;
-        parse_pair(Q, R, ht + d.ht_off, d.ht_cap, d.pos_bits, P, lane, seed_masks, m, l, c);
+        parse_pair<REGIONS>(Q, R, ht + d.ht_off, d.ht_cap, d.pos_bits, P, lane, seed_masks, m, l, c, sink, pair_base + idx);
         if (lane == 0) { stats[3 * (uint64_t)idx] = m; stats[3 * (uint64_t)idx + 1] = l; stats[3 * (uint64_t)idx + 2] = c; }
     }
 }
@@ -731,17 +837,20 @@ static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, con
 }
 
 static void parse_launch(vb_ctx *ctx, const DevGenomes &dg, const RefBatch &b, const uint32_t *d_pref, const uint32_t *d_pqry,
-                         uint32_t nb, const LzParams &P, unsigned int *d_cursor, int32_t *d_stats, cudaStream_t st)
+                         uint32_t nb, const LzParams &P, unsigned int *d_cursor, int32_t *d_stats, cudaStream_t st,
+                         const RegionSink *sink = nullptr, uint32_t pair_base = 0)
 {
     int per_sm = 0;
     static const int minb = getenv("VB_PARSE_MINB") ? atoi(getenv("VB_PARSE_MINB")) : 6;
-    auto kern = minb >= 8 ? parse_kernel<8> : (minb == 7 ? parse_kernel<7> : (minb == 6 ? parse_kernel<6> : parse_kernel<5>));
+    auto kern = minb >= 8 ? parse_kernel<8, false> : (minb == 7 ? parse_kernel<7, false> : (minb == 6 ? parse_kernel<6, false> : parse_kernel<5, false>));
+    if (sink) kern = parse_kernel<5, true>;
+    RegionSink rs = sink ? *sink : RegionSink{nullptr, nullptr, 0};
     VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
     int n_sm = 0;
     VB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
     int blocks = std::max(1, std::min<int>(per_sm * n_sm, (int)((nb + 3) / 4)));
     kern<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, dg.glen.p, b.d_refs.p, b.ref_s2.p, b.ref_nv.p, b.ht.p, d_pref,
-                                 d_pqry, nb, P, d_cursor, d_stats);
+                                 d_pqry, nb, P, d_cursor, d_stats, rs, pair_base);
     VB_LAUNCH_CHECK(ctx);
 }
 
@@ -799,7 +908,8 @@ vb_align_job *vb_align_job_begin(vb_ctx *ctx, const vb_genomes *g, const vb_alig
 
 void vb_align_job_end(vb_align_job *job) { delete job; }
 
-void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qry, uint64_t n, int32_t *stats)
+void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qry, uint64_t n, int32_t *stats,
+                      std::vector<int32_t> *regions)
 {
     vb_ctx *ctx = job->ctx;
     const vb_genomes *g = job->g;
@@ -872,7 +982,36 @@ void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qr
         VB_CUDA(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned int), st));
         if (n_batches == 0) host_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - job->h0).count();
         t_par.start();
-        parse_launch(ctx, dg, rb, d_pref.p, d_pqry.p, nb, P, d_cursor.p, d_stats.p, st);
+        if (!regions)
+            parse_launch(ctx, dg, rb, d_pref.p, d_pqry.p, nb, P, d_cursor.p, d_stats.p, st);
+        else {
+            // regions are appended to a bounded buffer; the kernel always counts them, so one re-run with the exact
+            // size suffices when the first guess was too small (the parse is deterministic)
+            unsigned long long cap = std::max<unsigned long long>(1 << 16, 16ULL * nb), produced = 0;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                DevBuf<int32_t> rec(7 * cap);
+                DevBuf<unsigned long long> cnt(1);
+                VB_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), st));
+                VB_CUDA(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned int), st));
+                RegionSink sink = {rec.p, cnt.p, cap};
+                parse_launch(ctx, dg, rb, d_pref.p, d_pqry.p, nb, P, d_cursor.p, d_stats.p, st, &sink, 0);
+                VB_CUDA(cudaMemcpyAsync(&produced, cnt.p, sizeof(produced), cudaMemcpyDeviceToHost, st));
+                VB_CUDA(cudaStreamSynchronize(st));
+                if (produced <= cap) {
+                    const size_t at = regions->size();
+                    regions->resize(at + 7 * produced);
+                    if (produced) {
+                        VB_CUDA(cudaMemcpyAsync(regions->data() + at, rec.p, sizeof(int32_t) * 7 * produced, cudaMemcpyDeviceToHost, st));
+                        VB_CUDA(cudaStreamSynchronize(st));
+                    }
+                    for (unsigned long long k = 0; k < produced; ++k)          // batch-local pair number -> caller's pair index
+                        (*regions)[at + 7 * k] = (int32_t)order[pos + (uint32_t)(*regions)[at + 7 * k]];
+                    break;
+                }
+                if (attempt == 1) throw vb_error(VB_ERR_INTERNAL, "region buffer overflow on the sized re-run");
+                cap = produced;
+            }
+        }
         t_par.stop();
         std::vector<int32_t> tmp(3 * (size_t)nb);
         VB_CUDA(cudaMemcpyAsync(tmp.data(), d_stats.p, sizeof(int32_t) * 3 * nb, cudaMemcpyDeviceToHost, st));
@@ -911,7 +1050,7 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
     }
     vb_align_job *job = vb_align_job_begin(ctx, g, ap, is_ref.data());
     try {
-        vb_align_job_run(job, ref, qry, n, stats);
+        vb_align_job_run(job, ref, qry, n, stats, nullptr);
     } catch (...) {
         vb_align_job_end(job);
         throw;

@@ -313,3 +313,59 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
     fwrite(out.data(), 1, out.size(), f);
     fclose(f);
 }
+
+// lz-ani lz_matcher.cpp:102-169 (store_alignment): one line per region; coordinates 1-based inclusive; a region on the
+// reverse-complement half of the reference text is reported on the forward genome with rstart > rend (:158-162).
+void vb_write_aln_impl(const vb_genomes *g, const vb_regions *r, const char *path, const double out_filters[5])
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) throw vb_error(VB_ERR_IO, std::string("Cannot open output file for alignment storage: ") + path);
+    std::string out;
+    out.reserve(4 << 20);
+    out += "query\treference\tpident\talnlen\tqstart\tqend\trstart\trend\tnt_match\tnt_mismatch\n";
+    bool any_filter = false;
+    double flt[5] = {0, 0, 0, 0, 0};
+    if (out_filters) for (int i = 0; i < 5; ++i) { flt[i] = out_filters[i]; any_filter |= out_filters[i] != 0; }
+    const uint32_t ng = g->count();
+    char num[64];
+    for (uint64_t b = 0; b < r->n;) {
+        uint64_t e = b;
+        while (e < r->n && r->ref[e] == r->ref[b] && r->qry[e] == r->qry[b]) ++e;      // the regions of one directed pair
+        const uint32_t ref = r->ref[b], qry = r->qry[b];
+        if (ref >= ng || qry >= ng) { fclose(f); throw vb_error(VB_ERR_ARG, "vb_write_aln: genome id out of range"); }
+        const int seq1_len = (int)g->length(ref), seq2_len = (int)g->length(qry);
+        const int rc_correction = 2 * seq1_len + 2 * r->mrd + 1;
+        bool keep = true;
+        if (any_filter) {
+            int32_t si_mat = 0, si_lit = 0;
+            for (uint64_t i = b; i < e; ++i) { si_mat += r->matches[i]; si_lit += r->mismatches[i]; }
+            const double global_ani = (double)si_mat / seq2_len;
+            const double local_ani = si_mat + si_lit != 0 ? (double)si_mat / (si_mat + si_lit) : 0;
+            const double qcov = (double)(si_mat + si_lit) / seq2_len;
+            keep = !(global_ani < flt[1] || local_ani < flt[2] || qcov < flt[3]);
+        }
+        if (keep)
+            for (uint64_t i = b; i < e; ++i) {
+                const int len = r->q_end[i] - r->q_start[i];
+                out += g->names[qry]; out += '\t';
+                out += g->names[ref]; out += '\t';
+                out.append(num, vb_fmt_real(100.0 * r->matches[i] / len, 6, num)); out += '\t';
+                out.append(num, put_u64((uint64_t)len, num)); out += '\t';
+                out.append(num, put_u64((uint64_t)(1 + r->q_start[i]), num)); out += '\t';
+                out.append(num, put_u64((uint64_t)r->q_end[i], num)); out += '\t';
+                if (r->r_start[i] < seq1_len) {
+                    out.append(num, put_u64((uint64_t)(1 + r->r_start[i]), num)); out += '\t';
+                    out.append(num, put_u64((uint64_t)r->r_end[i], num)); out += '\t';
+                } else {
+                    out.append(num, put_u64((uint64_t)(rc_correction - (1 + r->r_start[i])), num)); out += '\t';
+                    out.append(num, put_u64((uint64_t)(rc_correction - r->r_end[i]), num)); out += '\t';
+                }
+                out.append(num, put_u64((uint64_t)r->matches[i], num)); out += '\t';
+                out.append(num, put_u64((uint64_t)r->mismatches[i], num)); out += '\n';
+                if (out.size() > (3u << 20)) { fwrite(out.data(), 1, out.size(), f); out.clear(); }
+            }
+        b = e;
+    }
+    fwrite(out.data(), 1, out.size(), f);
+    fclose(f);
+}

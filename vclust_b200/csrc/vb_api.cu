@@ -306,10 +306,104 @@ int vb_align_pairs(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const 
     VB_GUARD_END
 }
 
+// regions from the kernel's 7-int records (pair index first), sorted by pair, then like calc_regions
+static vb_regions *vb_regions_build(const std::vector<int32_t> &rec, const uint32_t *ref, const uint32_t *qry, int mrd)
+{
+    const uint64_t n = rec.size() / 7;
+    std::vector<uint64_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0ULL);
+    std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) {
+        const int32_t *x = &rec[7 * a], *y = &rec[7 * b];
+        if (x[0] != y[0]) return (uint32_t)x[0] < (uint32_t)y[0];
+        const int lx = x[2] - x[1], ly = y[2] - y[1];
+        if (lx != ly) return lx > ly;                                   // parser.cpp:826-833
+        return x[1] < y[1];
+    });
+    vb_regions *r = (vb_regions *)calloc(1, sizeof(vb_regions));
+    if (!r) throw vb_error(VB_ERR_MEM, "out of memory");
+    r->n = n; r->mrd = mrd;
+    const size_t m = std::max<uint64_t>(n, 1);
+    r->ref = (uint32_t *)malloc(m * 4); r->qry = (uint32_t *)malloc(m * 4);
+    r->q_start = (int32_t *)malloc(m * 4); r->q_end = (int32_t *)malloc(m * 4);
+    r->r_start = (int32_t *)malloc(m * 4); r->r_end = (int32_t *)malloc(m * 4);
+    r->matches = (int32_t *)malloc(m * 4); r->mismatches = (int32_t *)malloc(m * 4);
+    if (!r->ref || !r->qry || !r->q_start || !r->q_end || !r->r_start || !r->r_end || !r->matches || !r->mismatches) {
+        vb_regions_free(r);
+        throw vb_error(VB_ERR_MEM, "out of memory");
+    }
+    for (uint64_t o = 0; o < n; ++o) {
+        const int32_t *x = &rec[7 * idx[o]];
+        r->ref[o] = ref[(uint32_t)x[0]]; r->qry[o] = qry[(uint32_t)x[0]];
+        r->q_start[o] = x[1]; r->q_end[o] = x[2]; r->r_start[o] = x[3]; r->r_end[o] = x[4];
+        r->matches[o] = x[5]; r->mismatches[o] = x[6];
+    }
+    return r;
+}
+
+void vb_regions_free(vb_regions *r)
+{
+    if (!r) return;
+    free(r->ref); free(r->qry); free(r->q_start); free(r->q_end); free(r->r_start); free(r->r_end);
+    free(r->matches); free(r->mismatches); free(r);
+}
+
+int vb_align_pairs_regions(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
+                           const vb_align_params *p, int32_t *stats, vb_regions **regions)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || !g || !p || !regions || (n && (!ref || !qry || !stats))) throw vb_error(VB_ERR_ARG, "vb_align_pairs_regions: bad arguments");
+    vb_enter(ctx);
+    const uint32_t ng = g->count();
+    std::vector<uint8_t> is_ref(ng, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (ref[i] >= ng || qry[i] >= ng) throw vb_error(VB_ERR_ARG, "pair id out of range");
+        is_ref[ref[i]] = 1;
+    }
+    std::vector<int32_t> rec;
+    vb_align_job *job = vb_align_job_begin(ctx, g, p, is_ref.data());
+    try {
+        vb_align_job_run(job, ref, qry, n, stats, &rec);
+    } catch (...) {
+        vb_align_job_end(job);
+        throw;
+    }
+    vb_align_job_end(job);
+    *regions = vb_regions_build(rec, ref, qry, p->mrd);
+    VB_GUARD_END
+}
+
+int vb_write_aln(const vb_genomes *g, const vb_regions *regions, const char *path, const double out_filters[5])
+{
+    VB_GUARD_BEGIN
+    if (!g || !regions || !path) throw vb_error(VB_ERR_ARG, "vb_write_aln: bad arguments");
+    vb_write_aln_impl(g, regions, path, out_filters);
+    VB_GUARD_END
+}
+
+static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_align_params *p, vb_align_out **out,
+                            vb_regions **regions);
+
 int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_align_params *p, vb_align_out **out)
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_align: bad arguments");
+    vb_align_common(ctx, g, pairs, p, out, nullptr);
+    VB_GUARD_END
+}
+
+int vb_align_regions(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_align_params *p, vb_align_out **out,
+                     vb_regions **regions)
+{
+    VB_GUARD_BEGIN
+    if (!ctx || !g || !p || (!out && !regions)) throw vb_error(VB_ERR_ARG, "vb_align_regions: bad arguments");
+    vb_align_common(ctx, g, pairs, p, out, regions);
+    VB_GUARD_END
+}
+
+static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_align_params *p, vb_align_out **out,
+                            vb_regions **regions)
+{
+    {
     vb_enter(ctx);
     const auto h0 = std::chrono::steady_clock::now();
     const uint32_t n = g->count();
@@ -364,8 +458,10 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
         for (uint64_t w = 0; w < total; ++w) { in_ref[w] = order[res->ref[w]]; in_qry[w] = order[res->qry[w]]; }
         std::vector<int32_t> stats(3 * std::max<uint64_t>(total, 1));
         const double api_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
-        vb_align_job_run(job, in_ref.data(), in_qry.data(), total, stats.data());
+        std::vector<int32_t> rec;
+        vb_align_job_run(job, in_ref.data(), in_qry.data(), total, stats.data(), regions ? &rec : nullptr);
         ctx->set_timing("align.api_prep_ms", api_prep_ms);
+        if (regions) *regions = vb_regions_build(rec, in_ref.data(), in_qry.data(), p->mrd);
         for (uint64_t i = 0; i < total; ++i) {
             res->sym_in_matches[i] = stats[3 * i];
             res->sym_in_literals[i] = stats[3 * i + 1];
@@ -377,8 +473,8 @@ int vb_align(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_a
         throw;
     }
     vb_align_job_end(job);
-    *out = res;
-    VB_GUARD_END
+    if (out) *out = res; else vb_align_out_free(res);
+    }
 }
 
 int vb_write_ani(const vb_genomes *g, const vb_align_out *res, const char *ani_path, const char *ids_path,

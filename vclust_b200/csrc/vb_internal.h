@@ -33,6 +33,7 @@ struct vb_genomes {
 // ---- text formats (host_format.cpp) ---------------------------------------------------------------------------
 int vb_fmt_fixed6(double v, char *out);                 // kmer-db conversion.h:167-219 Double2PChar(v, 6)
 int vb_fmt_real(double v, int prec, char *out);         // refresh numeric_conversions.h:229-299 real_to_pchar
+void vb_write_aln_impl(const vb_genomes *g, const vb_regions *regions, const char *path, const double out_filters[5]);
 double vb_ani_shorter(uint32_t common, uint32_t cnt1, uint32_t cnt2, int k);   // kmer-db params.cpp:28-32
 
 // ---- device side (declared here, defined in the .cu files) -----------------------------------------------------
@@ -69,7 +70,10 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
 // flagged) and returns the statistics; _end releases the device buffers (LIFO after everything _run allocated).
 struct vb_align_job;
 vb_align_job *vb_align_job_begin(vb_ctx *ctx, const vb_genomes *g, const vb_align_params *p, const uint8_t *is_ref);
-void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qry, uint64_t n, int32_t *stats);
+// regions != nullptr: also collect the alignment regions (lz-ani --out-alignment), 7 ints each:
+// pair index (into ref/qry), q_start, q_end, r_start, r_end (0-based half-open, reference text coordinates), matches, mismatches
+void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qry, uint64_t n, int32_t *stats,
+                      std::vector<int32_t> *regions);
 void vb_align_job_end(vb_align_job *job);
 void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
                          const vb_align_params *p, int32_t *stats);
