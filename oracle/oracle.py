@@ -231,8 +231,11 @@ def fraction_str(f: float) -> str:
     return "%g" % f            # ostream << double (K/console_distance.cpp:40)
 
 
-def prefilter_pairs(sets, k: int, min_kmers: int, min_ident: float):
-    """(row, col, common, ani_shorter) for pairs passing K/sparse_filters.h:49-61 with vclust's two -min filters."""
+def prefilter_pairs(sets, k: int, min_kmers: int, min_ident: float, max_seqs: int = 0):
+    """(row, col, common, ani_shorter) for pairs passing K/sparse_filters.h:49-61 with vclust's two -min filters.
+    max_seqs > 0: then `-sample-rows ani-shorter:N` (K/sampler.h:45-121, K/array.h:450-543): each passing pair is
+    offered to both of its rows, a row keeps its N best items (the heap evicts the lowest score, ties the largest
+    item id), and the list holds entries on both sides of the diagonal, sorted by (row, item)."""
     L = lib()
     rows, cols, vals = common_matrix(sets)
     tot = [s.size for s in sets]
@@ -243,12 +246,21 @@ def prefilter_pairs(sets, k: int, min_kmers: int, min_ident: float):
         a = L.kmo_ani_shorter(v, tot[r], tot[c], k)
         if a >= min_ident:
             out.append((r, c, v, a))
+    if max_seqs > 0:
+        rows = {}
+        for r, c, v, a in out:
+            rows.setdefault(r, []).append((c, v, a))
+            rows.setdefault(c, []).append((r, v, a))
+        out = []
+        for r in sorted(rows):
+            best = sorted(rows[r], key=lambda e: (-e[2], e[0]))[:max_seqs]
+            out += [(r, c, v, a) for c, v, a in sorted(best)]
     return out
 
 
-def filter_text(names, sets, k: int, fraction: float, min_kmers: int, min_ident: float) -> str:
+def filter_text(names, sets, k: int, fraction: float, min_kmers: int, min_ident: float, max_seqs: int = 0) -> str:
     """The `kmer-db distance ani-shorter -sparse` text (K/console_distance.cpp:37-42,183-204)."""
-    pairs = prefilter_pairs(sets, k, min_kmers, min_ident)
+    pairs = prefilter_pairs(sets, k, min_kmers, min_ident, max_seqs)
     by_row = {}
     for r, c, v, a in pairs:
         by_row.setdefault(r, []).append((c, a))
@@ -259,7 +271,7 @@ def filter_text(names, sets, k: int, fraction: float, min_kmers: int, min_ident:
     return "\n".join(lines) + "\n"
 
 
-def prefilter_text_from_fasta(paths, multifasta: bool, k=25, fraction=1.0, min_kmers=20, min_ident=0.7) -> str:
+def prefilter_text_from_fasta(paths, multifasta: bool, k=25, fraction=1.0, min_kmers=20, min_ident=0.7, max_seqs=0) -> str:
     names, samples = [], []
     if multifasta:
         for p in paths:
@@ -270,7 +282,7 @@ def prefilter_text_from_fasta(paths, multifasta: bool, k=25, fraction=1.0, min_k
         for p in paths:
             names.append(Path(p).name)
             samples.append([s for _, s in read_records_kmerdb(p)])
-    return filter_text(names, kmer_sets(samples, k, fraction), k, fraction, min_kmers, min_ident)
+    return filter_text(names, kmer_sets(samples, k, fraction), k, fraction, min_kmers, min_ident, max_seqs)
 
 
 # ----------------------------------------------------------------------------------------------------------------

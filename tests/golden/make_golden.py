@@ -8,7 +8,7 @@ Two kinds of fixtures:
       3rd_party/kmer-db/test/synth/{synth.fa,a2a-sparse}                                            (k=21 KAT)
  2. outputs of the UNMODIFIED reference binaries (oracle/_ref, built by oracle/build_ref.sh) on small seeded
     synthetic genome sets from vclust_b200.synth -- these pin flag combinations the reference goldens do not
-    cover (k=15 / k=30, --kmers-fraction 0.2, N runs + lower case, non-default LZ parameters).
+    cover (k=15 / k=30, --kmers-fraction 0.2, --max-seqs, N runs + lower case, non-default LZ parameters).
 """
 import gzip
 import shutil
@@ -31,8 +31,17 @@ def gz_write(path: Path, data: bytes):
 
 
 def main():
+    """No arguments: everything.  Arguments: only the named ref_synth cases (kmer-db build at k=30 needs ~60 GB of RAM,
+    so s40_k30 can only be regenerated on a large host)."""
     assert REF.exists(), "needs the reference checkout"
     oracle.build_ref()
+    only = set(sys.argv[1:])
+    if not only:
+        copy_reference_goldens()
+    make_ref_synth(only)
+
+
+def copy_reference_goldens():
     ex = HERE / "example"
     ex.mkdir(exist_ok=True)
     shutil.copy(REF / "example/multifasta.fna.gz", ex / "multifasta.fna.gz")
@@ -52,6 +61,9 @@ def main():
     for f in ("synth.fa", "a2a-sparse"):
         shutil.copy(REF / "3rd_party/kmer-db/test/synth" / f, ks / f)
 
+
+
+def make_ref_synth(only):
     # ---- reference-binary outputs on seeded synthetic sets
     rs = HERE / "ref_synth"
     rs.mkdir(exist_ok=True)
@@ -65,10 +77,16 @@ def main():
                     dict(k=25, fraction=0.2, min_kmers=4, min_ident=0.7), {}),
         "s40_k30": (dict(n=40, length=(2000, 30000), family=5, seed=synth.BASE_SEED + 101, max_div=0.2),
                     dict(k=30, fraction=1.0, min_kmers=1, min_ident=0.3), dict(mal=13, msl=8, mrd=60, mqd=50, reg=40, aw=20, am=9, ar=4)),
+        # --max-seqs 3: families of 6 => every row is cut from 5 to 3 items, the filter gets entries on both sides of
+        # the diagonal and lz-ani reports a pair once per row that kept it
+        "s60_ms3": (dict(n=60, length=8000, family=6, seed=synth.BASE_SEED + 100, n_frac=0.2, lower_frac=0.2),
+                    dict(k=25, fraction=1.0, min_kmers=20, min_ident=0.7, max_seqs=3), {}),
     }
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
         for name, (gk, pk, lk) in cases.items():
+            if only and name not in only:
+                continue
             names, seqs = synth.make_genomes(**gk)
             fa = td / (name + ".fna")
             synth.write_fasta(fa, names, seqs)
@@ -79,11 +97,12 @@ def main():
                              columns=oracle.OUTFMT["complete"])
             (rs / (name + ".ani.ids.tsv")).unlink()
         # one unfiltered all-vs-all (many unrelated pairs) with default parameters
-        names, seqs = synth.make_genomes(n=30, length=(3000, 20000), family=3, seed=synth.BASE_SEED + 102, n_frac=0.3)
-        fa = td / "s30_all.fna"
-        synth.write_fasta(fa, names, seqs)
-        oracle.ref_align([fa], rs / "s30_all.ani.tsv", td / "s30_a", columns=oracle.OUTFMT["complete"])
-        (rs / "s30_all.ani.ids.tsv").unlink()
+        if not only or "s30_all" in only:
+            names, seqs = synth.make_genomes(n=30, length=(3000, 20000), family=3, seed=synth.BASE_SEED + 102, n_frac=0.3)
+            fa = td / "s30_all.fna"
+            synth.write_fasta(fa, names, seqs)
+            oracle.ref_align([fa], rs / "s30_all.ani.tsv", td / "s30_a", columns=oracle.OUTFMT["complete"])
+            (rs / "s30_all.ani.ids.tsv").unlink()
     (rs / "CASES.txt").write_text("\n".join("%s\t%r\t%r\t%r" % (k, *v) for k, v in cases.items()) +
                                   "\ns30_all\t%r\t-\t{}\n" % dict(n=30, length=(3000, 20000), family=3,
                                                                  seed=synth.BASE_SEED + 102, n_frac=0.3))

@@ -85,3 +85,21 @@ def test_merge_pairs_sums_duplicates_and_filters():
     assert list(zip(m.rows.tolist(), m.cols.tolist(), m.common.tolist())) == [(1, 0, 70), (2, 0, 5), (2, 1, 3)]
     m2 = api.merge_pairs([1, 2, 1, 2, 2], [0, 0, 0, 1, 1], [30, 5, 40, 1, 2], totals, k=21, min_kmers=3, min_ident=0.95)
     assert list(zip(m2.rows.tolist(), m2.cols.tolist())) == [(1, 0)]
+
+
+def test_merge_pairs_max_seqs_matches_oracle_sampler():
+    """--max-seqs (kmer-db -sample-rows ani-shorter:N) through the host code of the C ABI vs the oracle restatement,
+    which tests/test_oracle_kmer.py pins against the reference binaries (golden s60_ms3)."""
+    from oracle import oracle
+    from vclust_b200 import api, build, synth
+    build.build()
+    names, seqs = synth.make_genomes(n=40, length=3000, family=8, seed=77)
+    sets = oracle.kmer_sets([[s.tobytes()] for s in seqs], 21, 1.0)
+    rows, cols, vals = oracle.common_matrix(sets)
+    totals = np.array([s.size for s in sets], dtype=np.uint32)
+    for ms in (1, 2, 5, 100):
+        want = oracle.prefilter_pairs(sets, 21, 5, 0.5, max_seqs=ms)
+        m = api.merge_pairs(rows, cols, vals, totals, k=21, min_kmers=5, min_ident=0.5, max_seqs=ms)
+        assert list(zip(m.rows.tolist(), m.cols.tolist(), m.common.tolist())) == [(r, c, v) for r, c, v, _ in want]
+        assert np.array_equal(m.ani, np.array([a for *_, a in want]))
+        assert any(r < c for r, c, *_ in want)          # entries on both sides of the diagonal

@@ -18,9 +18,10 @@ PRE = {
     "s60_k15": dict(k=15, kmers_fraction=1.0, min_kmers=10, min_ident=0.5),
     "s60_f02": dict(k=25, kmers_fraction=0.2, min_kmers=4, min_ident=0.7),
     "s40_k30": dict(k=30, kmers_fraction=1.0, min_kmers=1, min_ident=0.3),
+    "s60_ms3": dict(k=25, kmers_fraction=1.0, min_kmers=20, min_ident=0.7, max_seqs=3),
 }
 LZP = {
-    "s60": {}, "s60_f02": {},
+    "s60": {}, "s60_f02": {}, "s60_ms3": {},
     "s60_k15": dict(mal=9, msl=6, mrd=30, mqd=25, reg=30, aw=12, am=5, ar=2),
     "s40_k30": dict(mal=13, msl=8, mrd=60, mqd=50, reg=40, aw=20, am=9, ar=4),
     "s30_all": {},
@@ -58,7 +59,7 @@ def test_prefilter_vs_reference_binary_outputs(ctx, golden, tmp_path, case):
     out = tmp_path / "fltr.txt"
     kw = PRE[case]
     api.prefilter([fa], out, True, kmer_size=kw["k"], kmers_fraction=kw["kmers_fraction"], min_kmers=kw["min_kmers"],
-                  min_ident=kw["min_ident"])
+                  min_ident=kw["min_ident"], max_seqs=kw.get("max_seqs", 0))
     assert out.read_bytes() == (golden / "ref_synth" / (case + ".fltr.txt")).read_bytes()
 
 

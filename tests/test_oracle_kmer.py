@@ -86,6 +86,7 @@ def test_minhash_spec():
     ("s60_k15", dict(k=15, fraction=1.0, min_kmers=10, min_ident=0.5)),
     ("s60_f02", dict(k=25, fraction=0.2, min_kmers=4, min_ident=0.7)),
     ("s40_k30", dict(k=30, fraction=1.0, min_kmers=1, min_ident=0.3)),
+    ("s60_ms3", dict(k=25, fraction=1.0, min_kmers=20, min_ident=0.7, max_seqs=3)),
 ])
 def test_against_reference_binary_outputs(golden, tmp_path, case, kw):
     gen = {

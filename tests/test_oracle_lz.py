@@ -44,7 +44,7 @@ GEN = {
     "s30_all": dict(n=30, length=(3000, 20000), family=3, seed=synth.BASE_SEED + 102, n_frac=0.3),
 }
 LZP = {
-    "s60": {}, "s60_f02": {},
+    "s60": {}, "s60_f02": {}, "s60_ms3": {},
     "s60_k15": dict(mal=9, msl=6, mrd=30, mqd=25, reg=30, aw=12, am=5, ar=2),
     "s40_k30": dict(mal=13, msl=8, mrd=60, mqd=50, reg=40, aw=20, am=9, ar=4),
     "s30_all": {},

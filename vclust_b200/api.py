@@ -271,13 +271,13 @@ def prefilter_partial(ctx: Context, genomes: Genomes, shard_index: int, shard_co
 
 
 def merge_pairs(rows, cols, common, total_kmers, k: int = 25, min_kmers: int = 20, min_ident: float = 0.7,
-                kmers_fraction: float = 1.0) -> PairList:
-    """Sum partial (row, col, common) triples, apply the two -min filters exactly; host only."""
+                kmers_fraction: float = 1.0, max_seqs: int = 0) -> PairList:
+    """Sum partial (row, col, common) triples, apply the two -min filters exactly (and --max-seqs); host only."""
     r = np.ascontiguousarray(rows, dtype=np.uint32)
     c = np.ascontiguousarray(cols, dtype=np.uint32)
     v = np.ascontiguousarray(common, dtype=np.uint32)
     t = np.ascontiguousarray(total_kmers, dtype=np.uint32)
-    p = PrefilterParams(k, min_kmers, min_ident, kmers_fraction, 0, 0)
+    p = PrefilterParams(k, min_kmers, min_ident, kmers_fraction, max_seqs, 0)
     out = C.POINTER(Pairs)()
     check(_lib.load().vb_pairs_merge(r.ctypes.data, c.ctypes.data, v.ctypes.data, r.size, t.ctypes.data, t.size,
                                      C.byref(p), C.byref(out)))

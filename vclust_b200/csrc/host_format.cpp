@@ -129,6 +129,40 @@ void vb_write_filter_impl(const vb_genomes *g, const vb_pairs *pr, const char *p
     fclose(f);
 }
 
+// kmer-db `all2all-sp -sample-rows ani-shorter:N` (vclust --max-seqs N).  Every pair (i, j), i > j, that passed the -min
+// filters is offered to row i as item j and -- through the transposed pass -- to row j as item i (array.h:450-543); a
+// row keeps its N best items, where the heap of sampler.h:45-66 always evicts the item that is worst by
+// (score ascending, item id descending), i.e. the survivors are the top N by (score desc, item asc) whatever the
+// insertion order; rows are written with the items ascending (sampler.h:123-139).  The result therefore has entries
+// on both sides of the diagonal, and a pair kept by both of its rows appears twice.
+void vb_sample_rows(uint32_t n_genomes, uint32_t max_items, std::vector<uint32_t> &row, std::vector<uint32_t> &col,
+                    std::vector<uint32_t> &common, std::vector<double> &ani)
+{
+    const size_t n = row.size();
+    std::vector<uint64_t> start((size_t)n_genomes + 1, 0);
+    for (size_t i = 0; i < n; ++i) { start[row[i] + 1]++; start[col[i] + 1]++; }
+    for (uint32_t r = 0; r < n_genomes; ++r) start[r + 1] += start[r];
+    struct Item { uint32_t item, common; double score; };
+    std::vector<Item> items(2 * n);
+    std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+    for (size_t i = 0; i < n; ++i) {
+        items[fill[row[i]]++] = {col[i], common[i], ani[i]};
+        items[fill[col[i]]++] = {row[i], common[i], ani[i]};
+    }
+    row.clear(); col.clear(); common.clear(); ani.clear();
+    for (uint32_t r = 0; r < n_genomes; ++r) {
+        Item *b = items.data() + start[r], *e = items.data() + start[r + 1];
+        if ((uint64_t)(e - b) > max_items) {
+            std::partial_sort(b, b + max_items, e, [](const Item &x, const Item &y) {
+                return x.score != y.score ? x.score > y.score : x.item < y.item;
+            });
+            e = b + max_items;
+        }
+        std::sort(b, e, [](const Item &x, const Item &y) { return x.item < y.item; });
+        for (Item *p = b; p != e; ++p) { row.push_back(r); col.push_back(p->item); common.push_back(p->common); ani.push_back(p->score); }
+    }
+}
+
 static std::vector<std::string> split_keep(const std::string &s, char sep)
 {   // lz-ani utils.cpp:15-36: empty middle tokens kept, empty trailing token dropped
     std::vector<std::string> parts;

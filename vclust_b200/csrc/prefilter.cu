@@ -821,7 +821,6 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     if (shard_count == 0 || shard_index >= shard_count) throw vb_error(VB_ERR_ARG, "bad k-mer shard");
     if (p->k < 10 || p->k > 31) throw vb_error(VB_ERR_ARG, "k must be in [10, 31]");
     if (!(p->kmers_fraction > 0)) throw vb_error(VB_ERR_ARG, "kmers_fraction must be > 0");
-    if (p->max_seqs > 0) throw vb_error(VB_ERR_ARG, "--max-seqs is not implemented on the GPU path yet");
     cudaStream_t st = (cudaStream_t)ctx->stream;
     VB_CUDA(cudaSetDevice(ctx->device));
     const uint32_t n = g->count();
@@ -1076,23 +1075,20 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
 
     // ---- host: exact IEEE-double metric (params.cpp:28-32) and the two -min filters (sparse_filters.h:49-61)
     const auto hp0 = std::chrono::steady_clock::now();
-    std::vector<uint64_t> keep;
-    keep.reserve(n_emit);
-    std::vector<double> ani(n_emit);
+    std::vector<uint32_t> o_row, o_col, o_common;
+    std::vector<double> o_ani;
+    o_row.reserve(n_emit); o_col.reserve(n_emit); o_common.reserve(n_emit); o_ani.reserve(n_emit);
     const uint64_t cmask = (1ULL << em.gbits) - 1;
     for (uint64_t i = 0; i < n_emit; ++i) {
-        uint32_t r = (uint32_t)(h_keys[i] >> em.gbits), c = (uint32_t)(h_keys[i] & cmask);
-        if (partial) { ani[i] = 0; keep.push_back(i); continue; }
-        ani[i] = vb_ani_shorter(h_vals[i], h_tot[r], h_tot[c], p->k);
-        if (ani[i] >= p->min_ident) keep.push_back(i);
+        const uint32_t r = (uint32_t)(h_keys[i] >> em.gbits), c = (uint32_t)(h_keys[i] & cmask);
+        const double a = partial ? 0.0 : vb_ani_shorter(h_vals[i], h_tot[r], h_tot[c], p->k);
+        if (partial || a >= p->min_ident) { o_row.push_back(r); o_col.push_back(c); o_common.push_back(h_vals[i]); o_ani.push_back(a); }
     }
-    vb_pairs *res = vb_pairs_alloc(keep.size(), n);
-    for (uint64_t o = 0; o < keep.size(); ++o) {
-        uint64_t i = keep[o];
-        res->row[o] = (uint32_t)(h_keys[i] >> em.gbits);
-        res->col[o] = (uint32_t)(h_keys[i] & cmask);
-        res->common[o] = h_vals[i];
-        res->ani[o] = ani[i];
+    // --max-seqs: the per-row sampler needs complete counts, so a k-mer shard leaves it to vb_pairs_merge
+    if (!partial && p->max_seqs > 0) vb_sample_rows(n, (uint32_t)p->max_seqs, o_row, o_col, o_common, o_ani);
+    vb_pairs *res = vb_pairs_alloc(o_row.size(), n);
+    for (uint64_t o = 0; o < o_row.size(); ++o) {
+        res->row[o] = o_row[o]; res->col[o] = o_col[o]; res->common[o] = o_common[o]; res->ani[o] = o_ani[o];
     }
     for (uint32_t i = 0; i < n; ++i) res->total_kmers[i] = h_tot[i];
     res->k = p->k;

@@ -241,6 +241,7 @@ int vb_pairs_merge(const uint32_t *row, const uint32_t *col, const uint32_t *com
         }
         i = j;
     }
+    if (p->max_seqs > 0) vb_sample_rows(n_genomes, (uint32_t)p->max_seqs, r, c, v, a);
     vb_pairs *res = vb_pairs_alloc(r.size(), n_genomes);
     for (size_t i = 0; i < r.size(); ++i) { res->row[i] = r[i]; res->col[i] = c[i]; res->common[i] = v[i]; res->ani[i] = a[i]; }
     for (uint32_t i = 0; i < n_genomes; ++i) res->total_kmers[i] = total_kmers[i];

@@ -35,6 +35,9 @@ int vb_fmt_fixed6(double v, char *out);                 // kmer-db conversion.h:
 int vb_fmt_real(double v, int prec, char *out);         // refresh numeric_conversions.h:229-299 real_to_pchar
 void vb_write_aln_impl(const vb_genomes *g, const vb_regions *regions, const char *path, const double out_filters[5]);
 double vb_ani_shorter(uint32_t common, uint32_t cnt1, uint32_t cnt2, int k);   // kmer-db params.cpp:28-32
+// kmer-db -sample-rows ani-shorter:N on a list of passing pairs (row > col); rewrites the list, sorted by (row, item)
+void vb_sample_rows(uint32_t n_genomes, uint32_t max_items, std::vector<uint32_t> &row, std::vector<uint32_t> &col,
+                    std::vector<uint32_t> &common, std::vector<double> &ani);
 
 // ---- device side (declared here, defined in the .cu files) -----------------------------------------------------
 struct vb_timing { std::string key; double ms; };
