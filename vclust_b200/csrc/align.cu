@@ -205,7 +205,7 @@ __device__ __forceinline__ int count_matches(const Text &Q, int qp, const Text &
 // Sliding-window rule of try_extend_forward/backward (parser.cpp:377-441) on one lane's 32 flags.
 // x = (this lane's mismatch flags << 32) | the 32 flags before them.  Returns the flags of positions where the
 // number of mismatches among the last aw positions exceeds am (only mismatch positions can be such positions).
-__device__ __forceinline__ uint32_t window_violations(uint64_t x, int aw, int am)
+__device__ __noinline__ uint32_t window_violations(uint64_t x, int aw, int am)
 {
     uint32_t mm = (uint32_t)(x >> 32);
     uint32_t viol = 0;
@@ -255,71 +255,47 @@ __device__ __forceinline__ uint32_t window_violations_15_7(uint64_t x)
 __device__ __forceinline__ uint32_t run_ends(uint64_t x, int ar)
 {
     uint64_t z = ~x, acc = z;
-    for (int s = 1; s < ar; ++s) acc &= z << s;
+    if (ar == 3) acc = z & (z << 1) & (z << 2);
+    else {
+#pragma unroll 1
+        for (int s = 1; s < ar; ++s) acc &= z << s;
+    }
     return (uint32_t)(acc >> 32);
 }
 
 struct ExtResult { int len; int matches; };
 
-// parser.cpp:377-409 for the whole warp: lane l looks at offsets [base + 32 l, base + 32 l + 32).
-// Returns the extension length (end of the last run of >= ar matches before the window rule fires) and the number
-// of matching positions inside it.
-__device__ ExtResult extend_forward(const Text &Q, int qp, const Text &R, int rp, const LzParams &P, int lane)
+// parser.cpp:377-409 (forward) and :412-441 (backward) for the whole warp: lane l looks at offsets [base + 32 l,
+// base + 32 l + 32) counted from (qp, rp) in the direction of the scan.  lim_all = number of offsets the reference's loop
+// may examine (forward: until either text ends; backward: e < max_len, qp - e > 0, rp - e > 0); offsets beyond it read as
+// mismatches, which can neither end a run nor be reached before the stop.  Returns the extension length (end of the last
+// run of >= ar matches before the window rule fires) and the number of matching positions inside it.
+// One body for both directions keeps the kernel's instruction footprint small (the parse is instruction-fetch bound).
+__device__ __noinline__ ExtResult extend(const Text Q, int qp, const Text R, int rp, int lim_all, bool backward, int aw, int am,
+                                         int ar, int lane)
 {
     ExtResult res = {0, 0};
-    const int total_rem = min(Q.n - qp, R.n - rp);
     uint32_t prev_hi = 0;           // flags of the 32 positions before this super-chunk (virtual matches at start)
     int cum = 0;                    // matches in all earlier super-chunks
     for (int base = 0;; base += 1024) {
-        uint32_t m = mm32(Q, qp + base + 32 * lane, R, rp + base + 32 * lane);
+        const int off = base + 32 * lane;
+        uint32_t m;
+        if (backward) m = mm32_back(Q, qp - off, R, rp - off, lim_all - off);
+        else {
+            const int lim = lim_all - off;
+            m = 0xffffffffu;
+            if (lim > 0) {
+                m = mismatch32(fetch2(Q.s2, (uint64_t)(qp + off)), fetch2(R.s2, (uint64_t)(rp + off))) |
+                    fetch1(Q.nv, (uint64_t)(qp + off)) | fetch1(R.nv, (uint64_t)(rp + off));
+                if (lim < 32) m |= 0xffffffffu << lim;
+            }
+        }
         uint32_t pm = __shfl_up_sync(0xffffffffu, m, 1);
         if (lane == 0) pm = prev_hi;
         uint64_t x = ((uint64_t)m << 32) | pm;
-        uint32_t viol = (P.aw == 15 && P.am == 7) ? window_violations_15_7(x) : window_violations(x, P.aw, P.am);
-        uint32_t ends = run_ends(x, P.ar);
-        unsigned vb = __ballot_sync(0xffffffffu, viol != 0);
-        int limit = 1024;
-        if (vb) {
-            int vl = __ffs(vb) - 1;
-            uint32_t v = __shfl_sync(0xffffffffu, viol, vl);
-            limit = 32 * vl + __ffs(v) - 1;
-        }
-        int my_lim = limit - 32 * lane;                         // positions of this lane that are before the stop
-        uint32_t keep = my_lim >= 32 ? 0xffffffffu : (my_lim <= 0 ? 0u : ((1u << my_lim) - 1));
-        ends &= keep;
-        unsigned eb = __ballot_sync(0xffffffffu, ends != 0);
-        if (eb) {
-            int el = 31 - __clz(eb);
-            uint32_t e = __shfl_sync(0xffffffffu, ends, el);
-            int last_local = 32 * el + (31 - __clz(e)) + 1;
-            int upto = last_local - 32 * lane;
-            uint32_t cm = upto >= 32 ? 0xffffffffu : (upto <= 0 ? 0u : ((1u << upto) - 1));
-            res.len = base + last_local;
-            res.matches = cum + __reduce_add_sync(0xffffffffu, __popc(~m & cm));
-        }
-        if (vb || base + 1024 >= total_rem) return res;           // window rule fired, or both texts are exhausted
-        cum += __reduce_add_sync(0xffffffffu, __popc(~m));
-        prev_hi = __shfl_sync(0xffffffffu, m, 31);
-    }
-}
-
-// parser.cpp:412-441 for the whole warp; offsets count backwards from (qp, rp), at most max_len of them
-__device__ ExtResult extend_backward(const Text &Q, int qp, const Text &R, int rp, int max_len, const LzParams &P, int lane)
-{
-    ExtResult res = {0, 0};
-    int lim_all = min(max_len, min(qp, rp));                      // e < max_len, qp - e > 0, rp - e > 0
-    uint32_t prev_hi = 0;
-    int cum = 0;
-    for (int base = 0;; base += 1024) {
-        int off = base + 32 * lane;
-        uint32_t m = mm32_back(Q, qp - off, R, rp - off, lim_all - off);
-        uint32_t pm = __shfl_up_sync(0xffffffffu, m, 1);
-        if (lane == 0) pm = prev_hi;
-        uint64_t x = ((uint64_t)m << 32) | pm;
-        uint32_t viol = (P.aw == 15 && P.am == 7) ? window_violations_15_7(x) : window_violations(x, P.aw, P.am);
-        uint32_t ends = run_ends(x, P.ar);
-        // the loop also stops (without looking at the symbol) at offset lim_all
-        int stop_all = lim_all - base;                            // first offset of this super-chunk not examined
+        uint32_t viol = (aw == 15 && am == 7) ? window_violations_15_7(x) : window_violations(x, aw, am);
+        uint32_t ends = run_ends(x, ar);
+        const int stop_all = lim_all - base;                      // first offset of this super-chunk not examined
         unsigned vb = __ballot_sync(0xffffffffu, viol != 0);
         int limit = 1024;
         if (vb) {
@@ -329,7 +305,7 @@ __device__ ExtResult extend_backward(const Text &Q, int qp, const Text &R, int r
         }
         bool done = vb != 0;
         if (stop_all <= limit) { limit = max(stop_all, 0); done = true; }
-        int my_lim = limit - 32 * lane;
+        int my_lim = limit - 32 * lane;                           // positions of this lane that are before the stop
         uint32_t keep = my_lim >= 32 ? 0xffffffffu : (my_lim <= 0 ? 0u : ((1u << my_lim) - 1));
         ends &= keep;
         unsigned eb = __ballot_sync(0xffffffffu, ends != 0);
@@ -413,7 +389,7 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, ui
         bool in_chain = empties == 0 || lane < (__ffs(empties) - 1);
         if (in_chain && (s >> pos_bits) == fp) {
             const int pf = (int)(s & pmask);
-#pragma unroll
+#pragma unroll 1
             for (int strand = 0; strand < 2; ++strand) {    // forward occurrence, reverse-complement occurrence
                 const int pos = strand ? rc0 + (len - P.mal - pf) : pf;
                 int ml = equal_len(Q, i, R, pos, 0);
@@ -623,6 +599,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
                 for (int j0 = 0; j0 < max_w; j0 += 32) {
                     uint64_t rk;
                     if (!kmer_at(R, lo + j0 + lane, P.msl, rk)) rk = ~0ULL;
+#pragma unroll 1
                     for (int s = 0; s < 32; ++s) {
                         uint64_t c = __shfl_sync(0xffffffffu, rk, s);
                         if (qv && c == qk && j0 + s < my_w) flag = true;
@@ -638,20 +615,16 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
             continue;
         }
         // ---- 2. exact evaluation at i (parser.cpp:503-624) ----------------------------------------------------
-        int best_len = 0, best_pos = 0;
-        if (lost)
-            anchor_search(tab, tcap, pos_bits, Q, i, R, P, lane, best_len, best_pos);
-        else {
-            close_search(Q, i, R, pred, lit, P, lane, best_len, best_pos);
-            int a_len, a_pos;
-            anchor_search(tab, tcap, pos_bits, Q, i, R, P, lane, a_len, a_pos);
-            if (a_pos) {                                  // positions double as booleans in the reference (:604-606)
-                if (!best_pos) { best_pos = a_pos; best_len = a_len; }
-                else {
-                    double anchor_prob = ipow(1.0 - prob_len(a_len), (uint32_t)(2 * (R.n + 1 - a_len)));
-                    double close_prob = ipow(1.0 - prob_len(best_len), (uint32_t)(lit + P.mrd + 1 - best_len));
-                    if (anchor_prob > close_prob) { best_pos = a_pos; best_len = a_len; }
-                }
+        int best_len = 0, best_pos = 0, a_len, a_pos;
+        if (!lost) close_search(Q, i, R, pred, lit, P, lane, best_len, best_pos);
+        anchor_search(tab, tcap, pos_bits, Q, i, R, P, lane, a_len, a_pos);
+        if (lost) { best_len = a_len; best_pos = a_pos; }
+        else if (a_pos) {                                 // positions double as booleans in the reference (:604-606)
+            if (!best_pos) { best_pos = a_pos; best_len = a_len; }
+            else {
+                double anchor_prob = ipow(1.0 - prob_len(a_len), (uint32_t)(2 * (R.n + 1 - a_len)));
+                double close_prob = ipow(1.0 - prob_len(best_len), (uint32_t)(lit + P.mrd + 1 - best_len));
+                if (anchor_prob > close_prob) { best_pos = a_pos; best_len = a_len; }
             }
         }
         if (best_len < P.msl) {                           // fingerprint collision or the position-0 quirk
@@ -697,7 +670,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
             saved_lme = last_match_end;
             int tail = i - last_match_end;                // length of the literal run in front of the anchor
             ExtResult back = {0, 0};
-            if (tail > 0) back = extend_backward(Q, i, R, best_pos, tail, P, lane);
+            if (tail > 0) back = extend(Q, i, R, best_pos, min(tail, min(i, best_pos)), true, P.aw, P.am, P.ar, lane);
             comp_active = true;
             comp_start = i - back.len;
             comp_match = back.matches + best_len;
@@ -707,7 +680,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         pred = best_pos + best_len;
         lit = 0;
         lost = false;
-        ExtResult fw = extend_forward(Q, i, R, pred, P, lane);
+        ExtResult fw = extend(Q, i, R, pred, min(Q.n - i, R.n - pred), false, P.aw, P.am, P.ar, lane);
         comp_match += fw.matches;
         comp_lit += fw.len - fw.matches;
         if (REGIONS) {
@@ -829,7 +802,7 @@ static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, con
     VB_CUDA(cudaMemcpyAsync(b.d_refs.p, b.refs.data(), sizeof(RefDesc) * b.refs.size(), cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemsetAsync(b.ht.p, 0xff, b.ht.bytes(), st));
     dim3 grid_b(16, (unsigned)std::min<size_t>(b.refs.size(), 32768));
-    build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, b.d_refs.p, (uint32_t)b.refs.size(), ap->mrd,
+    build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.seq2.p, dg.inv_lz.p, dg.gofs.p, b.d_refs.p, (uint32_t)b.refs.size(), ap->mrd,
                                                  b.ref_s2.p, b.ref_nv.p);
     VB_LAUNCH_CHECK(ctx);
     build_ref_index_kernel<<<grid_b, 256, 0, st>>>(b.d_refs.p, (uint32_t)b.refs.size(), ap->mal, b.ref_s2.p, b.ref_nv.p, b.ht.p);
@@ -841,7 +814,7 @@ static void parse_launch(vb_ctx *ctx, const DevGenomes &dg, const RefBatch &b, c
                          const RegionSink *sink = nullptr, uint32_t pair_base = 0)
 {
     int per_sm = 0;
-    static const int minb = getenv("VB_PARSE_MINB") ? atoi(getenv("VB_PARSE_MINB")) : 6;
+    static const int minb = getenv("VB_PARSE_MINB") ? atoi(getenv("VB_PARSE_MINB")) : 7;
     auto kern = minb >= 8 ? parse_kernel<8, false> : (minb == 7 ? parse_kernel<7, false> : (minb == 6 ? parse_kernel<6, false> : parse_kernel<5, false>));
     if (sink) kern = parse_kernel<5, true>;
     RegionSink rs = sink ? *sink : RegionSink{nullptr, nullptr, 0};
@@ -849,7 +822,7 @@ static void parse_launch(vb_ctx *ctx, const DevGenomes &dg, const RefBatch &b, c
     int n_sm = 0;
     VB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
     int blocks = std::max(1, std::min<int>(per_sm * n_sm, (int)((nb + 3) / 4)));
-    kern<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv.p, dg.gofs.p, dg.glen.p, b.d_refs.p, b.ref_s2.p, b.ref_nv.p, b.ht.p, d_pref,
+    kern<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv_lz.p, dg.gofs.p, dg.glen.p, b.d_refs.p, b.ref_s2.p, b.ref_nv.p, b.ht.p, d_pref,
                                  d_pqry, nb, P, d_cursor, d_stats, rs, pair_base);
     VB_LAUNCH_CHECK(ctx);
 }
@@ -861,7 +834,6 @@ struct vb_align_job {
     cudaStream_t st;
     std::chrono::steady_clock::time_point h0;
     EventTimer t_all, t_up, t_idx;
-    DevGenomes dg_scratch;
     const DevGenomes *dg = nullptr;
     bool prebuilt = false;               // all references of the call fit one batch and are being indexed already
     std::vector<int32_t> slot_of_gid;    // prebuilt: index of a genome's RefDesc, -1 if it is not a reference
@@ -883,7 +855,7 @@ vb_align_job *vb_align_job_begin(vb_ctx *ctx, const vb_genomes *g, const vb_alig
         job->h0 = std::chrono::steady_clock::now();
         job->t_all.start();
         job->t_up.start();
-        job->dg = &vb_get_dev_genomes(ctx, g, /*u_is_t=*/false, (uint32_t)ap->mrd + 128, job->dg_scratch);
+        job->dg = &vb_get_dev_genomes(ctx, g, (uint32_t)ap->mrd + 128);
         job->t_up.stop();
         // reference texts + anchor tables of one batch may take up to 40 % of the device (no per-call memory query)
         const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
@@ -909,7 +881,7 @@ vb_align_job *vb_align_job_begin(vb_ctx *ctx, const vb_genomes *g, const vb_alig
 void vb_align_job_end(vb_align_job *job) { delete job; }
 
 void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qry, uint64_t n, int32_t *stats,
-                      std::vector<int32_t> *regions)
+                      std::vector<int32_t> *regions, const float *cost)
 {
     vb_ctx *ctx = job->ctx;
     const vb_genomes *g = job->g;
@@ -933,6 +905,28 @@ void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qr
         for (uint64_t i = 0; i < n && grouped; ++i)
             if (i == 0 || ref[i] != ref[i - 1]) { if (seen[ref[i]]) grouped = false; seen[ref[i]] = 1; }
         if (!grouped) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ref[a] < ref[b]; });
+    }
+    // Longest-processing-time-first for the expensive tail: a parse costs 10-100x more for a divergent pair than for a
+    // near-identical one, and warps take pairs from a shared cursor in list order, so the (estimated) most expensive
+    // 1/8 of the pairs goes to the front (fewer than one wave of warps, so their mutual order does not matter); the rest
+    // keeps the by-reference grouping (L2 locality of the anchor tables).  Only when all references are indexed in one
+    // batch (any order is valid then).
+    static const bool lpt_off = getenv("VB_ALIGN_NO_LPT") != nullptr;
+    if (cost && job->prebuilt && !lpt_off && n >= 64) {
+        const uint64_t n_heavy = n / 8;
+        std::vector<uint32_t> by_cost(order);
+        std::nth_element(by_cost.begin(), by_cost.begin() + n_heavy, by_cost.end(),
+                         [&](uint32_t a, uint32_t b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
+        by_cost.resize(n_heavy);
+        if (n_heavy > 4096)     // more than one wave of warps: most expensive first
+            std::sort(by_cost.begin(), by_cost.end(), [&](uint32_t a, uint32_t b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
+        std::vector<uint8_t> heavy(n, 0);
+        for (uint32_t i : by_cost) heavy[i] = 1;
+        std::vector<uint32_t> merged;
+        merged.reserve(n);
+        merged.insert(merged.end(), by_cost.begin(), by_cost.end());
+        for (uint32_t i : order) if (!heavy[i]) merged.push_back(i);
+        order.swap(merged);
     }
     const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
 
@@ -1050,7 +1044,7 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
     }
     vb_align_job *job = vb_align_job_begin(ctx, g, ap, is_ref.data());
     try {
-        vb_align_job_run(job, ref, qry, n, stats, nullptr);
+        vb_align_job_run(job, ref, qry, n, stats, nullptr, nullptr);
     } catch (...) {
         vb_align_job_end(job);
         throw;

@@ -8,28 +8,29 @@ __constant__ uint8_t c_code[2][256];
 
 __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const uint64_t *__restrict__ src_off,
                             const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
-                            const uint32_t *__restrict__ tile_gid, uint64_t n_chunks, int rule,
-                            uint32_t *__restrict__ seq2, uint32_t *__restrict__ inv)
+                            const uint32_t *__restrict__ tile_gid, uint64_t n_chunks,
+                            uint32_t *__restrict__ seq2, uint32_t *__restrict__ inv_kdb, uint32_t *__restrict__ inv_lz)
 {
-    // one thread per 32 base slots: two seq2 words and one inv word
+    // one thread per 32 base slots: two seq2 words and one word of each validity plane
     for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n_chunks;
          c += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t slot = c * 32;
         uint32_t gid = tile_gid[slot >> 7];
-        uint32_t w0 = 0, w1 = 0, bad = 0xffffffffu;
+        uint32_t w0 = 0, w1 = 0, bad = 0xffffffffu, bad_lz = 0xffffffffu;
         if (gid != 0xffffffffu) {
             uint64_t local = slot - gofs[gid];
             uint32_t len = glen[gid];
             if (local < len) {
                 const uint8_t *src = ascii + src_off[gid] + local;
                 uint32_t m = (len - local) < 32 ? (uint32_t)(len - local) : 32u;
-                bad = 0;
+                bad = 0; bad_lz = 0;
 #pragma unroll 8
                 for (uint32_t j = 0; j < 32; ++j) {
-                    uint32_t code = 4;
-                    if (j < m) code = c_code[rule][src[j]];
+                    uint32_t code = 4, code_lz = 4;
+                    if (j < m) { code = c_code[1][src[j]]; code_lz = c_code[0][src[j]]; }
                     uint32_t two = code & 3;
                     if (code > 3) { bad |= 1u << j; two = 0; }
+                    if (code_lz > 3) bad_lz |= 1u << j;
                     if (j < 16) w0 |= two << (2 * j);
                     else w1 |= two << (2 * (j - 16));
                 }
@@ -37,15 +38,16 @@ __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const uint64_t *_
         }
         seq2[2 * c] = w0;
         seq2[2 * c + 1] = w1;
-        inv[c] = bad;
+        inv_kdb[c] = bad;
+        inv_lz[c] = bad_lz;
     }
 }
 
 }  // namespace
 
-void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes &out, uint32_t min_pad)
+void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad)
 {
-    if (min_pad < 128) min_pad = 128;
+    if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
     cudaStream_t st = (cudaStream_t)ctx->stream;
     static bool table_ready[64] = {false};
     if (!table_ready[ctx->device & 63]) {
@@ -77,7 +79,8 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes
         for (uint64_t t = out.h_gofs[i] / 128; t * 128 < out.h_gofs[i] + out.h_glen[i]; ++t) tile[t] = i;
 
     out.seq2.alloc(slots / 16 + 8);
-    out.inv.alloc(slots / 32 + 8);
+    out.inv_kdb.alloc(slots / 32 + 8);
+    out.inv_lz.alloc(slots / 32 + 8);
     out.gofs.alloc(n ? n : 1);
     out.glen.alloc(n ? n : 1);
     out.tile_gid.alloc(tile.size());
@@ -86,10 +89,14 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes
         if (cudaHostRegister((void *)g->bases.data(), g->bases.size(), cudaHostRegisterDefault) == cudaSuccess) g->pinned = true;
         else cudaGetLastError();
     }
+    const bool pool_mode = vb_tls_pool_alloc;
+    vb_tls_pool_alloc = false;                   // the ASCII copy is call-scoped: arena
     DevBuf<uint8_t> ascii(g->bases.size() + 64);
     DevBuf<uint64_t> src_off(n + 1);
+    vb_tls_pool_alloc = pool_mode;
     VB_CUDA(cudaMemsetAsync(out.seq2.p, 0, out.seq2.bytes(), st));
-    VB_CUDA(cudaMemsetAsync(out.inv.p, 0xff, out.inv.bytes(), st));
+    VB_CUDA(cudaMemsetAsync(out.inv_kdb.p, 0xff, out.inv_kdb.bytes(), st));
+    VB_CUDA(cudaMemsetAsync(out.inv_lz.p, 0xff, out.inv_lz.bytes(), st));
     if (!g->bases.empty())
         VB_CUDA(cudaMemcpyAsync(ascii.p, g->bases.data(), g->bases.size(), cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemcpyAsync(src_off.p, g->offset.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, st));
@@ -102,46 +109,71 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes
     int threads = 256;
     int blocks = (int)std::min<uint64_t>((n_chunks + threads - 1) / threads, 148 * 16);
     pack_kernel<<<blocks, threads, 0, st>>>((const uint8_t *)ascii.p, src_off.p, out.gofs.p, out.glen.p, out.tile_gid.p,
-                                            n_chunks, u_is_t ? 1 : 0, out.seq2.p, out.inv.p);
+                                            n_chunks, out.seq2.p, out.inv_kdb.p, out.inv_lz.p);
     VB_LAUNCH_CHECK(ctx);
     VB_CUDA(cudaStreamSynchronize(st));     // ascii / tile vectors go out of scope
 }
 
-const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32_t min_pad, DevGenomes &scratch,
-                                     bool *was_resident)
+static void drop_last(vb_ctx *ctx)
 {
-    for (auto &r : ctx->resident)
-        if (r.g == g && r.u_is_t == (int)u_is_t && r.min_pad >= min_pad) {
-            if (was_resident) *was_resident = true;
-            return *r.dev;
-        }
-    if (was_resident) *was_resident = false;
-    vb_upload_genomes(ctx, g, u_is_t, scratch, min_pad);
-    return scratch;
+    if (!ctx->last.dev) return;
+    cudaStream_t saved = vb_tls_stream;
+    vb_tls_stream = (cudaStream_t)ctx->stream;
+    delete ctx->last.dev;                         // stream-ordered frees: safe behind whatever still reads the buffers
+    vb_tls_stream = saved;
+    ctx->last = {nullptr, 0, 0, nullptr};
 }
 
-void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32_t min_pad)
+// upload into buffers that outlive the call (stream-ordered pool)
+static DevGenomes *upload_persistent(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad)
 {
-    for (auto &r : ctx->resident)
-        if (r.g == g && r.u_is_t == (int)u_is_t && r.min_pad >= min_pad) return;
     auto *d = new DevGenomes();
-    vb_arena *saved = vb_tls_arena;
-    vb_tls_arena = nullptr;                       // resident buffers outlive the call: plain cudaMalloc
-    try { vb_upload_genomes(ctx, g, u_is_t, *d, min_pad); } catch (...) { vb_tls_arena = saved; delete d; throw; }
-    vb_tls_arena = saved;
-    ctx->resident.push_back({g, (int)u_is_t, min_pad < 128 ? 128u : min_pad, d});
+    const bool saved = vb_tls_pool_alloc;
+    vb_tls_pool_alloc = true;
+    try { vb_upload_genomes(ctx, g, *d, min_pad); } catch (...) { vb_tls_pool_alloc = saved; delete d; throw; }
+    vb_tls_pool_alloc = saved;
+    return d;
+}
+
+const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident)
+{
+    if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
+    if (was_resident) *was_resident = true;
+    for (auto &r : ctx->resident)
+        if (r.g == g && r.uid == g->uid && r.min_pad >= min_pad) return *r.dev;
+    if (ctx->last.dev && ctx->last.g == g && ctx->last.uid == g->uid && ctx->last.min_pad >= min_pad) return *ctx->last.dev;
+    if (was_resident) *was_resident = false;
+    drop_last(ctx);
+    ctx->last = {g, g->uid, min_pad, upload_persistent(ctx, g, min_pad)};
+    return *ctx->last.dev;
+}
+
+void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad)
+{
+    if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
+    for (auto &r : ctx->resident)
+        if (r.g == g && r.uid == g->uid && r.min_pad >= min_pad) return;
+    if (ctx->last.dev && ctx->last.g == g && ctx->last.uid == g->uid && ctx->last.min_pad >= min_pad) {
+        ctx->resident.push_back(ctx->last);       // promote the cached copy
+        ctx->last = {nullptr, 0, 0, nullptr};
+        return;
+    }
+    ctx->resident.push_back({g, g->uid, min_pad, upload_persistent(ctx, g, min_pad)});
 }
 
 void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g)
 {
+    cudaStream_t saved = vb_tls_stream;
+    vb_tls_stream = (cudaStream_t)ctx->stream;
+    if (g == nullptr || ctx->last.g == g) drop_last(ctx);
     for (size_t i = 0; i < ctx->resident.size();) {
         if (g == nullptr || ctx->resident[i].g == g) {
-            cudaStreamSynchronize((cudaStream_t)ctx->stream);
             delete ctx->resident[i].dev;
             ctx->resident.erase(ctx->resident.begin() + i);
         }
         else ++i;
     }
+    vb_tls_stream = saved;
 }
 
 void vb_unpin_genomes(const vb_genomes *g)
@@ -150,6 +182,7 @@ void vb_unpin_genomes(const vb_genomes *g)
 }
 
 thread_local vb_arena *vb_tls_arena = nullptr;
+thread_local bool vb_tls_pool_alloc = false;
 
 uint64_t vb_device_available(vb_ctx *ctx)
 {

@@ -36,20 +36,25 @@ struct vb_arena {
 };
 extern thread_local vb_arena *vb_tls_arena;
 extern thread_local cudaStream_t vb_tls_stream;
+// true while buffers that OUTLIVE the call are being allocated (packed genome stores): they come from the device's
+// stream-ordered pool (cudaMallocAsync on the context stream; release threshold set to "never" in vb_ctx_create), so
+// that dropping one store and uploading the next -- every step of the host-buffer path -- costs no cudaMalloc/cudaFree
+extern thread_local bool vb_tls_pool_alloc;
 
 template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
     vb_arena *arena = nullptr;
+    cudaStream_t pool_stream = nullptr;      // non-null: allocated with cudaMallocAsync on this stream
     DevBuf() = default;
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), arena(o.arena) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), arena(o.arena), pool_stream(o.pool_stream) { o.p = nullptr; o.n = 0; }
     DevBuf &operator=(DevBuf &&o) noexcept
     {
-        if (this != &o) { release(); p = o.p; n = o.n; arena = o.arena; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; arena = o.arena; pool_stream = o.pool_stream; o.p = nullptr; o.n = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
@@ -58,9 +63,16 @@ struct DevBuf {
         release();
         n = count;
         if (!count) return;
-        arena = vb_tls_arena;
-        if (arena) { p = (T *)arena->alloc(count * sizeof(T)); return; }
-        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        arena = nullptr; pool_stream = nullptr;
+        cudaError_t e;
+        if (vb_tls_pool_alloc && vb_tls_stream) {
+            e = cudaMallocAsync((void **)&p, count * sizeof(T), vb_tls_stream);
+            if (e == cudaSuccess) { pool_stream = vb_tls_stream; return; }
+        } else {
+            arena = vb_tls_arena;
+            if (arena) { p = (T *)arena->alloc(count * sizeof(T)); return; }
+            e = cudaMalloc((void **)&p, count * sizeof(T));
+        }
         if (e != cudaSuccess) {
             p = nullptr; n = 0;
             cudaGetLastError();
@@ -70,7 +82,11 @@ struct DevBuf {
     }
     void release()
     {
-        if (p) { if (arena) arena->pop(p, n * sizeof(T)); else cudaFree(p); }
+        if (p) {
+            if (pool_stream) cudaFreeAsync(p, pool_stream);
+            else if (arena) arena->pop(p, n * sizeof(T));
+            else cudaFree(p);
+        }
         p = nullptr; n = 0;
     }
     size_t bytes() const { return n * sizeof(T); }
@@ -94,14 +110,16 @@ struct EventTimer {
 //   Genome g occupies base slots [gofs[g], gofs[g] + glen[g]) of one global base axis; every genome starts at a
 //   multiple of 128 bases and is followed by at least 128 slots of padding marked invalid, so a kernel may read up
 //   to 64 bases past the end of a genome without a bounds check.
-//   seq2 : 2 bits per base, 16 bases per uint32 word, base b of a word at bits [2b, 2b+1]  (A0 C1 G2 T3)
-//   inv  : 1 bit per base, 32 bases per uint32 word, set when the base is not ACGT(U) or is padding
+//   seq2 : 2 bits per base, 16 bases per uint32 word, base b of a word at bits [2b, 2b+1]  (A0 C1 G2 T3; U is stored as T)
+//   inv_kdb / inv_lz : 1 bit per base, 32 bases per uint32 word, set when the base is not a valid symbol or is
+//          padding.  Two planes because the tools disagree on U: kmer-db reads it as T (alphabet.h:80-85), lz-ani as N
+//          (seq_reservoir.h:243-247); everything else is shared, so ONE upload serves the prefilter and the align stage.
 //   tile_gid : genome id owning each 128-base tile (0xffffffff for none)
 // ---------------------------------------------------------------------------------------------------------------
 struct DevGenomes {
     uint32_t n = 0;
     uint64_t total_slots = 0;        // multiple of 128
-    DevBuf<uint32_t> seq2, inv;
+    DevBuf<uint32_t> seq2, inv_kdb, inv_lz;
     DevBuf<uint64_t> gofs;           // n entries
     DevBuf<uint32_t> glen;           // n entries
     DevBuf<uint32_t> tile_gid;       // total_slots / 128
@@ -109,14 +127,14 @@ struct DevGenomes {
     std::vector<uint32_t> h_glen;
 };
 
-// Upload ASCII and pack on the device.  u_is_t: kmer-db treats U/u as T; lz-ani treats it as N.
-// min_pad: invalid slots guaranteed after every genome (>= 128).
-void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, DevGenomes &out, uint32_t min_pad = 128);
+// Upload ASCII and pack on the device.  min_pad: invalid slots guaranteed after every genome (>= VB_STORE_PAD).
+constexpr uint32_t VB_STORE_PAD = 128 + 64;      // covers the prefilter (128) and align with --mrd up to 64
+void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad = VB_STORE_PAD);
 
-// Returns the packed copy of g for this rule: the resident one when vb_genomes_make_resident was called for it
-// (no transfer), otherwise uploads into `scratch` and returns that.
-const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32_t min_pad, DevGenomes &scratch,
-                                     bool *was_resident = nullptr);
+// Returns the packed copy of g: the resident one when vb_genomes_make_resident was called for it, else the copy the
+// previous call on this context uploaded (vclust prefilter followed by vclust align on the same set transfers the
+// genomes once), else uploads now and keeps the copy for the next call (vb_genomes_evict drops it).
+const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident = nullptr);
 
 #ifdef __CUDACC__
 // 32 bases (64 bits) starting at base slot p of a 2-bit array; base p lands in bits [0,1].

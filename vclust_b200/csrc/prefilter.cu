@@ -828,8 +828,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
 
     t_all.start();
     t_up.start();
-    DevGenomes dg_scratch;
-    const DevGenomes &dg = vb_get_dev_genomes(ctx, g, /*u_is_t=*/true, 128, dg_scratch);
+    const DevGenomes &dg = vb_get_dev_genomes(ctx, g, VB_STORE_PAD);
     t_up.stop();
 
     const uint64_t n_slots = dg.total_slots;
@@ -890,7 +889,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         const uint64_t n_pad = ((n_slots + rsort::TILE - 1) / rsort::TILE) * rsort::TILE;
         DevBuf<uint64_t> keys_a(n_pad), keys_b(n_pad);
         DevBuf<uint32_t> vals_a(n_pad), vals_b(n_pad);
-        extract_kernel<<<grid_for(n_pad), 256, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_pad, ep, keys_a.p,
+        extract_kernel<<<grid_for(n_pad), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, n_slots, n_pad, ep, keys_a.p,
                                                        vals_a.p, valid_cnt);
         VB_LAUNCH_CHECK(ctx);
         t_ext.stop();
@@ -934,14 +933,14 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
             DevBuf<uint32_t> seen_words((1ULL << seen_bits) / 16);
             VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
             SeenTable seen = {seen_words.p, (1ULL << seen_bits) - 1};
-            hash_kernel<true><<<n_sm * 4, 512, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep, hbuf.p, seen,
+            hash_kernel<true><<<n_sm * 4, 512, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, n_slots, n_iter, ep, hbuf.p, seen,
                                                         valid_cnt, scalars.p + 4, d_cursor, keys0.p, vals0.p, fine_hist.p);
             VB_LAUNCH_CHECK(ctx);
             compact_kernel<<<n_sm * 8, 256, 0, st>>>(hbuf.p, n_iter, seen, dg.tile_gid.p, d_cursor, keys0.p, vals0.p, fine_hist.p);
             VB_LAUNCH_CHECK(ctx);
         } else {
             SeenTable seen = {nullptr, 0};
-            hash_kernel<false><<<n_sm * 4, 512, 0, st>>>(dg.seq2.p, dg.inv.p, dg.tile_gid.p, n_slots, n_iter, ep, nullptr, seen,
+            hash_kernel<false><<<n_sm * 4, 512, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, n_slots, n_iter, ep, nullptr, seen,
                                                          valid_cnt, scalars.p + 4, d_cursor, keys0.p, vals0.p, fine_hist.p);
             VB_LAUNCH_CHECK(ctx);
         }

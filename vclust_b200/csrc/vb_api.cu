@@ -2,6 +2,7 @@
 // status translation, and the host-side bookkeeping LZ-ANI does around its matching loop (genome re-ordering,
 // filter symmetrisation: seq_reservoir.cpp:215-251, filter.cpp:80-81,253-345, lz_matcher.cpp:172-277).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <numeric>
 
@@ -15,11 +16,16 @@ void vb_pairs_free_impl(vb_pairs *p);
 void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char *ani_path, const char *ids_path,
                        const char *const *columns, int n_columns, const double out_filters[5]);
 
-void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, bool u_is_t, uint32_t min_pad);
+void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad);
 void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g);
 void vb_unpin_genomes(const vb_genomes *g);
 
 thread_local cudaStream_t vb_tls_stream = nullptr;
+uint64_t vb_next_uid()
+{
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1);
+}
 static thread_local std::string g_last_error;
 void vb_set_error(const std::string &msg) { g_last_error = msg; }
 
@@ -103,6 +109,14 @@ int vb_ctx_create(int device, vb_ctx **out)
     VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     ctx->stream = (void *)st;
     ctx->arena = new vb_arena();
+    {   // packed genome stores live in the device's stream-ordered pool: never hand freed blocks back to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     size_t free_b = 0, total_b = 0;
     VB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     ctx->mem_total = total_b;
@@ -151,7 +165,8 @@ int vb_genomes_make_resident(vb_ctx *ctx, const vb_genomes *g, vb_fasta_flavor r
     VB_GUARD_BEGIN
     if (!ctx || !g) throw vb_error(VB_ERR_ARG, "vb_genomes_make_resident: bad arguments");
     vb_enter(ctx);
-    vb_make_resident_impl(ctx, g, rule == VB_FASTA_KMERDB, rule == VB_FASTA_KMERDB ? 128u : (uint32_t)std::max(mrd, 0) + 128u);
+    (void)rule;     // one packed store serves both stages (two validity planes)
+    vb_make_resident_impl(ctx, g, (uint32_t)std::max(mrd, 0) + 128u);
     VB_GUARD_END
 }
 
@@ -437,6 +452,7 @@ static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pa
             for (uint32_t r = 0; r < n; ++r) start[r + 1] += start[r];
         }
         const uint64_t total = start[n];
+        std::vector<float> cost;
         res = vb_align_out_alloc(total, n);
         std::copy(order.begin(), order.end(), res->order);
         if (!pairs) {
@@ -444,15 +460,26 @@ static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pa
             for (uint32_t r = 0; r < n; ++r)
                 for (uint32_t q = 0; q < n; ++q) if (q != r) { res->ref[w] = r; res->qry[w] = q; ++w; }
         } else {
+            // (query, estimated cost) per row; cost model: a parse scans the query once (extension, ~0.25 instructions
+            // per base) and pays ~1000 instructions per seed event; events happen where the sliding-window rule (more
+            // than 7 mismatches in 15) fires, i.e. at a rate of about C(15,8) p^8 (1-p)^7 per base at divergence p
+            std::vector<std::pair<uint32_t, float>> ent(total);
             std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+            auto rate = [](double ani) {
+                const double p = std::min(std::max(1.0 - ani, 0.0), 0.5), q = 1.0 - p;
+                const double p2 = p * p, p4 = p2 * p2, q2 = q * q, q4 = q2 * q2;
+                return 0.25 + 1000.0 * 6435.0 * (p4 * p4) * (q4 * q2 * q);
+            };
             for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
                 uint32_t a = rank[pairs->row[i]], b = rank[pairs->col[i]];
-                res->qry[fill[a]++] = b;
-                res->qry[fill[b]++] = a;
+                const double r = pairs->ani ? rate(pairs->ani[i]) : 1.0;
+                ent[fill[a]++] = {b, (float)(r * (double)g->length(pairs->col[i]))};
+                ent[fill[b]++] = {a, (float)(r * (double)g->length(pairs->row[i]))};
             }
+            cost.resize(total);
             for (uint32_t r = 0; r < n; ++r) {
-                std::sort(res->qry + start[r], res->qry + start[r + 1]);
-                std::fill(res->ref + start[r], res->ref + start[r + 1], r);
+                std::sort(ent.begin() + start[r], ent.begin() + start[r + 1]);
+                for (uint64_t w = start[r]; w < start[r + 1]; ++w) { res->ref[w] = r; res->qry[w] = ent[w].first; cost[w] = ent[w].second; }
             }
         }
         std::vector<uint32_t> in_ref(total), in_qry(total);
@@ -460,7 +487,8 @@ static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pa
         std::vector<int32_t> stats(3 * std::max<uint64_t>(total, 1));
         const double api_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         std::vector<int32_t> rec;
-        vb_align_job_run(job, in_ref.data(), in_qry.data(), total, stats.data(), regions ? &rec : nullptr);
+        vb_align_job_run(job, in_ref.data(), in_qry.data(), total, stats.data(), regions ? &rec : nullptr,
+                         cost.empty() ? nullptr : cost.data());
         ctx->set_timing("align.api_prep_ms", api_prep_ms);
         if (regions) *regions = vb_regions_build(rec, in_ref.data(), in_qry.data(), p->mrd);
         for (uint64_t i = 0; i < total; ++i) {

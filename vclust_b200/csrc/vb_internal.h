@@ -17,6 +17,8 @@ struct vb_error : std::runtime_error {
 
 void vb_set_error(const std::string &msg);
 
+uint64_t vb_next_uid();
+
 // Host-side genome set.  Sequences are kept as ASCII exactly as read (separators between the records of one
 // file already inserted as 'N' bytes); symbol coding happens on the device, per stage, because kmer-db and
 // lz-ani disagree on 'U' (kmer-db alphabet.h:80-85 vs lz-ani seq_reservoir.h:243-247).
@@ -26,6 +28,7 @@ struct vb_genomes {
     std::vector<char> bases;        // concatenated ASCII
     vb_fasta_flavor flavor = VB_FASTA_KMERDB;
     mutable bool pinned = false;    // bases page-locked with cudaHostRegister (done lazily by the first upload)
+    uint64_t uid = vb_next_uid();   // distinguishes a new set that re-uses the address of a freed one (device-copy cache)
     uint32_t count() const { return (uint32_t)names.size(); }
     uint64_t length(uint32_t i) const { return offset[i + 1] - offset[i]; }
 };
@@ -46,7 +49,7 @@ struct DevGenomes;
 struct vb_arena;
 struct vb_resident {                 // a genome set kept packed in HBM across calls (vb_genomes_make_resident)
     const vb_genomes *g;
-    int u_is_t;
+    uint64_t uid;
     uint32_t min_pad;
     DevGenomes *dev;
 };
@@ -59,6 +62,7 @@ struct vb_ctx {
     vb_arena *arena = nullptr;       // call-scoped device temporaries (dev_util.cuh)
     uint64_t mem_total = 0;          // device memory, queried once (cudaMemGetInfo is slow and synchronising)
     std::vector<vb_resident> resident;
+    vb_resident last = {nullptr, 0, 0, nullptr};   // the most recent upload that was not made resident (implicit cache)
     std::vector<vb_timing> timings;
     void set_timing(const std::string &k, double ms) {
         for (auto &t : timings) if (t.key == k) { t.ms = ms; return; }
@@ -75,8 +79,9 @@ struct vb_align_job;
 vb_align_job *vb_align_job_begin(vb_ctx *ctx, const vb_genomes *g, const vb_align_params *p, const uint8_t *is_ref);
 // regions != nullptr: also collect the alignment regions (lz-ani --out-alignment), 7 ints each:
 // pair index (into ref/qry), q_start, q_end, r_start, r_end (0-based half-open, reference text coordinates), matches, mismatches
+// cost (optional, n entries): estimated relative cost of each parse, used only to schedule expensive pairs first
 void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qry, uint64_t n, int32_t *stats,
-                      std::vector<int32_t> *regions);
+                      std::vector<int32_t> *regions, const float *cost = nullptr);
 void vb_align_job_end(vb_align_job *job);
 void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, const uint32_t *qry, uint64_t n,
                          const vb_align_params *p, int32_t *stats);
