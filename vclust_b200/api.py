@@ -72,7 +72,8 @@ class Context:
         keys = {
             "prefilter": ["total_ms", "upload_pack_ms", "extract_ms", "sort_ms", "segment_ms", "emit_ms", "host_post_ms", "tuples",
                           "survivors", "pair_increments", "table_slots", "candidates"],
-            "align": ["total_ms", "upload_pack_ms", "index_ms", "parse_ms", "api_prep_ms", "host_prep_ms", "host_post_ms", "batches", "pairs"],
+            "align": ["total_ms", "upload_pack_ms", "index_ms", "parse_ms", "api_prep_ms", "host_prep_ms", "host_post_ms", "batches", "pairs",
+                      "hp1_begin_ms", "hp2_order_ms", "hp3_csr_ms", "hp4_sched_ms", "hp6_run_done_ms", "hp7_end_ms"],
         }[prefix]
         out = {}
         for k in keys:

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <functional>
 
 #include "dev_util.cuh"
 
@@ -265,6 +266,8 @@ __device__ __forceinline__ uint32_t run_ends(uint64_t x, int ar)
 
 struct ExtResult { int len; int matches; };
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // parser.cpp:377-409 (forward) and :412-441 (backward) for the whole warp: lane l looks at offsets [base + 32 l,
 // base + 32 l + 32) counted from (qp, rp) in the direction of the scan.  lim_all = number of offsets the reference's loop
 // may examine (forward: until either text ends; backward: e < max_len, qp - e > 0, rp - e > 0); offsets beyond it read as
@@ -277,19 +280,24 @@ __device__ __noinline__ ExtResult extend(const Text Q, int qp, const Text R, int
     ExtResult res = {0, 0};
     uint32_t prev_hi = 0;           // flags of the 32 positions before this super-chunk (virtual matches at start)
     int cum = 0;                    // matches in all earlier super-chunks
+    auto flags_at = [&](int off) -> uint32_t {      // mismatch flags of this lane's 32 offsets starting at off
+        if (backward) return mm32_back(Q, qp - off, R, rp - off, lim_all - off);
+        const int lim = lim_all - off;
+        if (lim <= 0) return 0xffffffffu;
+        uint32_t f = mismatch32(fetch2(Q.s2, (uint64_t)(qp + off)), fetch2(R.s2, (uint64_t)(rp + off))) |
+                     fetch1(Q.nv, (uint64_t)(qp + off)) | fetch1(R.nv, (uint64_t)(rp + off));
+        if (lim < 32) f |= 0xffffffffu << lim;
+        return f;
+    };
     for (int base = 0;; base += 1024) {
         const int off = base + 32 * lane;
-        uint32_t m;
-        if (backward) m = mm32_back(Q, qp - off, R, rp - off, lim_all - off);
-        else {
-            const int lim = lim_all - off;
-            m = 0xffffffffu;
-            if (lim > 0) {
-                m = mismatch32(fetch2(Q.s2, (uint64_t)(qp + off)), fetch2(R.s2, (uint64_t)(rp + off))) |
-                    fetch1(Q.nv, (uint64_t)(qp + off)) | fetch1(R.nv, (uint64_t)(rp + off));
-                if (lim < 32) m |= 0xffffffffu << lim;
-            }
+        if (lim_all > off + 1024) {
+            // the next super-chunk is pulled into L1 while this one is evaluated (no register target, so no stall)
+            const int d = backward ? -min(off + 1024 + 32, min(qp, rp)) : off + 1024;
+            prefetch_l1(Q.s2 + ((qp + d) >> 4)); prefetch_l1(R.s2 + ((rp + d) >> 4));
+            prefetch_l1(Q.nv + ((qp + d) >> 5)); prefetch_l1(R.nv + ((rp + d) >> 5));
         }
+        const uint32_t m = flags_at(off);
         uint32_t pm = __shfl_up_sync(0xffffffffu, m, 1);
         if (lane == 0) pm = prev_hi;
         uint64_t x = ((uint64_t)m << 32) | pm;
@@ -348,21 +356,6 @@ __device__ __forceinline__ bool kmer_at(const Text &T, int p, int len, uint64_t 
     if (fetch1(T.nv, (uint64_t)p) & nm) return false;
     code = fetch2(T.s2, (uint64_t)p) & ((~0ULL) >> (64 - 2 * len));
     return true;
-}
-
-// one lane: does the anchor table hold any entry with this k-mer's fingerprint?
-__device__ __forceinline__ bool anchor_probe(const uint32_t *__restrict__ tab, uint32_t cap, uint32_t pos_bits, uint64_t code,
-                                             int mal)
-{
-    uint64_t h = fmix64(canonical_kmer(code, mal, (~0ULL) >> (64 - 2 * mal)));
-    uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
-    uint32_t slot = ht_slot(h, cap);
-    for (;;) {
-        uint32_t s = __ldg(tab + slot);
-        if (s == HT_EMPTY) return false;
-        if ((s >> pos_bits) == fp) return true;
-        slot = (slot + 1 == cap) ? 0u : slot + 1;
-    }
 }
 
 // whole warp, parser.cpp:514-531 / :585-602: longest exact match among all reference positions of Q's mal-mer at i
@@ -539,16 +532,30 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         if (!lost) steps = min(steps, P.mqd - lit + 1);  // after that many literal steps the parser is lost
         steps = min(steps, 32);
         bool flag = false;
+        // both k-mers of query position i + lane from one fetch; the anchor-table probe is ISSUED here and resolved after
+        // the seed-window work below, so its L2/DRAM round trip overlaps ~250 instructions instead of stalling the warp
+        uint64_t qk = 0;
+        bool qv = false, pr_live = false;
+        uint32_t pr_s = HT_EMPTY, pr_slot = 0, pr_fp = 0;
         if (lane < steps) {
-            uint64_t code;
-            if (kmer_at(Q, i + lane, P.mal, code)) flag = anchor_probe(tab, tcap, pos_bits, code, P.mal);
+            const int qp = i + lane;
+            const uint32_t qn = fetch1(Q.nv, (uint64_t)qp);
+            const uint64_t qw = fetch2(Q.s2, (uint64_t)qp);
+            qv = qp + P.msl <= Q.n && (qn & ((1u << P.msl) - 1)) == 0;
+            qk = qw & ((~0ULL) >> (64 - 2 * P.msl));
+            if (qp + P.mal <= Q.n && (qn & ((P.mal >= 32) ? 0xffffffffu : ((1u << P.mal) - 1))) == 0) {
+                const uint64_t km = (~0ULL) >> (64 - 2 * P.mal);
+                const uint64_t h = fmix64(canonical_kmer(qw & km, P.mal, km));
+                pr_fp = (uint32_t)(h >> 32) >> pos_bits;
+                pr_slot = ht_slot(h, tcap);
+                pr_s = __ldg(tab + pr_slot);
+                pr_live = true;
+            }
         }
         if (!lost) {
             // short seeds: lane t (query position i + t) may use reference positions [lo, pred + t + mrd).  The window is
             // shared by all lanes, so it is turned once into four position bit masks E_c ("symbol at window position w is
             // c", an N sets no bit); lane t then ANDs E_{q_j} >> j over the msl symbols of its k-mer (Shift-And).
-            uint64_t qk = 0;
-            const bool qv = lane < steps && !flag && kmer_at(Q, i + lane, P.msl, qk);
             const int lo = max(pred - lit, 0);
             const int my_w = pred + lane + P.mrd - lo;
             const int max_w = pred + (steps - 1) + P.mrd - lo;
@@ -606,6 +613,12 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
                     }
                 }
             }
+        }
+        while (pr_live) {                                 // resolve the probe: any entry with this fingerprint in the chain?
+            if (pr_s == HT_EMPTY) break;
+            if ((pr_s >> pos_bits) == pr_fp) { flag = true; break; }
+            pr_slot = (pr_slot + 1 == tcap) ? 0u : pr_slot + 1;
+            pr_s = __ldg(tab + pr_slot);
         }
         unsigned fb = __ballot_sync(0xffffffffu, flag);
         int adv = fb ? (__ffs(fb) - 1) : steps;
@@ -914,11 +927,13 @@ void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qr
     static const bool lpt_off = getenv("VB_ALIGN_NO_LPT") != nullptr;
     if (cost && job->prebuilt && !lpt_off && n >= 64) {
         const uint64_t n_heavy = n / 8;
-        std::vector<uint32_t> by_cost(order);
-        std::nth_element(by_cost.begin(), by_cost.begin() + n_heavy, by_cost.end(),
-                         [&](uint32_t a, uint32_t b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
-        by_cost.resize(n_heavy);
-        if (n_heavy > 4096)     // more than one wave of warps: most expensive first
+        std::vector<float> sorted_cost(cost, cost + n);
+        std::nth_element(sorted_cost.begin(), sorted_cost.begin() + n_heavy, sorted_cost.end(), std::greater<float>());
+        const float thr = sorted_cost[n_heavy];
+        std::vector<uint32_t> by_cost;
+        by_cost.reserve(n_heavy + 16);
+        for (uint32_t i : order) if (cost[i] > thr) by_cost.push_back(i);
+        if (by_cost.size() > 4096)     // more than one wave of warps: most expensive first
             std::sort(by_cost.begin(), by_cost.end(), [&](uint32_t a, uint32_t b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
         std::vector<uint8_t> heavy(n, 0);
         for (uint32_t i : by_cost) heavy[i] = 1;
@@ -929,6 +944,7 @@ void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qr
         order.swap(merged);
     }
     const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
+    ctx->set_timing("align.hp4_sched_ms", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - job->h0).count());
 
     DevBuf<int32_t> d_stats(3 * std::max<uint64_t>(n, 1));
     DevBuf<uint32_t> d_pref(std::max<uint64_t>(n, 1)), d_pqry(std::max<uint64_t>(n, 1));

@@ -433,10 +433,15 @@ static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pa
             is_ref[a] = 1; is_ref[b] = 1;
         }
     if (!pairs && n < 2) std::fill(is_ref.begin(), is_ref.end(), 0);
+    auto lap = [&](const char *key) {
+        ctx->set_timing(key, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
+    };
     vb_align_job *job = vb_align_job_begin(ctx, g, p, is_ref.data());
+    lap("align.hp1_begin_ms");
     vb_align_out *res = nullptr;
     try {
         std::vector<uint32_t> order = vb_lz_order(g);
+        lap("align.hp2_order_ms");
         std::vector<uint32_t> rank(n);
         for (uint32_t i = 0; i < n; ++i) rank[order[i]] = i;
         // directed pair list in LZ-ANI ids, grouped by reference with the queries ascending (results rows are sorted,
@@ -460,28 +465,36 @@ static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pa
             for (uint32_t r = 0; r < n; ++r)
                 for (uint32_t q = 0; q < n; ++q) if (q != r) { res->ref[w] = r; res->qry[w] = q; ++w; }
         } else {
-            // (query, estimated cost) per row; cost model: a parse scans the query once (extension, ~0.25 instructions
-            // per base) and pays ~1000 instructions per seed event; events happen where the sliding-window rule (more
-            // than 7 mismatches in 15) fires, i.e. at a rate of about C(15,8) p^8 (1-p)^7 per base at divergence p
-            std::vector<std::pair<uint32_t, float>> ent(total);
-            std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+            // directed pairs sorted by (reference, query) with two stable counting passes (by query, then by reference)
+            // instead of one small sort per row.  The estimated cost rides along; cost model: a parse scans the query
+            // once (extension, ~0.25 instructions per base) and pays ~1000 instructions per seed event; events happen
+            // where the sliding-window rule (more than 7 mismatches in 15) fires, i.e. at a rate of about
+            // C(15,8) p^8 (1-p)^7 per base at divergence p
             auto rate = [](double ani) {
                 const double p = std::min(std::max(1.0 - ani, 0.0), 0.5), q = 1.0 - p;
                 const double p2 = p * p, p4 = p2 * p2, q2 = q * q, q4 = q2 * q2;
                 return 0.25 + 1000.0 * 6435.0 * (p4 * p4) * (q4 * q2 * q);
             };
-            for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
-                uint32_t a = rank[pairs->row[i]], b = rank[pairs->col[i]];
-                const double r = pairs->ani ? rate(pairs->ani[i]) : 1.0;
-                ent[fill[a]++] = {b, (float)(r * (double)g->length(pairs->col[i]))};
-                ent[fill[b]++] = {a, (float)(r * (double)g->length(pairs->row[i]))};
+            struct Dir { uint32_t ref, qry; float cost; };
+            std::vector<Dir> by_qry(total);
+            {
+                std::vector<uint64_t> fill(start.begin(), start.end() - 1);      // the list is symmetric: same counts
+                for (uint64_t i = 0; i < pairs->n_pairs; ++i) {
+                    const uint32_t a = rank[pairs->row[i]], b = rank[pairs->col[i]];
+                    const double r = pairs->ani ? rate(pairs->ani[i]) : 1.0;
+                    by_qry[fill[b]++] = {a, b, (float)(r * (double)g->length(pairs->col[i]))};   // reference a, query b
+                    by_qry[fill[a]++] = {b, a, (float)(r * (double)g->length(pairs->row[i]))};   // reference b, query a
+                }
             }
             cost.resize(total);
-            for (uint32_t r = 0; r < n; ++r) {
-                std::sort(ent.begin() + start[r], ent.begin() + start[r + 1]);
-                for (uint64_t w = start[r]; w < start[r + 1]; ++w) { res->ref[w] = r; res->qry[w] = ent[w].first; cost[w] = ent[w].second; }
+            std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+            for (uint64_t i = 0; i < total; ++i) {                                // by_qry is grouped by query, ascending
+                const Dir &d = by_qry[i];
+                const uint64_t w = fill[d.ref]++;
+                res->ref[w] = d.ref; res->qry[w] = d.qry; cost[w] = d.cost;
             }
         }
+        lap("align.hp3_csr_ms");
         std::vector<uint32_t> in_ref(total), in_qry(total);
         for (uint64_t w = 0; w < total; ++w) { in_ref[w] = order[res->ref[w]]; in_qry[w] = order[res->qry[w]]; }
         std::vector<int32_t> stats(3 * std::max<uint64_t>(total, 1));
@@ -490,6 +503,7 @@ static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pa
         vb_align_job_run(job, in_ref.data(), in_qry.data(), total, stats.data(), regions ? &rec : nullptr,
                          cost.empty() ? nullptr : cost.data());
         ctx->set_timing("align.api_prep_ms", api_prep_ms);
+        lap("align.hp6_run_done_ms");
         if (regions) *regions = vb_regions_build(rec, in_ref.data(), in_qry.data(), p->mrd);
         for (uint64_t i = 0; i < total; ++i) {
             res->sym_in_matches[i] = stats[3 * i];
@@ -503,6 +517,7 @@ static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pa
     }
     vb_align_job_end(job);
     if (out) *out = res; else vb_align_out_free(res);
+    lap("align.hp7_end_ms");
     }
 }
 
