@@ -81,6 +81,8 @@ uint32_t vb_genomes_count(const vb_genomes *g);
 const char *vb_genomes_name(const vb_genomes *g, uint32_t i);
 uint64_t vb_genomes_length(const vb_genomes *g, uint32_t i);
 uint64_t vb_genomes_total_bases(const vb_genomes *g);
+/* the ASCII sequence of genome i as the stage will see it (records of a file already joined); borrowed, not NUL-terminated */
+const char *vb_genomes_sequence(const vb_genomes *g, uint32_t i);
 void vb_genomes_free(vb_genomes *g);
 
 /* ---- prefilter ---------------------------------------------------------------------------------------------- */

@@ -55,6 +55,78 @@ def test_fasta_ingest_matches_reference_rules(lib, golden, tmp_path):
     assert g.length(0) == 8 + 1 + 4
 
 
+def _spec_kmerdb(data: bytes):
+    """kmer-db record rules, stated byte by byte (genome_input_file.h:287-338)."""
+    recs = []
+    pos = data.find(b">")
+    while pos >= 0:
+        eol = data.find(b"\n", pos)
+        if eol < 0:
+            eol = len(data)
+        hend = eol - 1 if eol > pos + 1 and data[eol - 1:eol] == b"\r" else eol
+        name = data[pos + 1:hend]
+        nxt = data.find(b">", eol) if eol < len(data) else -1
+        bend = nxt if nxt >= 0 else len(data)
+        body = bytes(c for c in data[min(eol + 1, bend):bend] if c not in (10, 13))
+        recs.append((name.split(b" ")[0] if b" " in name else name, body))
+        pos = nxt
+    return recs
+
+
+def _spec_lzani(data: bytes, dir_mode: bool):
+    """lz-ani record rules, stated line by line (seq_reservoir.cpp:90-210, file_wrapper.h:917-950)."""
+    recs, cur, have = [], [b"", b""], False
+
+    def push():
+        if (have and cur[0]) or (dir_mode and (have or cur[1])):
+            recs.append((cur[0], cur[1]))
+
+    lines = data.split(b"\n")
+    tail = lines.pop()
+    if dir_mode and tail:
+        lines.append(tail)
+    for ln in lines:
+        if ln.endswith(b"\r"):
+            ln = ln[:-1]
+        if not ln:
+            continue
+        if ln[:1] == b">":
+            push()
+            cur, have = [ln[1:], b""], True
+        else:
+            cur[1] += ln
+    push()
+    return [((n.split(b" ")[0] if b" " in n else n), s) for n, s in recs]
+
+
+def test_fasta_ingest_fuzz_against_record_rules(lib, tmp_path):
+    """Random byte soup over the alphabet that matters (>, space, CR, LF, bases): the single-pass loader must give
+    exactly the records the two tools' rules give, in all four (flavor, mode) combinations."""
+    rng = np.random.default_rng(123)
+    alphabet = np.frombuffer(b">> \r\n\n\n\nACGTNacgtUXY", dtype=np.uint8)
+    for trial in range(60):
+        data = alphabet[rng.integers(0, alphabet.size, size=int(rng.integers(0, 400)))].tobytes()
+        if trial % 3 == 0:
+            data = b">s1 d\n" + data
+        fa = tmp_path / ("f%d.fa" % trial)
+        fa.write_bytes(data)
+        want = _spec_kmerdb(data)
+        g = api.Genomes.load([fa], True, api.FASTA_KMERDB)
+        assert [(g.name(i).encode(), g.sequence(i)) for i in range(len(g))] == want, (trial, data)
+        g = api.Genomes.load([fa], False, api.FASTA_KMERDB)
+        assert len(g) == 1 and g.sequence(0) == b"N".join(s for _, s in want), (trial, data)
+        want = _spec_lzani(data, False)
+        g = api.Genomes.load([fa], True, api.FASTA_LZANI)
+        assert [(g.name(i).encode(), g.sequence(i)) for i in range(len(g))] == want, (trial, data)
+        joined = b""
+        for _, s in _spec_lzani(data, True):
+            if joined:
+                joined += b"N" * 7
+            joined += s
+        g = api.Genomes.load([fa, fa], False, api.FASTA_LZANI, sep_len=7)
+        assert len(g) == 2 and g.sequence(0) == joined and g.sequence(1) == joined, (trial, data)
+
+
 def test_filter_roundtrip_and_format(lib, golden, tmp_path):
     p = golden / "example" / "multifasta.fna.gz"
     g = api.Genomes.load([p], True, api.FASTA_LZANI)

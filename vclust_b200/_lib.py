@@ -11,7 +11,7 @@ LIB_PATH = HERE / "libvclust_b200.so"
 EXPORTS = [
     "vb_version", "vb_device_count", "vb_last_error", "vb_ctx_create", "vb_ctx_destroy", "vb_ctx_timing",
     "vb_ctx_launches", "vb_ctx_mark", "vb_ctx_elapsed_ms", "vb_genomes_make_resident", "vb_genomes_evict", "vb_genomes_load", "vb_genomes_from_memory", "vb_genomes_count", "vb_genomes_name",
-    "vb_genomes_length", "vb_genomes_total_bases", "vb_genomes_free", "vb_prefilter", "vb_write_filter",
+    "vb_genomes_length", "vb_genomes_total_bases", "vb_genomes_sequence", "vb_genomes_free", "vb_prefilter", "vb_write_filter",
     "vb_read_filter", "vb_pairs_free", "vb_prefilter_partial", "vb_pairs_merge", "vb_align_out_from_pairs", "vb_align", "vb_align_pairs", "vb_write_ani", "vb_align_out_free",
     "vb_align_regions", "vb_align_pairs_regions", "vb_write_aln", "vb_regions_free",
 ]
@@ -81,6 +81,7 @@ def load():
         "vb_genomes_name": (cp, [vp, u32]),
         "vb_genomes_length": (u64, [vp, u32]),
         "vb_genomes_total_bases": (u64, [vp]),
+        "vb_genomes_sequence": (vp, [vp, u32]),
         "vb_genomes_free": (None, [vp]),
         "vb_prefilter": (i32, [vp, vp, C.POINTER(PrefilterParams), C.POINTER(C.POINTER(Pairs))]),
         "vb_prefilter_partial": (i32, [vp, vp, C.POINTER(PrefilterParams), u32, u32, C.POINTER(C.POINTER(Pairs))]),

@@ -144,6 +144,11 @@ class Genomes:
     def length(self, i: int) -> int:
         return int(self._L.vb_genomes_length(self._h, i))
 
+    def sequence(self, i: int) -> bytes:
+        n = self.length(i)
+        p = self._L.vb_genomes_sequence(self._h, i)
+        return C.string_at(p, n) if n else b""
+
     @property
     def total_bases(self) -> int:
         return int(self._L.vb_genomes_total_bases(self._h))

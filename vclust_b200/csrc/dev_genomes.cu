@@ -84,8 +84,10 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
     out.gofs.alloc(n ? n : 1);
     out.glen.alloc(n ? n : 1);
     out.tile_gid.alloc(tile.size());
-    if (!g->pinned && !g->bases.empty()) {
-        // page-lock the host copy once so that H2D runs at full PCIe rate (and truly asynchronously)
+    if (!g->pinned && !g->bases.empty() && ++g->uploads >= 2) {
+        // Page-locking costs about as much as one pageable transfer (it touches every page), so it only pays when the
+        // same host buffer is uploaded again: the first upload goes through the driver's staging path, from the second
+        // one on the buffer is pinned and H2D runs at full PCIe rate.
         if (cudaHostRegister((void *)g->bases.data(), g->bases.size(), cudaHostRegisterDefault) == cudaSuccess) g->pinned = true;
         else cudaGetLastError();
     }

@@ -6,99 +6,187 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstring>
 #include <filesystem>
 
 #include "vb_internal.h"
 
 namespace {
 
-std::string read_whole(const char *path)
+// Appends the whole (decompressed) file to `out` and returns the number of bytes added; gzip is detected by its magic
+// bytes (kmer-db genome_input_file.h:98-118; lz-ani reads through the same kind of wrapper), plain files are one fread.
+size_t read_whole(const char *path, vb_bytes &out)
 {
-    gzFile f = gzopen(path, "rb");          // transparently reads plain files too
-    if (!f) throw vb_error(VB_ERR_IO, std::string("Cannot open file: ") + path);
-    gzbuffer(f, 1 << 20);
-    std::string data;
-    std::vector<char> buf(8 << 20);
-    for (;;) {
-        int n = gzread(f, buf.data(), (unsigned)buf.size());
-        if (n < 0) { gzclose(f); throw vb_error(VB_ERR_IO, std::string("Cannot read file: ") + path); }
-        if (n == 0) break;
-        data.append(buf.data(), (size_t)n);
+    FILE *fp = fopen(path, "rb");
+    if (!fp) throw vb_error(VB_ERR_IO, std::string("Cannot open file: ") + path);
+    unsigned char magic[2] = {0, 0};
+    const size_t got = fread(magic, 1, 2, fp);
+    const size_t start = out.size();
+    size_t used = 0;
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        fclose(fp);
+        gzFile f = gzopen(path, "rb");
+        if (!f) throw vb_error(VB_ERR_IO, std::string("Cannot open file: ") + path);
+        gzbuffer(f, 1 << 20);
+        out.resize(start + (16 << 20));
+        for (;;) {
+            if (out.size() - start - used < (4u << 20)) out.resize(start + 2 * (out.size() - start));
+            int n = gzread(f, out.data() + start + used, (unsigned)std::min<size_t>(out.size() - start - used, 1u << 30));
+            if (n < 0) { gzclose(f); out.resize(start); throw vb_error(VB_ERR_IO, std::string("Cannot read file: ") + path); }
+            if (n == 0) break;
+            used += (size_t)n;
+        }
+        gzclose(f);
+        out.resize(start + used);
+        return used;
     }
-    gzclose(f);
-    return data;
+    std::error_code ec;
+    const auto fsize = std::filesystem::file_size(path, ec);
+    rewind(fp);
+    if (!ec && fsize > 0) {
+        out.resize(start + (size_t)fsize);
+        used = fread(out.data() + start, 1, (size_t)fsize, fp);
+    } else {                                            // not a regular file (pipe ...): read until EOF
+        out.resize(start + (1 << 20));
+        for (;;) {
+            if (start + used == out.size()) out.resize(start + 2 * (out.size() - start));
+            size_t n = fread(out.data() + start + used, 1, out.size() - start - used, fp);
+            if (n == 0) break;
+            used += n;
+        }
+    }
+    const bool bad = ferror(fp) != 0;
+    fclose(fp);
+    out.resize(start + used);
+    if (bad) { out.resize(start); throw vb_error(VB_ERR_IO, std::string("Cannot read file: ") + path); }
+    return used;
 }
 
-struct record { std::string name; std::string seq; };
+// Receives the records of one file in order and writes the sequence bytes straight into vb_genomes::bases (no
+// per-record strings).  A multi-FASTA is read INTO bases and compacted in place -- the write position never passes
+// the read position, hence memmove -- so a 400 MB input is one fread plus one memchr/memmove pass over the same pages.
+//   multisample : every kept record is a genome.
+//   otherwise   : the file is ONE genome named by its file name; kmer-db pools the records and k-mers must not span
+//                 them -> one 'N' between consecutive records (loader_ex.cpp:150-257); lz-ani joins them with sep_len
+//                 N symbols whenever the sequence so far is non-empty (seq_reservoir.cpp:90-153).
+struct Sink {
+    vb_genomes *g;
+    bool multisample, kmerdb;
+    size_t sep_len;
+    char *base = nullptr;          // g->bases.data() after reserve_for()
+    size_t w = 0;                  // write position in g->bases
+    size_t file_start = 0, rec_start = 0;
+    bool first_record = true;
+    std::string rec_name;
+
+    // in place (multisample): the file's bytes already sit at bases[w ...); otherwise room for bytes + separators
+    void start_file(size_t file_bytes, size_t max_records_hint, bool in_place)
+    {
+        if (!in_place) g->bases.resize(w + file_bytes + (max_records_hint + 1) * std::max<size_t>(sep_len, 1));
+        base = g->bases.data();
+        file_start = w;
+        first_record = true;
+    }
+    void begin_record(const char *name, size_t name_len)
+    {
+        if (multisample) rec_name.assign(name, name_len);
+        else if (kmerdb) { if (!first_record) base[w++] = 'N'; }
+        else if (w > file_start) { memset(base + w, 'N', sep_len); w += sep_len; }
+        first_record = false;
+        rec_start = w;
+    }
+    inline void append(const char *p, size_t n) { memmove(base + w, p, n); w += n; }
+    void end_record(bool keep)
+    {
+        if (!multisample) return;
+        if (!keep) { w = rec_start; return; }
+        size_t sp = rec_name.find(' ');
+        if (sp != std::string::npos) rec_name.resize(sp);
+        g->names.push_back(rec_name);
+        g->offset.push_back(w);
+    }
+    void end_file(const char *path)
+    {
+        if (!multisample) {
+            g->names.push_back(std::filesystem::path(path).filename().string());
+            g->offset.push_back(w);
+        }
+        g->bases.resize(w);
+    }
+};
+
+// append [b, e) without '\n' and '\r'
+inline void append_stripped(Sink &s, const char *b, const char *e)
+{
+    while (b < e) {
+        const char *nl = (const char *)memchr(b, '\n', (size_t)(e - b));
+        const char *le = nl ? nl : e;
+        const char *cr = (const char *)memchr(b, '\r', (size_t)(le - b));
+        if (!cr) s.append(b, (size_t)(le - b));
+        else
+            for (const char *p = b; p < le; ++p) if (*p != '\r') s.base[s.w++] = *p;       // rare: CR inside a line / CRLF
+        b = nl ? nl + 1 : e;
+    }
+}
 
 // kmer-db rule: a record starts at every '>' byte; header ends at '\n' (a preceding '\r' is dropped) and is cut at
 // the first space; the sequence is everything up to the next '>' without '\n' and '\r'.
-void split_kmerdb(const std::string &d, std::vector<record> &out)
+void split_kmerdb(const char *d, size_t n, Sink &s)
 {
-    size_t pos = d.find('>');
-    while (pos != std::string::npos) {
-        size_t eol = d.find('\n', pos);
-        if (eol == std::string::npos) eol = d.size();
-        size_t hend = eol;
-        if (hend > pos + 1 && d[hend - 1] == '\r') --hend;
-        record r;
-        r.name.assign(d, pos + 1, hend - pos - 1);
-        size_t sp = r.name.find(' ');
-        if (sp != std::string::npos) r.name.resize(sp);
-        size_t nxt = d.find('>', eol);
-        size_t bend = (nxt == std::string::npos) ? d.size() : nxt;
-        size_t bbeg = std::min(eol + 1, bend);
-        r.seq.reserve(bend - bbeg);
-        for (size_t i = bbeg; i < bend; ++i) {
-            char c = d[i];
-            if (c != '\n' && c != '\r') r.seq.push_back(c);
-        }
-        out.push_back(std::move(r));
+    const char *end = d + n;
+    const char *pos = (const char *)memchr(d, '>', n);
+    while (pos) {
+        const char *eol = (const char *)memchr(pos, '\n', (size_t)(end - pos));
+        if (!eol) eol = end;
+        const char *hend = eol;
+        if (hend > pos + 1 && hend[-1] == '\r') --hend;
+        s.begin_record(pos + 1, (size_t)(hend - pos - 1));
+        const char *nxt = eol < end ? (const char *)memchr(eol, '>', (size_t)(end - eol)) : nullptr;
+        const char *bend = nxt ? nxt : end;
+        const char *bbeg = std::min(eol + 1, bend);
+        append_stripped(s, bbeg, bend);
+        s.end_record(true);
         pos = nxt;
     }
 }
 
 // lz-ani rule: line based; '>' counts only in column 0; every line loses one trailing '\r'; empty lines are skipped.
-// keep_unterminated_tail: directory mode keeps a last line without '\n', multi-FASTA mode drops it.
-// dir_mode additionally keeps records with an empty name and header-less leading sequence (load_fasta ignores names).
-void split_lzani(const std::string &d, bool dir_mode, std::vector<record> &out)
+// Directory mode keeps a last line without '\n', multi-FASTA mode drops it; directory mode also keeps records with an
+// empty name and a header-less leading sequence (load_fasta ignores names), multi-FASTA mode drops both.
+void split_lzani(const char *d, size_t n, bool dir_mode, Sink &s)
 {
-    const bool keep_unterminated_tail = dir_mode;
-    record cur;
-    bool have = false;
-    size_t pos = 0;
-    auto handle = [&](size_t b, size_t e) {
-        if (e > b && d[e - 1] == '\r') --e;
-        if (e == b) return;
-        if (d[b] == '>') {
-            if ((have && !cur.name.empty()) || (dir_mode && (have || !cur.seq.empty()))) out.push_back(std::move(cur));
-            cur = record();
-            cur.name.assign(d, b + 1, e - b - 1);
-            have = true;
-        } else
-            cur.seq.append(d, b, e - b);
+    const char *end = d + n;
+    const char *pos = d;
+    bool have = false, open = false, named = false;      // a header was seen / a record is open / its name is non-empty
+    auto close = [&]() {
+        if (!open) return;
+        const bool keep = dir_mode ? true : (have && named);
+        s.end_record(keep);
+        open = false;
     };
-    while (pos < d.size()) {
-        size_t eol = d.find('\n', pos);
-        if (eol == std::string::npos) {
-            if (keep_unterminated_tail) handle(pos, d.size());
+    auto handle = [&](const char *b, const char *e) {
+        if (e > b && e[-1] == '\r') --e;
+        if (e == b) return;
+        if (*b == '>') {
+            close();
+            s.begin_record(b + 1, (size_t)(e - b - 1));
+            have = true; open = true; named = e - b - 1 > 0;
+        } else {
+            if (!open) { s.begin_record(b, 0); open = true; named = false; }    // header-less leading sequence
+            s.append(b, (size_t)(e - b));
+        }
+    };
+    while (pos < end) {
+        const char *eol = (const char *)memchr(pos, '\n', (size_t)(end - pos));
+        if (!eol) {
+            if (dir_mode) handle(pos, end);
             break;
         }
         handle(pos, eol);
         pos = eol + 1;
     }
-    if ((have && !cur.name.empty()) || (dir_mode && (have || !cur.seq.empty()))) out.push_back(std::move(cur));
-    for (auto &r : out) {
-        size_t sp = r.name.find(' ');
-        if (sp != std::string::npos) r.name.resize(sp);
-    }
-}
-
-void push_genome(vb_genomes *g, const std::string &name, const std::string &seq)
-{
-    g->names.push_back(name);
-    g->bases.insert(g->bases.end(), seq.begin(), seq.end());
-    g->offset.push_back(g->bases.size());
+    close();
 }
 
 }  // namespace
@@ -110,28 +198,28 @@ vb_genomes *vb_genomes_load_impl(const char *const *paths, int n_paths, int mult
     g->flavor = flavor;
     g->offset.push_back(0);
     try {
+        Sink s{g, multisample != 0, flavor == VB_FASTA_KMERDB, (size_t)std::max(sep_len, 0)};
+        vb_bytes tmp;
         for (int i = 0; i < n_paths; ++i) {
-            std::string data = read_whole(paths[i]);
-            std::vector<record> recs;
-            if (flavor == VB_FASTA_KMERDB) split_kmerdb(data, recs);
-            else split_lzani(data, !multisample, recs);
-            if (multisample) {
-                for (auto &r : recs) push_genome(g, r.name, r.seq);
-            } else {
-                // one genome per file.  kmer-db: records pooled, k-mers must not span records -> one 'N' between
-                // them.  lz-ani: records joined by sep_len N symbols whenever the sequence so far is non-empty.
-                std::string joined;
-                size_t sep = (flavor == VB_FASTA_KMERDB) ? 1 : (size_t)std::max(sep_len, 0);
-                bool first = true;
-                for (auto &r : recs) {
-                    if (flavor == VB_FASTA_KMERDB) { if (!first) joined.append(sep, 'N'); }
-                    else if (!joined.empty()) joined.append(sep, 'N');
-                    joined += r.seq;
-                    first = false;
-                }
-                push_genome(g, std::filesystem::path(paths[i]).filename().string(), joined);
+            const char *d;
+            size_t n;
+            if (multisample) {                          // read into the store, compact in place
+                n = read_whole(paths[i], g->bases);
+                d = g->bases.data() + s.w;
+                s.start_file(n, 0, true);
+            } else {                                    // separators may outgrow the headers they replace: two buffers
+                tmp.resize(0);
+                n = read_whole(paths[i], tmp);
+                d = tmp.data();
+                size_t hdrs = 0;                        // at most one separator per header line
+                for (const char *p = d, *e = d + n; (p = (const char *)memchr(p, '>', (size_t)(e - p))); ++p) ++hdrs;
+                s.start_file(n, hdrs, false);
             }
+            if (flavor == VB_FASTA_KMERDB) split_kmerdb(d, n, s);
+            else split_lzani(d, n, !multisample, s);
+            s.end_file(paths[i]);
         }
+        g->bases.shrink_to_fit();
     } catch (...) {
         delete g;
         throw;
@@ -149,7 +237,7 @@ vb_genomes *vb_genomes_from_memory_impl(const char *const *names, const char *co
     g->bases.reserve(total);
     for (uint32_t i = 0; i < n; ++i) {
         g->names.emplace_back(names[i]);
-        g->bases.insert(g->bases.end(), seqs[i], seqs[i] + lens[i]);
+        g->bases.append(seqs[i], lens[i]);
         g->offset.push_back(g->bases.size());
     }
     return g;

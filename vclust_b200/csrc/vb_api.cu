@@ -211,6 +211,7 @@ uint32_t vb_genomes_count(const vb_genomes *g) { return g ? g->count() : 0; }
 const char *vb_genomes_name(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->names[i].c_str() : ""; }
 uint64_t vb_genomes_length(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->length(i) : 0; }
 uint64_t vb_genomes_total_bases(const vb_genomes *g) { return g ? g->bases.size() : 0; }
+const char *vb_genomes_sequence(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->bases.data() + g->offset[i] : nullptr; }
 void vb_genomes_free(vb_genomes *g) { if (g) { vb_unpin_genomes(g); delete g; } }
 
 int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out)

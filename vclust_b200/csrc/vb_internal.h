@@ -1,6 +1,8 @@
 // Internal declarations shared by the translation units of libvclust_b200.so (not part of the C ABI).
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <new>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,15 +21,46 @@ void vb_set_error(const std::string &msg);
 
 uint64_t vb_next_uid();
 
+// growable byte buffer WITHOUT value-initialisation: a 400 MB FASTA is read straight into it and compacted in place, so
+// every page is touched once (std::vector<char>::resize would zero-fill the pages first)
+struct vb_bytes {
+    char *p = nullptr;
+    size_t n = 0, cap = 0;
+    vb_bytes() = default;
+    vb_bytes(const vb_bytes &) = delete;
+    vb_bytes &operator=(const vb_bytes &) = delete;
+    ~vb_bytes() { free(p); }
+    char *data() { return p; }
+    const char *data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    void reserve(size_t c)
+    {
+        if (c <= cap) return;
+        char *q = (char *)realloc(p, c);
+        if (!q) throw std::bad_alloc();
+        p = q; cap = c;
+    }
+    void resize(size_t m) { if (m > cap) reserve(std::max(m, cap + cap / 2)); n = m; }
+    void append(const char *s, size_t len) { resize(n + len); if (len) memcpy(p + n - len, s, len); }
+    void shrink_to_fit()
+    {
+        if (n == cap || !p) return;
+        char *q = (char *)realloc(p, n ? n : 1);
+        if (q) { p = q; cap = n ? n : 1; }
+    }
+};
+
 // Host-side genome set.  Sequences are kept as ASCII exactly as read (separators between the records of one
 // file already inserted as 'N' bytes); symbol coding happens on the device, per stage, because kmer-db and
 // lz-ani disagree on 'U' (kmer-db alphabet.h:80-85 vs lz-ani seq_reservoir.h:243-247).
 struct vb_genomes {
     std::vector<std::string> names;
     std::vector<uint64_t> offset;   // n+1 offsets into bases
-    std::vector<char> bases;        // concatenated ASCII
+    vb_bytes bases;                 // concatenated ASCII
     vb_fasta_flavor flavor = VB_FASTA_KMERDB;
-    mutable bool pinned = false;    // bases page-locked with cudaHostRegister (done lazily by the first upload)
+    mutable bool pinned = false;    // bases page-locked with cudaHostRegister (done lazily by the second upload)
+    mutable int uploads = 0;
     uint64_t uid = vb_next_uid();   // distinguishes a new set that re-uses the address of a freed one (device-copy cache)
     uint32_t count() const { return (uint32_t)names.size(); }
     uint64_t length(uint32_t i) const { return offset[i + 1] - offset[i]; }
