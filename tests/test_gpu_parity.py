@@ -76,6 +76,32 @@ def test_prefilter_counts_vs_oracle(ctx, golden, k, f):
     assert got == want
 
 
+@pytest.mark.parametrize("env", [
+    {"VB_PREFILTER_CHUNK": "4096"},                                  # slot axis walked in many small chunks (> 2^32-slot inputs)
+    {"VB_PREFILTER_CHUNK": "6144", "VB_PREFILTER_EXACT": "1"},       # + survivors counted before the list is allocated
+    {"VB_PREFILTER_SEEN": "0"},                                      # singleton screen off (large inputs)
+    {"VB_PREFILTER_SEEN": "0", "VB_PREFILTER_EXACT": "1", "VB_PREFILTER_CHUNK": "2048"},
+    {"VB_PREFILTER_SEEN": "12"},                                     # tiny seen table: heavy slot collisions must be harmless
+    {"VB_PREFILTER_HASH": "1"},                                      # hashed pair table (N(N-1)/2 > 2^26)
+    {"VB_PREFILTER_LSD": "1"},                                       # full radix sort instead of the hash-bucket partition
+])
+def test_prefilter_large_input_paths_vs_oracle(ctx, golden, monkeypatch, env):
+    """The code paths that only very large inputs select by themselves, forced on a small input: same integers."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    names, seqs = synth.make_genomes(n=36, length=(3000, 9000), family=6, seed=31, n_frac=0.2, lower_frac=0.2)
+    raw = [s.tobytes() for s in seqs] + [b"", b"ACGTAC", b"N" * 500]
+    names = names + ["e0", "e1", "e2"]
+    for k, f in ((25, 1.0), (17, 0.5)):
+        sets = oracle.kmer_sets([[s] for s in raw], k, f)
+        rows, cols, vals = oracle.common_matrix(sets)
+        g = api.Genomes.from_memory(names, raw)
+        pairs = api.prefilter_genomes(ctx, g, k=k, min_kmers=1, min_ident=0.0, kmers_fraction=f)
+        assert pairs.total_kmers.tolist() == [int(s.size) for s in sets]
+        assert {(int(r), int(c)): int(v) for r, c, v in zip(pairs.rows, pairs.cols, pairs.common)} == \
+               {(int(r), int(c)): int(v) for r, c, v in zip(rows, cols, vals)}
+
+
 def test_prefilter_edge_cases(ctx):
     # empty genome, genome shorter than k, all-N genome, U handled as T, lower case, duplicate genomes
     seqs = [b"", b"ACGTACGT", b"N" * 100, b"ACGU" * 30, b"acgt" * 30, b"ACGT" * 30, b"ACGTTGCAAGGCTA" * 10]

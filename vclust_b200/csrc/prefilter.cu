@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) segment_pairs_kernel(const uint64_t *__re
 constexpr int PART_THREADS = 512;
 constexpr int PART_ITEMS = 8;
 constexpr int PART_TILE = PART_THREADS * PART_ITEMS;      // 4096 tuples per block
-constexpr int MAX_BUCKET_BITS = 9;                        // per level
+constexpr int MAX_BUCKET_BITS = 10;                       // per level
 constexpr int BUCKET_CAP = 2048;                          // tuples a bucket may hold to be grouped in shared memory
 constexpr int BUCKET_SLOTS = 4096;                        // hash slots per bucket (load <= 0.5)
 constexpr int BUCKET_TARGET = 1280;                       // planned mean bucket size (CAP is 20 sigma above it)
@@ -200,24 +200,6 @@ struct MsdPlan {
     int b1, b2;              // bucket bits of level 1 and level 2 (b2 == 0: one level)
     uint32_t B1, B2, NB;     // 1 << b1, 1 << b2, B1 * B2
 };
-
-__device__ __forceinline__ bool extract_at(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
-                                           const uint32_t *__restrict__ tile_gid, uint64_t p, uint64_t n_slots,
-                                           const ExtractParams &ep, uint64_t kmask, uint32_t wmask, uint64_t &h, uint32_t &gid)
-{
-    if (p >= n_slots) return false;
-    gid = tile_gid[p >> 7];
-    if (gid == 0xffffffffu || (fetch1(inv, p) & wmask) != 0) return false;
-    uint64_t w = fetch2(seq2, p) & kmask;
-    uint64_t rc = (~w) & kmask;
-    uint64_t fw = reverse_digits(w) >> (64 - 2 * ep.k);
-    uint64_t can = fw < rc ? fw : rc;
-    can = (can << ep.shift) | (can & ep.tail_mask);
-    if (ep.use_filter && !(minhash64(can, ep.c) < ep.max_thr)) return false;
-    h = fmix64(can);
-    if (ep.shard_count > 1 && (h % ep.shard_count) != ep.shard_index) return false;
-    return true;
-}
 
 // Singleton screen.  A k-mer that occurs once in the whole input shares nothing and is the common case (92 % of the
 // distinct k-mers of c2), so it is dropped before the partition: a table of 2-bit slots indexed by hash bits records
@@ -236,23 +218,22 @@ __device__ __forceinline__ bool seen_twice(const SeenTable &T, uint64_t h)
     return (__ldg(T.words + (s >> 4)) >> (2 * (uint32_t)(s & 15) + 1)) & 1u;
 }
 
-constexpr int FINE_BITS = 2 * MAX_BUCKET_BITS;          // resolution of the survivor histogram taken during compaction
+constexpr int FINE_BITS_SMALL = 18, FINE_BITS_LARGE = 2 * MAX_BUCKET_BITS;   // resolution of the survivor histogram
 
-// Append this block's surviving tuples (up to ITEMS per thread) to the compact list -- order is irrelevant, tuples are
-// grouped by hash later -- and count them in the fine histogram.  One global cursor atomic per call and block.  All
-// threads of the block must call; s_warp is [2][33] shared words, `phase` alternates 0/1 between successive calls so that
-// a call never overwrites prefixes another warp is still reading (two barriers per call instead of three).
+// Append this block's surviving tuples (bit r of `keep` selects h[r]; all of one thread's tuples share a genome) to the
+// compact list -- order is irrelevant, tuples are grouped by hash later -- and count them in the fine histogram.  One
+// global cursor atomic per call and block.  All threads of the block must call; s_warp is [2][33] shared words, `phase`
+// alternates 0/1 between successive calls so that a call never overwrites prefixes another warp is still reading (two
+// barriers per call instead of three).  write == 0: only count (cursor and histogram untouched except the cursor).
 template <int ITEMS>
-__device__ __forceinline__ void block_append(const bool (&keep)[ITEMS], const uint64_t (&h)[ITEMS], const uint32_t (&gid)[ITEMS],
-                                             uint32_t (*s_warp)[33], int phase, unsigned long long *__restrict__ cursor,
+__device__ __forceinline__ void block_append(uint32_t keep, const uint64_t (&h)[ITEMS], uint32_t gid, uint32_t (*s_warp)[33],
+                                             int phase, unsigned long long *__restrict__ cursor, int write,
                                              uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
-                                             uint32_t *__restrict__ fine_hist)
+                                             uint32_t *__restrict__ fine_hist, int fine_bits)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t *sw = s_warp[phase];
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int r = 0; r < ITEMS; ++r) cnt += keep[r];
+    const uint32_t cnt = (uint32_t)__popc(keep);
     uint32_t x = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -266,119 +247,152 @@ __device__ __forceinline__ void block_append(const bool (&keep)[ITEMS], const ui
         unsigned long long base = 0;
         if (lane == 0 && total) base = atomicAdd(cursor, (unsigned long long)total);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < nw) sw[lane] = (uint32_t)base + z - v;      // fewer than 2^32 slots per call, so the low word is enough
+        if (lane < nw) sw[lane] = (uint32_t)base + z - v;      // the list holds fewer than 2^32 tuples: the low word is enough
     }
     __syncthreads();
+    if (!write) return;
     uint32_t o = sw[wid] + x - cnt;
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r)
-        if (keep[r]) {
+        if ((keep >> r) & 1u) {
             out_keys[o] = h[r];
-            out_vals[o] = gid[r];
+            out_vals[o] = gid;
             ++o;
-            atomicAdd(&fine_hist[(uint32_t)(h[r] >> (64 - FINE_BITS))], 1u);
+            atomicAdd(&fine_hist[(uint32_t)(h[r] >> (64 - fine_bits))], 1u);
         }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k1.  One thread takes KM_ITEMS consecutive base slots (p a multiple of KM_ITEMS): three words of bases and two words
+// of validity bits are loaded once and every k-mer window is cut out of them with funnel shifts, so a k-mer costs
+// ~50 instructions instead of ~150 with one thread (and five loads) per slot.  h = fmix64(canonical k-mer) is a
+// bijection; only the grouping of equal k-mers matters downstream, not their numeric order.
+// Nothing is stored per slot: the screen pass only marks the seen table, the collect pass RECOMPUTES the hashes from
+// the packed genomes (0.375 B/base) -- 8 B/slot written and read back cost more than hashing twice.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KM_ITEMS = 8;
 
-// k1: one thread per base slot: h = fmix64(canonical k-mer) (a bijection; the preimage of ~0 is >= 2^63, not a k-mer, so
-// KEY_SENTINEL marks "no k-mer here"); valid k-mers per genome.  Each block owns a contiguous range of slots, so a warp
-// stays inside one genome for many iterations and keeps that genome's count in a register (one atomic per genome change).
-//   SCREEN: hbuf[p] = h, the seen table is updated, *n_again counts tuples that found their slot already marked;
-//           compact_kernel then picks the survivors.
-//   !SCREEN: every valid tuple survives and is appended to the compact list right here.
-template <bool SCREEN>
-__global__ void __launch_bounds__(512) hash_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
-                                                   const uint32_t *__restrict__ tile_gid, uint64_t n_slots, uint64_t n_iter,
-                                                   ExtractParams ep, uint64_t *__restrict__ hbuf, SeenTable T,
-                                                   uint32_t *__restrict__ valid_cnt, unsigned long long *__restrict__ n_again,
-                                                   unsigned long long *__restrict__ cursor, uint64_t *__restrict__ out_keys,
-                                                   uint32_t *__restrict__ out_vals, uint32_t *__restrict__ fine_hist)
+__device__ __forceinline__ uint32_t kmer_hashes(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv, uint64_t p,
+                                                const ExtractParams &ep, uint64_t kmask, uint32_t wmask, uint64_t (&h)[KM_ITEMS])
 {
-    constexpr int HASH_ITEMS = SCREEN ? 1 : 4;             // the append amortises its barriers and cursor atomic over 4
+    const uint32_t *q = seq2 + (p >> 4);
+    const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    const uint32_t *qi = inv + (p >> 5);
+    const uint32_t i0 = __ldg(qi), i1 = __ldg(qi + 1);
+    const unsigned ib = (unsigned)(p & 31);                                  // 0, 8, 16 or 24
+    const uint32_t iv0 = __funnelshift_r(i0, i1, ib), iv1 = i1 >> ib;        // >= 40 validity bits from slot p on
+    const unsigned o = (unsigned)(p & 15) * 2;                               // 0 or 16
+    const uint32_t w0 = __funnelshift_r(a, b, o), w1 = __funnelshift_r(b, c, o), w2 = c >> o;   // >= 40 bases from slot p on
+    uint32_t ok = 0;
+#pragma unroll
+    for (int j = 0; j < KM_ITEMS; ++j) {
+        const uint32_t bad = __funnelshift_r(iv0, iv1, j) & wmask;
+        const uint32_t lo = __funnelshift_r(w0, w1, 2 * j), hi = __funnelshift_r(w1, w2, 2 * j);
+        const uint64_t w = (((uint64_t)hi << 32) | lo) & kmask;              // digit t = base p + j + t
+        const uint64_t rc = (~w) & kmask;                                    // == reference's kmer_rev as an integer
+        const uint64_t fw = reverse_digits(w) >> (64 - 2 * ep.k);            // == reference's kmer_str
+        uint64_t can = fw < rc ? fw : rc;
+        can = (can << ep.shift) | (can & ep.tail_mask);
+        bool keep = bad == 0;
+        if (ep.use_filter) keep = keep && minhash64(can, ep.c) < ep.max_thr;
+        const uint64_t hh = fmix64(can);
+        if (ep.shard_count > 1) keep = keep && (hh % ep.shard_count) == ep.shard_index;
+        h[j] = hh;
+        ok |= (uint32_t)keep << j;
+    }
+    return ok;
+}
+
+// valid k-mers per genome: a warp covers 32 * KM_ITEMS = 256 consecutive slots = two 128-slot tiles = at most two genomes
+__device__ __forceinline__ void count_valid(uint32_t ok, uint32_t gid, int lane, uint32_t *__restrict__ valid_cnt)
+{
+    const uint32_t c = gid == 0xffffffffu ? 0u : (uint32_t)__popc(ok);
+    const uint32_t total = __reduce_add_sync(0xffffffffu, c);
+    if (!total) return;
+    const uint32_t lo = __reduce_add_sync(0xffffffffu, lane < 16 ? c : 0u);
+    const uint32_t g_lo = __shfl_sync(0xffffffffu, gid, 0), g_hi = __shfl_sync(0xffffffffu, gid, 16);
+    if (lane == 0 && lo) atomicAdd(&valid_cnt[g_lo], lo);
+    if (lane == 16 && total - lo) atomicAdd(&valid_cnt[g_hi], total - lo);
+}
+
+// Singleton screen, pass 1 over the slots [p_lo, p_hi) (multiples of 256): mark every k-mer in the seen table; *n_again
+// counts the tuples that found their slot already marked (survivors = *n_again + number of slots with bit 1).
+__global__ void __launch_bounds__(256) screen_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
+                                                     const uint32_t *__restrict__ tile_gid, uint64_t p_lo, uint64_t p_hi,
+                                                     ExtractParams ep, SeenTable T, uint32_t *__restrict__ valid_cnt,
+                                                     unsigned long long *__restrict__ n_again)
+{
+    const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
+    const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_groups = (p_hi - p_lo) / KM_ITEMS;
+    uint32_t again = 0;
+    // whole warps enter and leave the loop together (count_valid synchronises the warp)
+    for (uint64_t gi = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; gi - lane < n_groups; gi += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = p_lo + gi * KM_ITEMS;
+        const uint32_t gid = gi < n_groups ? tile_gid[p >> 7] : 0xffffffffu;
+        uint64_t h[KM_ITEMS];
+        uint32_t ok = 0;
+        if (gid != 0xffffffffu) ok = kmer_hashes(seq2, inv, p, ep, kmask, wmask, h);
+#pragma unroll
+        for (int j = 0; j < KM_ITEMS; ++j)
+            if ((ok >> j) & 1u) {
+                const uint64_t s = (h[j] >> 16) & T.slot_mask;
+                uint32_t *w = T.words + (s >> 4);
+                const uint32_t b0 = 1u << (2 * (uint32_t)(s & 15));
+                const uint32_t old = atomicOr(w, b0);
+                if (old & b0) {
+                    ++again;
+                    if (!(old & (b0 << 1))) atomicOr(w, b0 << 1);            // only the second occurrence pays for this one
+                }
+            }
+        count_valid(ok, gid, lane, valid_cnt);
+    }
+    again = __reduce_add_sync(0xffffffffu, again);
+    if (lane == 0 && again) atomicAdd(n_again, (unsigned long long)again);
+}
+
+// Pass 2 (or the only pass when the screen is off): recompute the hashes, keep the tuples whose seen slot says "twice",
+// append them to the compact list (write == 0: only count them).  COUNT_VALID: also count valid k-mers per genome.
+template <bool COUNT_VALID>
+__global__ void __launch_bounds__(256) collect_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
+                                                      const uint32_t *__restrict__ tile_gid, uint64_t p_lo, uint64_t p_hi,
+                                                      ExtractParams ep, SeenTable T, uint32_t *__restrict__ valid_cnt,
+                                                      unsigned long long *__restrict__ cursor, int write,
+                                                      uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
+                                                      uint32_t *__restrict__ fine_hist, int fine_bits)
+{
     __shared__ uint32_t s_warp[2][33];
     const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
     const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
-    const uint64_t chunk = (uint64_t)blockDim.x * HASH_ITEMS;
-    const uint64_t per_block = ((n_iter + gridDim.x - 1) / gridDim.x + chunk - 1) / chunk * chunk;
-    const uint64_t p_beg = min(n_iter, blockIdx.x * per_block), p_end = min(n_iter, p_beg + per_block);
-    uint32_t acc_gid = 0xffffffffu, acc = 0, again = 0;
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_groups = (p_hi - p_lo) / KM_ITEMS;
     int phase = 0;
-    for (uint64_t base = p_beg; base < p_end; base += chunk, phase ^= 1) {  // uniform trip count: block_append synchronises
-        bool ok[HASH_ITEMS];
-        uint64_t h[HASH_ITEMS];
-        uint32_t gid[HASH_ITEMS];
+    // whole blocks enter and leave the loop together (block_append synchronises the block)
+    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < n_groups; base += (uint64_t)gridDim.x * blockDim.x, phase ^= 1) {
+        const uint64_t p = p_lo + (base + threadIdx.x) * KM_ITEMS;
+        const uint32_t gid = base + threadIdx.x < n_groups ? tile_gid[p >> 7] : 0xffffffffu;
+        uint64_t h[KM_ITEMS];
+        uint32_t ok = 0;
+        if (gid != 0xffffffffu) ok = kmer_hashes(seq2, inv, p, ep, kmask, wmask, h);
+        if (COUNT_VALID) count_valid(ok, gid, lane, valid_cnt);
+        if (T.words) {
 #pragma unroll
-        for (int r = 0; r < HASH_ITEMS; ++r) {
-            const uint64_t p = base + (uint64_t)r * blockDim.x + threadIdx.x;       // whole warps are inside or outside
-            h[r] = KEY_SENTINEL; gid[r] = 0;
-            ok[r] = p < p_end && extract_at(seq2, inv, tile_gid, p, n_slots, ep, kmask, wmask, h[r], gid[r]);
-            if (SCREEN) {
-                if (p < p_end) hbuf[p] = ok[r] ? h[r] : KEY_SENTINEL;
-                if (ok[r]) {
-                    const uint64_t s = (h[r] >> 16) & T.slot_mask;
-                    uint32_t *w = T.words + (s >> 4);
-                    const uint32_t b0 = 1u << (2 * (uint32_t)(s & 15));
-                    if (atomicOr(w, b0) & b0) { atomicOr(w, b0 << 1); ++again; }
-                }
-            }
+            for (int j = 0; j < KM_ITEMS; ++j)
+                if (((ok >> j) & 1u) && !seen_twice(T, h[j])) ok &= ~(1u << j);
         }
-        if (!SCREEN) block_append<HASH_ITEMS>(ok, h, gid, s_warp, phase, cursor, out_keys, out_vals, fine_hist);
-#pragma unroll
-        for (int r = 0; r < HASH_ITEMS; ++r) {
-            unsigned m = __ballot_sync(0xffffffffu, ok[r]);
-            if (m) {
-                uint32_t g = __shfl_sync(0xffffffffu, gid[r], __ffs(m) - 1);    // a warp's 32 slots share the genome
-                if (g != acc_gid) {
-                    if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
-                    acc_gid = g; acc = 0;
-                }
-                acc += (uint32_t)__popc(m);
-            }
-        }
-    }
-    if (acc && (threadIdx.x & 31) == 0) atomicAdd(&valid_cnt[acc_gid], acc);
-    if (SCREEN) {
-        again = __reduce_add_sync(0xffffffffu, again);
-        if ((threadIdx.x & 31) == 0 && again) atomicAdd(n_again, (unsigned long long)again);
-    }
-}
-
-// SCREEN path: hbuf + seen table -> compact list of survivors + fine histogram
-constexpr int COMPACT_ITEMS = 8;
-__global__ void __launch_bounds__(256) compact_kernel(const uint64_t *__restrict__ hbuf, uint64_t n_iter, SeenTable T,
-                                                      const uint32_t *__restrict__ tile_gid,
-                                                      unsigned long long *__restrict__ cursor, uint64_t *__restrict__ out_keys,
-                                                      uint32_t *__restrict__ out_vals, uint32_t *__restrict__ fine_hist)
-{
-    __shared__ uint32_t s_warp[2][33];
-    const uint64_t chunk = 256ull * COMPACT_ITEMS;
-    int phase = 0;
-    for (uint64_t base = blockIdx.x * chunk; base < n_iter; base += (uint64_t)gridDim.x * chunk, phase ^= 1) {
-        bool keep[COMPACT_ITEMS];
-        uint64_t h[COMPACT_ITEMS];
-        uint32_t gid[COMPACT_ITEMS];
-#pragma unroll
-        for (int r = 0; r < COMPACT_ITEMS; ++r) {
-            const uint64_t p = base + r * 256 + threadIdx.x;
-            h[r] = p < n_iter ? hbuf[p] : KEY_SENTINEL;
-        }
-#pragma unroll
-        for (int r = 0; r < COMPACT_ITEMS; ++r) {
-            keep[r] = h[r] != KEY_SENTINEL && seen_twice(T, h[r]);
-            gid[r] = keep[r] ? tile_gid[(base + r * 256 + threadIdx.x) >> 7] : 0u;
-        }
-        block_append<COMPACT_ITEMS>(keep, h, gid, s_warp, phase, cursor, out_keys, out_vals, fine_hist);
+        block_append<KM_ITEMS>(ok, h, gid, s_warp, phase, cursor, write, out_keys, out_vals, fine_hist, fine_bits);
     }
 }
 
 // coarse bucket histogram (NB = 2^total_bits bins) from the fine one
-__global__ void __launch_bounds__(256) coarsen_kernel(const uint32_t *__restrict__ fine_hist, int total_bits, uint32_t *__restrict__ hist)
+__global__ void __launch_bounds__(256) coarsen_kernel(const uint32_t *__restrict__ fine_hist, int fine_bits, int total_bits,
+                                                      uint32_t *__restrict__ hist)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (1u << FINE_BITS)) return;
+    if (i >= (1u << fine_bits)) return;
     const uint32_t c = fine_hist[i];
-    if (c) atomicAdd(&hist[total_bits ? (i >> (FINE_BITS - total_bits)) : 0u], c);
+    if (c) atomicAdd(&hist[total_bits ? (i >> (fine_bits - total_bits)) : 0u], c);
 }
 
 // number of slots with bit 1 set (= distinct slots that hold a repeated k-mer); survivors = *n_again + that number
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *__restrict__
     if (threadIdx.x == 0) off[pl.NB] = s_total;
     __syncthreads();                    // block-wide visibility of the off[] writes (the same block reads them below)
     uint32_t tiles = 0, beg = 0;
-    if (threadIdx.x < pl.B1) {          // B1 <= 512
+    if (threadIdx.x < pl.B1) {          // B1 <= 1024
         beg = off[threadIdx.x * pl.B2];
         uint32_t end = off[(threadIdx.x + 1) * pl.B2];
         tiles = (end - beg + PART_TILE - 1) / PART_TILE;
@@ -454,10 +468,11 @@ __global__ void __launch_bounds__(PART_THREADS) part_kernel(uint64_t n_in, MsdPl
     extern __shared__ unsigned char smem_raw[];
     uint64_t *st_keys = (uint64_t *)smem_raw;                          // PART_TILE
     uint32_t *st_vals = (uint32_t *)(st_keys + PART_TILE);              // PART_TILE
-    uint32_t *s_cnt = st_vals + PART_TILE;                              // 512 each
-    uint32_t *s_start = s_cnt + 512;
-    uint32_t *s_fill = s_start + 512;
-    uint32_t *s_gbase = s_fill + 512;
+    constexpr int MAXB = 1 << MAX_BUCKET_BITS;
+    uint32_t *s_cnt = st_vals + PART_TILE;                              // MAXB each
+    uint32_t *s_start = s_cnt + MAXB;
+    uint32_t *s_fill = s_start + MAXB;
+    uint32_t *s_gbase = s_fill + MAXB;
     __shared__ uint32_t s_total, s_bucket, s_tile_lo;
     const uint32_t NBK = (LEVEL == 1) ? pl.B1 : pl.B2;
     const int shift = (LEVEL == 1) ? (64 - pl.b1) : (64 - pl.b1 - pl.b2);
@@ -499,7 +514,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_kernel(uint64_t n_in, MsdPl
             }
         }
         __syncthreads();
-        // exclusive scan of s_cnt (NBK <= 512) + one global reservation per non-empty bucket
+        // exclusive scan of s_cnt (NBK <= 1024) + one global reservation per non-empty bucket
         if (threadIdx.x < 32) {
             uint32_t carry = 0;
             for (uint32_t base = 0; base < NBK; base += 32) {
@@ -849,7 +864,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     VB_CUDA(cudaMemsetAsync(scalars.p, 0, scalars.bytes(), st));
     const unsigned long long max_pairs = (unsigned long long)n * (n > 0 ? n - 1 : 0) / 2;
     unsigned long long n_inc = max_pairs;
-    static const bool force_hash = getenv("VB_PREFILTER_HASH") != nullptr;   // test hook: exercise the large-N layout
+    const bool force_hash = getenv("VB_PREFILTER_HASH") != nullptr;   // test hook: exercise the large-N layout
     const bool count_first = force_hash || max_pairs > (1ULL << 26);   // large N: hashed pair table sized by a counting pass
     DevBuf<uint64_t> tkeys;
     DevBuf<uint32_t> tvals, dense;
@@ -881,7 +896,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     };
     rsort::Workspace ws;
     unsigned long long n_survivors = 0;
-    static const bool use_lsd = getenv("VB_PREFILTER_LSD") != nullptr;      // A/B switch: the round-1 LSD radix path
+    const bool use_lsd = getenv("VB_PREFILTER_LSD") != nullptr;      // A/B switch: the round-1 LSD radix path
 
     if (use_lsd) {
         // ---- k1 + k2 + k3, LSD flavour: full stable sort of (k-mer, genome) tuples, then a run scan
@@ -911,46 +926,88 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     } else {
         // ---- k1 + k2 + k3, MSD flavour: hash once, screen out singletons, hash-bucket partition, shared-memory grouping
         t_ext.start();
-        if (n_slots >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 base slots in one prefilter call");
-        const uint64_t n_iter = (n_slots + 31) / 32 * 32;
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+        // The slot axis is walked in chunks (kernel-side offsets inside a chunk stay small; inputs beyond 2^32 base
+        // slots just take more launches).  VB_PREFILTER_CHUNK (slots, test hook) forces many small chunks.
+        const uint64_t chunk_env = getenv("VB_PREFILTER_CHUNK") ? strtoull(getenv("VB_PREFILTER_CHUNK"), nullptr, 10) : 0;
+        const uint64_t chunk = chunk_env ? std::max<uint64_t>(2048, chunk_env / 2048 * 2048) : (1ULL << 31);
         // seen table: >= 4 slots per expected k-mer, at most 2^28 slots (64 MB, stays in the 126 MB L2); for inputs
         // beyond ~2^27 k-mers the collision rate would let most singletons through, so the screen is switched off
-        static const char *seen_env = getenv("VB_PREFILTER_SEEN");          // "0": off, "N": force 2^N slots
+        const char *seen_env = getenv("VB_PREFILTER_SEEN");          // "0": off, "N": force 2^N slots
         const double est_all = (double)n_slots * std::min(1.0, p->kmers_fraction) / shard_count;
         int seen_bits = 20;
         while ((double)(1ULL << seen_bits) < 4.0 * est_all && seen_bits < 28) ++seen_bits;
         bool use_seen = est_all <= (double)(1ULL << 27);
         if (seen_env) { int v = atoi(seen_env); use_seen = v > 0; if (v >= 10 && v <= 34) seen_bits = v; }
-        DevBuf<uint32_t> fine_hist(1u << FINE_BITS);
+        const int fine_bits = est_all > (double)BUCKET_TARGET * (double)(1u << FINE_BITS_SMALL) ? FINE_BITS_LARGE : FINE_BITS_SMALL;
+        DevBuf<uint32_t> fine_hist(1u << fine_bits);
         VB_CUDA(cudaMemsetAsync(fine_hist.p, 0, fine_hist.bytes(), st));
-        DevBuf<uint64_t> keys0(n_iter + 64);                 // compact list of surviving (hash, genome) tuples
-        DevBuf<uint32_t> vals0(n_iter + 64);
         unsigned long long *d_cursor = scalars.p + 6;
+        // small inputs: room for every slot's tuple, no counting pass.  Large inputs: count the survivors first.
+        const bool exact_alloc = n_slots >= (1ULL << 31) || 12.0 * (double)n_slots > 0.125 * (double)ctx->mem_total ||
+                                 getenv("VB_PREFILTER_EXACT") != nullptr;
+        DevBuf<uint32_t> seen_words;
+        SeenTable seen = {nullptr, 0};
+        auto for_chunks = [&](auto &&launch) {
+            for (uint64_t lo = 0; lo < n_slots; lo += chunk) launch(lo, std::min(n_slots, lo + chunk));
+        };
+        auto grid_of = [&](uint64_t lo, uint64_t hi, int per_sm) {
+            return (int)std::max<uint64_t>(1, std::min<uint64_t>(((hi - lo) / KM_ITEMS + 255) / 256, (uint64_t)n_sm * per_sm));
+        };
+        bool counted_valid = false;
         if (use_seen) {
-            DevBuf<uint64_t> hbuf(n_iter);
-            DevBuf<uint32_t> seen_words((1ULL << seen_bits) / 16);
+            seen_words.alloc((1ULL << seen_bits) / 16);
             VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
-            SeenTable seen = {seen_words.p, (1ULL << seen_bits) - 1};
-            hash_kernel<true><<<n_sm * 4, 512, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, n_slots, n_iter, ep, hbuf.p, seen,
-                                                        valid_cnt, scalars.p + 4, d_cursor, keys0.p, vals0.p, fine_hist.p);
-            VB_LAUNCH_CHECK(ctx);
-            compact_kernel<<<n_sm * 8, 256, 0, st>>>(hbuf.p, n_iter, seen, dg.tile_gid.p, d_cursor, keys0.p, vals0.p, fine_hist.p);
-            VB_LAUNCH_CHECK(ctx);
-        } else {
-            SeenTable seen = {nullptr, 0};
-            hash_kernel<false><<<n_sm * 4, 512, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, n_slots, n_iter, ep, nullptr, seen,
-                                                         valid_cnt, scalars.p + 4, d_cursor, keys0.p, vals0.p, fine_hist.p);
-            VB_LAUNCH_CHECK(ctx);
+            seen = {seen_words.p, (1ULL << seen_bits) - 1};
+            for_chunks([&](uint64_t lo, uint64_t hi) {
+                screen_kernel<<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen, valid_cnt,
+                                                                   scalars.p + 4);
+                VB_LAUNCH_CHECK(ctx);
+            });
+            counted_valid = true;
         }
+        uint64_t list_cap = n_slots + 64;
+        if (exact_alloc) {
+            unsigned long long cnt[2] = {0, 0};
+            if (use_seen) {
+                seen_popc_kernel<<<n_sm * 4, 256, 0, st>>>(seen_words.p, (1ULL << seen_bits) / 16, scalars.p + 5);
+                VB_LAUNCH_CHECK(ctx);
+                VB_CUDA(cudaMemcpyAsync(cnt, scalars.p + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                VB_CUDA(cudaStreamSynchronize(st));
+                list_cap = cnt[0] + cnt[1] + 64;
+            } else {
+                for_chunks([&](uint64_t lo, uint64_t hi) {
+                    collect_kernel<true><<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen,
+                                                                              valid_cnt, d_cursor, 0, nullptr, nullptr, nullptr, fine_bits);
+                    VB_LAUNCH_CHECK(ctx);
+                });
+                counted_valid = true;
+                VB_CUDA(cudaMemcpyAsync(cnt, d_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                VB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), st));
+                VB_CUDA(cudaStreamSynchronize(st));
+                list_cap = cnt[0] + 64;
+            }
+        }
+        if (list_cap >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 k-mer tuples in one prefilter call: split the input or shard the k-mers over more GPUs");
+        DevBuf<uint64_t> keys0(list_cap);                    // compact list of surviving (hash, genome) tuples
+        DevBuf<uint32_t> vals0(list_cap);
+        for_chunks([&](uint64_t lo, uint64_t hi) {
+            if (counted_valid)
+                collect_kernel<false><<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen, valid_cnt,
+                                                                           d_cursor, 1, keys0.p, vals0.p, fine_hist.p, fine_bits);
+            else
+                collect_kernel<true><<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen, valid_cnt,
+                                                                          d_cursor, 1, keys0.p, vals0.p, fine_hist.p, fine_bits);
+            VB_LAUNCH_CHECK(ctx);
+        });
         VB_CUDA(cudaMemcpyAsync(&n_survivors, d_cursor, sizeof(n_survivors), cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaStreamSynchronize(st));                  // the bucket plan and the grids below depend on the count
         const uint64_t n_keep = n_survivors;
         MsdPlan pl;
         {
             int bits = 0;
-            while ((double)n_keep / (double)(1ULL << bits) > BUCKET_TARGET && bits < FINE_BITS) ++bits;
+            while ((double)n_keep / (double)(1ULL << bits) > BUCKET_TARGET && bits < fine_bits) ++bits;
             pl.b1 = (bits + 1) / 2; pl.b2 = bits - pl.b1;
             pl.B1 = 1u << pl.b1; pl.B2 = 1u << pl.b2; pl.NB = pl.B1 * pl.B2;
         }
@@ -958,7 +1015,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         DevBuf<uint32_t> n_big(1);
         VB_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
         VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
-        coarsen_kernel<<<(1u << FINE_BITS) / 256, 256, 0, st>>>(fine_hist.p, pl.b1 + pl.b2, hist.p);
+        coarsen_kernel<<<(1u << fine_bits) / 256, 256, 0, st>>>(fine_hist.p, fine_bits, pl.b1 + pl.b2, hist.p);
         VB_LAUNCH_CHECK(ctx);
         scan_kernel<<<1, 1024, 0, st>>>(hist.p, pl, off.p, cursor1.p, cursor2.p, tile_start.p);
         VB_LAUNCH_CHECK(ctx);
@@ -966,7 +1023,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         t_sort.start();
         DevBuf<uint64_t> keys1(n_keep + 64), keys2(pl.b2 ? n_keep + 64 : 1);
         DevBuf<uint32_t> vals1(n_keep + 64), vals2(pl.b2 ? n_keep + 64 : 1);
-        const size_t part_smem = PART_TILE * 12 + 4 * 512 * sizeof(uint32_t);
+        const size_t part_smem = PART_TILE * 12 + 4 * (1 << MAX_BUCKET_BITS) * sizeof(uint32_t);
         static bool attr_done = false;
         if (!attr_done) {
             VB_CUDA(cudaFuncSetAttribute(part_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
