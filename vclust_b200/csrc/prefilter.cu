@@ -334,18 +334,28 @@ __global__ void __launch_bounds__(256) screen_kernel(const uint32_t *__restrict_
         uint64_t h[KM_ITEMS];
         uint32_t ok = 0;
         if (gid != 0xffffffffu) ok = kmer_hashes(seq2, inv, p, ep, kmask, wmask, h);
+        else {
 #pragma unroll
-        for (int j = 0; j < KM_ITEMS; ++j)
-            if ((ok >> j) & 1u) {
-                const uint64_t s = (h[j] >> 16) & T.slot_mask;
-                uint32_t *w = T.words + (s >> 4);
-                const uint32_t b0 = 1u << (2 * (uint32_t)(s & 15));
-                const uint32_t old = atomicOr(w, b0);
-                if (old & b0) {
-                    ++again;
-                    if (!(old & (b0 << 1))) atomicOr(w, b0 << 1);            // only the second occurrence pays for this one
-                }
+            for (int j = 0; j < KM_ITEMS; ++j) h[j] = 0;
+        }
+        // all eight marks are issued before the first result is looked at (eight atomics in flight per thread instead
+        // of one: the kernel is bound by the round trip of the atomic, not by its throughput)
+        uint32_t old[KM_ITEMS], widx[KM_ITEMS];
+#pragma unroll
+        for (int j = 0; j < KM_ITEMS; ++j) {
+            const uint64_t s = (h[j] >> 16) & T.slot_mask;
+            widx[j] = (uint32_t)(s >> 4);
+            old[j] = 0;
+            if ((ok >> j) & 1u) old[j] = atomicOr(T.words + widx[j], 1u << (2 * ((uint32_t)(h[j] >> 16) & 15)));
+        }
+#pragma unroll
+        for (int j = 0; j < KM_ITEMS; ++j) {
+            const uint32_t b0 = 1u << (2 * ((uint32_t)(h[j] >> 16) & 15));
+            if (old[j] & b0) {                                                // (old is 0 for slots without a k-mer)
+                ++again;
+                if (!(old[j] & (b0 << 1))) atomicOr(T.words + widx[j], b0 << 1);   // only the second occurrence pays for this one
             }
+        }
         count_valid(ok, gid, lane, valid_cnt);
     }
     again = __reduce_add_sync(0xffffffffu, again);
@@ -375,11 +385,18 @@ __global__ void __launch_bounds__(256) collect_kernel(const uint32_t *__restrict
         uint64_t h[KM_ITEMS];
         uint32_t ok = 0;
         if (gid != 0xffffffffu) ok = kmer_hashes(seq2, inv, p, ep, kmask, wmask, h);
+        else {
+#pragma unroll
+            for (int j = 0; j < KM_ITEMS; ++j) h[j] = 0;
+        }
         if (COUNT_VALID) count_valid(ok, gid, lane, valid_cnt);
-        if (T.words) {
+        if (T.words) {                                                       // eight independent table reads in flight
+            uint32_t tw[KM_ITEMS];
+#pragma unroll
+            for (int j = 0; j < KM_ITEMS; ++j) tw[j] = __ldg(T.words + (((h[j] >> 16) & T.slot_mask) >> 4));
 #pragma unroll
             for (int j = 0; j < KM_ITEMS; ++j)
-                if (((ok >> j) & 1u) && !seen_twice(T, h[j])) ok &= ~(1u << j);
+                if (!((tw[j] >> (2 * ((uint32_t)(h[j] >> 16) & 15) + 1)) & 1u)) ok &= ~(1u << j);
         }
         block_append<KM_ITEMS>(ok, h, gid, s_warp, phase, cursor, write, out_keys, out_vals, fine_hist, fine_bits);
     }
