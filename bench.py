@@ -137,6 +137,24 @@ def cpu_baseline(names, seqs, n_sample: int, threads: int):
             "prefilter_s": t_pre, "align_s": t_al}
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` summary (profiles/r01_kernels_ncu_full.txt,
+    written by profiles/ncu_summary.py from the capture of this same bench command); None when absent."""
+    f = ROOT / "profiles" / "r01_kernels_ncu_full.txt"
+    if not f.exists():
+        return None
+    total, inside = 0.0, False
+    for ln in f.read_text().splitlines():
+        if ln.startswith("## "):
+            if inside:
+                break
+            inside = ln[3:].startswith(kernel)
+        elif inside and ("dram__bytes_read.sum" in ln or "dram__bytes_write.sum" in ln):
+            parts = ln.split()
+            total += float(parts[1]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(parts[2], 1)
+    return total if inside and total else None
+
+
 def main_reference(args, rank: int, world: int):
     if rank != 0:
         return
@@ -319,10 +337,11 @@ def main_ours(args, rank: int, world: int, local_rank: int):
                           "wall_prefilter_call": float(np.mean([i["wall_prefilter_ms"] for i in infos])),
                           "wall_align_call": float(np.mean([i["wall_align_ms"] for i in infos]))},
             "roofline": {"kernel": "parse_kernel (align)", "bound": "hbm", "achieved": a_bytes / (parse_ms / 1000) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": a_bytes / (parse_ms / 1000) / 1e9 / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": a_bytes / (parse_ms / 1000) / 1e9 / peak, "traffic": ncu_traffic("parse_kernel"),
+                         "algorithmic_bytes": a_bytes,
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = sum over directed pairs of Lq/4 + 2*Lr/4 + 12; the parse is issue/latency bound, not HBM bound (DESIGN.md)"},
-            "roofline_prefilter": {"kernels": "extract+radix sort+segment+emit", "bound": "hbm",
+            "roofline_prefilter": {"kernels": "screen+collect+partition+bucket+emit (whole prefilter device time)", "bound": "hbm",
                                    "achieved": pre_bytes / (pre_kernel_ms / 1000) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": pre_bytes / (pre_kernel_ms / 1000) / 1e9 / peak,
                                    "note": "algorithmic bytes = 24.25 B/base + 12 B/pair + 4 B/genome (SURVEY 8(d))"},
