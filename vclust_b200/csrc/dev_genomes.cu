@@ -43,6 +43,16 @@ __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const uint64_t *_
     }
 }
 
+// tile map from the store offsets: one warp per genome marks its 128-slot tiles (the array is pre-set to "none")
+__global__ void tile_map_kernel(const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen, uint32_t n,
+                                uint32_t *__restrict__ tile_gid)
+{
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n) return;
+    const uint64_t t0 = gofs[g] >> 7, t1 = (gofs[g] + glen[g] + 127) >> 7;       // genomes start on tile boundaries
+    for (uint64_t t = t0 + lane; t < t1; t += 32) tile_gid[t] = g;
+}
+
 }  // namespace
 
 void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad)
@@ -74,16 +84,13 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
     }
     slots += 128;
     out.total_slots = slots;
-    std::vector<uint32_t> tile(slots / 128, 0xffffffffu);
-    for (uint32_t i = 0; i < n; ++i)
-        for (uint64_t t = out.h_gofs[i] / 128; t * 128 < out.h_gofs[i] + out.h_glen[i]; ++t) tile[t] = i;
 
     out.seq2.alloc(slots / 16 + 8);
     out.inv_kdb.alloc(slots / 32 + 8);
     out.inv_lz.alloc(slots / 32 + 8);
     out.gofs.alloc(n ? n : 1);
     out.glen.alloc(n ? n : 1);
-    out.tile_gid.alloc(tile.size());
+    out.tile_gid.alloc(slots / 128);
     if (!g->pinned && !g->bases.empty() && ++g->uploads >= 2) {
         // Page-locking costs about as much as one pageable transfer (it touches every page), so it only pays when the
         // same host buffer is uploaded again: the first upload goes through the driver's staging path, from the second
@@ -106,14 +113,19 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
         VB_CUDA(cudaMemcpyAsync(out.gofs.p, out.h_gofs.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
         VB_CUDA(cudaMemcpyAsync(out.glen.p, out.h_glen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
     }
-    VB_CUDA(cudaMemcpyAsync(out.tile_gid.p, tile.data(), sizeof(uint32_t) * tile.size(), cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemsetAsync(out.tile_gid.p, 0xff, out.tile_gid.bytes(), st));
+    if (n) {
+        tile_map_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(out.gofs.p, out.glen.p, n, out.tile_gid.p);
+        VB_LAUNCH_CHECK(ctx);
+    }
     uint64_t n_chunks = slots / 32;
     int threads = 256;
     int blocks = (int)std::min<uint64_t>((n_chunks + threads - 1) / threads, 148 * 16);
     pack_kernel<<<blocks, threads, 0, st>>>((const uint8_t *)ascii.p, src_off.p, out.gofs.p, out.glen.p, out.tile_gid.p,
                                             n_chunks, out.seq2.p, out.inv_kdb.p, out.inv_lz.p);
     VB_LAUNCH_CHECK(ctx);
-    VB_CUDA(cudaStreamSynchronize(st));     // ascii / tile vectors go out of scope
+    // no synchronisation: the ASCII staging buffer is an arena block (re-used only by later work on this stream), the
+    // small host arrays are pageable (staged by the runtime before cudaMemcpyAsync returns) or owned by g / out
 }
 
 static void drop_last(vb_ctx *ctx)
