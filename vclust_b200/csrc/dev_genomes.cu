@@ -8,11 +8,11 @@ __constant__ uint8_t c_code[2][256];
 
 __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const uint64_t *__restrict__ src_off,
                             const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
-                            const uint32_t *__restrict__ tile_gid, uint64_t n_chunks,
+                            const uint32_t *__restrict__ tile_gid, uint64_t c_lo, uint64_t c_hi,
                             uint32_t *__restrict__ seq2, uint32_t *__restrict__ inv_kdb, uint32_t *__restrict__ inv_lz)
 {
-    // one thread per 32 base slots: two seq2 words and one word of each validity plane
-    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n_chunks;
+    // one thread per 32 base slots [32 c, 32 c + 32), c in [c_lo, c_hi): two seq2 words and one word of each validity plane
+    for (uint64_t c = c_lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < c_hi;
          c += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t slot = c * 32;
         uint32_t gid = tile_gid[slot >> 7];
@@ -55,7 +55,15 @@ __global__ void tile_map_kernel(const uint64_t *__restrict__ gofs, const uint32_
 
 }  // namespace
 
-void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad)
+uint64_t vb_store_slots(const vb_genomes *g, uint32_t min_pad)
+{
+    if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
+    uint64_t slots = 0;
+    for (uint32_t i = 0, n = g->count(); i < n; ++i) slots += ((g->length(i) + min_pad + 127) / 128) * 128;
+    return slots + 128;
+}
+
+void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad, const vb_chunk_fn *on_chunk)
 {
     if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
     cudaStream_t st = (cudaStream_t)ctx->stream;
@@ -106,8 +114,6 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
     VB_CUDA(cudaMemsetAsync(out.seq2.p, 0, out.seq2.bytes(), st));
     VB_CUDA(cudaMemsetAsync(out.inv_kdb.p, 0xff, out.inv_kdb.bytes(), st));
     VB_CUDA(cudaMemsetAsync(out.inv_lz.p, 0xff, out.inv_lz.bytes(), st));
-    if (!g->bases.empty())
-        VB_CUDA(cudaMemcpyAsync(ascii.p, g->bases.data(), g->bases.size(), cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemcpyAsync(src_off.p, g->offset.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, st));
     if (n) {
         VB_CUDA(cudaMemcpyAsync(out.gofs.p, out.h_gofs.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
@@ -118,12 +124,43 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
         tile_map_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(out.gofs.p, out.glen.p, n, out.tile_gid.p);
         VB_LAUNCH_CHECK(ctx);
     }
-    uint64_t n_chunks = slots / 32;
-    int threads = 256;
-    int blocks = (int)std::min<uint64_t>((n_chunks + threads - 1) / threads, 148 * 16);
-    pack_kernel<<<blocks, threads, 0, st>>>((const uint8_t *)ascii.p, src_off.p, out.gofs.p, out.glen.p, out.tile_gid.p,
-                                            n_chunks, out.seq2.p, out.inv_kdb.p, out.inv_lz.p);
-    VB_LAUNCH_CHECK(ctx);
+    // The genomes travel in up to 8 chunks (whole genomes, >= 4 MB each) on the copy stream; the pack of chunk c -- and
+    // whatever the caller enqueues from on_chunk -- runs on the main stream while chunk c + 1 is in flight.
+    cudaStream_t cs = (cudaStream_t)ctx->copy_stream;
+    const uint64_t total_bytes = g->bases.size();
+    const int max_chunks = (g->pinned && cs) ? (int)std::min<uint64_t>(8, std::max<uint64_t>(1, total_bytes >> 22)) : 1;
+    cudaEvent_t ev0 = (cudaEvent_t)ctx->copy_events[8];
+    if (max_chunks > 1) {                        // the copy stream may touch the fresh buffers only after this point of `st`
+        VB_CUDA(cudaEventRecord(ev0, st));
+        VB_CUDA(cudaStreamWaitEvent(cs, ev0, 0));
+    }
+    uint32_t g0 = 0;
+    for (int c = 0; c < max_chunks && g0 < n; ++c) {
+        uint32_t g1 = n;
+        if (c + 1 < max_chunks) {
+            const uint64_t want = total_bytes * (uint64_t)(c + 1) / max_chunks;
+            g1 = (uint32_t)(std::lower_bound(g->offset.begin() + g0 + 1, g->offset.begin() + n, want) - g->offset.begin());
+            g1 = std::min(std::max(g1, g0 + 1), n);
+        }
+        const uint64_t b0 = g->offset[g0], b1 = g->offset[g1];
+        const uint64_t s0 = out.h_gofs[g0], s1 = g1 < n ? out.h_gofs[g1] : slots;
+        if (b1 > b0) {
+            if (max_chunks > 1) {
+                VB_CUDA(cudaMemcpyAsync(ascii.p + b0, g->bases.data() + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+                VB_CUDA(cudaEventRecord((cudaEvent_t)ctx->copy_events[c], cs));
+                VB_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->copy_events[c], 0));
+            } else
+                VB_CUDA(cudaMemcpyAsync(ascii.p + b0, g->bases.data() + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        }
+        const uint64_t c_lo = s0 / 32, c_hi = s1 / 32;
+        const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((c_hi - c_lo + 255) / 256, 148 * 16));
+        pack_kernel<<<blocks, 256, 0, st>>>((const uint8_t *)ascii.p, src_off.p, out.gofs.p, out.glen.p, out.tile_gid.p, c_lo, c_hi,
+                                            out.seq2.p, out.inv_kdb.p, out.inv_lz.p);
+        VB_LAUNCH_CHECK(ctx);
+        if (on_chunk) (*on_chunk)(out, s0, s1);
+        g0 = g1;
+    }
+    if (n == 0 && on_chunk) (*on_chunk)(out, 0, slots);
     // no synchronisation: the ASCII staging buffer is an arena block (re-used only by later work on this stream), the
     // small host arrays are pageable (staged by the runtime before cudaMemcpyAsync returns) or owned by g / out
 }
@@ -139,17 +176,18 @@ static void drop_last(vb_ctx *ctx)
 }
 
 // upload into buffers that outlive the call (stream-ordered pool)
-static DevGenomes *upload_persistent(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad)
+static DevGenomes *upload_persistent(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, const vb_chunk_fn *on_chunk = nullptr)
 {
     auto *d = new DevGenomes();
     const bool saved = vb_tls_pool_alloc;
     vb_tls_pool_alloc = true;
-    try { vb_upload_genomes(ctx, g, *d, min_pad); } catch (...) { vb_tls_pool_alloc = saved; delete d; throw; }
+    try { vb_upload_genomes(ctx, g, *d, min_pad, on_chunk); } catch (...) { vb_tls_pool_alloc = saved; delete d; throw; }
     vb_tls_pool_alloc = saved;
     return d;
 }
 
-const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident)
+const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident,
+                                     const vb_chunk_fn *on_chunk)
 {
     if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
     if (was_resident) *was_resident = true;
@@ -158,7 +196,7 @@ const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t 
     if (ctx->last.dev && ctx->last.g == g && ctx->last.uid == g->uid && ctx->last.min_pad >= min_pad) return *ctx->last.dev;
     if (was_resident) *was_resident = false;
     drop_last(ctx);
-    ctx->last = {g, g->uid, min_pad, upload_persistent(ctx, g, min_pad)};
+    ctx->last = {g, g->uid, min_pad, upload_persistent(ctx, g, min_pad, on_chunk)};
     return *ctx->last.dev;
 }
 

@@ -129,12 +129,21 @@ struct DevGenomes {
 
 // Upload ASCII and pack on the device.  min_pad: invalid slots guaranteed after every genome (>= VB_STORE_PAD).
 constexpr uint32_t VB_STORE_PAD = 128 + 64;      // covers the prefilter (128) and align with --mrd up to 64
-void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad = VB_STORE_PAD);
+// on_chunk(slot_lo, slot_hi), optional: called after the pack of each chunk of genomes has been enqueued -- the H2D of
+// the next chunk runs on the context's copy stream meanwhile, so a consumer that enqueues its first pass over
+// [slot_lo, slot_hi) from the callback overlaps that pass with the transfer.
+#include <functional>
+struct DevGenomes;
+using vb_chunk_fn = std::function<void(const DevGenomes &, uint64_t, uint64_t)>;
+uint64_t vb_store_slots(const vb_genomes *g, uint32_t min_pad);    // base slots the packed store of g will have
+void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad = VB_STORE_PAD,
+                       const vb_chunk_fn *on_chunk = nullptr);
 
 // Returns the packed copy of g: the resident one when vb_genomes_make_resident was called for it, else the copy the
 // previous call on this context uploaded (vclust prefilter followed by vclust align on the same set transfers the
 // genomes once), else uploads now and keeps the copy for the next call (vb_genomes_evict drops it).
-const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident = nullptr);
+const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident = nullptr,
+                                     const vb_chunk_fn *on_chunk = nullptr);
 
 #ifdef __CUDACC__
 // 32 bases (64 bits) starting at base slot p of a 2-bit array; base p lands in bits [0,1].

@@ -859,11 +859,6 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     EventTimer t_all(st), t_up(st), t_ext(st), t_sort(st), t_seg(st), t_emit(st);
 
     t_all.start();
-    t_up.start();
-    const DevGenomes &dg = vb_get_dev_genomes(ctx, g, VB_STORE_PAD);
-    t_up.stop();
-
-    const uint64_t n_slots = dg.total_slots;
     DevBuf<uint32_t> counters(3 * (size_t)std::max<uint32_t>(n, 1));        // valid | dup | totals
     uint32_t *valid_cnt = counters.p, *dup_cnt = counters.p + n, *totals = counters.p + 2 * (size_t)n;
     VB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
@@ -876,9 +871,53 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     ep.c = (uint64_t)std::ceil((double)p->k / 4);
     ep.shard_index = shard_index;
     ep.shard_count = shard_count;
-
     DevBuf<unsigned long long> scalars(8);
     VB_CUDA(cudaMemsetAsync(scalars.p, 0, scalars.bytes(), st));
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const bool use_lsd = getenv("VB_PREFILTER_LSD") != nullptr;            // A/B switch: the round-1 LSD radix path
+
+    // ---- singleton screen set-up (MSD path), before the genomes are fetched: when they have to be uploaded, the
+    // screen pass over each chunk of genomes is enqueued while the next chunk is still on the PCIe bus
+    // seen table: >= 4 slots per expected k-mer, at most 2^28 slots (64 MB, stays in the 126 MB L2); for inputs
+    // beyond ~2^27 k-mers the collision rate would let most singletons through, so the screen is switched off
+    const char *seen_env = getenv("VB_PREFILTER_SEEN");                    // "0": off, "N": force 2^N slots
+    const double est_all = (double)vb_store_slots(g, VB_STORE_PAD) * std::min(1.0, p->kmers_fraction) / shard_count;
+    int seen_bits = 20;
+    while ((double)(1ULL << seen_bits) < 4.0 * est_all && seen_bits < 28) ++seen_bits;
+    bool use_seen = !use_lsd && est_all <= (double)(1ULL << 27);
+    if (seen_env && !use_lsd) { int v = atoi(seen_env); use_seen = v > 0; if (v >= 10 && v <= 34) seen_bits = v; }
+    // The slot axis is walked in chunks (kernel-side offsets inside a chunk stay small; inputs beyond 2^32 base
+    // slots just take more launches).  VB_PREFILTER_CHUNK (slots, test hook) forces many small chunks.
+    const uint64_t chunk_env = getenv("VB_PREFILTER_CHUNK") ? strtoull(getenv("VB_PREFILTER_CHUNK"), nullptr, 10) : 0;
+    const uint64_t chunk = chunk_env ? std::max<uint64_t>(2048, chunk_env / 2048 * 2048) : (1ULL << 31);
+    auto grid_of = [&](uint64_t lo, uint64_t hi, int per_sm) {
+        return (int)std::max<uint64_t>(1, std::min<uint64_t>(((hi - lo) / KM_ITEMS + 255) / 256, (uint64_t)n_sm * per_sm));
+    };
+    DevBuf<uint32_t> seen_words;
+    SeenTable seen = {nullptr, 0};
+    if (use_seen) {
+        seen_words.alloc((1ULL << seen_bits) / 16);
+        VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
+        seen = {seen_words.p, (1ULL << seen_bits) - 1};
+    }
+    auto screen_range = [&](const DevGenomes &d, uint64_t lo_all, uint64_t hi_all) {
+        for (uint64_t lo = lo_all; lo < hi_all; lo += chunk) {
+            const uint64_t hi = std::min(hi_all, lo + chunk);
+            screen_kernel<<<grid_of(lo, hi, 8), 256, 0, st>>>(d.seq2.p, d.inv_kdb.p, d.tile_gid.p, lo, hi, ep, seen, valid_cnt,
+                                                               scalars.p + 4);
+            VB_LAUNCH_CHECK(ctx);
+        }
+    };
+    bool screened = false;
+    const vb_chunk_fn hook = [&](const DevGenomes &d, uint64_t lo, uint64_t hi) {
+        if (use_seen) { screen_range(d, lo, hi); screened = true; }
+    };
+    t_up.start();
+    const DevGenomes &dg = vb_get_dev_genomes(ctx, g, VB_STORE_PAD, nullptr, &hook);
+    t_up.stop();
+    const uint64_t n_slots = dg.total_slots;
+
     const unsigned long long max_pairs = (unsigned long long)n * (n > 0 ? n - 1 : 0) / 2;
     unsigned long long n_inc = max_pairs;
     const bool force_hash = getenv("VB_PREFILTER_HASH") != nullptr;   // test hook: exercise the large-N layout
@@ -913,7 +952,6 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     };
     rsort::Workspace ws;
     unsigned long long n_survivors = 0;
-    const bool use_lsd = getenv("VB_PREFILTER_LSD") != nullptr;      // A/B switch: the round-1 LSD radix path
 
     if (use_lsd) {
         // ---- k1 + k2 + k3, LSD flavour: full stable sort of (k-mer, genome) tuples, then a run scan
@@ -943,20 +981,6 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     } else {
         // ---- k1 + k2 + k3, MSD flavour: hash once, screen out singletons, hash-bucket partition, shared-memory grouping
         t_ext.start();
-        int n_sm = 148;
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-        // The slot axis is walked in chunks (kernel-side offsets inside a chunk stay small; inputs beyond 2^32 base
-        // slots just take more launches).  VB_PREFILTER_CHUNK (slots, test hook) forces many small chunks.
-        const uint64_t chunk_env = getenv("VB_PREFILTER_CHUNK") ? strtoull(getenv("VB_PREFILTER_CHUNK"), nullptr, 10) : 0;
-        const uint64_t chunk = chunk_env ? std::max<uint64_t>(2048, chunk_env / 2048 * 2048) : (1ULL << 31);
-        // seen table: >= 4 slots per expected k-mer, at most 2^28 slots (64 MB, stays in the 126 MB L2); for inputs
-        // beyond ~2^27 k-mers the collision rate would let most singletons through, so the screen is switched off
-        const char *seen_env = getenv("VB_PREFILTER_SEEN");          // "0": off, "N": force 2^N slots
-        const double est_all = (double)n_slots * std::min(1.0, p->kmers_fraction) / shard_count;
-        int seen_bits = 20;
-        while ((double)(1ULL << seen_bits) < 4.0 * est_all && seen_bits < 28) ++seen_bits;
-        bool use_seen = est_all <= (double)(1ULL << 27);
-        if (seen_env) { int v = atoi(seen_env); use_seen = v > 0; if (v >= 10 && v <= 34) seen_bits = v; }
         const int fine_bits = est_all > (double)BUCKET_TARGET * (double)(1u << FINE_BITS_SMALL) ? FINE_BITS_LARGE : FINE_BITS_SMALL;
         DevBuf<uint32_t> fine_hist(1u << fine_bits);
         VB_CUDA(cudaMemsetAsync(fine_hist.p, 0, fine_hist.bytes(), st));
@@ -964,24 +988,12 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         // small inputs: room for every slot's tuple, no counting pass.  Large inputs: count the survivors first.
         const bool exact_alloc = n_slots >= (1ULL << 31) || 12.0 * (double)n_slots > 0.125 * (double)ctx->mem_total ||
                                  getenv("VB_PREFILTER_EXACT") != nullptr;
-        DevBuf<uint32_t> seen_words;
-        SeenTable seen = {nullptr, 0};
         auto for_chunks = [&](auto &&launch) {
             for (uint64_t lo = 0; lo < n_slots; lo += chunk) launch(lo, std::min(n_slots, lo + chunk));
         };
-        auto grid_of = [&](uint64_t lo, uint64_t hi, int per_sm) {
-            return (int)std::max<uint64_t>(1, std::min<uint64_t>(((hi - lo) / KM_ITEMS + 255) / 256, (uint64_t)n_sm * per_sm));
-        };
         bool counted_valid = false;
         if (use_seen) {
-            seen_words.alloc((1ULL << seen_bits) / 16);
-            VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
-            seen = {seen_words.p, (1ULL << seen_bits) - 1};
-            for_chunks([&](uint64_t lo, uint64_t hi) {
-                screen_kernel<<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen, valid_cnt,
-                                                                   scalars.p + 4);
-                VB_LAUNCH_CHECK(ctx);
-            });
+            if (!screened) screen_range(dg, 0, n_slots);         // (already enqueued chunk by chunk when the genomes were uploaded)
             counted_valid = true;
         }
         uint64_t list_cap = n_slots + 64;

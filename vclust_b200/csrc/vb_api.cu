@@ -108,6 +108,10 @@ int vb_ctx_create(int device, vb_ctx **out)
     cudaStream_t st;
     VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     ctx->stream = (void *)st;
+    cudaStream_t cs;
+    VB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    ctx->copy_stream = (void *)cs;
+    for (auto &e : ctx->copy_events) { cudaEvent_t ev; VB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e = (void *)ev; }
     ctx->arena = new vb_arena();
     {   // packed genome stores live in the device's stream-ordered pool: never hand freed blocks back to the driver
         cudaMemPool_t pool;
@@ -134,6 +138,8 @@ void vb_ctx_destroy(vb_ctx *ctx)
     cudaStreamSynchronize((cudaStream_t)ctx->stream);
     if (ctx->arena) { ctx->arena->destroy(); delete ctx->arena; }
     for (auto &e : ctx->events) if (e) cudaEventDestroy((cudaEvent_t)e);
+    for (auto &e : ctx->copy_events) if (e) cudaEventDestroy((cudaEvent_t)e);
+    if (ctx->copy_stream) { cudaStreamSynchronize((cudaStream_t)ctx->copy_stream); cudaStreamDestroy((cudaStream_t)ctx->copy_stream); }
     if (ctx->stream) cudaStreamDestroy((cudaStream_t)ctx->stream);
     delete ctx;
 }

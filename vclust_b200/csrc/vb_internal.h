@@ -91,6 +91,8 @@ struct vb_ctx {
     int device = 0;
     void *stream = nullptr;          // cudaStream_t
     void *events[8] = {nullptr};     // cudaEvent_t, vb_ctx_mark / vb_ctx_elapsed_ms
+    void *copy_stream = nullptr;     // cudaStream_t: chunked H2D of a genome upload, overlapped with the kernels on `stream`
+    void *copy_events[9] = {nullptr};
     uint64_t launches = 0;
     vb_arena *arena = nullptr;       // call-scoped device temporaries (dev_util.cuh)
     uint64_t mem_total = 0;          // device memory, queried once (cudaMemGetInfo is slow and synchronising)
