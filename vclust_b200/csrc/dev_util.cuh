@@ -69,7 +69,8 @@ struct DevBuf {
             e = cudaMallocAsync((void **)&p, count * sizeof(T), vb_tls_stream);
             if (e == cudaSuccess) { pool_stream = vb_tls_stream; return; }
         } else {
-            arena = vb_tls_arena;
+            static const bool no_arena = getenv("VB_NO_ARENA") != nullptr;      // debugging: one cudaMalloc per buffer, so
+            arena = no_arena ? nullptr : vb_tls_arena;                          // compute-sanitizer sees every overrun
             if (arena) { p = (T *)arena->alloc(count * sizeof(T)); return; }
             e = cudaMalloc((void **)&p, count * sizeof(T));
         }

@@ -630,18 +630,24 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
         }
         __syncthreads();
         // ---- duplicates: same genome earlier in the chain
-        for (uint32_t i = tid; i < size; i += 256) {
+        uint32_t dup_mask = 0;                                                // bit t: this thread's t-th tuple is a duplicate
+        int t = 0;
+        for (uint32_t i = tid; i < size; i += 256, ++t) {                     // size <= BUCKET_CAP = 8 * 256
             const uint32_t g = S.gids[i];
-            uint32_t j = S.prev[i];                                           // no flag set yet in the own entry
+            uint32_t j = S.prev[i];                                           // no flags are set during this phase
             while (j != CHAIN_END) {
                 if (S.gids[j] == g) {
-                    S.prev[i] = (uint16_t)(S.prev[i] | CHAIN_DUP);
+                    dup_mask |= 1u << t;
                     if (!count_only) atomicAdd(&dup_cnt[g], 1u);
                     break;
                 }
-                j = S.prev[j] & CHAIN_END;
+                j = S.prev[j];
             }
         }
+        __syncthreads();                                                      // all chain walks done: now flag the duplicates
+        t = 0;
+        for (uint32_t i = tid; i < size; i += 256, ++t)
+            if ((dup_mask >> t) & 1u) S.prev[i] = (uint16_t)(S.prev[i] | CHAIN_DUP);
         __syncthreads();
         // ---- pair increments: every non-duplicate tuple with every non-duplicate tuple before it in its chain
         for (uint32_t i = tid; i < size; i += 256) {
