@@ -89,9 +89,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+CONFIG_NAME = "c2"     # --workload c3 / c3_s200: the other single-GPU BASELINE configurations (not the headline line)
+
+
 def make_set(rank: int):
     from vclust_b200 import synth
-    cfg = dict(synth.CONFIGS["c2"])
+    cfg = dict(synth.CONFIGS[CONFIG_NAME])
     cfg["seed"] += 1000 * rank
     return synth.make_genomes(**cfg)
 
@@ -366,12 +369,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c3_s200"],
+                    help="c2 = the configuration the metric is quoted on (default); c3: 10 000 x 40 kb genomes")
     ap.add_argument("--quick", action="store_true", help="profiling run: 1 warm-up, no e2e leg, no CPU baseline (never a bench value)")
     args = ap.parse_args()
     if args.quick:
         args.warmup, args.no_cpu_baseline = 1, True
     elif args.impl == "ours":
         args.warmup = max(args.warmup, 3)
+    global CONFIG_NAME, WORKLOAD
+    if args.workload != "c2":
+        from vclust_b200 import synth
+        CONFIG_NAME = args.workload
+        c = synth.CONFIGS[CONFIG_NAME]
+        WORKLOAD = "%s: %d synthetic %d kb genomes (families of %d), prefilter k=25 min-kmers 20 min-ident 0.7 + LZ-ANI align of all candidate pairs" % (
+            CONFIG_NAME, c["n"], c["length"] // 1000, c["family"])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -926,21 +926,27 @@ void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qr
     // batch (any order is valid then).
     static const bool lpt_off = getenv("VB_ALIGN_NO_LPT") != nullptr;
     if (cost && job->prebuilt && !lpt_off && n >= 64) {
+        // counting sort on the top 13 bits of the (positive) float: 4096 cost classes, monotone in the cost -- O(n), and
+        // a coarse order is all the scheduling needs
+        constexpr int NB = 4096;
+        auto cls = [&](uint32_t i) { uint32_t b; memcpy(&b, &cost[i], 4); return (int)(b >> 19) & (NB - 1); };
+        std::vector<uint32_t> hist(NB + 1, 0);
+        for (uint64_t i = 0; i < n; ++i) hist[cls((uint32_t)i)]++;
         const uint64_t n_heavy = n / 8;
-        std::vector<float> sorted_cost(cost, cost + n);
-        std::nth_element(sorted_cost.begin(), sorted_cost.begin() + n_heavy, sorted_cost.end(), std::greater<float>());
-        const float thr = sorted_cost[n_heavy];
-        std::vector<uint32_t> by_cost;
-        by_cost.reserve(n_heavy + 16);
-        for (uint32_t i : order) if (cost[i] > thr) by_cost.push_back(i);
-        if (by_cost.size() > 4096)     // more than one wave of warps: most expensive first
-            std::sort(by_cost.begin(), by_cost.end(), [&](uint32_t a, uint32_t b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
-        std::vector<uint8_t> heavy(n, 0);
-        for (uint32_t i : by_cost) heavy[i] = 1;
-        std::vector<uint32_t> merged;
-        merged.reserve(n);
-        merged.insert(merged.end(), by_cost.begin(), by_cost.end());
-        for (uint32_t i : order) if (!heavy[i]) merged.push_back(i);
+        int cut = NB;                                    // classes >= cut are "heavy": the smallest suffix with >= n/8 pairs
+        uint64_t acc = 0;
+        while (cut > 0 && acc < n_heavy) acc += hist[--cut];
+        if (acc > n / 2) { acc -= hist[cut]; ++cut; }          // one huge class: do not reorder half the list
+        std::vector<uint32_t> start(NB + 1, 0);          // heavy classes in descending order
+        uint64_t run = 0;
+        for (int c = NB - 1; c >= cut; --c) { start[c] = (uint32_t)run; run += hist[c]; }
+        std::vector<uint32_t> merged(n);
+        uint64_t light_at = run;
+        for (uint32_t i : order) {
+            const int c = cls(i);
+            if (c >= cut) merged[start[c]++] = i;
+            else merged[light_at++] = i;
+        }
         order.swap(merged);
     }
     const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
