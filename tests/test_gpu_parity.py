@@ -102,6 +102,31 @@ def test_prefilter_large_input_paths_vs_oracle(ctx, golden, monkeypatch, env):
                {(int(r), int(c)): int(v) for r, c, v in zip(rows, cols, vals)}
 
 
+def test_chunked_pinned_upload_gives_the_same_result(ctx):
+    """From the second upload of a host set on, the genomes travel in several chunks on a copy stream and the screen
+    pass of each chunk is enqueued while the next chunk is in flight (e2e path of bench.py): same pairs, same counts,
+    and the align stage finds the store the prefilter uploaded."""
+    names, seqs = synth.make_genomes(n=320, length=40_000, family=8, seed=5, n_frac=0.05, lower_frac=0.05)
+    g = api.Genomes.from_memory(names, seqs)
+    runs = []
+    for _ in range(3):                      # 1st: pageable, one chunk; 2nd, 3rd: pinned, chunked
+        ctx.evict()
+        pairs = api.prefilter_genomes(ctx, g)
+        res = api.align_genomes(ctx, g, pairs)
+        runs.append((pairs.rows.tolist(), pairs.cols.tolist(), pairs.common.tolist(), pairs.total_kmers.tolist(),
+                     res.ref.tolist(), res.qry.tolist(), res.stats.tolist()))
+        pairs.close(); res.close()
+    ctx.evict()
+    assert runs[0] == runs[1] == runs[2]
+    assert len(runs[0][0]) == 320 * 7 // 2
+    # spot-check against the oracle on two families
+    sub = list(range(16))
+    sets = oracle.kmer_sets([[seqs[i].tobytes()] for i in sub], 25, 1.0)
+    want = {(r, c): v for r, c, v, _ in oracle.prefilter_pairs(sets, 25, 20, 0.7)}
+    got = {(r, c): v for r, c, v in zip(*runs[0][:3]) if r < 16 and c < 16}
+    assert got == want
+
+
 def test_prefilter_edge_cases(ctx):
     # empty genome, genome shorter than k, all-N genome, U handled as T, lower case, duplicate genomes
     seqs = [b"", b"ACGTACGT", b"N" * 100, b"ACGU" * 30, b"acgt" * 30, b"ACGT" * 30, b"ACGTTGCAAGGCTA" * 10]
