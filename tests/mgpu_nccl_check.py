@@ -6,7 +6,11 @@ from vclust_b200 import api, distributed, synth
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-names, seqs = synth.make_genomes(n=200, length=20000, family=10, seed=77, n_frac=0.05)
+# default: 200 x 20 kb; "c4mini": variable lengths 5-200 kb, families of 50, N runs and lower-case blocks (c4's shape)
+if len(sys.argv) > 1 and sys.argv[1] == "c4mini":
+    names, seqs = synth.make_genomes(n=1500, length=(5000, 200000), family=50, seed=synth.BASE_SEED + 4, n_frac=0.01, lower_frac=0.01)
+else:
+    names, seqs = synth.make_genomes(n=200, length=20000, family=10, seed=77, n_frac=0.05)
 ctx = api.Context(lr)
 g = api.Genomes.from_memory(names, seqs)
 res = distributed.prefilter_align_sharded(ctx, g, g, dist, torch.device("cuda", lr))
@@ -21,6 +25,7 @@ if rank == 0:
     want = {(int(r), int(q)): tuple(s) for r, q, s in zip(ref, qry, st.tolist())}
     got = {(int(r), int(q)): tuple(s) for r, q, s in zip(res["ref"], res["qry"], res["stats"].tolist())}
     assert got == want, "align stats differ"
-    print("MGPU OK: %d pairs, %d directed parses over %d ranks" % (full.n_pairs, len(got), world))
+    print("MGPU OK: %d genomes, %d bases, %d pairs, %d directed parses over %d ranks" %
+          (len(names), sum(s.size for s in seqs), full.n_pairs, len(got), world))
 dist.barrier()
 dist.destroy_process_group()

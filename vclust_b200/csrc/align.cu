@@ -932,11 +932,12 @@ void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qr
         auto cls = [&](uint32_t i) { uint32_t b; memcpy(&b, &cost[i], 4); return (int)(b >> 19) & (NB - 1); };
         std::vector<uint32_t> hist(NB + 1, 0);
         for (uint64_t i = 0; i < n; ++i) hist[cls((uint32_t)i)]++;
-        const uint64_t n_heavy = n / 8;
+        static const int heavy_div = getenv("VB_ALIGN_HEAVY_DIV") ? std::max(1, atoi(getenv("VB_ALIGN_HEAVY_DIV"))) : 8;
+        const uint64_t n_heavy = n / heavy_div;
         int cut = NB;                                    // classes >= cut are "heavy": the smallest suffix with >= n/8 pairs
         uint64_t acc = 0;
         while (cut > 0 && acc < n_heavy) acc += hist[--cut];
-        if (acc > n / 2) { acc -= hist[cut]; ++cut; }          // one huge class: do not reorder half the list
+        if (acc > n / 2 && heavy_div > 2) { acc -= hist[cut]; ++cut; }   // one huge class: do not reorder half the list
         std::vector<uint32_t> start(NB + 1, 0);          // heavy classes in descending order
         uint64_t run = 0;
         for (int c = NB - 1; c >= cut; --c) { start[c] = (uint32_t)run; run += hist[c]; }
