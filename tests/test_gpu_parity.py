@@ -1,5 +1,7 @@
 """GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the committed
 golden vectors and against the CPU oracle on seeded inputs.  Integer/byte results must be bit-exact."""
+import gzip
+
 import numpy as np
 import pytest
 
@@ -163,6 +165,31 @@ def test_align_vs_reference_binary_outputs(ctx, golden, tmp_path, case):
     flt = None if case == "s30_all" else golden / "ref_synth" / (case + ".fltr.txt")
     api.align([fa], out, True, out_format=api.ALIGN_OUTFMT["complete"], filter_file=flt, **LZP[case])
     assert out.read_bytes() == (golden / "ref_synth" / (case + ".ani.tsv")).read_bytes()
+
+
+def test_align_reference_batches_vs_single_batch(ctx, monkeypatch, golden, tmp_path):
+    """When the reference texts + anchor tables of a call exceed the memory budget they are built batch by batch
+    (c4 on one GPU); forced here with a 1 MB budget: same statistics, same files, regions included."""
+    names, seqs = synth.make_genomes(n=40, length=(3000, 9000), family=5, seed=8, n_frac=0.2)
+    raw = [s.tobytes() for s in seqs]
+    rng = np.random.default_rng(3)
+    ref = rng.integers(0, 40, size=400)
+    qry = (ref // 5) * 5 + rng.integers(0, 5, size=400)
+    qry[:50] = rng.integers(0, 40, size=50)
+    g = api.Genomes.from_memory(names, raw)
+    want = api.align_pairs(ctx, g, ref, qry)
+    monkeypatch.setenv("VB_ALIGN_BUDGET_MB", "1")
+    got = api.align_pairs(ctx, g, ref, qry)
+    assert ctx.timing("align.batches") > 3
+    assert np.array_equal(got, want)
+    out = tmp_path / "ani.tsv"
+    aln = tmp_path / "ani.aln.tsv"
+    monkeypatch.setenv("VB_ALIGN_BUDGET_MB", "4")           # 64 kb genomes: ~1.3 MB per reference
+    api.align([golden / "example" / "multifasta.fna.gz"], out, True, out_aln=aln)
+    assert out.read_bytes() == (golden / "example" / "ani.tsv").read_bytes()
+    want_aln = gzip.open(golden / "example" / "ani.aln.tsv.gz", "rt").read().splitlines()
+    got_aln = aln.read_text().splitlines()
+    assert got_aln[0] == want_aln[0] and sorted(got_aln[1:]) == sorted(want_aln[1:])
 
 
 def test_align_pairs_vs_oracle_random(ctx):

@@ -840,6 +840,15 @@ static void parse_launch(vb_ctx *ctx, const DevGenomes &dg, const RefBatch &b, c
     VB_LAUNCH_CHECK(ctx);
 }
 
+// device memory one batch of reference texts + anchor tables may take (no per-call memory query); VB_ALIGN_BUDGET_MB
+// (test hook) forces small batches so that the multi-batch path runs on small inputs
+static uint64_t ref_budget(const vb_ctx *ctx)
+{
+    const char *e = getenv("VB_ALIGN_BUDGET_MB");
+    if (e && atoll(e) > 0) return (uint64_t)atoll(e) << 20;
+    return (uint64_t)(ctx->mem_total * 0.4);
+}
+
 struct vb_align_job {
     vb_ctx *ctx;
     const vb_genomes *g;
@@ -871,7 +880,7 @@ vb_align_job *vb_align_job_begin(vb_ctx *ctx, const vb_genomes *g, const vb_alig
         job->dg = &vb_get_dev_genomes(ctx, g, (uint32_t)ap->mrd + 128);
         job->t_up.stop();
         // reference texts + anchor tables of one batch may take up to 40 % of the device (no per-call memory query)
-        const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
+        const uint64_t budget = ref_budget(ctx);
         const uint32_t ng = g->count();
         uint64_t need = 0;
         uint32_t n_refs = 0;
@@ -950,7 +959,7 @@ void vb_align_job_run(vb_align_job *job, const uint32_t *ref, const uint32_t *qr
         }
         order.swap(merged);
     }
-    const uint64_t budget = (uint64_t)(ctx->mem_total * 0.4);
+    const uint64_t budget = ref_budget(ctx);
     ctx->set_timing("align.hp4_sched_ms", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - job->h0).count());
 
     DevBuf<int32_t> d_stats(3 * std::max<uint64_t>(n, 1));
