@@ -7,8 +7,9 @@
 //   per-pair statistics       CParser::calc_stats         parser.cpp:734-783
 //
 // This is a re-formulation, not a transcription (DESIGN.md "align" has the derivation):
-//   * texts are 2-bit packed with a 1-bit "not ACGT" plane; an N never matches anything (the reference gets this
-//     from code 4 in the reference text vs code 5 in the query), so every comparison is  xor | N_q | N_r  on 32 bases.
+//   * texts are three bit planes (code bit 0, code bit 1, "not ACGT") in 16-byte records of 32 symbols; an N never
+//     matches anything (the reference gets this from code 4 in the reference text vs code 5 in the query), so every
+//     comparison is  (lo^lo') | (hi^hi') | N_q | N_r  on 32 bases -- two 128-bit loads per text, no bit shuffling.
 //   * the reference's 4 MB open-addressing table of 11-mer positions becomes a per-reference table of
 //     (fingerprint, position) slots; lookups take the max over ALL entries with the same k-mer, ties to the
 //     smallest position, which is what the reference's ascending insertion + first-wins scan computes.
@@ -31,8 +32,7 @@ constexpr uint32_t HT_EMPTY = 0xffffffffu;
 struct LzParams { int mal, msl, mrd, mqd, reg, aw, am, ar; };
 
 struct RefDesc {
-    uint64_t s2_off;     // word offset of the packed text in ref_s2
-    uint64_t nv_off;     // word offset of the N plane in ref_nv
+    uint64_t rec_off;    // record offset of the text in ref_rec (one uint4 per 32 symbols)
     uint64_t ht_off;     // slot offset of the anchor table
     uint32_t ht_cap;     // slots (any size >= 2 * forward positions; range reduction by multiply-shift)
     uint32_t pos_bits;   // a slot is fingerprint << pos_bits | position, 2^pos_bits > n
@@ -41,11 +41,32 @@ struct RefDesc {
     uint32_t gid;        // genome id in the packed store
 };
 
+// A text is an array of 16-byte records, one per 32 symbols: .x = bit 0 of the 32 codes (A0 C1 G2 T3), .y = bit 1,
+// .z = "not ACGT" flags (bit b <-> symbol 32 c + b); .w is not used here.  Every text is followed by padding records
+// that are all N, so reading up to 96 symbols past n needs no bounds check.
 struct Text {
-    const uint32_t *s2;
-    const uint32_t *nv;
+    const uint4 *rec;
     int n;
 };
+
+struct W3 { uint32_t lo, hi, nv; };
+
+// the 32 symbols starting at position p >= 0: two 128-bit loads, three funnel shifts
+__device__ __forceinline__ W3 fetch3(const uint4 *__restrict__ rec, uint64_t p)
+{
+    const uint4 a = __ldg(rec + (p >> 5)), b = __ldg(rec + (p >> 5) + 1);
+    const unsigned sh = (unsigned)(p & 31);
+    W3 w;
+    w.lo = __funnelshift_r(a.x, b.x, sh); w.hi = __funnelshift_r(a.y, b.y, sh); w.nv = __funnelshift_r(a.z, b.z, sh);
+    return w;
+}
+
+// k-mer of `len` <= 31 symbols as an integer: low plane in bits [0, 32), high plane in bits [32, 64)
+__device__ __forceinline__ uint64_t kmer_code(const W3 &w, int len)
+{
+    const uint32_t m = (1u << len) - 1;
+    return (uint64_t)(w.lo & m) | ((uint64_t)(w.hi & m) << 32);
+}
 
 __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 {
@@ -64,58 +85,56 @@ __device__ __forceinline__ uint64_t reverse_digits(uint64_t x)
 // home slot of a hash in a table of `cap` slots (low 32 bits; the fingerprint comes from the high 32)
 __device__ __forceinline__ uint32_t ht_slot(uint64_t h, uint32_t cap) { return __umulhi((uint32_t)h, cap); }
 
-// min(K, reverse complement of K) for a k-mer of `len` 2-bit digits
-__device__ __forceinline__ uint64_t canonical_kmer(uint64_t code, int len, uint64_t kmask)
+// min(K, reverse complement of K) under the integer order of kmer_code -- any fixed order works, the table is built and
+// probed with the same rule.  Reverse complement in plane form: complement both planes, reverse the symbol order.
+__device__ __forceinline__ uint64_t canonical_kmer(uint64_t code, int len)
 {
-    uint64_t rc = reverse_digits((~code) & kmask) >> (64 - 2 * len);
+    const uint32_t l = (uint32_t)code, h = (uint32_t)(code >> 32);
+    const uint64_t rc = (uint64_t)(__brev(~l) >> (32 - len)) | ((uint64_t)(__brev(~h) >> (32 - len)) << 32);
     return code < rc ? code : rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // k5a: reference text  R = fwd | N^mrd | N^mrd | revcomp(fwd) | N^mrd   (parser.cpp:16-34), packed
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) build_ref_text_kernel(const uint32_t *__restrict__ g2, const uint32_t *__restrict__ gn,
-                                                             const uint64_t *__restrict__ gofs, const RefDesc *__restrict__ refs,
-                                                             uint32_t n_refs, int mrd, uint32_t *__restrict__ ref_s2,
-                                                             uint32_t *__restrict__ ref_nv)
+__global__ void __launch_bounds__(256) build_ref_text_kernel(const uint4 *__restrict__ grec, const uint64_t *__restrict__ gofs,
+                                                             const RefDesc *__restrict__ refs, uint32_t n_refs, int mrd,
+                                                             uint4 *__restrict__ ref_rec)
 {
     for (uint32_t r = blockIdx.y; r < n_refs; r += gridDim.y) {
         const RefDesc d = refs[r];
-        const uint64_t gbase = gofs[d.gid];
+        const uint4 *src = grec + (gofs[d.gid] >> 5);             // genomes start on 128-slot boundaries
         const uint32_t L = d.len;
         const uint32_t rc0 = L + 2 * (uint32_t)mrd;              // first position of the reverse-complement part
         const uint32_t n_chunks = (d.n + 31) / 32 + 4;           // + padding chunks (all N)
         for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += gridDim.x * blockDim.x) {
-            uint32_t x0 = c * 32;
-            uint64_t w;
-            uint32_t bad;
+            const uint32_t x0 = c * 32;
+            uint32_t lo, hi, bad;
             if (x0 + 32 <= L) {                                   // inside the forward copy
-                w = fetch2(g2, gbase + x0);
-                bad = fetch1(gn, gbase + x0);
+                const W3 w = fetch3(src, x0);
+                lo = w.lo; hi = w.hi; bad = w.nv;
             } else if (x0 >= rc0 && x0 + 32 <= rc0 + L) {         // inside the reverse complement
-                uint32_t s_lo = L - 32 - (x0 - rc0);
-                w = ~reverse_digits(fetch2(g2, gbase + s_lo));
-                bad = __brev(fetch1(gn, gbase + s_lo));
+                const W3 w = fetch3(src, L - 32 - (x0 - rc0));
+                lo = __brev(~w.lo); hi = __brev(~w.hi); bad = __brev(w.nv);
             } else {                                              // boundary chunk: base by base
-                w = 0; bad = 0;
+                lo = 0; hi = 0; bad = 0;
                 for (uint32_t j = 0; j < 32; ++j) {
-                    uint32_t x = x0 + j;
+                    const uint32_t x = x0 + j;
                     uint32_t code = 0, isn = 1;
                     if (x < L) {
-                        code = (uint32_t)(fetch2(g2, gbase + x) & 3); isn = fetch1(gn, gbase + x) & 1;
+                        const uint4 q = __ldg(src + (x >> 5));
+                        code = ((q.x >> (x & 31)) & 1u) | (((q.y >> (x & 31)) & 1u) << 1); isn = (q.z >> (x & 31)) & 1u;
                     } else if (x >= rc0 && x < rc0 + L) {
-                        uint32_t s = L - 1 - (x - rc0);
-                        code = 3 - (uint32_t)(fetch2(g2, gbase + s) & 3); isn = fetch1(gn, gbase + s) & 1;
+                        const uint32_t sp = L - 1 - (x - rc0);
+                        const uint4 q = __ldg(src + (sp >> 5));
+                        code = 3u - (((q.x >> (sp & 31)) & 1u) | (((q.y >> (sp & 31)) & 1u) << 1)); isn = (q.z >> (sp & 31)) & 1u;
                     }
                     if (isn) { code = 0; bad |= 1u << j; }
-                    w |= (uint64_t)code << (2 * j);
+                    lo |= (code & 1u) << j; hi |= (code >> 1) << j;
                 }
             }
-                                                                  // N positions keep whatever 2-bit code they had:
-            ref_s2[d.s2_off + 2 * (uint64_t)c] = (uint32_t)w;     // the N plane decides every comparison
-            ref_s2[d.s2_off + 2 * (uint64_t)c + 1] = (uint32_t)(w >> 32);
-            ref_nv[d.nv_off + c] = bad;
-        }
+            ref_rec[d.rec_off + c] = make_uint4(lo, hi, bad, 0u);  // N positions keep whatever code bits they had: the
+        }                                                          // N plane decides every comparison
     }
 }
 
@@ -127,22 +146,19 @@ __global__ void __launch_bounds__(256) build_ref_text_kernel(const uint32_t *__r
 // slot (32 bit) = fingerprint << pos_bits | forward position; fingerprint = top 32 - pos_bits bits of the hash
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_ref_index_kernel(const RefDesc *__restrict__ refs, uint32_t n_refs, int mal,
-                                                              const uint32_t *__restrict__ ref_s2,
-                                                              const uint32_t *__restrict__ ref_nv, uint32_t *__restrict__ ht)
+                                                              const uint4 *__restrict__ ref_rec, uint32_t *__restrict__ ht)
 {
-    const uint64_t kmask = (~0ULL) >> (64 - 2 * mal);
-    const uint32_t nmask = (mal >= 32) ? 0xffffffffu : ((1u << mal) - 1);
+    const uint32_t nmask = (1u << mal) - 1;
     for (uint32_t r = blockIdx.y; r < n_refs; r += gridDim.y) {
         const RefDesc d = refs[r];
-        const uint32_t *s2 = ref_s2 + d.s2_off;
-        const uint32_t *nv = ref_nv + d.nv_off;
+        const uint4 *rec = ref_rec + d.rec_off;
         uint32_t *tab = ht + d.ht_off;
         if (d.len < (uint32_t)mal) continue;
         const uint32_t n_pos = d.len - mal + 1;
         for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += gridDim.x * blockDim.x) {
-            if (fetch1(nv, p) & nmask) continue;
-            uint64_t code = fetch2(s2, p) & kmask;
-            uint64_t h = fmix64(canonical_kmer(code, mal, kmask));
+            const W3 w = fetch3(rec, p);
+            if (w.nv & nmask) continue;
+            uint64_t h = fmix64(canonical_kmer(kmer_code(w, mal), mal));
             uint32_t val = ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | p;
             uint32_t slot = ht_slot(h, d.ht_cap);
             while (atomicCAS(&tab[slot], HT_EMPTY, val) != HT_EMPTY) slot = (slot + 1 == d.ht_cap) ? 0u : slot + 1;
@@ -158,8 +174,8 @@ __device__ __forceinline__ uint32_t mm32(const Text &Q, int qp, const Text &R, i
 {
     int rem = min(Q.n - qp, R.n - rp);
     if (rem <= 0 || qp < 0 || rp < 0) return 0xffffffffu;
-    uint32_t m = mismatch32(fetch2(Q.s2, (uint64_t)qp), fetch2(R.s2, (uint64_t)rp)) | fetch1(Q.nv, (uint64_t)qp) |
-                 fetch1(R.nv, (uint64_t)rp);
+    const W3 q = fetch3(Q.rec, (uint64_t)qp), r = fetch3(R.rec, (uint64_t)rp);
+    uint32_t m = (q.lo ^ r.lo) | (q.hi ^ r.hi) | q.nv | r.nv;
     if (rem < 32) m |= 0xffffffffu << rem;
     return m;
 }
@@ -171,8 +187,8 @@ __device__ __forceinline__ uint32_t mm32_back(const Text &Q, int qp, const Text 
     int qs = qp - 32, rs = rp - 32;
     int sh = 0;
     if (qs < 0 || rs < 0) { sh = max(-qs, -rs); qs += sh; rs += sh; }      // sh < 32 because lim > 0
-    uint32_t m = mismatch32(fetch2(Q.s2, (uint64_t)qs), fetch2(R.s2, (uint64_t)rs)) | fetch1(Q.nv, (uint64_t)qs) |
-                 fetch1(R.nv, (uint64_t)rs);
+    const W3 q = fetch3(Q.rec, (uint64_t)qs), r = fetch3(R.rec, (uint64_t)rs);
+    uint32_t m = (q.lo ^ r.lo) | (q.hi ^ r.hi) | q.nv | r.nv;
     m <<= sh;                       // ascending positions now end at bit 31 = position qp-1
     m = __brev(m);                  // bit t = position qp-1-t
     if (lim < 32) m |= 0xffffffffu << lim;
@@ -284,8 +300,8 @@ __device__ __noinline__ ExtResult extend(const Text Q, int qp, const Text R, int
         if (backward) return mm32_back(Q, qp - off, R, rp - off, lim_all - off);
         const int lim = lim_all - off;
         if (lim <= 0) return 0xffffffffu;
-        uint32_t f = mismatch32(fetch2(Q.s2, (uint64_t)(qp + off)), fetch2(R.s2, (uint64_t)(rp + off))) |
-                     fetch1(Q.nv, (uint64_t)(qp + off)) | fetch1(R.nv, (uint64_t)(rp + off));
+        const W3 q = fetch3(Q.rec, (uint64_t)(qp + off)), r = fetch3(R.rec, (uint64_t)(rp + off));
+        uint32_t f = (q.lo ^ r.lo) | (q.hi ^ r.hi) | q.nv | r.nv;
         if (lim < 32) f |= 0xffffffffu << lim;
         return f;
     };
@@ -294,8 +310,7 @@ __device__ __noinline__ ExtResult extend(const Text Q, int qp, const Text R, int
         if (lim_all > off + 1024) {
             // the next super-chunk is pulled into L1 while this one is evaluated (no register target, so no stall)
             const int d = backward ? -min(off + 1024 + 32, min(qp, rp)) : off + 1024;
-            prefetch_l1(Q.s2 + ((qp + d) >> 4)); prefetch_l1(R.s2 + ((rp + d) >> 4));
-            prefetch_l1(Q.nv + ((qp + d) >> 5)); prefetch_l1(R.nv + ((rp + d) >> 5));
+            prefetch_l1(Q.rec + ((qp + d) >> 5)); prefetch_l1(R.rec + ((rp + d) >> 5));
         }
         const uint32_t m = flags_at(off);
         uint32_t pm = __shfl_up_sync(0xffffffffu, m, 1);
@@ -352,9 +367,9 @@ __device__ __forceinline__ double ipow(double base, uint32_t e)
 __device__ __forceinline__ bool kmer_at(const Text &T, int p, int len, uint64_t &code)
 {
     if (p < 0 || p + len > T.n) return false;
-    uint32_t nm = (len >= 32) ? 0xffffffffu : ((1u << len) - 1);
-    if (fetch1(T.nv, (uint64_t)p) & nm) return false;
-    code = fetch2(T.s2, (uint64_t)p) & ((~0ULL) >> (64 - 2 * len));
+    const W3 w = fetch3(T.rec, (uint64_t)p);
+    if (w.nv & ((1u << len) - 1)) return false;
+    code = kmer_code(w, len);
     return true;
 }
 
@@ -366,7 +381,7 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, ui
     best_len = 0; best_pos = 0;
     uint64_t code;
     if (!kmer_at(Q, i, P.mal, code)) return;
-    uint64_t h = fmix64(canonical_kmer(code, P.mal, (~0ULL) >> (64 - 2 * P.mal)));
+    uint64_t h = fmix64(canonical_kmer(code, P.mal));
     uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
     uint32_t slot0 = ht_slot(h, cap);
     const uint32_t pmask = (1u << pos_bits) - 1;
@@ -539,13 +554,11 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         uint32_t pr_s = HT_EMPTY, pr_slot = 0, pr_fp = 0;
         if (lane < steps) {
             const int qp = i + lane;
-            const uint32_t qn = fetch1(Q.nv, (uint64_t)qp);
-            const uint64_t qw = fetch2(Q.s2, (uint64_t)qp);
-            qv = qp + P.msl <= Q.n && (qn & ((1u << P.msl) - 1)) == 0;
-            qk = qw & ((~0ULL) >> (64 - 2 * P.msl));
-            if (qp + P.mal <= Q.n && (qn & ((P.mal >= 32) ? 0xffffffffu : ((1u << P.mal) - 1))) == 0) {
-                const uint64_t km = (~0ULL) >> (64 - 2 * P.mal);
-                const uint64_t h = fmix64(canonical_kmer(qw & km, P.mal, km));
+            const W3 qw = fetch3(Q.rec, (uint64_t)qp);
+            qv = qp + P.msl <= Q.n && (qw.nv & ((1u << P.msl) - 1)) == 0;
+            qk = kmer_code(qw, P.msl);
+            if (qp + P.mal <= Q.n && (qw.nv & ((1u << P.mal) - 1)) == 0) {
+                const uint64_t h = fmix64(canonical_kmer(kmer_code(qw, P.mal), P.mal));
                 pr_fp = (uint32_t)(h >> 32) >> pos_bits;
                 pr_slot = ht_slot(h, tcap);
                 pr_s = __ldg(tab + pr_slot);
@@ -562,16 +575,18 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
             const int nw = (max_w + P.msl - 1 + 31) >> 5;
             if (nw <= SEED_WORDS) {
                 uint32_t(*E)[SEED_WORDS + 1] = seed_masks[threadIdx.x >> 5];
-                for (int k = 0; k < nw; ++k) {
-                    const int pos = lo + 32 * k + lane;
-                    uint32_t sym = 4;
-                    if (pos < R.n) {
-                        sym = (__ldg(R.s2 + (pos >> 4)) >> ((pos & 15) * 2)) & 3;
-                        if ((__ldg(R.nv + (pos >> 5)) >> (pos & 31)) & 1) sym = 4;
+                if (lane < nw) {                          // lane k turns window word k into the four symbol masks
+                    const int pos = lo + 32 * lane;
+                    const int rem = R.n - pos;            // symbols of this word inside the text
+                    uint32_t ok = 0;
+                    W3 w = {0, 0, 0};
+                    if (rem > 0) {
+                        w = fetch3(R.rec, (uint64_t)pos);
+                        ok = ~w.nv;
+                        if (rem < 32) ok &= (1u << rem) - 1;
                     }
-                    uint32_t b0 = __ballot_sync(0xffffffffu, sym == 0), b1 = __ballot_sync(0xffffffffu, sym == 1);
-                    uint32_t b2 = __ballot_sync(0xffffffffu, sym == 2), b3 = __ballot_sync(0xffffffffu, sym == 3);
-                    if (lane < 4) E[lane][k] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+                    E[0][lane] = ~w.lo & ~w.hi & ok; E[1][lane] = w.lo & ~w.hi & ok;
+                    E[2][lane] = ~w.lo & w.hi & ok;  E[3][lane] = w.lo & w.hi & ok;
                 }
                 if (lane < 4) E[lane][nw] = 0;
                 __syncwarp();
@@ -580,7 +595,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
 #pragma unroll
                     for (int k = 0; k < SEED_WORDS; ++k) acc[k] = 0xffffffffu;
                     for (int j = 0; j < P.msl; ++j) {
-                        const uint32_t *e = E[(qk >> (2 * j)) & 3];
+                        const uint32_t *e = E[((qk >> j) & 1) | ((qk >> (31 + j)) & 2)];
                         uint32_t cur = e[0];
 #pragma unroll
                         for (int k = 0; k < SEED_WORDS; ++k) {
@@ -736,10 +751,10 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
 }
 
 template <int MINB, bool REGIONS>
-__global__ void __launch_bounds__(128, MINB) parse_kernel(const uint32_t *__restrict__ g2, const uint32_t *__restrict__ gn,
+__global__ void __launch_bounds__(128, MINB) parse_kernel(const uint4 *__restrict__ grec,
                                                     const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
-                                                    const RefDesc *__restrict__ refs, const uint32_t *__restrict__ ref_s2,
-                                                    const uint32_t *__restrict__ ref_nv, const uint32_t *__restrict__ ht,
+                                                    const RefDesc *__restrict__ refs, const uint4 *__restrict__ ref_rec,
+                                                    const uint32_t *__restrict__ ht,
                                                     const uint32_t *__restrict__ pair_ref, const uint32_t *__restrict__ pair_qry,
                                                     uint32_t n_pairs, LzParams P, unsigned int *__restrict__ cursor,
                                                     int32_t *__restrict__ stats, RegionSink sink, uint32_t pair_base)
@@ -753,9 +768,9 @@ __global__ void __launch_bounds__(128, MINB) parse_kernel(const uint32_t *__rest
         if (idx >= n_pairs) return;
         const RefDesc d = refs[pair_ref[idx]];
         const uint32_t q = pair_qry[idx];
-        Text R = {ref_s2 + d.s2_off, ref_nv + d.nv_off, (int)d.n};
+        Text R = {ref_rec + d.rec_off, (int)d.n};
         uint64_t qo = gofs[q];
-        Text Q = {g2 + (qo >> 4), gn + (qo >> 5), (int)glen[q] + P.mrd};
+        Text Q = {grec + (qo >> 5), (int)glen[q] + P.mrd};
         int m, l, c;
         parse_pair<REGIONS>(Q, R, ht + d.ht_off, d.ht_cap, d.pos_bits, P, lane, seed_masks, m, l, c, sink, pair_base + idx);
         if (lane == 0) { stats[3 * (uint64_t)idx] = m; stats[3 * (uint64_t)idx + 1] = l; stats[3 * (uint64_t)idx + 2] = c; }
@@ -771,9 +786,10 @@ __global__ void __launch_bounds__(128, MINB) parse_kernel(const uint32_t *__rest
 // the host builds and sorts the pair list while the GPU works on it (vb_align_job_begin ... vb_align_job_run).
 struct RefBatch {
     std::vector<RefDesc> refs;
-    uint64_t s2_words = 0, nv_words = 0, slots = 0, bytes = 0;
+    uint64_t recs = 0, slots = 0, bytes = 0;
     DevBuf<RefDesc> d_refs;
-    DevBuf<uint32_t> ref_s2, ref_nv, ht;
+    DevBuf<uint4> ref_rec;
+    DevBuf<uint32_t> ht;
 };
 
 static uint64_t ref_table_slots(uint64_t len)
@@ -786,7 +802,7 @@ static uint64_t ref_table_slots(uint64_t len)
 static uint64_t ref_bytes(uint64_t len, int mrd)
 {
     const uint64_t chunks = (2 * len + 3 * (uint64_t)mrd + 31) / 32 + 4;
-    return chunks * 12 + ref_table_slots(len) * 4;
+    return chunks * 16 + ref_table_slots(len) * 4;
 }
 
 static void ref_batch_add(RefBatch &b, const vb_genomes *g, uint32_t gid, int mrd)
@@ -799,26 +815,24 @@ static void ref_batch_add(RefBatch &b, const vb_genomes *g, uint32_t gid, int mr
     uint32_t pos_bits = 1;
     while ((1ULL << pos_bits) <= nR) ++pos_bits;
     RefDesc d;
-    d.s2_off = b.s2_words; d.nv_off = b.nv_words; d.ht_off = b.slots;
+    d.rec_off = b.recs; d.ht_off = b.slots;
     d.ht_cap = (uint32_t)cap; d.pos_bits = pos_bits; d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = gid;
     b.refs.push_back(d);
-    b.s2_words += 2 * chunks + 4; b.nv_words += chunks + 4; b.slots += cap; b.bytes += chunks * 12 + cap * 4;
+    b.recs += chunks + 2; b.slots += cap; b.bytes += chunks * 16 + cap * 4;
 }
 
 // allocate, upload the descriptors, clear the tables, build texts and anchor tables (all asynchronous)
 static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, const vb_align_params *ap, cudaStream_t st)
 {
     b.d_refs.alloc(b.refs.size());
-    b.ref_s2.alloc(b.s2_words + 8);
-    b.ref_nv.alloc(b.nv_words + 8);
+    b.ref_rec.alloc(b.recs + 8);
     b.ht.alloc(b.slots);
     VB_CUDA(cudaMemcpyAsync(b.d_refs.p, b.refs.data(), sizeof(RefDesc) * b.refs.size(), cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaMemsetAsync(b.ht.p, 0xff, b.ht.bytes(), st));
     dim3 grid_b(16, (unsigned)std::min<size_t>(b.refs.size(), 32768));
-    build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.seq2.p, dg.inv_lz.p, dg.gofs.p, b.d_refs.p, (uint32_t)b.refs.size(), ap->mrd,
-                                                 b.ref_s2.p, b.ref_nv.p);
+    build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.rec.p, dg.gofs.p, b.d_refs.p, (uint32_t)b.refs.size(), ap->mrd, b.ref_rec.p);
     VB_LAUNCH_CHECK(ctx);
-    build_ref_index_kernel<<<grid_b, 256, 0, st>>>(b.d_refs.p, (uint32_t)b.refs.size(), ap->mal, b.ref_s2.p, b.ref_nv.p, b.ht.p);
+    build_ref_index_kernel<<<grid_b, 256, 0, st>>>(b.d_refs.p, (uint32_t)b.refs.size(), ap->mal, b.ref_rec.p, b.ht.p);
     VB_LAUNCH_CHECK(ctx);
 }
 
@@ -835,7 +849,7 @@ static void parse_launch(vb_ctx *ctx, const DevGenomes &dg, const RefBatch &b, c
     int n_sm = 0;
     VB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
     int blocks = std::max(1, std::min<int>(per_sm * n_sm, (int)((nb + 3) / 4)));
-    kern<<<blocks, 128, 0, st>>>(dg.seq2.p, dg.inv_lz.p, dg.gofs.p, dg.glen.p, b.d_refs.p, b.ref_s2.p, b.ref_nv.p, b.ht.p, d_pref,
+    kern<<<blocks, 128, 0, st>>>(dg.rec.p, dg.gofs.p, dg.glen.p, b.d_refs.p, b.ref_rec.p, b.ht.p, d_pref,
                                  d_pqry, nb, P, d_cursor, d_stats, rs, pair_base);
     VB_LAUNCH_CHECK(ctx);
 }

@@ -115,12 +115,16 @@ struct EventTimer {
 //   inv_kdb / inv_lz : 1 bit per base, 32 bases per uint32 word, set when the base is not a valid symbol or is
 //          padding.  Two planes because the tools disagree on U: kmer-db reads it as T (alphabet.h:80-85), lz-ani as N
 //          (seq_reservoir.h:243-247); everything else is shared, so ONE upload serves the prefilter and the align stage.
+//   rec  : one uint4 per 32 slots = {bit 0 of the 32 codes, bit 1 of the 32 codes, inv_lz word, inv_kdb word}.  The LZ parse
+//          compares texts 32 bases at a time: with bit PLANES a comparison is (lo^lo')|(hi^hi')|N|N' straight from two
+//          128-bit loads per text, where the interleaved 2-bit form needs a 36-instruction bit squeeze per comparison
 //   tile_gid : genome id owning each 128-base tile (0xffffffff for none)
 // ---------------------------------------------------------------------------------------------------------------
 struct DevGenomes {
     uint32_t n = 0;
     uint64_t total_slots = 0;        // multiple of 128
     DevBuf<uint32_t> seq2, inv_kdb, inv_lz;
+    DevBuf<uint4> rec;               // the align stage's view: per 32 slots {low bit plane, high bit plane, inv_lz, inv_kdb}
     DevBuf<uint64_t> gofs;           // n entries
     DevBuf<uint32_t> glen;           // n entries
     DevBuf<uint32_t> tile_gid;       // total_slots / 128
