@@ -9,10 +9,10 @@ __constant__ uint8_t c_code[2][256];
 __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const uint64_t *__restrict__ src_off,
                             const uint64_t *__restrict__ gofs, const uint32_t *__restrict__ glen,
                             const uint32_t *__restrict__ tile_gid, uint64_t c_lo, uint64_t c_hi,
-                            uint32_t *__restrict__ seq2, uint32_t *__restrict__ inv_kdb, uint32_t *__restrict__ inv_lz,
-                            uint4 *__restrict__ rec)
+                            uint32_t *__restrict__ seq2, uint32_t *__restrict__ inv_kdb, uint4 *__restrict__ rec)
 {
-    // one thread per 32 base slots [32 c, 32 c + 32), c in [c_lo, c_hi): two seq2 words and one word of each validity plane
+    // one thread per 32 base slots [32 c, 32 c + 32), c in [c_lo, c_hi): two seq2 words, the kmer-db validity word and
+    // the align stage's plane record
     for (uint64_t c = c_lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < c_hi;
          c += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t slot = c * 32;
@@ -42,7 +42,6 @@ __global__ void pack_kernel(const uint8_t *__restrict__ ascii, const uint64_t *_
         seq2[2 * c] = w0;
         seq2[2 * c + 1] = w1;
         inv_kdb[c] = bad;
-        inv_lz[c] = bad_lz;
         rec[c] = make_uint4(p_lo, p_hi, bad_lz, bad);
     }
 }
@@ -99,7 +98,6 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
 
     out.seq2.alloc(slots / 16 + 8);
     out.inv_kdb.alloc(slots / 32 + 8);
-    out.inv_lz.alloc(slots / 32 + 8);
     out.rec.alloc(slots / 32 + 8);
     out.gofs.alloc(n ? n : 1);
     out.glen.alloc(n ? n : 1);
@@ -118,7 +116,6 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
     vb_tls_pool_alloc = pool_mode;
     VB_CUDA(cudaMemsetAsync(out.seq2.p, 0, out.seq2.bytes(), st));
     VB_CUDA(cudaMemsetAsync(out.inv_kdb.p, 0xff, out.inv_kdb.bytes(), st));
-    VB_CUDA(cudaMemsetAsync(out.inv_lz.p, 0xff, out.inv_lz.bytes(), st));
     VB_CUDA(cudaMemsetAsync(out.rec.p, 0xff, out.rec.bytes(), st));          // slack records: all invalid
     VB_CUDA(cudaMemcpyAsync(src_off.p, g->offset.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, st));
     if (n) {
@@ -161,7 +158,7 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
         const uint64_t c_lo = s0 / 32, c_hi = s1 / 32;
         const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((c_hi - c_lo + 255) / 256, 148 * 16));
         pack_kernel<<<blocks, 256, 0, st>>>((const uint8_t *)ascii.p, src_off.p, out.gofs.p, out.glen.p, out.tile_gid.p, c_lo, c_hi,
-                                            out.seq2.p, out.inv_kdb.p, out.inv_lz.p, out.rec.p);
+                                            out.seq2.p, out.inv_kdb.p, out.rec.p);
         VB_LAUNCH_CHECK(ctx);
         if (on_chunk) (*on_chunk)(out, s0, s1);
         g0 = g1;

@@ -112,9 +112,10 @@ struct EventTimer {
 //   multiple of 128 bases and is followed by at least 128 slots of padding marked invalid, so a kernel may read up
 //   to 64 bases past the end of a genome without a bounds check.
 //   seq2 : 2 bits per base, 16 bases per uint32 word, base b of a word at bits [2b, 2b+1]  (A0 C1 G2 T3; U is stored as T)
-//   inv_kdb / inv_lz : 1 bit per base, 32 bases per uint32 word, set when the base is not a valid symbol or is
-//          padding.  Two planes because the tools disagree on U: kmer-db reads it as T (alphabet.h:80-85), lz-ani as N
-//          (seq_reservoir.h:243-247); everything else is shared, so ONE upload serves the prefilter and the align stage.
+//   inv_kdb : 1 bit per base, 32 bases per uint32 word, set when the base is not a valid symbol for kmer-db or is
+//          padding.  The tools disagree on U: kmer-db reads it as T (alphabet.h:80-85), lz-ani as N
+//          (seq_reservoir.h:243-247) -- the lz-ani flags live in `rec`; everything else is shared, so ONE upload serves
+//          the prefilter and the align stage.
 //   rec  : one uint4 per 32 slots = {bit 0 of the 32 codes, bit 1 of the 32 codes, inv_lz word, inv_kdb word}.  The LZ parse
 //          compares texts 32 bases at a time: with bit PLANES a comparison is (lo^lo')|(hi^hi')|N|N' straight from two
 //          128-bit loads per text, where the interleaved 2-bit form needs a 36-instruction bit squeeze per comparison
@@ -123,7 +124,7 @@ struct EventTimer {
 struct DevGenomes {
     uint32_t n = 0;
     uint64_t total_slots = 0;        // multiple of 128
-    DevBuf<uint32_t> seq2, inv_kdb, inv_lz;
+    DevBuf<uint32_t> seq2, inv_kdb;
     DevBuf<uint4> rec;               // the align stage's view: per 32 slots {low bit plane, high bit plane, inv_lz, inv_kdb}
     DevBuf<uint64_t> gofs;           // n entries
     DevBuf<uint32_t> glen;           // n entries
