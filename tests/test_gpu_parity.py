@@ -334,3 +334,40 @@ def test_c2_unrelated_pairs_sample_vs_oracle(ctx):
     remap = {x: i for i, x in enumerate(sub)}
     want = oracle.run_pairs([oracle.lz_codes(raw[x]) for x in sub], [remap[x] for x in ref], [remap[x] for x in qry])
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- the command line (vclust.py's two sub-commands)
+def test_cli_reproduces_the_reference_example(golden, tmp_path, capfd):
+    """`vclust prefilter` + `vclust align --filter ... --out-aln ...` through vclust_b200.cli, multi-FASTA and directory
+    input, against example/output/* (the reference's own test.py:300-530 checks the same files); -v 0 prints nothing."""
+    from vclust_b200 import cli
+    fa = golden / "example" / "multifasta.fna.gz"
+    flt, ani, aln = tmp_path / "fltr.txt", tmp_path / "ani.tsv", tmp_path / "ani.aln.tsv"
+    cli.main(["prefilter", "-i", str(fa), "-o", str(flt), "--min-ident", "0.7", "-v", "0", "--batch-size", "4"])
+    assert flt.read_bytes() == (golden / "example" / "fltr.txt").read_bytes()
+    cli.main(["align", "-i", str(fa), "-o", str(ani), "--out-aln", str(aln), "-v", "0"])
+    assert ani.read_bytes() == (golden / "example" / "ani.tsv").read_bytes()
+    assert (tmp_path / "ani.ids.tsv").read_bytes() == (golden / "example" / "ani.ids.tsv").read_bytes()
+    want_aln = gzip.open(golden / "example" / "ani.aln.tsv.gz", "rt").read().splitlines()
+    got_aln = aln.read_text().splitlines()
+    assert got_aln[0] == want_aln[0] and sorted(got_aln[1:]) == sorted(want_aln[1:])
+    out, err = capfd.readouterr()
+    assert out == "" and err == ""
+    # filtered align, lite format, output filter: the rows of the golden that pass --out-ani 0.95
+    ani2 = tmp_path / "ani2.tsv"
+    cli.main(["align", "-i", str(fa), "-o", str(ani2), "--filter", str(flt), "--outfmt", "lite", "--out-ani", "0.95", "-v", "0"])
+    rows = [ln.split("\t") for ln in ani2.read_text().splitlines()]
+    assert rows[0] == api.ALIGN_OUTFMT["lite"]
+    assert len(rows) > 1 and all(float(r[4]) >= 0.95 for r in rows[1:])
+    # directory mode: one genome per file, named by the file name (vclust.py:685-702)
+    d = tmp_path / "fna"
+    d.mkdir()
+    recs = oracle.read_records_kmerdb(fa)
+    for name, seq in recs[:4]:
+        (d / (name + ".fna")).write_bytes(b">" + name.encode() + b"\n" + seq + b"\n")
+    flt_d = tmp_path / "fltr_dir.txt"
+    cli.main(["prefilter", "-i", str(d), "-o", str(flt_d), "-v", "0"])
+    want = oracle.prefilter_text_from_fasta(sorted(d.iterdir()), False)
+    assert flt_d.read_text() == want
+    with pytest.raises(SystemExit):
+        cli.main(["prefilter", "-i", str(d), "-o", str(flt_d), "--batch-size", "2"])     # vclust.py:731-736
