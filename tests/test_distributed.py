@@ -22,7 +22,7 @@ def _fmix64(x):
     return x
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, max_seqs=0):
     sys.path.insert(0, str(ROOT))
     import torch.distributed as dist
 
@@ -41,10 +41,11 @@ def _worker(rank, world, port, out_dir):
     codes = [oracle.lz_codes(s) for s in raw]
 
     def merge_fn(r, c, v, totals):
-        m = api.merge_pairs(r, c, v, totals, k=k, min_kmers=min_kmers, min_ident=min_ident)
+        m = api.merge_pairs(r, c, v, totals, k=k, min_kmers=min_kmers, min_ident=min_ident, max_seqs=max_seqs)
         return m.rows, m.cols, m.common, m.ani
 
-    res = distributed.exchange_and_align(dist, "cpu", partial, merge_fn, lambda r, q: oracle.run_pairs(codes, r, q))
+    res = distributed.exchange_and_align(dist, "cpu", partial, merge_fn, lambda r, q: oracle.run_pairs(codes, r, q),
+                                         sampled=max_seqs > 0)
     if rank == 0:
         np.savez(Path(out_dir) / "res.npz", totals=res["totals"], prow=res["pairs"][0], pcol=res["pairs"][1],
                  pcommon=res["pairs"][2], pani=res["pairs"][3], ref=res["ref"], qry=res["qry"], stats=res["stats"])
@@ -73,6 +74,32 @@ def test_sharded_exchange_matches_single_process(tmp_path):
     # every candidate pair parsed in both directions, exactly once, with the single-process statistics
     pairs = sorted(zip(got["ref"].tolist(), got["qry"].tolist()))
     assert pairs == sorted([(r, c) for r, c, *_ in want] + [(c, r) for r, c, *_ in want])
+    st = oracle.run_pairs([oracle.lz_codes(s) for s in raw], got["ref"], got["qry"])
+    assert np.array_equal(st, got["stats"])
+
+
+def test_sharded_exchange_with_max_seqs(tmp_path):
+    """--max-seqs over two ranks: every owner samples the rows of its own genomes, a second all-to-all returns the kept
+    entries to the owners of their items; filter rows and the multiset of directed parses equal the single-process ones."""
+    import torch.multiprocessing as mp
+
+    from oracle import oracle
+    from vclust_b200 import build, synth
+    build.build()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path), 2), nprocs=2, join=True)
+    got = np.load(tmp_path / "res.npz")
+    names, seqs = synth.make_genomes(n=30, length=5000, family=5, seed=4242, n_frac=0.2)
+    raw = [s.tobytes() for s in seqs]
+    sets = oracle.kmer_sets([[s] for s in raw], 21, 1.0)
+    want = oracle.prefilter_pairs(sets, 21, 10, 0.6, max_seqs=2)
+    assert any(r < c for r, c, *_ in want) and len(want) < 2 * len(oracle.prefilter_pairs(sets, 21, 10, 0.6))
+    assert list(zip(got["prow"].tolist(), got["pcol"].tolist(), got["pcommon"].tolist())) == [(r, c, v) for r, c, v, _ in want]
+    assert np.array_equal(got["pani"], np.array([a for *_, a in want]))
+    pairs = sorted(zip(got["ref"].tolist(), got["qry"].tolist()))
+    assert pairs == sorted([(r, c) for r, c, *_ in want] + [(c, r) for r, c, *_ in want])       # duplicates included
     st = oracle.run_pairs([oracle.lz_codes(s) for s in raw], got["ref"], got["qry"])
     assert np.array_equal(st, got["stats"])
 

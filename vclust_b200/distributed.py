@@ -59,10 +59,14 @@ def _gather_rows(dist, rows: np.ndarray, device, width: int, dst: int = 0):
 
 
 def exchange_and_align(dist, device, partial: Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray],
-                       merge_fn: Callable, align_fn: Callable):
+                       merge_fn: Callable, align_fn: Callable, sampled: bool = False):
     """Steps 2-5.  partial = (rows, cols, common, partial_totals) of this rank's k-mer shard.
     merge_fn(rows, cols, common, totals) -> (rows, cols, common, ani) kept pairs (thresholds applied, sorted).
     align_fn(ref, qry) -> (n, 3) int32.
+    sampled: merge_fn applies --max-seqs, i.e. returns ROWS of the filter (entries on both sides of the diagonal).  An
+    owner then only trusts the rows of its own genomes (it holds every pair they occur in, so their top-N is exact) and
+    a second, small all-to-all sends each kept entry (row, item) to the owner of `item`: LZ-ANI symmetrises every filter
+    entry (L/filter.cpp:80-81), so genome x is parsed as the reference of y once per entry (x, y) and once per (y, x).
     Returns on rank 0: dict(totals, pairs=(row, col, common, ani), ref, qry, stats); on other ranks None."""
     import torch
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -84,9 +88,20 @@ def exchange_and_align(dist, device, partial: Tuple[np.ndarray, np.ndarray, np.n
                                                got[:, 2].astype(np.uint32), totals)
     m_rows, m_cols = np.asarray(m_rows, np.int64), np.asarray(m_cols, np.int64)
     mine_r = owner(m_rows, world) == rank
-    mine_c = owner(m_cols, world) == rank
-    ref = np.concatenate([m_rows[mine_r], m_cols[mine_c]])
-    qry = np.concatenate([m_cols[mine_r], m_rows[mine_c]])
+    if sampled:
+        # rows of foreign genomes were sampled from an incomplete candidate list: drop them, their owners have them
+        m_rows, m_cols = m_rows[mine_r], m_cols[mine_r]
+        m_common, m_ani = np.asarray(m_common)[mine_r], np.asarray(m_ani)[mine_r]
+        mine_r = np.ones(m_rows.size, dtype=bool)
+        ent = np.stack([m_rows, m_cols], axis=1) if m_rows.size else np.zeros((0, 2), np.int64)
+        o_item = owner(ent[:, 1], world)
+        back = _a2a_variable(dist, [ent[o_item == d] for d in range(world)], device, 2)    # entries (row, item), item is mine
+        ref = np.concatenate([m_rows, back[:, 1]])
+        qry = np.concatenate([m_cols, back[:, 0]])
+    else:
+        mine_c = owner(m_cols, world) == rank
+        ref = np.concatenate([m_rows[mine_r], m_cols[mine_c]])
+        qry = np.concatenate([m_cols[mine_r], m_rows[mine_c]])
     stats = np.asarray(align_fn(ref.astype(np.uint32), qry.astype(np.uint32)), dtype=np.int64).reshape(-1, 3)
 
     res_rows = np.concatenate([ref[:, None], qry[:, None], stats], axis=1) if ref.size else np.zeros((0, 5), np.int64)
@@ -108,7 +123,7 @@ def exchange_and_align(dist, device, partial: Tuple[np.ndarray, np.ndarray, np.n
 
 
 def prefilter_align_sharded(ctx, genomes_kmerdb, genomes_lzani, dist, device, k=25, min_kmers=20, min_ident=0.7,
-                            kmers_fraction=1.0, lz_params=None) -> Optional[dict]:
+                            kmers_fraction=1.0, lz_params=None, max_seqs=0) -> Optional[dict]:
     """The GPU instantiation: vb_prefilter_partial -> exchange -> vb_pairs_merge -> vb_align_pairs.
     genomes_kmerdb / genomes_lzani: the same input loaded with the two FASTA flavours (they may be the same object
     when the input has no corner cases, e.g. synthetic data)."""
@@ -119,7 +134,8 @@ def prefilter_align_sharded(ctx, genomes_kmerdb, genomes_lzani, dist, device, k=
     part.close()
 
     def merge_fn(r, c, v, totals):
-        m = api.merge_pairs(r, c, v, totals, k=k, min_kmers=min_kmers, min_ident=min_ident, kmers_fraction=kmers_fraction)
+        m = api.merge_pairs(r, c, v, totals, k=k, min_kmers=min_kmers, min_ident=min_ident, kmers_fraction=kmers_fraction,
+                            max_seqs=max_seqs)
         out = (m.rows, m.cols, m.common, m.ani)
         m.close()
         return out
@@ -127,4 +143,4 @@ def prefilter_align_sharded(ctx, genomes_kmerdb, genomes_lzani, dist, device, k=
     def align_fn(ref, qry):
         return api.align_pairs(ctx, genomes_lzani, ref, qry, lz_params)
 
-    return exchange_and_align(dist, device, partial, merge_fn, align_fn)
+    return exchange_and_align(dist, device, partial, merge_fn, align_fn, sampled=max_seqs > 0)
