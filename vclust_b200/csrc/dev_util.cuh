@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <string>
 
 #include "vb_internal.h"
@@ -138,7 +139,6 @@ constexpr uint32_t VB_STORE_PAD = 128 + 64;      // covers the prefilter (128) a
 // on_chunk(slot_lo, slot_hi), optional: called after the pack of each chunk of genomes has been enqueued -- the H2D of
 // the next chunk runs on the context's copy stream meanwhile, so a consumer that enqueues its first pass over
 // [slot_lo, slot_hi) from the callback overlaps that pass with the transfer.
-#include <functional>
 struct DevGenomes;
 using vb_chunk_fn = std::function<void(const DevGenomes &, uint64_t, uint64_t)>;
 uint64_t vb_store_slots(const vb_genomes *g, uint32_t min_pad);    // base slots the packed store of g will have
