@@ -130,3 +130,25 @@ def test_merge_pairs_max_seqs_matches_oracle_sampler():
         assert list(zip(m.rows.tolist(), m.cols.tolist(), m.common.tolist())) == [(r, c, v) for r, c, v, _ in want]
         assert np.array_equal(m.ani, np.array([a for *_, a in want]))
         assert any(r < c for r, c, *_ in want)          # entries on both sides of the diagonal
+
+
+def test_max_seqs_tie_break_is_smallest_item_first():
+    """kmer-db's heap (K/sampler.h:45-66) evicts, among equal scores, the LARGEST item id: with all scores tied a row keeps
+    its N smallest partners (confirmed with the reference binary on 7 identical genomes: rows `2:…,3:…` / `1:…,3:…` /
+    `1:…,2:…`) -- checked on the host code of the C ABI and on the oracle restatement."""
+    from oracle import oracle
+    from vclust_b200 import api, build
+    build.build()
+    n = 7
+    totals = np.full(n, 100, dtype=np.uint32)
+    rows, cols = zip(*[(r, c) for r in range(n) for c in range(r)])
+    m = api.merge_pairs(rows, cols, [50] * len(rows), totals, k=21, min_kmers=1, min_ident=0.0, max_seqs=2)
+    got = {}
+    for r, c in zip(m.rows.tolist(), m.cols.tolist()):
+        got.setdefault(r, []).append(c)
+    assert got == {r: sorted(x for x in range(n) if x != r)[:2] for r in range(n)}
+    assert len(set(m.ani.tolist())) == 1
+    # the same rule in the oracle (fed with k-mer sets that give identical counts: identical genomes)
+    sets = [np.arange(100, dtype=np.uint64) for _ in range(n)]
+    want = oracle.prefilter_pairs(sets, 21, 1, 0.0, max_seqs=2)
+    assert [(r, c) for r, c, *_ in want] == list(zip(m.rows.tolist(), m.cols.tolist()))
