@@ -129,6 +129,37 @@ def test_chunked_pinned_upload_gives_the_same_result(ctx):
     assert got == want
 
 
+@pytest.mark.parametrize("env", [{}, {"VB_PREFILTER_HASH": "1"}])
+def test_prefilter_kmers_shared_by_thousands_of_genomes(ctx, monkeypatch, env):
+    """A k-mer present in more genomes than a shared-memory bucket holds (kmer-db's "bubble" case, c5) takes the generic
+    global-memory path of the grouping kernel: 2 200 copies of one short sequence + unrelated genomes."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(17)
+    core = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=140)].tobytes()
+    others = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=300)].tobytes() for _ in range(40)]
+    seqs = [core] * 2200 + others
+    names = ["g%d" % i for i in range(len(seqs))]
+    g = api.Genomes.from_memory(names, seqs)
+    pairs = api.prefilter_genomes(ctx, g, k=21, min_kmers=1, min_ident=0.0)
+    sets = oracle.kmer_sets([[core]] + [[s] for s in others], 21, 1.0)
+    n_core = int(sets[0].size)
+    assert pairs.total_kmers.tolist() == [n_core] * 2200 + [int(s.size) for s in sets[1:]]
+    rows, cols, common = pairs.rows.astype(np.int64), pairs.cols.astype(np.int64), pairs.common
+    among = (rows < 2200) & (cols < 2200)
+    assert int(among.sum()) == 2200 * 2199 // 2 and bool((common[among] == n_core).all())
+    # everything that involves an unrelated genome: as the oracle says for (core, others)
+    r2, c2, v2 = oracle.common_matrix(sets)
+    want = {}
+    for r, c, v in zip(r2.tolist(), c2.tolist(), v2.tolist()):
+        for rr in ([r + 2199] if r > 0 else range(2200)):
+            for cc in ([c + 2199] if c > 0 else range(2200)):
+                if rr != cc:
+                    want[(max(rr, cc), min(rr, cc))] = v
+    got = {(int(r), int(c)): int(v) for r, c, v in zip(rows[~among], cols[~among], common[~among])}
+    assert got == {k: v for k, v in want.items() if not (k[0] < 2200 and k[1] < 2200)}
+
+
 def test_prefilter_edge_cases(ctx):
     # empty genome, genome shorter than k, all-N genome, U handled as T, lower case, duplicate genomes
     seqs = [b"", b"ACGTACGT", b"N" * 100, b"ACGU" * 30, b"acgt" * 30, b"ACGT" * 30, b"ACGTTGCAAGGCTA" * 10]
