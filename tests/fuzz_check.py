@@ -67,6 +67,37 @@ def main():
             print("MISMATCH in round %d: params %r genomes %r first differing pairs %r" % (it, params, gen, [(int(ref[b]), int(qry[b]), st[b].tolist(), want_st[b].tolist()) for b in bad]))
             sys.exit(1)
     print("fuzz ok: %d rounds, %d directed pairs, stats and regions identical to the oracle" % (rounds, total_pairs))
+    # ---- prefilter: random k, fraction, thresholds, --max-seqs, genome shapes (U, N runs, lower case, tiny genomes)
+    n_cmp = 0
+    for it in range(rounds):
+        k = int(rng.integers(12, 32))
+        frac = float(rng.choice([1.0, 1.0, 0.5, 0.2, 0.05]))
+        min_kmers = int(rng.integers(1, 40))
+        min_ident = float(rng.choice([0.0, 0.5, 0.7, 0.9]))
+        max_seqs = int(rng.choice([0, 0, 1, 3]))
+        gen = dict(n=int(rng.integers(8, 60)), length=(int(rng.integers(40, 400)), int(rng.integers(400, 6000))),
+                   family=int(rng.choice([1, 2, 5, 8])), seed=int(rng.integers(1, 1 << 30)),
+                   max_div=float(rng.choice([0.01, 0.05, 0.15])), indel=int(rng.choice([0, 50, 500])),
+                   n_frac=float(rng.choice([0, 0.5])), lower_frac=float(rng.choice([0, 0.5])))
+        names, seqs = synth.make_genomes(**gen)
+        raw = [s.tobytes() for s in seqs]
+        raw[0] = raw[0].replace(b"T", b"U")                                # kmer-db reads U as T
+        raw += [b"", b"ACGTACGTAC", b"N" * 90, raw[1], raw[1][: len(raw[1]) // 2] + raw[1][: len(raw[1]) // 2]]
+        names = names + ["y%d" % i for i in range(5)]
+        g = api.Genomes.from_memory(names, raw)
+        pairs = api.prefilter_genomes(ctx, g, k=k, min_kmers=min_kmers, min_ident=min_ident, kmers_fraction=frac, max_seqs=max_seqs)
+        sets = oracle.kmer_sets([[s] for s in raw], k, frac)
+        want = oracle.prefilter_pairs(sets, k, min_kmers, min_ident, max_seqs)
+        got = list(zip(pairs.rows.tolist(), pairs.cols.tolist(), pairs.common.tolist()))
+        ok = pairs.total_kmers.tolist() == [int(s.size) for s in sets] and got == [(r, c, v) for r, c, v, _ in want] and \
+            np.array_equal(pairs.ani, np.array([a for *_, a in want], dtype=np.float64))
+        pairs.close(); g.close()
+        n_cmp += len(want)
+        if not ok:
+            print("PREFILTER MISMATCH in round %d: k=%d f=%g min_kmers=%d min_ident=%g max_seqs=%d genomes %r" %
+                  (it, k, frac, min_kmers, min_ident, max_seqs, gen))
+            sys.exit(1)
+    print("prefilter fuzz ok: %d rounds, %d filter entries identical to the oracle (counts, totals, ani bit patterns)" % (rounds, n_cmp))
 
 
 if __name__ == "__main__":
