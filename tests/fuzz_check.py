@@ -16,12 +16,10 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def main():
+def fuzz_align(ctx, rounds: int, rng) -> int:
+    """Returns the number of directed pairs compared; raises AssertionError with the draw at the first difference."""
     from oracle import oracle
     from vclust_b200 import api, synth
-    rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-    ctx = api.Context(0)
     total_pairs = 0
     for it in range(rounds):
         mal = int(rng.integers(6, 17))
@@ -64,10 +62,16 @@ def main():
         total_pairs += ref.size
         if not ok:
             bad = np.nonzero((st != want_st).any(axis=1))[0][:5]
-            print("MISMATCH in round %d: params %r genomes %r first differing pairs %r" % (it, params, gen, [(int(ref[b]), int(qry[b]), st[b].tolist(), want_st[b].tolist()) for b in bad]))
-            sys.exit(1)
-    print("fuzz ok: %d rounds, %d directed pairs, stats and regions identical to the oracle" % (rounds, total_pairs))
-    # ---- prefilter: random k, fraction, thresholds, --max-seqs, genome shapes (U, N runs, lower case, tiny genomes)
+            raise AssertionError("MISMATCH in round %d: params %r genomes %r first differing pairs %r" % (
+                it, params, gen, [(int(ref[b]), int(qry[b]), st[b].tolist(), want_st[b].tolist()) for b in bad]))
+    return total_pairs
+
+
+def fuzz_prefilter(ctx, rounds: int, rng) -> int:
+    """Random k, fraction, thresholds, --max-seqs, genome shapes (U, N runs, lower case, tiny genomes); returns the
+    number of filter entries compared."""
+    from oracle import oracle
+    from vclust_b200 import api, synth
     n_cmp = 0
     for it in range(rounds):
         k = int(rng.integers(12, 32))
@@ -94,10 +98,24 @@ def main():
         pairs.close(); g.close()
         n_cmp += len(want)
         if not ok:
-            print("PREFILTER MISMATCH in round %d: k=%d f=%g min_kmers=%d min_ident=%g max_seqs=%d genomes %r" %
-                  (it, k, frac, min_kmers, min_ident, max_seqs, gen))
-            sys.exit(1)
-    print("prefilter fuzz ok: %d rounds, %d filter entries identical to the oracle (counts, totals, ani bit patterns)" % (rounds, n_cmp))
+            raise AssertionError("PREFILTER MISMATCH in round %d: k=%d f=%g min_kmers=%d min_ident=%g max_seqs=%d genomes %r" %
+                                 (it, k, frac, min_kmers, min_ident, max_seqs, gen))
+    return n_cmp
+
+
+def main():
+    from vclust_b200 import api
+    rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    ctx = api.Context(0)
+    try:
+        n = fuzz_align(ctx, rounds, rng)
+        print("fuzz ok: %d rounds, %d directed pairs, stats and regions identical to the oracle" % (rounds, n))
+        n = fuzz_prefilter(ctx, rounds, rng)
+        print("prefilter fuzz ok: %d rounds, %d filter entries identical to the oracle (counts, totals, ani bit patterns)" % (rounds, n))
+    except AssertionError as e:
+        print(e)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

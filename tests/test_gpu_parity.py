@@ -402,3 +402,17 @@ def test_cli_reproduces_the_reference_example(golden, tmp_path, capfd):
     assert flt_d.read_text() == want
     with pytest.raises(SystemExit):
         cli.main(["prefilter", "-i", str(d), "-o", str(flt_d), "--batch-size", "2"])     # vclust.py:731-736
+
+
+# ---------------------------------------------------------------- randomised differential runs (tests/fuzz_check.py)
+def test_fuzz_rounds_vs_oracle(ctx):
+    """A few rounds of the randomised run (random LZ / prefilter parameters and genome shapes); `python tests/fuzz_check.py
+    120 1` is the long version (profiles/r01_fuzz.txt)."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("fuzz_check", Path(__file__).resolve().parent / "fuzz_check.py")
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(20261017)
+    assert fz.fuzz_align(ctx, 6, rng) > 0
+    assert fz.fuzz_prefilter(ctx, 8, rng) > 0
