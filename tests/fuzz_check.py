@@ -103,8 +103,36 @@ def fuzz_prefilter(ctx, rounds: int, rng) -> int:
     return n_cmp
 
 
+def long_genomes(ctx):
+    """Genomes of 150-260 kb and of ~1 Mb (wider position fields, narrower fingerprints, multi-megabyte anchor tables):
+    all-vs-all statistics and regions, and the prefilter, against the oracle."""
+    from oracle import oracle
+    from vclust_b200 import api, synth
+    for gen in (dict(n=8, length=(150000, 260000), family=4, seed=11, max_div=0.1, indel=2000, n_frac=0.5),
+                dict(n=6, length=(900000, 1200000), family=3, seed=12, max_div=0.05, indel=5000)):
+        names, seqs = synth.make_genomes(**gen)
+        raw = [s.tobytes() for s in seqs]
+        n = len(raw)
+        ref = np.repeat(np.arange(n), n); qry = np.tile(np.arange(n), n)
+        g = api.Genomes.from_memory(names, raw)
+        st, regs = api.align_pairs_regions(ctx, g, ref, qry)
+        want, wregs = oracle.run_pairs_regions([oracle.lz_codes(s) for s in raw], ref, qry)
+        rows = sorted((int(ref[k]), int(qry[k]), ss, se, rs, re_, m, mm) for k, rg in enumerate(wregs) for rs, re_, ss, se, m, mm in rg.tolist())
+        assert np.array_equal(st, want) and sorted(map(tuple, regs.table().tolist())) == rows, "long genomes: align differs %r" % gen
+        pairs = api.prefilter_genomes(ctx, g, k=25, min_kmers=20, min_ident=0.5)
+        sets = oracle.kmer_sets([[s] for s in raw], 25, 1.0)
+        wantp = oracle.prefilter_pairs(sets, 25, 20, 0.5)
+        assert list(zip(pairs.rows.tolist(), pairs.cols.tolist(), pairs.common.tolist())) == [(r, c, v) for r, c, v, _ in wantp] and \
+            pairs.total_kmers.tolist() == [int(x.size) for x in sets], "long genomes: prefilter differs %r" % gen
+        regs.close(); pairs.close(); g.close()
+        print("long genomes ok: %r, %d directed pairs" % (gen["length"], ref.size))
+
+
 def main():
     from vclust_b200 import api
+    if "--long" in sys.argv:
+        long_genomes(api.Context(0))
+        return
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
     ctx = api.Context(0)
