@@ -158,3 +158,48 @@ def test_number_formats_match_oracle(lib):
         for prec in (4, 6):
             n = fr(float(v), prec, buf)
             assert buf.raw[:n].decode() == oracle.real_str(float(v), prec), v
+
+
+def test_write_ani_threads_give_identical_bytes(lib, tmp_path, monkeypatch):
+    """Large results are formatted by several host threads on disjoint row ranges: same bytes as one thread, with
+    output filters and every column set."""
+    from vclust_b200 import synth
+    names, seqs = synth.make_genomes(n=600, length=150, family=12, seed=3)
+    g = api.Genomes.from_memory(names, seqs)
+    rows, cols = [], []
+    for i in range(600):
+        for j in range((i // 12) * 12, i):
+            rows.append(i); cols.append(j)
+    rows, cols = np.array(rows, dtype=np.uint32), np.array(cols, dtype=np.uint32)
+    ref, qry = np.concatenate([rows, cols, rows[:50]]), np.concatenate([cols, rows, cols[:50]])     # + duplicated pairs
+    st = np.random.default_rng(5).integers(0, 150, size=(ref.size, 3)).astype(np.int32)
+    res = api.align_result_from_pairs(g, ref, qry, st)
+    for fmt, flt in (("complete", None), ("lite", {"ani": 0.4, "qcov": 0.3})):
+        outs = []
+        for thr in ("1", "7"):
+            monkeypatch.setenv("VB_WRITE_THREADS", thr)
+            p = tmp_path / ("ani_%s_%s.tsv" % (fmt, thr))
+            api.write_ani(g, res, p, None, api.ALIGN_OUTFMT[fmt], flt)
+            outs.append(p.read_bytes())
+        assert outs[0] == outs[1] and outs[0].count(b"\n") > 1000
+
+
+def test_read_filter_token_rules(lib, tmp_path):
+    """lz-ani splits a row at ',' and every token at ':' with a split() that drops an empty last part (L/utils.cpp:15-36,
+    L/filter.cpp:60-81): only tokens with exactly two parts count."""
+    names = ["ga", "gb", "gc", "gd"]
+    g = api.Genomes.from_memory(names, [b"ACGT"] * 4)
+    p = tmp_path / "f.txt"
+    p.write_text("kmer-length: 25 fraction: 1 ,ga,gb,gc,gd,\n"
+                 "ga,\n"
+                 "gb,1:0.900000,,junk,2:,1:0.5:7,\r\n"
+                 "\n"                                   # lines of up to 2 bytes are skipped, row id not advanced
+                 "gc,2:0.800000,1:1e-1,4:0.75\n"         # last token without a trailing comma still counts
+                 "gd,3:0.650000,\n")
+    pr = api.read_filter(p, 0.0, g)
+    assert list(zip(pr.rows.tolist(), pr.cols.tolist(), pr.ani.tolist())) == [(1, 0, 0.9), (2, 1, 0.8), (2, 0, 0.1), (2, 3, 0.75), (3, 2, 0.65)]
+    pr = api.read_filter(p, 0.7, g)
+    assert list(zip(pr.rows.tolist(), pr.cols.tolist())) == [(1, 0), (2, 1), (2, 3)]
+    p.write_text("kmer-length: 25 fraction: 1 ,ga,gb,gc,gd,\ngb,:0.9,\n")
+    with pytest.raises(api.VbError):                     # id -1 is out of range
+        api.read_filter(p, 0.0, g)

@@ -218,16 +218,25 @@ vb_pairs *vb_read_filter_impl(const char *path, double thr, const vb_genomes *g)
     uint32_t row = 0;
     while (getline_cr(line)) {
         if (line.size() <= 2) continue;                 // filter.cpp:107-111: row id NOT advanced
-        auto parts = split_keep(line, ',');
-        for (size_t j = 1; j < parts.size(); ++j) {
-            auto e = split_keep(parts[j], ':');
-            if (e.size() != 2) continue;
-            double v = strtod(e[1].c_str(), nullptr);
-            if (v >= thr) {
-                rows.push_back(row);
-                cols.push_back((uint32_t)(atoi(e[0].c_str()) - 1));
-                vals.push_back(v);
+        // tokens between commas, the first one is the name; a token counts iff it splits at ':' into exactly two parts
+        // under lz-ani's split() (utils.cpp:15-36: an empty LAST part is dropped, so "3:" has one part and is skipped,
+        // ":0.9" has two); parsed in place -- one allocation-free pass instead of a vector of strings per line
+        const char *b = line.c_str(), *end = b + line.size();
+        const char *tok = (const char *)memchr(b, ',', (size_t)(end - b));
+        while (tok) {
+            const char *t0 = tok + 1;
+            const char *t1 = (const char *)memchr(t0, ',', (size_t)(end - t0));
+            const char *te = t1 ? t1 : end;
+            const char *c = (const char *)memchr(t0, ':', (size_t)(te - t0));
+            if (c && c + 1 < te && !memchr(c + 1, ':', (size_t)(te - c - 1))) {
+                const double v = strtod(c + 1, nullptr);        // stops at the ',' / end of line
+                if (v >= thr) {
+                    rows.push_back(row);
+                    cols.push_back((uint32_t)(atoi(t0) - 1));
+                    vals.push_back(v);
+                }
             }
+            tok = t1;
         }
         ++row;
     }
@@ -289,8 +298,11 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
         while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (res->qry[mid] < q) lo = mid + 1; else hi = mid; }
         return (lo < start[r + 1] && res->qry[lo] == q) ? (int64_t)lo : -1;
     };
+    // rows [a_lo, a_hi) formatted into `out`; big results are formatted by several host threads on disjoint row ranges
+    // (equal numbers of directed pairs) and written in row order -- number formatting is the whole cost of this call
+    auto format_rows = [&](uint32_t a_lo, uint32_t a_hi, std::string &out) {
     char num[64];
-    for (uint32_t a = 0; a < n; ++a) {
+    for (uint32_t a = a_lo; a < a_hi; ++a) {
         for (uint64_t qi = start[a]; qi < start[a + 1]; ++qi) {
             uint32_t b = res->qry[qi];
             if (a >= b) continue;
@@ -342,9 +354,30 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
                 if (cols.empty()) out += '\n';
             }
         }
-        if (out.size() > (4 << 20)) { fwrite(out.data(), 1, out.size(), f); out.clear(); }
     }
-    fwrite(out.data(), 1, out.size(), f);
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const char *thr_env = getenv("VB_WRITE_THREADS");                  // test hook
+    const unsigned n_thr = thr_env ? (unsigned)std::clamp(atoi(thr_env), 1, 64) : (res->n < 50000 ? 1u : std::min(hw, 16u));
+    if (n_thr == 1) {
+        format_rows(0, n, out);
+        fwrite(out.data(), 1, out.size(), f);
+    } else {
+        std::vector<uint32_t> cut(n_thr + 1, n);
+        cut[0] = 0;
+        for (unsigned t = 1; t < n_thr; ++t) {
+            const uint64_t want = res->n * (uint64_t)t / n_thr;
+            cut[t] = (uint32_t)(std::lower_bound(start.begin(), start.end(), want) - start.begin());
+            cut[t] = std::min(std::max(cut[t], cut[t - 1]), n);
+        }
+        std::vector<std::string> parts(n_thr);
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_thr; ++t)
+            pool.emplace_back([&, t]() { parts[t].reserve(1 << 20); format_rows(cut[t], cut[t + 1], parts[t]); });
+        for (auto &th : pool) th.join();
+        fwrite(out.data(), 1, out.size(), f);                  // header
+        for (auto &part : parts) fwrite(part.data(), 1, part.size(), f);
+    }
     fclose(f);
 }
 

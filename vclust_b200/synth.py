@@ -97,6 +97,8 @@ CONFIGS = {
     "c2": dict(n=1_000, length=40_000, family=20, seed=BASE_SEED + 2),
     "c3": dict(n=10_000, length=40_000, family=20, seed=BASE_SEED + 3),
     "c3_s200": dict(n=10_000, length=40_000, family=200, seed=BASE_SEED + 3),
+    # more than 11 585 genomes: N(N-1)/2 > 2^26, the prefilter switches to the hashed pair table by itself
+    "n20k": dict(n=20_000, length=10_000, family=20, seed=BASE_SEED + 6),
     "c4": dict(n=100_000, length=(5_000, 200_000), family=200, seed=BASE_SEED + 4, n_frac=0.01, lower_frac=0.01),
     "c5": dict(n=1_000_000, length=30_000, family=20, seed=BASE_SEED + 5),
 }
