@@ -86,6 +86,8 @@ def test_prefilter_counts_vs_oracle(ctx, golden, k, f):
     {"VB_PREFILTER_SEEN": "12"},                                     # tiny seen table: heavy slot collisions must be harmless
     {"VB_PREFILTER_HASH": "1"},                                      # hashed pair table (N(N-1)/2 > 2^26)
     {"VB_PREFILTER_LSD": "1"},                                       # full radix sort instead of the hash-bucket partition
+    {"VB_PREFILTER_PASSES": "3"},                                    # > 10^9 k-mers: several passes over k-mer hash shards
+    {"VB_PREFILTER_PASSES": "2", "VB_PREFILTER_HASH": "1", "VB_PREFILTER_SEEN": "0"},
 ])
 def test_prefilter_large_input_paths_vs_oracle(ctx, golden, monkeypatch, env):
     """The code paths that only very large inputs select by themselves, forced on a small input: same integers."""
@@ -416,3 +418,19 @@ def test_fuzz_rounds_vs_oracle(ctx):
     rng = np.random.default_rng(20261017)
     assert fz.fuzz_align(ctx, 6, rng) > 0
     assert fz.fuzz_prefilter(ctx, 8, rng) > 0
+
+
+def test_prefilter_passes_same_filter_file(ctx, golden, tmp_path, monkeypatch):
+    """Several passes over k-mer hash shards (inputs beyond 10^9 k-mers; --batch-size in spirit): byte-identical filter,
+    thresholds and --max-seqs applied after the partial counts are summed."""
+    monkeypatch.setenv("VB_PREFILTER_PASSES", "4")
+    out = tmp_path / "fltr.txt"
+    api.prefilter([golden / "example" / "multifasta.fna.gz"], out, True)
+    assert out.read_bytes() == (golden / "example" / "fltr.txt").read_bytes()
+    names, seqs = synth.make_genomes(**GEN["s60"])
+    fa = tmp_path / "s60.fna"
+    synth.write_fasta(fa, names, seqs)
+    api.prefilter([fa], out, True, max_seqs=3)
+    assert out.read_bytes() == (golden / "ref_synth" / "s60_ms3.fltr.txt").read_bytes()
+    api.prefilter([fa], out, True, kmers_fraction=0.2, min_kmers=4)
+    assert out.read_bytes() == (golden / "ref_synth" / "s60_f02.fltr.txt").read_bytes()

@@ -220,12 +220,74 @@ uint64_t vb_genomes_total_bases(const vb_genomes *g) { return g ? g->bases.size(
 const char *vb_genomes_sequence(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->bases.data() + g->offset[i] : nullptr; }
 void vb_genomes_free(vb_genomes *g) { if (g) { vb_unpin_genomes(g); delete g; } }
 
+// Sum partial (row, col, common) lists that are each sorted by (row, col), apply the thresholds exactly
+// (sparse_filters.h:49-61) and --max-seqs.  lists[s] = {row, col, common, n}.
+struct PartialList { const uint32_t *row, *col, *common; uint64_t n; };
+static vb_pairs *merge_sorted_partials(const std::vector<PartialList> &lists, const uint32_t *total_kmers, uint32_t n_genomes,
+                                       const vb_prefilter_params *p)
+{
+    std::vector<uint64_t> at(lists.size(), 0);
+    std::vector<uint32_t> r, c, v;
+    std::vector<double> a;
+    auto key = [&](size_t s) { return ((uint64_t)lists[s].row[at[s]] << 32) | lists[s].col[at[s]]; };
+    for (;;) {
+        uint64_t best = ~0ULL;
+        for (size_t s = 0; s < lists.size(); ++s) if (at[s] < lists[s].n) best = std::min(best, key(s));
+        if (best == ~0ULL) break;
+        uint64_t sum = 0;
+        for (size_t s = 0; s < lists.size(); ++s)
+            while (at[s] < lists[s].n && key(s) == best) sum += lists[s].common[at[s]++];
+        const uint32_t rr = (uint32_t)(best >> 32), cc = (uint32_t)best;
+        if (rr >= n_genomes || cc >= n_genomes) throw vb_error(VB_ERR_ARG, "pair id out of range");
+        if (sum > 0 && sum >= (uint64_t)std::max(p->min_kmers, 0)) {
+            const double ani = vb_ani_shorter((uint32_t)sum, total_kmers[rr], total_kmers[cc], p->k);
+            if (ani >= p->min_ident) { r.push_back(rr); c.push_back(cc); v.push_back((uint32_t)sum); a.push_back(ani); }
+        }
+    }
+    if (p->max_seqs > 0) vb_sample_rows(n_genomes, (uint32_t)p->max_seqs, r, c, v, a);
+    vb_pairs *res = vb_pairs_alloc(r.size(), n_genomes);
+    for (size_t i = 0; i < r.size(); ++i) { res->row[i] = r[i]; res->col[i] = c[i]; res->common[i] = v[i]; res->ani[i] = a[i]; }
+    for (uint32_t i = 0; i < n_genomes; ++i) res->total_kmers[i] = total_kmers[i];
+    res->k = p->k;
+    res->kmers_fraction = p->kmers_fraction;
+    return res;
+}
+
 int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out)
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter: bad arguments");
-    vb_enter(ctx);
-    vb_prefilter_impl(ctx, g, p, 0, 1, out);
+    // One pass holds at most ~10^9 k-mer tuples (2^20 shared-memory buckets of ~1 280 tuples; 2^32 list entries).  Larger
+    // inputs are processed in P passes over disjoint shards of the k-mer hash space -- the same split that spreads one
+    // data set over several GPUs, run back to back on one -- and the partial counts are summed on the host.  This is what
+    // vclust's --batch-size is for (the reference builds partial databases and runs all2all-parts); the output does not
+    // depend on it.  VB_PREFILTER_PASSES (test hook) forces P.
+    const char *pe = getenv("VB_PREFILTER_PASSES");
+    const double est = (double)vb_store_slots(g, 0) * std::min(1.0, std::max(p->kmers_fraction, 0.0));
+    uint32_t passes = pe ? (uint32_t)std::max(1, atoi(pe)) : (uint32_t)std::ceil(est / 1.0e9);
+    passes = std::max(1u, std::min(passes, 1024u));
+    if (passes == 1) {
+        vb_enter(ctx);
+        vb_prefilter_impl(ctx, g, p, 0, 1, out);
+    } else {
+        std::vector<vb_pairs *> parts;
+        auto release = [&]() { for (auto *q : parts) vb_pairs_free_impl(q); parts.clear(); };
+        try {
+            std::vector<uint32_t> totals(g->count(), 0);
+            std::vector<PartialList> lists;
+            for (uint32_t s = 0; s < passes; ++s) {
+                vb_pairs *part = nullptr;
+                vb_enter(ctx);
+                vb_prefilter_impl(ctx, g, p, s, passes, &part);
+                parts.push_back(part);
+                lists.push_back({part->row, part->col, part->common, part->n_pairs});
+                for (uint32_t i = 0; i < g->count(); ++i) totals[i] += part->total_kmers[i];
+            }
+            *out = merge_sorted_partials(lists, totals.data(), g->count(), p);
+            ctx->set_timing("prefilter.passes", (double)passes);
+        } catch (...) { release(); throw; }
+        release();
+    }
     VB_GUARD_END
 }
 

@@ -99,6 +99,8 @@ CONFIGS = {
     "c3_s200": dict(n=10_000, length=40_000, family=200, seed=BASE_SEED + 3),
     # more than 11 585 genomes: N(N-1)/2 > 2^26, the prefilter switches to the hashed pair table by itself
     "n20k": dict(n=20_000, length=10_000, family=20, seed=BASE_SEED + 6),
+    # 1.2 x 10^9 k-mers: more than one prefilter pass holds, two passes over k-mer hash shards
+    "n30k": dict(n=30_000, length=40_000, family=20, seed=BASE_SEED + 7),
     "c4": dict(n=100_000, length=(5_000, 200_000), family=200, seed=BASE_SEED + 4, n_frac=0.01, lower_frac=0.01),
     "c5": dict(n=1_000_000, length=30_000, family=20, seed=BASE_SEED + 5),
 }
