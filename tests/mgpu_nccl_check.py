@@ -13,7 +13,8 @@ else:
     names, seqs = synth.make_genomes(n=200, length=20000, family=10, seed=77, n_frac=0.05)
 ctx = api.Context(lr)
 g = api.Genomes.from_memory(names, seqs)
-res = distributed.prefilter_align_sharded(ctx, g, g, dist, torch.device("cuda", lr))
+res = distributed.prefilter_align_sharded(ctx, g, g, dist, torch.device("cuda", lr),
+                                          passes=3 if "passes3" in sys.argv else 0)
 if rank == 0:
     full = api.prefilter_genomes(ctx, g)
     assert list(zip(res["pairs"][0].tolist(), res["pairs"][1].tolist(), res["pairs"][2].tolist())) == \

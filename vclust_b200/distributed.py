@@ -123,15 +123,23 @@ def exchange_and_align(dist, device, partial: Tuple[np.ndarray, np.ndarray, np.n
 
 
 def prefilter_align_sharded(ctx, genomes_kmerdb, genomes_lzani, dist, device, k=25, min_kmers=20, min_ident=0.7,
-                            kmers_fraction=1.0, lz_params=None, max_seqs=0) -> Optional[dict]:
+                            kmers_fraction=1.0, lz_params=None, max_seqs=0, passes=0) -> Optional[dict]:
     """The GPU instantiation: vb_prefilter_partial -> exchange -> vb_pairs_merge -> vb_align_pairs.
     genomes_kmerdb / genomes_lzani: the same input loaded with the two FASTA flavours (they may be the same object
     when the input has no corner cases, e.g. synthetic data)."""
     from . import api
     rank, world = dist.get_rank(), dist.get_world_size()
-    part = api.prefilter_partial(ctx, genomes_kmerdb, rank, world, k=k, kmers_fraction=kmers_fraction)
-    partial = (part.rows, part.cols, part.common, part.total_kmers)
-    part.close()
+    # one pass holds ~10^9 k-mer tuples: a rank whose hash shard is larger splits it further and runs the sub-shards back to
+    # back (c5: 3 x 10^10 k-mers over 8 GPUs = 4 passes per rank); their partial counts simply join the rank's list
+    if passes <= 0:
+        passes = max(1, int(np.ceil(genomes_kmerdb.total_bases * min(1.0, kmers_fraction) / world / 1.0e9)))
+    rows, cols, common, totals = [], [], [], None
+    for s in range(passes):
+        part = api.prefilter_partial(ctx, genomes_kmerdb, rank * passes + s, world * passes, k=k, kmers_fraction=kmers_fraction)
+        rows.append(part.rows); cols.append(part.cols); common.append(part.common)
+        totals = part.total_kmers.astype(np.int64) if totals is None else totals + part.total_kmers
+        part.close()
+    partial = (np.concatenate(rows), np.concatenate(cols), np.concatenate(common), totals)
 
     def merge_fn(r, c, v, totals):
         m = api.merge_pairs(r, c, v, totals, k=k, min_kmers=min_kmers, min_ident=min_ident, kmers_fraction=kmers_fraction,
