@@ -222,17 +222,25 @@ constexpr int FINE_BITS_SMALL = 18, FINE_BITS_LARGE = 2 * MAX_BUCKET_BITS;   // 
 
 // Append this block's surviving tuples (bit r of `keep` selects h[r]; all of one thread's tuples share a genome) to the
 // compact list -- order is irrelevant, tuples are grouped by hash later -- and count them in the fine histogram.  One
-// global cursor atomic per call and block.  All threads of the block must call; s_warp is [2][33] shared words, `phase`
-// alternates 0/1 between successive calls so that a call never overwrites prefixes another warp is still reading (two
-// barriers per call instead of three).  write == 0: only count (cursor and histogram untouched except the cursor).
+// global cursor atomic per call and block.  All threads of the block must call; `phase` alternates 0/1 between successive
+// calls so that a call never overwrites prefixes another warp is still reading.  The survivors are compacted in shared
+// memory first and leave with fully coalesced stores (c3, screen off: 6.8 -> 4.5 ms).  write == 0: only count.
 template <int ITEMS>
-__device__ __forceinline__ void block_append(uint32_t keep, const uint64_t (&h)[ITEMS], uint32_t gid, uint32_t (*s_warp)[33],
+struct AppendSmem {
+    uint32_t warp[2][33];                  // warp totals / prefixes, two phases
+    uint32_t base[2];                      // the block's reservation in the list
+    uint64_t keys[256 * ITEMS];            // the block's survivors of this call, compacted: written to the list with
+    uint32_t vals[256 * ITEMS];            // fully coalesced stores (a thread's own tuples would be 64-byte-strided)
+};
+
+template <int ITEMS>
+__device__ __forceinline__ void block_append(uint32_t keep, const uint64_t (&h)[ITEMS], uint32_t gid, AppendSmem<ITEMS> &S,
                                              int phase, unsigned long long *__restrict__ cursor, int write,
                                              uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
                                              uint32_t *__restrict__ fine_hist, int fine_bits)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    uint32_t *sw = s_warp[phase];
+    uint32_t *sw = S.warp[phase];
     const uint32_t cnt = (uint32_t)__popc(keep);
     uint32_t x = cnt;
 #pragma unroll
@@ -246,8 +254,9 @@ __device__ __forceinline__ void block_append(uint32_t keep, const uint64_t (&h)[
         const uint32_t total = __shfl_sync(0xffffffffu, z, 31);
         unsigned long long base = 0;
         if (lane == 0 && total) base = atomicAdd(cursor, (unsigned long long)total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < nw) sw[lane] = (uint32_t)base + z - v;      // the list holds fewer than 2^32 tuples: the low word is enough
+        if (lane == 0) S.base[phase] = (uint32_t)base;         // the list holds fewer than 2^32 tuples: the low word is enough
+        if (lane < nw) sw[lane] = z - v;                       // block-local offset of every warp
+        if (lane == 31) sw[32] = total;
     }
     __syncthreads();
     if (!write) return;
@@ -255,11 +264,17 @@ __device__ __forceinline__ void block_append(uint32_t keep, const uint64_t (&h)[
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r)
         if ((keep >> r) & 1u) {
-            out_keys[o] = h[r];
-            out_vals[o] = gid;
+            S.keys[o] = h[r];
+            S.vals[o] = gid;
             ++o;
             atomicAdd(&fine_hist[(uint32_t)(h[r] >> (64 - fine_bits))], 1u);
         }
+    __syncthreads();
+    const uint32_t total = sw[32], base = S.base[phase];
+    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+        out_keys[base + j] = S.keys[j];
+        out_vals[base + j] = S.vals[j];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -372,7 +387,7 @@ __global__ void __launch_bounds__(256) collect_kernel(const uint32_t *__restrict
                                                       uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
                                                       uint32_t *__restrict__ fine_hist, int fine_bits)
 {
-    __shared__ uint32_t s_warp[2][33];
+    __shared__ AppendSmem<KM_ITEMS> s_app;
     const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
     const uint32_t wmask = (ep.k >= 32) ? 0xffffffffu : ((1u << ep.k) - 1);
     const int lane = threadIdx.x & 31;
@@ -398,7 +413,7 @@ __global__ void __launch_bounds__(256) collect_kernel(const uint32_t *__restrict
             for (int j = 0; j < KM_ITEMS; ++j)
                 if (!((tw[j] >> (2 * ((uint32_t)(h[j] >> 16) & 15) + 1)) & 1u)) ok &= ~(1u << j);
         }
-        block_append<KM_ITEMS>(ok, h, gid, s_warp, phase, cursor, write, out_keys, out_vals, fine_hist, fine_bits);
+        block_append<KM_ITEMS>(ok, h, gid, s_app, phase, cursor, write, out_keys, out_vals, fine_hist, fine_bits);
     }
 }
 
