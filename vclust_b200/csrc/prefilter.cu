@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *__restrict__
 // bits of h.  LEVEL 2: tuples come from a level-1 bucket, bucket = next b2 bits.  Inside the block the tile is first
 // grouped by bucket in shared memory, so that every bucket receives one contiguous run per tile.
 template <int LEVEL>
-__global__ void __launch_bounds__(PART_THREADS) part_kernel(uint64_t n_in, MsdPlan pl, const uint64_t *__restrict__ in_keys,
+__global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, MsdPlan pl, const uint64_t *__restrict__ in_keys,
                                                             const uint32_t *__restrict__ in_vals, const uint32_t *__restrict__ off,
                                                             const uint32_t *__restrict__ tile_start, uint32_t n_tiles,
                                                             uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys,
