@@ -3,6 +3,8 @@
 
     python tests/scale_check.py c3            # 10 000 x 40 kb, families of 20 (95 000 candidate pairs)
     python tests/scale_check.py c3_s200 --no-ref
+    python tests/scale_check.py n20k          # 20 000 x 10 kb: the hashed pair table (more than 11 585 genomes)
+    python tests/scale_check.py n30k          # 30 000 x 40 kb: 1.2 x 10^9 k-mers, two prefilter passes
 
 Runs `prefilter` + `align` through the file-level API (FASTA in, filter / ani.tsv / ids.tsv out), then the unmodified
 reference tools from oracle/_ref on the same FASTA with all host cores, and compares the three output files byte for
