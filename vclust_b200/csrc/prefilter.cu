@@ -1074,7 +1074,8 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         DevBuf<uint64_t> keys1(n_keep + 64), keys2(pl.b2 ? n_keep + 64 : 1);
         DevBuf<uint32_t> vals1(n_keep + 64), vals2(pl.b2 ? n_keep + 64 : 1);
         const size_t part_smem = PART_TILE * 12 + 4 * (1 << MAX_BUCKET_BITS) * sizeof(uint32_t);
-        static bool attr_done = false;
+        static bool attr_done_dev[64] = {false};             // the opt-in is per device (one process may hold several contexts)
+        bool &attr_done = attr_done_dev[ctx->device & 63];
         if (!attr_done) {
             VB_CUDA(cudaFuncSetAttribute(part_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
             VB_CUDA(cudaFuncSetAttribute(part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
