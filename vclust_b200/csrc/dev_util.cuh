@@ -4,6 +4,7 @@
 
 #include <functional>
 #include <string>
+#include <vector>
 
 #include "vb_internal.h"
 
@@ -97,11 +98,36 @@ struct DevBuf {
 // bytes this context could still allocate: free device memory + what the pool holds but is not using
 uint64_t vb_device_available(vb_ctx *ctx);
 
+// CUDA events are recycled through a per-thread free list: creating and destroying a dozen events per call cost more
+// host time than the calls' own bookkeeping.  (Events are device-bound: the list is keyed by the current device.)
+struct EventPool {
+    std::vector<cudaEvent_t> free_list[64];
+    cudaEvent_t get()
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        auto &fl = free_list[dev & 63];
+        if (!fl.empty()) { cudaEvent_t e = fl.back(); fl.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void put(cudaEvent_t e)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        free_list[dev & 63].push_back(e);
+    }
+};
+inline EventPool &vb_event_pool() { static thread_local EventPool p; return p; }
+
 struct EventTimer {
     cudaEvent_t a, b;
     cudaStream_t s;
-    explicit EventTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
-    ~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    explicit EventTimer(cudaStream_t st) : s(st) { a = vb_event_pool().get(); b = vb_event_pool().get(); }
+    EventTimer(const EventTimer &) = delete;
+    EventTimer &operator=(const EventTimer &) = delete;
+    ~EventTimer() { vb_event_pool().put(a); vb_event_pool().put(b); }
     void start() { cudaEventRecord(a, s); }
     void stop() { cudaEventRecord(b, s); }
     double ms() { cudaEventSynchronize(b); float t = 0; cudaEventElapsedTime(&t, a, b); return t; }
