@@ -50,6 +50,11 @@ int vb_device_count(void);                           /* number of CUDA devices v
 const char *vb_last_error(void);
 
 int vb_ctx_create(int device, vb_ctx **out);
+/* Same, but every kernel and copy of the context is enqueued on the caller's CUDA stream (`cuda_stream` is a
+ * cudaStream_t passed as a plain pointer; NULL = vb_ctx_create's own non-blocking stream).  A host that drives
+ * collectives on a stream of its own (torch.distributed / NCCL) hands that stream in, so the library's kernels and the
+ * collectives are ordered by the stream and need no host synchronisation in between. */
+int vb_ctx_create_on_stream(int device, void *cuda_stream, vb_ctx **out);
 void vb_ctx_destroy(vb_ctx *ctx);
 /* Timings of the last vb_prefilter / vb_align call on this context, in milliseconds (CUDA events on the
  * context's stream).  Keys are fixed strings; unknown key => returns VB_ERR_ARG. */
@@ -71,6 +76,9 @@ int vb_genomes_load(const char *const *paths, int n_paths, int multisample, vb_f
 /* Same, from memory: n sequences of ASCII bases (used by the bench and the tests; no file I/O). */
 int vb_genomes_from_memory(const char *const *names, const char *const *seqs, const uint64_t *lens, uint32_t n,
                            vb_genomes **out);
+/* Names and lengths only, no sequence data: what the ranks of a multi-GPU run know about the genomes they do not hold
+ * (vb_shard_create), and all that vb_write_filter / vb_write_ani need. */
+int vb_genomes_skeleton(const char *const *names, const uint64_t *lens, uint32_t n, vb_genomes **out);
 /* Keep the 2-bit packed copy of g in HBM on this context until vb_genomes_evict / vb_ctx_destroy, so that later
  * vb_prefilter (rule VB_FASTA_KMERDB: U == T) or vb_align* (rule VB_FASTA_LZANI: U == N, padded for `mrd`) calls
  * on the same g start with their input already on the device.  Without it every call uploads g itself.
@@ -194,6 +202,49 @@ int vb_align_pairs_regions(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref
  * The reference writes the pairs in thread-completion order; this writer uses the deterministic order of `regions`. */
 int vb_write_aln(const vb_genomes *g, const vb_regions *regions, const char *path, const double out_filters[5]);
 void vb_regions_free(vb_regions *r);
+
+/* ---- one genome set over the GPUs of one node ------------------------------------------------------------------
+ * No reference counterpart (kmer-db and lz-ani are single-process; their analogue of the split is the tiling of
+ * all2all-parts, console_all2all_parts.cpp:143-331, and lz-ani's per-reference work queue, lz_matcher.cpp:190-270).
+ * One process per GPU.  The genomes are block-partitioned: rank r loads genomes [first_id, first_id + count(local)) and
+ * only knows names and lengths of the rest (`meta`).  The library does the compute and owns every device buffer; the
+ * HOST supplies the collectives as callbacks (torch.distributed over NCCL in vclust_b200/distributed.py), all of them
+ * on DEVICE memory and enqueued on the context's stream (vb_ctx_create_on_stream):
+ *   all_to_all   records of `width` bytes; send_counts[p] records go to peer p (the send buffer is ordered by peer),
+ *                recv_counts[p] records arrive from peer p (both sides already know the counts)
+ *   all_gather   `bytes` bytes from every rank, concatenated in rank order
+ *   all_reduce_sum_u32   in place
+ * Each returns 0 on success.  Data path of vb_shard_prefilter + vb_shard_align:
+ *   setup     pack the local genomes, all-gather the packed align-stage records (every GPU can read every genome)
+ *   extract   k-mers of the LOCAL genomes -> (hash, genome) tuples, partitioned by hash range
+ *   exchange  all-to-all #1: every tuple travels to the rank that owns its hash range
+ *   count     grouping + pair counting on the owner's range -> partial common-k-mer counts per genome pair
+ *   reduce    all-reduce of total-kmers; all-to-all #2: partial counts travel to the owners of both genomes
+ *             (owner(g) = g mod world), which sum them and apply the -min filters
+ *   align     every owner parses (reference = own genome, query) for its candidate pairs; results are gathered on rank 0 */
+typedef struct vb_comm {
+    int32_t rank, world;
+    void *user;
+    int (*all_to_all)(void *user, const void *send, const uint64_t *send_counts, void *recv, const uint64_t *recv_counts,
+                      uint32_t width);
+    int (*all_gather)(void *user, const void *send, void *recv, uint64_t bytes);
+    int (*all_reduce_sum_u32)(void *user, void *buf, uint64_t n);
+} vb_comm;
+
+typedef struct vb_shard vb_shard;
+/* Collective.  meta: all genomes (names + lengths; vb_genomes_skeleton or a full set); local: this rank's block, with
+ * sequences; comm is copied (its callbacks must stay valid until vb_shard_destroy).  mrd: the --mrd the align stage
+ * will use (padding of the packed store). */
+int vb_shard_create(vb_ctx *ctx, const vb_comm *comm, const vb_genomes *meta, const vb_genomes *local, uint32_t first_id,
+                    int mrd, vb_shard **out);
+/* Collective.  On rank 0 *out is the complete result of vb_prefilter on the whole set; on the other ranks it holds no
+ * pairs.  Every rank keeps its share of the candidate list on the device for vb_shard_align. */
+int vb_shard_prefilter(vb_shard *sh, const vb_prefilter_params *p, vb_pairs **out);
+/* Collective, after vb_shard_prefilter.  On rank 0 *out is the complete result of vb_align; elsewhere it is empty. */
+int vb_shard_align(vb_shard *sh, const vb_align_params *p, vb_align_out **out);
+void vb_shard_destroy(vb_shard *sh);
+/* Exercises the three callbacks of comm on small device buffers and checks what comes back (used by the tests). */
+int vb_comm_selftest(vb_ctx *ctx, const vb_comm *comm);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ typedef struct {
     lzo_params p;
     /* reference side (parser.cpp:16-34) */
     uint8_t *R; int nR;
+    int oob;                                 /* the last parse read outside R (undefined in the reference) */
     int64_t *kR_long, *kR_short;           /* k-mer code at every position or -1 */
     int *ht_long; uint32_t ht_long_size, ht_long_mask;
     int *hs_start, *hs_cnt, *hs_pos;       /* CSR over 4^msl short seeds */
@@ -182,15 +183,25 @@ static int equal_len(const lzo_ctx *c, int rp, int qp, int start)
     return r;
 }
 
+/* The reference's compare_ranges has no bounds check, and with mqd > mrd its tail call (parser.cpp:713) can run past
+ * seq_ref.size(): what it then compares against is whatever the vector's capacity holds (undefined; thread-schedule
+ * dependent in lz-ani).  The oracle reads such positions as a symbol that matches nothing and raises c->oob, so that a
+ * test can tell "defined by the reference" from "undefined in the reference". */
+static int ref_sym(lzo_ctx *c, int idx)
+{
+    if (idx < 0 || idx >= c->nR) { c->oob = 1; return 0xff; }
+    return c->R[idx];
+}
+
 /* parser.cpp:210-248: run-length encode the match/mismatch string of Q[d..d+len) against R[r..r+len) */
 static void compare_ranges(lzo_ctx *c, int d, int r, int len, int backward)
 {
     int flag = backward ? F_MATCH_DISTANT : F_MATCH_CLOSE;
     int j = 0;
     while (j < len) {
-        int m = c->R[r + j] == c->Q[d + j];
+        int m = ref_sym(c, r + j) == c->Q[d + j];
         int s = j;
-        while (j < len && (c->R[r + j] == c->Q[d + j]) == m) ++j;
+        while (j < len && (ref_sym(c, r + j) == c->Q[d + j]) == m) ++j;
         if (m) {
             push_factor(c, d + s, flag, r + s, j - s);
             if (j < len) flag = F_MATCH_CLOSE;
@@ -482,17 +493,28 @@ static int calc_regions(const lzo_ctx *c, lzo_region *out, int cap)
 void lzo_parse_query(lzo_ctx *c, const uint8_t *qcodes, int qlen, int stats[3])
 {
     set_query(c, qcodes, qlen);
+    c->oob = 0;
     parse(c);
     calc_stats(c, stats);
 }
+/* 1 when the last parse compared against positions outside the reference text (undefined in the reference, see ref_sym) */
+int lzo_last_oob(const lzo_ctx *c) { return c->oob; }
 
 int lzo_last_regions(const lzo_ctx *c, lzo_region *out, int cap) { return calc_regions(c, out, cap); }
 int lzo_last_factors(const lzo_ctx *c, const lzo_factor **out) { *out = c->f; return c->nf; }
 
 /* Batch driver used by tests/bench: pairs (ref id, query id) grouped by reference for index reuse.
  * seqs: concatenated reservoir codes; off[g]..off[g+1] delimit genome g.  stats: 3 ints per pair. */
+void lzo_run_pairs_oob(const lzo_params *p, const uint8_t *seqs, const int64_t *off,
+                       const int32_t *pair_ref, const int32_t *pair_qry, int64_t n_pairs, int32_t *stats, uint8_t *oob);
 void lzo_run_pairs(const lzo_params *p, const uint8_t *seqs, const int64_t *off,
                    const int32_t *pair_ref, const int32_t *pair_qry, int64_t n_pairs, int32_t *stats)
+{
+    lzo_run_pairs_oob(p, seqs, off, pair_ref, pair_qry, n_pairs, stats, 0);
+}
+/* oob (optional): per pair, 1 when the parse left the reference text (see ref_sym) */
+void lzo_run_pairs_oob(const lzo_params *p, const uint8_t *seqs, const int64_t *off,
+                       const int32_t *pair_ref, const int32_t *pair_qry, int64_t n_pairs, int32_t *stats, uint8_t *oob)
 {
     lzo_ctx *c = lzo_create(p);
     int cur_ref = -1;
@@ -502,6 +524,7 @@ void lzo_run_pairs(const lzo_params *p, const uint8_t *seqs, const int64_t *off,
         int st[3];
         lzo_parse_query(c, seqs + off[q], (int)(off[q + 1] - off[q]), st);
         stats[3 * k] = st[0]; stats[3 * k + 1] = st[1]; stats[3 * k + 2] = st[2];
+        if (oob) oob[k] = (uint8_t)c->oob;
     }
     lzo_destroy(c);
 }

@@ -318,8 +318,10 @@ def read_filter(path, thr: float, names):
     return adj
 
 
-def run_pairs(codes, pair_ref, pair_qry, params: LzParams | None = None) -> np.ndarray:
-    """stats[k] = (sym_in_matches, sym_in_literals, no_components) for query pair_qry[k] parsed against pair_ref[k]."""
+def run_pairs(codes, pair_ref, pair_qry, params: LzParams | None = None, return_oob: bool = False):
+    """stats[k] = (sym_in_matches, sym_in_literals, no_components) for query pair_qry[k] parsed against pair_ref[k].
+    return_oob: also return a bool array, True where the parse compared against positions outside the reference text --
+    the reference reads uninitialised memory there (only possible with mqd > mrd), so its result is undefined."""
     L = lib()
     params = params or LzParams.default()
     off = np.zeros(len(codes) + 1, dtype=np.int64)
@@ -331,9 +333,17 @@ def run_pairs(codes, pair_ref, pair_qry, params: LzParams | None = None) -> np.n
     st = np.zeros((pr.size, 3), dtype=np.int32)
     pr_s, pq_s = np.ascontiguousarray(pr[order]), np.ascontiguousarray(pq[order])
     st_s = np.zeros((pr.size, 3), dtype=np.int32)
-    L.lzo_run_pairs(C.byref(params), flat.ctypes.data, off.ctypes.data, pr_s.ctypes.data, pq_s.ctypes.data, pr.size,
-                    st_s.ctypes.data)
+    oob_s = np.zeros(pr.size, dtype=np.uint8)
+    L.lzo_run_pairs_oob.restype = None
+    L.lzo_run_pairs_oob.argtypes = [C.POINTER(LzParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p]
+    L.lzo_run_pairs_oob(C.byref(params), flat.ctypes.data, off.ctypes.data, pr_s.ctypes.data, pq_s.ctypes.data, pr.size,
+                        st_s.ctypes.data, oob_s.ctypes.data)
     st[order] = st_s
+    if return_oob:
+        oob = np.zeros(pr.size, dtype=bool)
+        oob[order] = oob_s.astype(bool)
+        return st, oob
     return st
 
 

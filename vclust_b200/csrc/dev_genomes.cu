@@ -66,23 +66,30 @@ uint64_t vb_store_slots(const vb_genomes *g, uint32_t min_pad)
     return slots + 128;
 }
 
-void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad, const vb_chunk_fn *on_chunk)
+void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad, const vb_chunk_fn *on_chunk,
+                       uint64_t force_slots)
 {
     if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
+    if (g->skeleton) throw vb_error(VB_ERR_ARG, "this genome set holds names and lengths only (vb_genomes_skeleton): nothing to upload");
     cudaStream_t st = (cudaStream_t)ctx->stream;
-    static bool table_ready[64] = {false};
-    if (!table_ready[ctx->device & 63]) {
-        uint8_t t[2][256];
-        memset(t, 4, sizeof(t));
-        const char *acgt = "ACGT";
-        for (int r = 0; r < 2; ++r)
-            for (int i = 0; i < 4; ++i) { t[r][(uint8_t)acgt[i]] = (uint8_t)i; t[r][(uint8_t)(acgt[i] | 0x20)] = (uint8_t)i; }
-        t[1][(uint8_t)'U'] = 3; t[1][(uint8_t)'u'] = 3;
-        VB_CUDA(cudaMemcpyToSymbol(c_code, t, sizeof(t)));
-        table_ready[ctx->device & 63] = true;
+    {   // one-time (per device) upload of the symbol table; contexts on several host threads may get here together
+        static std::mutex table_mutex;
+        static bool table_ready[64] = {false};
+        std::lock_guard<std::mutex> lock(table_mutex);
+        if (!table_ready[ctx->device & 63]) {
+            uint8_t t[2][256];
+            memset(t, 4, sizeof(t));
+            const char *acgt = "ACGT";
+            for (int r = 0; r < 2; ++r)
+                for (int i = 0; i < 4; ++i) { t[r][(uint8_t)acgt[i]] = (uint8_t)i; t[r][(uint8_t)(acgt[i] | 0x20)] = (uint8_t)i; }
+            t[1][(uint8_t)'U'] = 3; t[1][(uint8_t)'u'] = 3;
+            VB_CUDA(cudaMemcpyToSymbol(c_code, t, sizeof(t)));
+            table_ready[ctx->device & 63] = true;
+        }
     }
     const uint32_t n = g->count();
     out.n = n;
+    out.min_pad = min_pad;
     out.h_gofs.resize(n);
     out.h_glen.resize(n);
     uint64_t slots = 0;
@@ -94,6 +101,10 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
         slots += ((len + min_pad + 127) / 128) * 128;  // >= min_pad invalid slots after every genome
     }
     slots += 128;
+    if (force_slots) {
+        if (force_slots < slots || force_slots % 128) throw vb_error(VB_ERR_INTERNAL, "vb_upload_genomes: bad forced store size");
+        slots = force_slots;
+    }
     out.total_slots = slots;
 
     out.seq2.alloc(slots / 16 + 8);
@@ -179,12 +190,13 @@ static void drop_last(vb_ctx *ctx)
 }
 
 // upload into buffers that outlive the call (stream-ordered pool)
-static DevGenomes *upload_persistent(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, const vb_chunk_fn *on_chunk = nullptr)
+static DevGenomes *upload_persistent(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, const vb_chunk_fn *on_chunk = nullptr,
+                                     uint64_t force_slots = 0)
 {
     auto *d = new DevGenomes();
     const bool saved = vb_tls_pool_alloc;
     vb_tls_pool_alloc = true;
-    try { vb_upload_genomes(ctx, g, *d, min_pad, on_chunk); } catch (...) { vb_tls_pool_alloc = saved; delete d; throw; }
+    try { vb_upload_genomes(ctx, g, *d, min_pad, on_chunk, force_slots); } catch (...) { vb_tls_pool_alloc = saved; delete d; throw; }
     vb_tls_pool_alloc = saved;
     return d;
 }
@@ -203,9 +215,16 @@ const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t 
     return *ctx->last.dev;
 }
 
-void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad)
+void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g);
+
+void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, uint64_t force_slots)
 {
     if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
+    if (force_slots) {                            // a block of a multi-GPU run: always a fresh store of exactly that size
+        vb_evict_impl(ctx, g);
+        ctx->resident.push_back({g, g->uid, min_pad, upload_persistent(ctx, g, min_pad, nullptr, force_slots)});
+        return;
+    }
     for (auto &r : ctx->resident)
         if (r.g == g && r.uid == g->uid && r.min_pad >= min_pad) return;
     if (ctx->last.dev && ctx->last.g == g && ctx->last.uid == g->uid && ctx->last.min_pad >= min_pad) {

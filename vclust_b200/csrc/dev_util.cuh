@@ -99,38 +99,57 @@ struct DevBuf {
 uint64_t vb_device_available(vb_ctx *ctx);
 
 // CUDA events are recycled through a per-thread free list: creating and destroying a dozen events per call cost more
-// host time than the calls' own bookkeeping.  (Events are device-bound: the list is keyed by the current device.)
+// host time than the calls' own bookkeeping.  Events are device-bound: the list is keyed by the device the event was
+// created on (remembered by the timer, not re-queried when it is returned).  The list destroys its events when the
+// thread exits.
 struct EventPool {
     std::vector<cudaEvent_t> free_list[64];
-    cudaEvent_t get()
+    ~EventPool()
     {
-        int dev = 0;
-        cudaGetDevice(&dev);
+        for (auto &fl : free_list)
+            for (cudaEvent_t e : fl) cudaEventDestroy(e);      // best effort: the context may already be gone at thread exit
+    }
+    cudaEvent_t get(int dev)
+    {
         auto &fl = free_list[dev & 63];
         if (!fl.empty()) { cudaEvent_t e = fl.back(); fl.pop_back(); return e; }
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = nullptr;
+        cudaError_t rc = cudaEventCreate(&e);
+        if (rc != cudaSuccess) {
+            cudaGetLastError();
+            throw vb_error(VB_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(rc));
+        }
         return e;
     }
-    void put(cudaEvent_t e)
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        free_list[dev & 63].push_back(e);
-    }
+    void put(int dev, cudaEvent_t e) { free_list[dev & 63].push_back(e); }
 };
 inline EventPool &vb_event_pool() { static thread_local EventPool p; return p; }
 
 struct EventTimer {
-    cudaEvent_t a, b;
+    cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t s;
-    explicit EventTimer(cudaStream_t st) : s(st) { a = vb_event_pool().get(); b = vb_event_pool().get(); }
+    int dev = 0;
+    bool started = false, stopped = false;
+    explicit EventTimer(cudaStream_t st) : s(st)
+    {
+        if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+        a = vb_event_pool().get(dev);
+        try { b = vb_event_pool().get(dev); } catch (...) { vb_event_pool().put(dev, a); throw; }
+    }
     EventTimer(const EventTimer &) = delete;
     EventTimer &operator=(const EventTimer &) = delete;
-    ~EventTimer() { vb_event_pool().put(a); vb_event_pool().put(b); }
-    void start() { cudaEventRecord(a, s); }
-    void stop() { cudaEventRecord(b, s); }
-    double ms() { cudaEventSynchronize(b); float t = 0; cudaEventElapsedTime(&t, a, b); return t; }
+    ~EventTimer() { vb_event_pool().put(dev, a); vb_event_pool().put(dev, b); }
+    void start() { cudaEventRecord(a, s); started = true; stopped = false; }
+    void stop() { cudaEventRecord(b, s); stopped = true; }
+    // 0 for a timer that was not started and stopped in this use (a recycled event still holds its previous record)
+    double ms()
+    {
+        if (!started || !stopped) return 0.0;
+        cudaEventSynchronize(b);
+        float t = 0;
+        if (cudaEventElapsedTime(&t, a, b) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+        return t;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -158,6 +177,16 @@ struct DevGenomes {
     DevBuf<uint32_t> tile_gid;       // total_slots / 128
     std::vector<uint64_t> h_gofs;
     std::vector<uint32_t> h_glen;
+    uint32_t min_pad = 0;            // invalid slots guaranteed after every genome
+};
+
+// Candidate list of a prefilter call, kept on the device (stream-ordered pool) so that the align stage that follows
+// builds its directed pair list without a round trip through the host.
+struct DevPairs {
+    uint64_t uid = 0;                // vb_pairs_uid of the host list this mirrors
+    uint64_t n = 0;
+    DevBuf<uint64_t> keys;           // row << 32 | col (input-order ids, row > col), sorted
+    DevBuf<float> ani;               // device estimate of ani-shorter: scheduling cost model only
 };
 
 // Upload ASCII and pack on the device.  min_pad: invalid slots guaranteed after every genome (>= VB_STORE_PAD).
@@ -168,14 +197,27 @@ constexpr uint32_t VB_STORE_PAD = 128 + 64;      // covers the prefilter (128) a
 struct DevGenomes;
 using vb_chunk_fn = std::function<void(const DevGenomes &, uint64_t, uint64_t)>;
 uint64_t vb_store_slots(const vb_genomes *g, uint32_t min_pad);    // base slots the packed store of g will have
+// force_slots (0 = natural size): make the store exactly that many slots long (>= the natural size; the tail is invalid)
+// -- the blocks of a multi-GPU run are padded to a common size so that they can be all-gathered
 void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32_t min_pad = VB_STORE_PAD,
-                       const vb_chunk_fn *on_chunk = nullptr);
+                       const vb_chunk_fn *on_chunk = nullptr, uint64_t force_slots = 0);
 
 // Returns the packed copy of g: the resident one when vb_genomes_make_resident was called for it, else the copy the
 // previous call on this context uploaded (vclust prefilter followed by vclust align on the same set transfers the
 // genomes once), else uploads now and keeps the copy for the next call (vb_genomes_evict drops it).
 const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident = nullptr,
                                      const vb_chunk_fn *on_chunk = nullptr);
+
+// device-side result of vb_align_fast (align.cu): directed pairs sorted by (reference, query) in LZ-ANI ids, compact keys
+// ref << gbits | query, and 3 ints per pair; the buffers live in the call's arena
+struct AlignFastOut {
+    DevBuf<uint64_t> keys;
+    DevBuf<int32_t> stats;
+    uint64_t n = 0;
+    int gbits = 0;
+};
+bool vb_align_fast(vb_ctx *ctx, const vb_genomes *meta, const DevGenomes &store, const vb_align_params *ap, const uint64_t *d_pairs,
+                   const float *d_ani, uint64_t n_pairs, bool all_vs_all, uint32_t world, uint32_t me, AlignFastOut &out);
 
 #ifdef __CUDACC__
 // 32 bases (64 bits) starting at base slot p of a 2-bit array; base p lands in bits [0,1].

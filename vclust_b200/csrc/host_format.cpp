@@ -12,6 +12,30 @@
 
 #include "vb_internal.h"
 
+// Output file whose every write is checked: a full disk or an I/O error throws VB_ERR_IO and removes the partial
+// file (a silently truncated filter would silently drop candidate pairs in the align stage).
+struct OutFile {
+    FILE *f = nullptr;
+    std::string path;
+    OutFile(const char *p, const char *what) : path(p)
+    {
+        f = fopen(p, "wb");
+        if (!f) throw vb_error(VB_ERR_IO, std::string(what) + p);
+    }
+    OutFile(const OutFile &) = delete;
+    OutFile &operator=(const OutFile &) = delete;
+    void fail()
+    {
+        if (f) { fclose(f); f = nullptr; }
+        remove(path.c_str());
+        throw vb_error(VB_ERR_IO, "write error on " + path);
+    }
+    void write(const char *data, size_t n) { if (n && fwrite(data, 1, n, f) != n) fail(); }
+    void write(const std::string &s) { write(s.data(), s.size()); }
+    void close() { FILE *g = f; f = nullptr; if (g && fclose(g) != 0) { remove(path.c_str()); throw vb_error(VB_ERR_IO, "write error on " + path); } }
+    ~OutFile() { if (f) { fclose(f); remove(path.c_str()); } }       // left open = an exception is in flight: drop the partial file
+};
+
 int vb_fmt_fixed6(double v, char *out)
 {
     char *p = out;
@@ -100,8 +124,7 @@ double vb_ani_shorter(uint32_t common, uint32_t cnt1, uint32_t cnt2, int k)
 // ---------------------------------------------------------------------------------------------------------------
 void vb_write_filter_impl(const vb_genomes *g, const vb_pairs *pr, const char *path)
 {
-    FILE *f = fopen(path, "wb");
-    if (!f) throw vb_error(VB_ERR_IO, std::string("Cannot open output file: ") + path);
+    OutFile f(path, "Cannot open output file: ");
     std::string out;
     out.reserve(1 << 20);
     char num[64];
@@ -123,10 +146,10 @@ void vb_write_filter_impl(const vb_genomes *g, const vb_pairs *pr, const char *p
             out += ',';
         }
         out += '\n';
-        if (out.size() > (1 << 20)) { fwrite(out.data(), 1, out.size(), f); out.clear(); }
+        if (out.size() > (1 << 20)) { f.write(out); out.clear(); }
     }
-    fwrite(out.data(), 1, out.size(), f);
-    fclose(f);
+    f.write(out);
+    f.close();
 }
 
 // kmer-db `all2all-sp -sample-rows ani-shorter:N` (vclust --max-seqs N).  Every pair (i, j), i > j, that passed the -min
@@ -163,6 +186,8 @@ void vb_sample_rows(uint32_t n_genomes, uint32_t max_items, std::vector<uint32_t
     }
 }
 
+void vb_pairs_free_impl(vb_pairs *p);
+
 static std::vector<std::string> split_keep(const std::string &s, char sep)
 {   // lz-ani utils.cpp:15-36: empty middle tokens kept, empty trailing token dropped
     std::vector<std::string> parts;
@@ -177,7 +202,10 @@ static std::vector<std::string> split_keep(const std::string &s, char sep)
 
 vb_pairs *vb_pairs_alloc(uint64_t n, uint32_t n_genomes)
 {
-    auto *p = (vb_pairs *)calloc(1, sizeof(vb_pairs));
+    auto *box = (vb_pairs_box *)calloc(1, sizeof(vb_pairs_box));
+    if (!box) throw vb_error(VB_ERR_MEM, "out of host memory");
+    box->uid = vb_next_uid();
+    vb_pairs *p = &box->pub;
     p->n_pairs = n;
     p->n_genomes = n_genomes;
     p->row = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint64_t>(n, 1));
@@ -185,6 +213,10 @@ vb_pairs *vb_pairs_alloc(uint64_t n, uint32_t n_genomes)
     p->common = (uint32_t *)calloc(std::max<uint64_t>(n, 1), sizeof(uint32_t));
     p->ani = (double *)calloc(std::max<uint64_t>(n, 1), sizeof(double));
     p->total_kmers = (uint32_t *)calloc(std::max<uint32_t>(n_genomes, 1), sizeof(uint32_t));
+    if (!p->row || !p->col || !p->common || !p->ani || !p->total_kmers) {
+        vb_pairs_free_impl(p);
+        throw vb_error(VB_ERR_MEM, "out of host memory for " + std::to_string(n) + " pairs");
+    }
     return p;
 }
 
@@ -192,7 +224,19 @@ void vb_pairs_free_impl(vb_pairs *p)
 {
     if (!p) return;
     free(p->row); free(p->col); free(p->common); free(p->ani); free(p->total_kmers);
-    free(p);
+    free(p);                      // == the vb_pairs_box (pub is its first member)
+}
+
+void vb_parallel_for(uint64_t n, uint64_t min_per_thread, unsigned max_threads, const std::function<void(uint64_t, uint64_t)> &fn)
+{
+    if (!n) return;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned t = (unsigned)std::min<uint64_t>(std::min(hw, std::max(1u, max_threads)), std::max<uint64_t>(1, n / std::max<uint64_t>(1, min_per_thread)));
+    if (t <= 1) { fn(0, n); return; }
+    std::vector<std::thread> pool;
+    for (unsigned i = 1; i < t; ++i) pool.emplace_back([&, i]() { fn(n * i / t, n * (i + 1) / t); });
+    fn(0, n / t);
+    for (auto &th : pool) th.join();
 }
 
 vb_pairs *vb_read_filter_impl(const char *path, double thr, const vb_genomes *g)
@@ -275,15 +319,20 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
     if (out_filters) for (int i = 0; i < 5; ++i) { flt[i] = out_filters[i]; any_filter |= out_filters[i] != 0; }
 
     {   // ids file, in LZ-ANI order
-        FILE *f = fopen(ids_path, "wb");
-        if (!f) throw vb_error(VB_ERR_IO, std::string("Cannot open output file: ") + ids_path);
-        fputs("id\tseq_len\tno_parts\n", f);
-        for (uint32_t i = 0; i < n; ++i)
-            fprintf(f, "%s\t%llu\t1\n", g->names[res->order[i]].c_str(), (unsigned long long)g->length(res->order[i]));
-        fclose(f);
+        OutFile f(ids_path, "Cannot open output file: ");
+        std::string ids = "id\tseq_len\tno_parts\n";
+        char num[32];
+        for (uint32_t i = 0; i < n; ++i) {
+            ids += g->names[res->order[i]];
+            ids += '\t';
+            ids.append(num, put_u64(g->length(res->order[i]), num));
+            ids += "\t1\n";
+            if (ids.size() > (1 << 20)) { f.write(ids); ids.clear(); }
+        }
+        f.write(ids);
+        f.close();
     }
-    FILE *f = fopen(ani_path, "wb");
-    if (!f) throw vb_error(VB_ERR_IO, std::string("Cannot open output file: ") + ani_path);
+    OutFile f(ani_path, "Cannot open output file: ");
     std::string out;
     out.reserve(4 << 20);
     for (size_t i = 0; i < cols.size(); ++i) { if (i) out += '\t'; out += col_names[cols[i]]; }
@@ -361,7 +410,7 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
     const unsigned n_thr = thr_env ? (unsigned)std::clamp(atoi(thr_env), 1, 64) : (res->n < 50000 ? 1u : std::min(hw, 16u));
     if (n_thr == 1) {
         format_rows(0, n, out);
-        fwrite(out.data(), 1, out.size(), f);
+        f.write(out);
     } else {
         std::vector<uint32_t> cut(n_thr + 1, n);
         cut[0] = 0;
@@ -375,18 +424,17 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
         for (unsigned t = 0; t < n_thr; ++t)
             pool.emplace_back([&, t]() { parts[t].reserve(1 << 20); format_rows(cut[t], cut[t + 1], parts[t]); });
         for (auto &th : pool) th.join();
-        fwrite(out.data(), 1, out.size(), f);                  // header
-        for (auto &part : parts) fwrite(part.data(), 1, part.size(), f);
+        f.write(out);                                          // header
+        for (auto &part : parts) f.write(part);
     }
-    fclose(f);
+    f.close();
 }
 
 // lz-ani lz_matcher.cpp:102-169 (store_alignment): one line per region; coordinates 1-based inclusive; a region on the
 // reverse-complement half of the reference text is reported on the forward genome with rstart > rend (:158-162).
 void vb_write_aln_impl(const vb_genomes *g, const vb_regions *r, const char *path, const double out_filters[5])
 {
-    FILE *f = fopen(path, "wb");
-    if (!f) throw vb_error(VB_ERR_IO, std::string("Cannot open output file for alignment storage: ") + path);
+    OutFile f(path, "Cannot open output file for alignment storage: ");
     std::string out;
     out.reserve(4 << 20);
     out += "query\treference\tpident\talnlen\tqstart\tqend\trstart\trend\tnt_match\tnt_mismatch\n";
@@ -399,7 +447,7 @@ void vb_write_aln_impl(const vb_genomes *g, const vb_regions *r, const char *pat
         uint64_t e = b;
         while (e < r->n && r->ref[e] == r->ref[b] && r->qry[e] == r->qry[b]) ++e;      // the regions of one directed pair
         const uint32_t ref = r->ref[b], qry = r->qry[b];
-        if (ref >= ng || qry >= ng) { fclose(f); throw vb_error(VB_ERR_ARG, "vb_write_aln: genome id out of range"); }
+        if (ref >= ng || qry >= ng) throw vb_error(VB_ERR_ARG, "vb_write_aln: genome id out of range");
         const int seq1_len = (int)g->length(ref), seq2_len = (int)g->length(qry);
         const int rc_correction = 2 * seq1_len + 2 * r->mrd + 1;
         bool keep = true;
@@ -429,10 +477,10 @@ void vb_write_aln_impl(const vb_genomes *g, const vb_regions *r, const char *pat
                 }
                 out.append(num, put_u64((uint64_t)r->matches[i], num)); out += '\t';
                 out.append(num, put_u64((uint64_t)r->mismatches[i], num)); out += '\n';
-                if (out.size() > (3u << 20)) { fwrite(out.data(), 1, out.size(), f); out.clear(); }
+                if (out.size() > (3u << 20)) { f.write(out); out.clear(); }
             }
         b = e;
     }
-    fwrite(out.data(), 1, out.size(), f);
-    fclose(f);
+    f.write(out);
+    f.close();
 }

@@ -1,19 +1,32 @@
-// vb_prefilter: the all-vs-all shared-k-mer screen (kmer-db build + all2all-sp + the ani-shorter filter) on one B200.
+// The prefilter: all-vs-all shared-k-mer screen (kmer-db build + all2all-sp + the ani-shorter filter) on B200s.
 //
 // Reference computation (paths under /root/reference/3rd_party/kmer-db/src/):
 //   k-mer extraction   kmer_extract.h:13-96, MinHash threshold filter filter.h:33-146
 //   per-genome set     console_build.cpp:94-103 (sort + unique; set size = total-kmers, kmer_db.h:129)
-//   common counts      prefix_kmer_db.cpp:244-434 + similarity_calculator.cpp:442-657
+//   common counts      prefix_kmer_db.cpp:244-434 + similarity_calculator.cpp:442-657 (bubbles: bubble_helper.h:79-151)
+//   tiled variant      console_all2all_parts.cpp:143-331 + db2db_sp similarity_calculator.cpp:1225-1540
 //   pair filter        sparse_filters.h:12-61 with metric params.cpp:28-32
-// Pipeline here (all integer work, HBM-bound, no tensor cores):
-//   k1 extract_kernel   packed genomes -> one (canonical k-mer, genome id) tuple per base slot, in genome order
-//   k2 rsort::sort_kv   stable LSD radix sort by k-mer  => every k-mer's genome ids ascending, duplicates adjacent
-//   k3 segment kernels  runs of equal k-mers -> duplicate counts per genome, pair increments into an HBM hash table
-//   k4 emit kernels     table -> (row, col, common) passing the integer filter and a conservative ani test
-// The exact IEEE-double ani-shorter test and the text formatting run on the host (libm log() must match glibc's).
+//
+// Pipeline (integer work, HBM/L2 bound, no tensor cores).  h = fmix64(canonical k-mer) is a bijection, so equal h <=>
+// equal k-mer; only GROUPING matters, never numeric order, so nothing is ever fully sorted:
+//   extract   packed genomes -> (h, genome) tuples [+ optional singleton screen] + a fine histogram of bucket sizes
+//   level 1   tuples -> B1 "parent" buckets by hash range.  Parents are spread over the ranks of a multi-GPU run:
+//             this is the send buffer of all-to-all #1 (one rank: it is simply the next stage's input)
+//   level 2   parent -> final buckets of ~1 280 tuples
+//   group     one block per bucket: shared-memory hash chains -> duplicates per genome, pair increments into a dense
+//             triangular or an open-addressing accumulator; oversized buckets and k-mers shared by thousands of
+//             genomes ("bubbles") take dedicated paths
+//   finish    one rank: thresholds + ordered compaction.  Several ranks: partial counts travel to the owners of both
+//             genomes (all-to-all #2), which sort, sum and threshold them.
+// Inputs beyond ~10^9 k-mers per pass run in several passes over disjoint slices of the hash space into the SAME
+// accumulator (what --batch-size / all2all-parts is for; the result does not depend on it).
+// The exact IEEE-double ani-shorter value (libm log() must match glibc's) is computed on the host for the pairs that
+// passed; the device decides pass / fail with a margin and flags the (practically non-existent) borderline cases.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <memory>
+#include <thread>
 
 #include "dev_util.cuh"
 #include "radix_sort.cuh"
@@ -59,135 +72,19 @@ struct ExtractParams {
     int use_filter;
     uint64_t max_thr;       // filter.h:42-43
     uint64_t c;             // ceil(k/4)
-    uint32_t shard_index;   // multi-GPU: this rank keeps the k-mers with fmix64(kmer) % shard_count == shard_index
+    uint32_t shard_index;   // this pass keeps the k-mers with h % shard_count == shard_index (passes, vb_prefilter_partial)
     uint32_t shard_count;
+    uint32_t gid_base;      // global id of the store's genome 0 (multi-GPU: this rank's block)
 };
 
-// k1: one thread per base slot; a warp covers 32 consecutive slots of one 128-slot tile (= one genome).
-__global__ void __launch_bounds__(256) extract_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
-                                                      const uint32_t *__restrict__ tile_gid, uint64_t n_slots,
-                                                      uint64_t n_out, ExtractParams ep, uint64_t *__restrict__ keys,
-                                                      uint32_t *__restrict__ vals, uint32_t *__restrict__ valid_cnt)
-{
-    const int k = ep.k;
-    const uint64_t kmask = (~0ULL) >> (64 - 2 * k);
-    const uint32_t wmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1);
-    // n_out is a multiple of 32 and so is the thread count: whole warps enter and leave the loop together
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n_out; p += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t key = KEY_SENTINEL;
-        uint32_t gid = 0xffffffffu;
-        if (p < n_slots) {
-            gid = tile_gid[p >> 7];
-            if (gid != 0xffffffffu && (fetch1(inv, p) & wmask) == 0) {
-                uint64_t w = fetch2(seq2, p) & kmask;            // digit j = base p+j  (little-endian window)
-                uint64_t rc = (~w) & kmask;                      // == reference's kmer_rev as an integer
-                uint64_t fw = reverse_digits(w) >> (64 - 2 * k); // == reference's kmer_str (first base most significant)
-                uint64_t can = fw < rc ? fw : rc;
-                can = (can << ep.shift) | (can & ep.tail_mask);
-                bool keep = !ep.use_filter || minhash64(can, ep.c) < ep.max_thr;
-                if (keep && ep.shard_count > 1) keep = (fmix64(can) % ep.shard_count) == ep.shard_index;
-                if (keep) key = can;
-            }
-        }
-        keys[p] = key;
-        vals[p] = gid;
-        unsigned ok = __ballot_sync(0xffffffffu, key != KEY_SENTINEL);
-        // all active lanes of a warp share the 128-slot tile, hence the genome
-        if (ok && (threadIdx.x & 31) == (__ffs(ok) - 1)) atomicAdd(&valid_cnt[gid], (uint32_t)__popc(ok));
-    }
-}
+// How the hash selects a bucket.  hi = top 32 bits of h.  parent = floor(hi * B1 / 2^32) in [0, B1) -- contiguous hash
+// ranges, B1 need not be a power of two (B1 = ranks * parents per rank); the low 32 bits of the same product are the
+// position inside the parent's range, whose top bits select the level-2 bucket.  The bucket kernel's shared-memory hash
+// uses the LOW word of h, and the pass selection uses h % passes: all (practically) independent.
+constexpr int FINE_BITS = 10;                              // resolution of the histogram inside a parent (>= level-2 bits)
+__device__ __forceinline__ uint32_t parent_of(uint64_t h, uint32_t B1) { return __umulhi((uint32_t)(h >> 32), B1); }
+__device__ __forceinline__ uint32_t frac_of(uint64_t h, uint32_t B1) { return (uint32_t)(h >> 32) * B1; }
 
-// k3a (only for very large N): number of pair increments (sum over k-mer runs of m*(m-1)/2), to size the table
-__global__ void __launch_bounds__(256) segment_count_kernel(const uint64_t *__restrict__ keys,
-                                                            const uint32_t *__restrict__ vals, uint64_t n,
-                                                            unsigned long long *__restrict__ n_inc)
-{
-    unsigned long long local = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t key = keys[i];
-        if (key == KEY_SENTINEL) continue;
-        uint32_t g = vals[i];
-        if (i > 0 && keys[i - 1] == key && vals[i - 1] == g) continue;
-        // rank of this genome inside the run = number of distinct genomes before it
-        uint32_t prev = g;
-        for (uint64_t j = i; j-- > 0 && keys[j] == key;) {
-            uint32_t gj = vals[j];
-            if (gj != prev) { ++local; prev = gj; }
-        }
-    }
-    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_inc, local);
-}
-
-// Accumulator of pair increments.  Two layouts:
-//   dense  (N(N-1)/2 <= 2^26): one uint32 counter per pair at index row*(row-1)/2 + col -- an increment is a single
-//          fire-and-forget atomic, and an ordered scan of the array yields the pairs already sorted by (row, col);
-//   hashed (larger N): open addressing, uint64 key (row << 32 | col) + uint32 count.
-struct PairAcc {
-    uint32_t *dense;        // non-null selects the dense layout
-    uint64_t *tkeys;
-    uint32_t *tvals;
-    uint64_t cap_mask;
-    int *overflow;
-};
-
-__device__ __forceinline__ void table_add(const PairAcc &A, uint64_t key, uint32_t inc)
-{
-    uint64_t h = fmix64(key) & A.cap_mask;
-    for (uint64_t probes = 0; probes <= A.cap_mask; ++probes) {
-        uint64_t cur = A.tkeys[h];
-        if (cur == SLOT_EMPTY) {
-            cur = atomicCAS((unsigned long long *)&A.tkeys[h], (unsigned long long)SLOT_EMPTY, (unsigned long long)key);
-            if (cur == SLOT_EMPTY) cur = key;
-        }
-        if (cur == key) { atomicAdd(&A.tvals[h], inc); return; }
-        h = (h + 1) & A.cap_mask;
-    }
-    *A.overflow = 1;
-}
-
-// one increment for the pair (hi, lo), hi > lo
-__device__ __forceinline__ void pair_add(const PairAcc &A, uint32_t hi, uint32_t lo)
-{
-    if (A.dense) atomicAdd(&A.dense[(uint64_t)hi * (hi - 1) / 2 + lo], 1u);
-    else table_add(A, ((uint64_t)hi << 32) | lo, 1u);
-}
-
-// k3b: duplicates per genome; every distinct (k-mer, genome) occurrence pairs with the distinct genomes before it in the run;
-// row = the later (larger) genome id, col = the earlier one -- the lower triangle of all2all_sp.
-__global__ void __launch_bounds__(256) segment_pairs_kernel(const uint64_t *__restrict__ keys,
-                                                            const uint32_t *__restrict__ vals, uint64_t n,
-                                                            uint32_t *__restrict__ dup_cnt, PairAcc A)
-{
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t key = keys[i];
-        if (key == KEY_SENTINEL) continue;
-        uint32_t g = vals[i];
-        if (i > 0 && keys[i - 1] == key && vals[i - 1] == g) { atomicAdd(&dup_cnt[g], 1u); continue; }   // same k-mer twice in g
-        uint32_t prev = g;
-        for (uint64_t j = i; j-- > 0 && keys[j] == key;) {
-            uint32_t gj = vals[j];
-            if (gj != prev) {
-                pair_add(A, g, gj);
-                prev = gj;
-            }
-        }
-    }
-}
-
-
-// ===============================================================================================================
-// MSD path (default): group equal k-mers WITHOUT a full sort.
-//   Only the grouping of equal k-mers matters, not their numeric order, so tuples are keyed by h = fmix64(k-mer)
-//   (a bijection on 64 bits): the top b1 + b2 bits of h select one of B1*B2 buckets of ~1000 tuples; a bucket is then
-//   grouped entirely in shared memory (hash table keyed by h) and the pairs are emitted from there.
-//     count_kernel   genomes -> bucket histogram (+ valid k-mers per genome)                       0.375 B/base read
-//     scan_kernel    exclusive scan -> bucket offsets, write cursors, tile map
-//     part_kernel<A> genomes -> level-1 buckets (extraction fused, coalesced runs via smem staging)  12 B/tuple written
-//     part_kernel<B> level-1 -> level-2 buckets                                                     12 B read + 12 B written
-//     bucket_kernel  level-2 bucket -> smem grouping -> duplicates per genome + pair increments      12 B read
-//   = 48 B of HBM traffic per tuple instead of 7 radix passes x 32 B.
-// ===============================================================================================================
 constexpr int PART_THREADS = 512;
 constexpr int PART_ITEMS = 8;
 constexpr int PART_TILE = PART_THREADS * PART_ITEMS;      // 4096 tuples per block
@@ -195,36 +92,24 @@ constexpr int MAX_BUCKET_BITS = 10;                       // per level
 constexpr int BUCKET_CAP = 2048;                          // tuples a bucket may hold to be grouped in shared memory
 constexpr int BUCKET_SLOTS = 4096;                        // hash slots per bucket (load <= 0.5)
 constexpr int BUCKET_TARGET = 1280;                       // planned mean bucket size (CAP is 20 sigma above it)
-
-struct MsdPlan {
-    int b1, b2;              // bucket bits of level 1 and level 2 (b2 == 0: one level)
-    uint32_t B1, B2, NB;     // 1 << b1, 1 << b2, B1 * B2
-};
+constexpr uint32_t HUGE_MIN = 4096;                       // k-mers shared by at least this many tuples: the bubble path
 
 // Singleton screen.  A k-mer that occurs once in the whole input shares nothing and is the common case (92 % of the
 // distinct k-mers of c2), so it is dropped before the partition: a table of 2-bit slots indexed by hash bits records
 // "seen" (bit 0) and "seen again" (bit 1); only tuples whose slot has bit 1 go on.  Every occurrence of a k-mer maps to
 // the same slot, so a k-mer with two or more occurrences (in any genomes, or twice in one genome) always survives;
-// a singleton survives only when it collides with another k-mer (harmless).  The table is sized to stay L2-resident.
+// a singleton survives only when it collides with another k-mer (harmless).  The table is sized to stay L2-resident;
+// used on one rank only (a rank of a multi-GPU run sees only its own genomes at this point).
 struct SeenTable {
     uint32_t *words;        // nullptr: screen disabled, everything survives
     uint64_t slot_mask;     // slots - 1 (power of two); 16 slots per word
 };
 
-__device__ __forceinline__ bool seen_twice(const SeenTable &T, uint64_t h)
-{
-    if (!T.words) return true;
-    const uint64_t s = (h >> 16) & T.slot_mask;
-    return (__ldg(T.words + (s >> 4)) >> (2 * (uint32_t)(s & 15) + 1)) & 1u;
-}
-
-constexpr int FINE_BITS_SMALL = 18, FINE_BITS_LARGE = 2 * MAX_BUCKET_BITS;   // resolution of the survivor histogram
-
 // Append this block's surviving tuples (bit r of `keep` selects h[r]; all of one thread's tuples share a genome) to the
 // compact list -- order is irrelevant, tuples are grouped by hash later -- and count them in the fine histogram.  One
 // global cursor atomic per call and block.  All threads of the block must call; `phase` alternates 0/1 between successive
 // calls so that a call never overwrites prefixes another warp is still reading.  The survivors are compacted in shared
-// memory first and leave with fully coalesced stores (c3, screen off: 6.8 -> 4.5 ms).  write == 0: only count.
+// memory first and leave with fully coalesced stores.  write == 0: only count.
 template <int ITEMS>
 struct AppendSmem {
     uint32_t warp[2][33];                  // warp totals / prefixes, two phases
@@ -237,7 +122,7 @@ template <int ITEMS>
 __device__ __forceinline__ void block_append(uint32_t keep, const uint64_t (&h)[ITEMS], uint32_t gid, AppendSmem<ITEMS> &S,
                                              int phase, unsigned long long *__restrict__ cursor, int write,
                                              uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
-                                             uint32_t *__restrict__ fine_hist, int fine_bits)
+                                             uint32_t *__restrict__ fine_hist, uint32_t B1)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t *sw = S.warp[phase];
@@ -267,7 +152,7 @@ __device__ __forceinline__ void block_append(uint32_t keep, const uint64_t (&h)[
             S.keys[o] = h[r];
             S.vals[o] = gid;
             ++o;
-            atomicAdd(&fine_hist[(uint32_t)(h[r] >> (64 - fine_bits))], 1u);
+            atomicAdd(&fine_hist[(parent_of(h[r], B1) << FINE_BITS) | (frac_of(h[r], B1) >> (32 - FINE_BITS))], 1u);
         }
     __syncthreads();
     const uint32_t total = sw[32], base = S.base[phase];
@@ -330,6 +215,12 @@ __device__ __forceinline__ void count_valid(uint32_t ok, uint32_t gid, int lane,
     if (lane == 16 && total - lo) atomicAdd(&valid_cnt[g_hi], total - lo);
 }
 
+__device__ __forceinline__ uint32_t global_gid(const uint32_t *__restrict__ tile_gid, uint64_t p, bool in_range, uint32_t gid_base)
+{
+    const uint32_t l = in_range ? tile_gid[p >> 7] : 0xffffffffu;
+    return l == 0xffffffffu ? l : l + gid_base;
+}
+
 // Singleton screen, pass 1 over the slots [p_lo, p_hi) (multiples of 256): mark every k-mer in the seen table; *n_again
 // counts the tuples that found their slot already marked (survivors = *n_again + number of slots with bit 1).
 __global__ void __launch_bounds__(256) screen_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ inv,
@@ -345,7 +236,7 @@ __global__ void __launch_bounds__(256) screen_kernel(const uint32_t *__restrict_
     // whole warps enter and leave the loop together (count_valid synchronises the warp)
     for (uint64_t gi = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; gi - lane < n_groups; gi += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t p = p_lo + gi * KM_ITEMS;
-        const uint32_t gid = gi < n_groups ? tile_gid[p >> 7] : 0xffffffffu;
+        const uint32_t gid = global_gid(tile_gid, p, gi < n_groups, ep.gid_base);
         uint64_t h[KM_ITEMS];
         uint32_t ok = 0;
         if (gid != 0xffffffffu) ok = kmer_hashes(seq2, inv, p, ep, kmask, wmask, h);
@@ -385,7 +276,7 @@ __global__ void __launch_bounds__(256) collect_kernel(const uint32_t *__restrict
                                                       ExtractParams ep, SeenTable T, uint32_t *__restrict__ valid_cnt,
                                                       unsigned long long *__restrict__ cursor, int write,
                                                       uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals,
-                                                      uint32_t *__restrict__ fine_hist, int fine_bits)
+                                                      uint32_t *__restrict__ fine_hist, uint32_t B1)
 {
     __shared__ AppendSmem<KM_ITEMS> s_app;
     const uint64_t kmask = (~0ULL) >> (64 - 2 * ep.k);
@@ -396,7 +287,7 @@ __global__ void __launch_bounds__(256) collect_kernel(const uint32_t *__restrict
     // whole blocks enter and leave the loop together (block_append synchronises the block)
     for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < n_groups; base += (uint64_t)gridDim.x * blockDim.x, phase ^= 1) {
         const uint64_t p = p_lo + (base + threadIdx.x) * KM_ITEMS;
-        const uint32_t gid = base + threadIdx.x < n_groups ? tile_gid[p >> 7] : 0xffffffffu;
+        const uint32_t gid = global_gid(tile_gid, p, base + threadIdx.x < n_groups, ep.gid_base);
         uint64_t h[KM_ITEMS];
         uint32_t ok = 0;
         if (gid != 0xffffffffu) ok = kmer_hashes(seq2, inv, p, ep, kmask, wmask, h);
@@ -413,18 +304,8 @@ __global__ void __launch_bounds__(256) collect_kernel(const uint32_t *__restrict
             for (int j = 0; j < KM_ITEMS; ++j)
                 if (!((tw[j] >> (2 * ((uint32_t)(h[j] >> 16) & 15) + 1)) & 1u)) ok &= ~(1u << j);
         }
-        block_append<KM_ITEMS>(ok, h, gid, s_app, phase, cursor, write, out_keys, out_vals, fine_hist, fine_bits);
+        block_append<KM_ITEMS>(ok, h, gid, s_app, phase, cursor, write, out_keys, out_vals, fine_hist, B1);
     }
-}
-
-// coarse bucket histogram (NB = 2^total_bits bins) from the fine one
-__global__ void __launch_bounds__(256) coarsen_kernel(const uint32_t *__restrict__ fine_hist, int fine_bits, int total_bits,
-                                                      uint32_t *__restrict__ hist)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (1u << fine_bits)) return;
-    const uint32_t c = fine_hist[i];
-    if (c) atomicAdd(&hist[total_bits ? (i >> (fine_bits - total_bits)) : 0u], c);
 }
 
 // number of slots with bit 1 set (= distinct slots that hold a repeated k-mer); survivors = *n_again + that number
@@ -436,6 +317,25 @@ __global__ void __launch_bounds__(256) seen_popc_kernel(const uint32_t *__restri
         c += __popc(words[i] & 0xaaaaaaaau);
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_slots_again, (unsigned long long)c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// histograms and scans
+// ---------------------------------------------------------------------------------------------------------------
+// out[i] = sum over the `n_src` source histograms (stride src_stride) of the 2^(FINE_BITS - bits) fine bins of coarse bin i;
+// n_out coarse bins = parents << bits
+__global__ void __launch_bounds__(256) coarsen_kernel(const uint32_t *__restrict__ fine, uint32_t n_src, uint64_t src_stride,
+                                                      int bits, uint32_t n_out, uint32_t *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const uint32_t w = 1u << (FINE_BITS - bits);
+    uint32_t s = 0;
+    for (uint32_t src = 0; src < n_src; ++src) {
+        const uint32_t *f = fine + src * src_stride + (uint64_t)i * w;
+        for (uint32_t j = 0; j < w; ++j) s += f[j];
+    }
+    out[i] = s;
 }
 
 // exclusive scan of one value per thread over a 1024-thread block; returns the prefix, *total gets the sum
@@ -460,40 +360,58 @@ __device__ __forceinline__ uint32_t block_exscan_1024(uint32_t v, uint32_t *warp
     return pre;
 }
 
-// one block: off[i] = exclusive prefix of hist (NB + 1 entries); cursor2 = off; cursor1[b] = off[b * B2];
-// tile_start[b] = number of PART_TILE tiles in level-1 buckets < b (B1 + 1 entries)
-__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t *__restrict__ hist, MsdPlan pl, uint32_t *__restrict__ off,
-                                                    uint32_t *__restrict__ cursor1, uint32_t *__restrict__ cursor2,
-                                                    uint32_t *__restrict__ tile_start)
+// Exclusive scan of n <= 2^20 counters in three small launches: 1024-element chunks scanned independently (coalesced),
+// the chunk totals scanned by one block, the chunk bases added.  out has n + 1 entries (out[n] = total); out2 (optional)
+// receives a copy of the first n (the partition kernels' write cursors).
+__global__ void __launch_bounds__(1024) exscan_chunks_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out,
+                                                             uint32_t *__restrict__ chunk_tot)
 {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t s_total;
-    const uint32_t per = (pl.NB + 1023) / 1024;
-    const uint32_t lo = min(threadIdx.x * per, pl.NB), hi = min(lo + per, pl.NB);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) sum += hist[i];
-    uint32_t run = block_exscan_1024(sum, warp_tot, &s_total);
-    for (uint32_t i = lo; i < hi; ++i) { off[i] = run; cursor2[i] = run; run += hist[i]; }
-    if (threadIdx.x == 0) off[pl.NB] = s_total;
-    __syncthreads();                    // block-wide visibility of the off[] writes (the same block reads them below)
-    uint32_t tiles = 0, beg = 0;
-    if (threadIdx.x < pl.B1) {          // B1 <= 1024
-        beg = off[threadIdx.x * pl.B2];
-        uint32_t end = off[(threadIdx.x + 1) * pl.B2];
-        tiles = (end - beg + PART_TILE - 1) / PART_TILE;
-    }
-    uint32_t tpre = block_exscan_1024(tiles, warp_tot, &s_total);
-    if (threadIdx.x < pl.B1) { cursor1[threadIdx.x] = beg; tile_start[threadIdx.x] = tpre; }
-    if (threadIdx.x == 0) tile_start[pl.B1] = s_total;
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0u;
+    const uint32_t pre = block_exscan_1024(v, warp_tot, &s_total);
+    if (i < n) out[i] = pre;
+    if (threadIdx.x == 0) chunk_tot[blockIdx.x] = s_total;
+}
+__global__ void __launch_bounds__(1024) exscan_totals_kernel(uint32_t *__restrict__ chunk_tot, uint32_t n_chunks, uint32_t *__restrict__ grand)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_total;
+    const uint32_t v = threadIdx.x < n_chunks ? chunk_tot[threadIdx.x] : 0u;
+    const uint32_t pre = block_exscan_1024(v, warp_tot, &s_total);
+    if (threadIdx.x < n_chunks) chunk_tot[threadIdx.x] = pre;
+    if (threadIdx.x == 0) *grand = s_total;
+}
+__global__ void __launch_bounds__(1024) exscan_add_kernel(uint32_t *__restrict__ out, uint32_t n, const uint32_t *__restrict__ chunk_base,
+                                                          uint32_t *__restrict__ out2)
+{
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = out[i] + chunk_base[blockIdx.x];
+    out[i] = v;
+    if (out2) out2[i] = v;
 }
 
-// Partition one tile of tuples into buckets.  LEVEL 1: tuples come from the compact survivor list, bucket = top b1
-// bits of h.  LEVEL 2: tuples come from a level-1 bucket, bucket = next b2 bits.  Inside the block the tile is first
-// grouped by bucket in shared memory, so that every bucket receives one contiguous run per tile.
+// ---------------------------------------------------------------------------------------------------------------
+// partition
+// ---------------------------------------------------------------------------------------------------------------
+// A source segment of the level-2 partition: a run of tuples that all belong to one parent (one rank: the parent's
+// level-1 bucket; several ranks: the part of it that one peer sent).
+struct Segment {
+    uint32_t beg, len;       // in the level-1 / receive buffer
+    uint32_t parent;         // local parent index
+    uint32_t tile_start;     // number of PART_TILE tiles in the segments before this one
+};
+
+// Partition one tile of tuples into buckets.  LEVEL 1: tuples come from the compact survivor list, bucket = parent.
+// LEVEL 2: tuples come from a segment of one parent, bucket = top b2 bits of the position inside the parent's range.
+// Inside the block the tile is first grouped by bucket in shared memory, so that every bucket receives one contiguous
+// run per tile.  cursor[] holds the next free slot of every destination bucket.
 template <int LEVEL>
-__global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, MsdPlan pl, const uint64_t *__restrict__ in_keys,
-                                                            const uint32_t *__restrict__ in_vals, const uint32_t *__restrict__ off,
-                                                            const uint32_t *__restrict__ tile_start, uint32_t n_tiles,
+__global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, uint32_t B1, int b2, const uint64_t *__restrict__ in_keys,
+                                                            const uint32_t *__restrict__ in_vals, const Segment *__restrict__ segs,
+                                                            uint32_t n_segs, uint32_t n_tiles,
                                                             uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys,
                                                             uint32_t *__restrict__ out_vals)
 {
@@ -505,28 +423,30 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, Ms
     uint32_t *s_start = s_cnt + MAXB;
     uint32_t *s_fill = s_start + MAXB;
     uint32_t *s_gbase = s_fill + MAXB;
-    __shared__ uint32_t s_total, s_bucket, s_tile_lo;
-    const uint32_t NBK = (LEVEL == 1) ? pl.B1 : pl.B2;
-    const int shift = (LEVEL == 1) ? (64 - pl.b1) : (64 - pl.b1 - pl.b2);
+    __shared__ uint32_t s_total, s_seg;
+    const uint32_t NBK = (LEVEL == 1) ? B1 : (1u << b2);
+    auto bucket_of = [&](uint64_t h) -> uint32_t {
+        if (LEVEL == 1) return parent_of(h, B1);
+        return b2 ? (frac_of(h, B1) >> (32 - b2)) : 0u;
+    };
 
-    if (LEVEL == 2) n_tiles = tile_start[pl.B1];
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (uint32_t b = threadIdx.x; b < NBK; b += PART_THREADS) { s_cnt[b] = 0; s_fill[b] = 0; }
         uint64_t src_lo = 0, src_hi = 0;
-        uint32_t parent = 0;
+        uint32_t cur_base = 0;
         if (LEVEL == 2) {
-            if (threadIdx.x == 0) {                                     // which level-1 bucket does this tile belong to?
-                uint32_t lo = 0, hi = pl.B1;
-                while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (tile_start[mid] <= tile) lo = mid; else hi = mid; }
-                s_bucket = lo; s_tile_lo = tile_start[lo];
+            if (threadIdx.x == 0) {                                     // which segment does this tile belong to?
+                uint32_t lo = 0, hi = n_segs;
+                while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (segs[mid].tile_start <= tile) lo = mid; else hi = mid; }
+                s_seg = lo;
             }
         }
         __syncthreads();
         if (LEVEL == 2) {
-            parent = s_bucket;
-            uint64_t beg = off[parent * pl.B2], end = off[(parent + 1) * pl.B2];
-            src_lo = beg + (uint64_t)(tile - s_tile_lo) * PART_TILE;
-            src_hi = min(src_lo + PART_TILE, end);
+            const Segment sg = segs[s_seg];
+            src_lo = (uint64_t)sg.beg + (uint64_t)(tile - sg.tile_start) * PART_TILE;
+            src_hi = min(src_lo + PART_TILE, (uint64_t)sg.beg + sg.len);
+            cur_base = sg.parent << b2;
         } else {
             src_lo = (uint64_t)tile * PART_TILE;
             src_hi = min(src_lo + PART_TILE, n_in);
@@ -541,7 +461,7 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, Ms
             if (ok) { key[r] = in_keys[p]; val[r] = in_vals[p]; }
             bk[r] = 0xffffffffu;
             if (ok) {
-                bk[r] = (NBK > 1) ? (uint32_t)((key[r] >> shift) & (NBK - 1)) : 0u;
+                bk[r] = bucket_of(key[r]);
                 atomicAdd(&s_cnt[bk[r]], 1u);
             }
         }
@@ -562,7 +482,7 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, Ms
         __syncthreads();
         for (uint32_t b = threadIdx.x; b < NBK; b += PART_THREADS) {
             uint32_t c = s_cnt[b];
-            if (c) s_gbase[b] = atomicAdd(&cursor[(LEVEL == 1) ? b : parent * pl.B2 + b], c);
+            if (c) s_gbase[b] = atomicAdd(&cursor[cur_base + b], c);
         }
 #pragma unroll
         for (int r = 0; r < PART_ITEMS; ++r) {
@@ -576,12 +496,70 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, Ms
         const uint32_t total = s_total;
         for (uint32_t s = threadIdx.x; s < total; s += PART_THREADS) {
             uint64_t k = st_keys[s];
-            uint32_t b = (NBK > 1) ? (uint32_t)((k >> shift) & (NBK - 1)) : 0u;
+            uint32_t b = bucket_of(k);
             uint32_t dst = s_gbase[b] + (s - s_start[b]);
             out_keys[dst] = k;
             out_vals[dst] = st_vals[s];
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pair accumulator
+// ---------------------------------------------------------------------------------------------------------------
+// Two layouts:
+//   dense  (N(N-1)/2 <= 2^26): one uint32 counter per pair at index row*(row-1)/2 + col -- an increment is a single
+//          fire-and-forget atomic, and an ordered scan of the array yields the pairs already sorted by (row, col);
+//   hashed (larger N): open addressing, uint64 key (row << 32 | col) + uint32 count.  Sized by a guess, grown between
+//          passes when it fills up; an insert that finds no slot sets *overflow and the whole call is redone larger.
+struct PairAcc {
+    uint32_t *dense;        // non-null selects the dense layout
+    uint64_t *tkeys;
+    uint32_t *tvals;
+    uint64_t cap_mask;
+    unsigned long long *status;     // [0] overflow flag, [1] keys inserted so far
+};
+constexpr uint32_t MAX_PROBES = 4096;
+
+// returns 1 when the key was new
+__device__ __forceinline__ uint32_t table_add(const PairAcc &A, uint64_t key, uint32_t inc)
+{
+    uint64_t h = fmix64(key) & A.cap_mask;
+    for (uint32_t probes = 0; probes < MAX_PROBES; ++probes) {
+        uint64_t cur = A.tkeys[h];
+        uint32_t fresh = 0;
+        if (cur == SLOT_EMPTY) {
+            cur = atomicCAS((unsigned long long *)&A.tkeys[h], (unsigned long long)SLOT_EMPTY, (unsigned long long)key);
+            if (cur == SLOT_EMPTY) { cur = key; fresh = 1; }
+        }
+        if (cur == key) { atomicAdd(&A.tvals[h], inc); return fresh; }
+        h = (h + 1) & A.cap_mask;
+    }
+    A.status[0] = 1;
+    return 0;
+}
+
+// `inc` increments for the pair (a, b), a != b
+__device__ __forceinline__ uint32_t pair_add(const PairAcc &A, uint32_t a, uint32_t b, uint32_t inc = 1u)
+{
+    const uint32_t hi = a > b ? a : b, lo = a > b ? b : a;
+    if (A.dense) { atomicAdd(&A.dense[(uint64_t)hi * (hi - 1) / 2 + lo], inc); return 0; }
+    return table_add(A, ((uint64_t)hi << 32) | lo, inc);
+}
+
+__device__ __forceinline__ void flush_fresh(const PairAcc &A, uint32_t fresh)
+{
+    fresh = __reduce_add_sync(0xffffffffu, fresh);
+    if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(&A.status[1], (unsigned long long)fresh);
+}
+
+// move every entry of an old table into a new (larger) one
+__global__ void __launch_bounds__(256) rehash_kernel(const uint64_t *__restrict__ okeys, const uint32_t *__restrict__ ovals, uint64_t ocap, PairAcc A)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ocap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = okeys[i];
+        if (k != SLOT_EMPTY) table_add(A, k, ovals[i]);
     }
 }
 
@@ -595,28 +573,20 @@ struct BucketSmem {
     uint16_t prev[BUCKET_CAP];
 };
 
-__device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, int count_only, unsigned long long &local_inc, const PairAcc &A)
-{
-    if (count_only) { ++local_inc; return; }
-    pair_add(A, a > b ? a : b, a > b ? b : a);
-}
-
 // One block per final bucket.  Equal k-mers are linked into chains through a shared-memory hash table: a tuple finds the
 // slot of its key and swaps itself in as the slot's newest member, keeping the previous one as its predecessor.  A
 // tuple's chain is then exactly the set of tuples with the same k-mer inserted before it, so walking it enumerates every
 // unordered pair of the group once -- no sort, no regrouping.  A tuple whose genome already occurs in its chain is a
 // within-genome duplicate (counted in dup_cnt, skipped by everybody else).
-// count_only: only sum the number of pair increments (sizing pass for very large N).
 __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                                     const uint32_t *__restrict__ off, uint32_t n_buckets, int count_only,
+                                                     const uint32_t *__restrict__ off, uint32_t n_buckets,
                                                      uint32_t *__restrict__ dup_cnt, PairAcc A,
-                                                     uint32_t *__restrict__ big_list, uint32_t *__restrict__ n_big,
-                                                     unsigned long long *__restrict__ n_inc)
+                                                     uint32_t *__restrict__ big_list, uint32_t *__restrict__ n_big)
 {
     extern __shared__ unsigned char smem_raw[];
     BucketSmem &S = *(BucketSmem *)smem_raw;
-    const int tid = threadIdx.x, lane = tid & 31;
-    unsigned long long local_inc = 0;
+    const int tid = threadIdx.x;
+    uint32_t fresh = 0;
     for (uint32_t bkt = blockIdx.x; bkt < n_buckets; bkt += gridDim.x) {
         const uint32_t beg = off[bkt], size = off[bkt + 1] - beg;
         if (size < 2) continue;                                              // uniform for the block
@@ -653,7 +623,7 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             while (j != CHAIN_END) {
                 if (S.gids[j] == g) {
                     dup_mask |= 1u << t;
-                    if (!count_only) atomicAdd(&dup_cnt[g], 1u);
+                    atomicAdd(&dup_cnt[g], 1u);
                     break;
                 }
                 j = S.prev[j];
@@ -672,29 +642,28 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             uint32_t j = pi;
             while (j != CHAIN_END) {
                 const uint32_t pj = S.prev[j];
-                if (!(pj & CHAIN_DUP)) emit_pair(g, S.gids[j], count_only, local_inc, A);
+                if (!(pj & CHAIN_DUP)) fresh += pair_add(A, g, S.gids[j]);
                 j = pj & CHAIN_END;
             }
         }
         __syncthreads();
     }
-    if (count_only) {
-        for (int o = 16; o; o >>= 1) local_inc += __shfl_down_sync(0xffffffffu, local_inc, o);
-        if (lane == 0 && local_inc) atomicAdd(n_inc, local_inc);
-    }
+    if (!A.dense) flush_fresh(A, fresh);
 }
 
-// Generic path for buckets that do not fit shared memory (a k-mer shared by thousands of genomes lands here): the
-// block sorts the bucket in place in global memory by (h, genome) with the all-ascending bitonic network, then runs
-// the same run scan as the LSD path.
+// Generic path for buckets that do not fit shared memory: the block sorts the bucket in place in global memory by
+// (h, genome) with the all-ascending bitonic network, then scans the runs of equal k-mers.  A run of at least HUGE_MIN
+// tuples (a k-mer shared by thousands of genomes -- what kmer-db calls a bubble, bubble_helper.h:79-151) is not expanded
+// here: its position goes to huge_list and the bubble kernels below take it.
+struct HugeRun { uint32_t beg, len; };
+
 __global__ void __launch_bounds__(1024) big_bucket_kernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                                           const uint32_t *__restrict__ off, const uint32_t *__restrict__ big_list,
-                                                          const uint32_t *__restrict__ n_big, int count_only,
-                                                          uint32_t *__restrict__ dup_cnt, PairAcc A,
-                                                          unsigned long long *__restrict__ n_inc)
+                                                          const uint32_t *__restrict__ n_big, uint32_t *__restrict__ dup_cnt, PairAcc A,
+                                                          HugeRun *__restrict__ huge_list, uint32_t huge_cap, unsigned long long *__restrict__ n_huge)
 {
     const uint32_t nb = *n_big;
-    unsigned long long local_inc = 0;
+    uint32_t fresh = 0;
     for (uint32_t q = blockIdx.x; q < nb; q += gridDim.x) {
         const uint32_t bkt = big_list[q];
         const uint32_t beg = off[bkt], c = off[bkt + 1] - beg;
@@ -715,81 +684,162 @@ __global__ void __launch_bounds__(1024) big_bucket_kernel(uint64_t *__restrict__
             }
         }
         for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
-            uint64_t key = K[i];
-            uint32_t g = V[i];
-            if (i > 0 && K[i - 1] == key && V[i - 1] == g) { if (!count_only) atomicAdd(&dup_cnt[g], 1u); continue; }
+            const uint64_t key = K[i];
+            const uint32_t g = V[i];
+            // the run of equal keys around i, by binary search in the sorted bucket
+            uint32_t first = 0, end = c;
+            { uint32_t x = 0, y = i; while (x < y) { const uint32_t mid = x + (y - x) / 2; if (K[mid] < key) x = mid + 1; else y = mid; } first = x; }
+            { uint32_t x = i, y = c; while (y - x > 1) { const uint32_t mid = x + (y - x) / 2; if (K[mid] == key) x = mid; else y = mid; } end = y; }
+            const bool huge = end - first >= HUGE_MIN;
+            if (huge && i == first) {
+                const unsigned long long at = atomicAdd(n_huge, 1ULL);
+                if (at < huge_cap) huge_list[at] = {beg + first, end - first};
+            }
+            if (huge) continue;
+            if (i > 0 && K[i - 1] == key && V[i - 1] == g) { atomicAdd(&dup_cnt[g], 1u); continue; }
             uint32_t prev = g;
             for (uint32_t j = i; j-- > 0 && K[j] == key;) {
                 uint32_t gj = V[j];
-                if (gj != prev) { emit_pair(g, gj, count_only, local_inc, A); prev = gj; }
+                if (gj != prev) { fresh += pair_add(A, g, gj); prev = gj; }
             }
         }
         __syncthreads();
     }
-    if (count_only) {
-        for (int o = 16; o; o >>= 1) local_inc += __shfl_down_sync(0xffffffffu, local_inc, o);
-        if ((threadIdx.x & 31) == 0 && local_inc) atomicAdd(n_inc, local_inc);
+    if (!A.dense) flush_fresh(A, fresh);
+}
+
+// ---- bubbles: one k-mer shared by thousands of genomes ------------------------------------------------------------
+// bubble_prepare: the run is sorted by genome, so the distinct genomes are the positions whose predecessor differs;
+// they are compacted into members[] (at the run's own offset, so no allocation depends on the data), duplicates are
+// counted, and a 128-bit signature of the member set is formed.  Identical member sets -- "core" k-mers of one clade --
+// are then expanded ONCE with a weight (kmer-db's pattern collapse, prefix_kmer_db.cpp:181-240, for the case where it
+// matters): the host groups the signatures, bubble_equal verifies the candidates element by element.
+struct HugeInfo { uint32_t beg, m; uint64_t sig1, sig2; };
+
+__global__ void __launch_bounds__(1024) bubble_prepare_kernel(const uint32_t *__restrict__ vals, const HugeRun *__restrict__ runs,
+                                                              uint32_t n_runs, uint32_t *__restrict__ members, HugeInfo *__restrict__ info,
+                                                              uint32_t *__restrict__ dup_cnt)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_total, s_run;
+    __shared__ unsigned long long s_sig[2];
+    for (uint32_t r = blockIdx.x; r < n_runs; r += gridDim.x) {
+        const HugeRun run = runs[r];
+        const uint32_t *V = vals + run.beg;
+        if (threadIdx.x == 0) { s_run = 0; s_sig[0] = 0; s_sig[1] = 0; }
+        __syncthreads();
+        unsigned long long sig1 = 0, sig2 = 0;
+        for (uint32_t base = 0; base < run.len; base += 1024) {
+            const uint32_t i = base + threadIdx.x;
+            uint32_t g = 0, keep = 0;
+            if (i < run.len) {
+                g = V[i];
+                keep = (i == 0 || V[i - 1] != g) ? 1u : 0u;
+                if (!keep) atomicAdd(&dup_cnt[g], 1u);
+            }
+            const uint32_t pre = block_exscan_1024(keep, warp_tot, &s_total);
+            if (keep) {
+                members[run.beg + s_run + pre] = g;
+                sig1 += fmix64(0x9E3779B97F4A7C15ULL + g);
+                sig2 += fmix64(0xC2B2AE3D27D4EB4FULL ^ ((uint64_t)g << 17 | g));
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_run += s_total;
+            __syncthreads();
+        }
+        atomicAdd(&s_sig[0], sig1); atomicAdd(&s_sig[1], sig2);
+        __syncthreads();
+        if (threadIdx.x == 0) info[r] = {run.beg, s_run, (uint64_t)s_sig[0], (uint64_t)s_sig[1]};
+        __syncthreads();
     }
+}
+
+// same[i] = 1 when member list i equals member list rep[i] (both of length m)
+__global__ void __launch_bounds__(256) bubble_equal_kernel(const uint32_t *__restrict__ members, const HugeInfo *__restrict__ info,
+                                                           const uint32_t *__restrict__ rep, uint32_t n, uint32_t *__restrict__ differ)
+{
+    for (uint32_t r = blockIdx.y; r < n; r += gridDim.y) {
+        const uint32_t q = rep[r];
+        if (q == r) continue;
+        const uint32_t *a = members + info[r].beg, *b = members + info[q].beg;
+        const uint32_t m = info[r].m;
+        bool bad = false;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) bad |= a[i] != b[i];
+        if (bad) differ[r] = 1;
+    }
+}
+
+// all pairs of one member set, 128 x 128 tiles of the lower triangle, `weight` increments each
+struct BubbleJob { uint32_t beg, m, weight, tile0; };      // tile0: number of tiles of the jobs before this one
+__global__ void __launch_bounds__(256) bubble_pairs_kernel(const uint32_t *__restrict__ members, const BubbleJob *__restrict__ jobs,
+                                                           uint32_t n_jobs, uint32_t n_tiles, PairAcc A)
+{
+    __shared__ uint32_t s_row[128], s_col[128];
+    __shared__ uint32_t s_job;
+    uint32_t fresh = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) {
+            uint32_t lo = 0, hi = n_jobs;
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (jobs[mid].tile0 <= tile) lo = mid; else hi = mid; }
+            s_job = lo;
+        }
+        __syncthreads();
+        const BubbleJob jb = jobs[s_job];
+        // tile t of the job -> (tr, tc), tc <= tr, row-major over the lower triangle of T x T tiles
+        const uint32_t t = tile - jb.tile0;
+        uint32_t tr = (uint32_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((uint64_t)tr * (tr + 1) / 2 > t) --tr;
+        while ((uint64_t)(tr + 1) * (tr + 2) / 2 <= t) ++tr;
+        const uint32_t tc = t - (uint32_t)((uint64_t)tr * (tr + 1) / 2);
+        const uint32_t *M = members + jb.beg;
+        if (threadIdx.x < 128) { const uint32_t i = tr * 128 + threadIdx.x; s_row[threadIdx.x] = i < jb.m ? M[i] : 0xffffffffu; }
+        else { const uint32_t i = tc * 128 + threadIdx.x - 128; s_col[threadIdx.x - 128] = i < jb.m ? M[i] : 0xffffffffu; }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < 128 * 128; e += 256) {
+            const uint32_t r = e >> 7, c = e & 127;
+            if (tr == tc && c >= r) continue;                     // diagonal tile: strictly lower part only
+            const uint32_t a = s_row[r], b = s_col[c];
+            if (a == 0xffffffffu || b == 0xffffffffu) continue;
+            fresh += pair_add(A, a, b, jb.weight);
+        }
+        __syncthreads();
+    }
+    if (!A.dense) flush_fresh(A, fresh);
 }
 
 __global__ void totals_kernel(const uint32_t *__restrict__ valid_cnt, const uint32_t *__restrict__ dup_cnt, uint32_t n,
                               uint32_t *__restrict__ totals)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) totals[i] = valid_cnt[i] - dup_cnt[i];
+    if (i < n) totals[i] = valid_cnt[i] - dup_cnt[i];          // (mod 2^32: the ranks' partial values sum to the total)
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// finish: thresholds, ordered output
+// ---------------------------------------------------------------------------------------------------------------
 struct EmitParams {
     uint32_t min_kmers;
-    double min_ident_slack;     // min_ident minus a safety margin; the exact test is redone on the host
+    double min_ident;           // < 0: no ani test (partial counts)
     int k;
     int gbits;
+    uint32_t world, rank;       // multi-GPU: owner(g) = g % world
 };
+constexpr double ANI_MARGIN = 1e-9;         // |device ani - host ani| is ~1e-16; anything closer to the threshold is re-checked on the host
+constexpr uint32_t BORDERLINE = 0x80000000u;
 
-__device__ __forceinline__ bool emit_pass(uint64_t key, uint32_t common, const uint32_t *__restrict__ totals,
-                                          const EmitParams &ep)
+// ani-shorter (params.cpp:28-32) with the device's log(): returns 2 = passes for sure, 1 = borderline, 0 = fails
+__device__ __forceinline__ int ani_test(uint32_t common, uint32_t tr, uint32_t tc, const EmitParams &ep, float &ani_out)
 {
-    if (key == SLOT_EMPTY || common < ep.min_kmers || common == 0) return false;
-    uint32_t r = (uint32_t)(key >> 32), c = (uint32_t)key;
-    uint32_t tr = totals[r], tc = totals[c];
-    double j = (double)common / (double)(tr < tc ? tr : tc);
-    double d = (-1.0 / ep.k) * log((2 * j) / (j + 1));
-    return (1.0 - d) >= ep.min_ident_slack;
+    const double j = (double)common / (double)(tr < tc ? tr : tc);
+    const double d = (j == 0) ? 1.0 : (-1.0 / ep.k) * log((2 * j) / (j + 1));
+    const double a = 1.0 - d;
+    ani_out = (float)a;
+    if (ep.min_ident < 0) return 2;
+    if (a >= ep.min_ident + ANI_MARGIN) return 2;
+    if (a >= ep.min_ident - ANI_MARGIN) return 1;
+    return 0;
 }
 
-// k4: pass 0 counts, pass 1 writes (compact key = row << gbits | col, value = common)
-__global__ void __launch_bounds__(256) emit_kernel(const uint64_t *__restrict__ tkeys, const uint32_t *__restrict__ tvals,
-                                                   uint64_t cap, const uint32_t *__restrict__ totals, EmitParams ep,
-                                                   int write, unsigned long long *__restrict__ cursor,
-                                                   uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
-{
-    // cap is a multiple of 32 (power of two >= 1024): whole warps enter and leave the loop together
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        bool ok = false;
-        uint64_t key = SLOT_EMPTY;
-        uint32_t v = 0;
-        if (i < cap) {
-            key = tkeys[i];
-            if (key != SLOT_EMPTY) { v = tvals[i]; ok = emit_pass(key, v, totals, ep); }
-        }
-        unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (!m) continue;
-        int lane = threadIdx.x & 31;
-        int leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (ok && write) {
-            unsigned long long o = base + __popc(m & ((1u << lane) - 1));
-            out_keys[o] = ((uint64_t)(uint32_t)(key >> 32) << ep.gbits) | (uint32_t)key;
-            out_vals[o] = v;
-        }
-    }
-}
-
-
-// k4 (dense layout): ordered compaction of the triangular counter array.  pass 0: passing entries per block;
-// pass 1 (after a scan of the block counts): write them in index order = sorted by (row, col).
 __device__ __forceinline__ void tri_decode(uint64_t t, uint32_t &row, uint32_t &col)
 {
     uint32_t r = (uint32_t)((1.0 + sqrt(1.0 + 8.0 * (double)t)) * 0.5);
@@ -798,10 +848,13 @@ __device__ __forceinline__ void tri_decode(uint64_t t, uint32_t &row, uint32_t &
     row = r; col = (uint32_t)(t - (uint64_t)r * (r - 1) / 2);
 }
 
+// One rank, dense layout: ordered compaction of the triangular counter array.  pass 0: passing entries per block;
+// pass 1 (after a scan of the block counts): write them in index order = sorted by (row, col).
 __global__ void __launch_bounds__(256) dense_emit_kernel(const uint32_t *__restrict__ dense, uint64_t n_entries, uint64_t per_block,
                                                          const uint32_t *__restrict__ totals, EmitParams ep, int write,
                                                          uint32_t *__restrict__ block_cnt, uint64_t *__restrict__ out_keys,
-                                                         uint32_t *__restrict__ out_vals)
+                                                         uint32_t *__restrict__ out_vals, float *__restrict__ out_ani,
+                                                         unsigned long long *__restrict__ n_border)
 {
     __shared__ uint32_t warp_cnt[8];
     __shared__ uint32_t s_run;
@@ -811,16 +864,17 @@ __global__ void __launch_bounds__(256) dense_emit_kernel(const uint32_t *__restr
     __syncthreads();
     for (uint64_t base = lo; base < hi; base += 256) {
         const uint64_t t = base + threadIdx.x;
-        bool ok = false;
+        int ok = 0;
         uint32_t v = 0, row = 0, col = 0;
+        float ani = 0;
         if (t < hi) {
             v = dense[t];
             if (v >= ep.min_kmers && v > 0) {
                 tri_decode(t, row, col);
-                ok = emit_pass(((uint64_t)row << 32) | col, v, totals, ep);
+                ok = ani_test(v, totals[row], totals[col], ep, ani);
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const unsigned m = __ballot_sync(0xffffffffu, ok != 0);
         if (lane == 0) warp_cnt[wid] = __popc(m);
         __syncthreads();
         uint32_t before = 0, all = 0;
@@ -828,8 +882,10 @@ __global__ void __launch_bounds__(256) dense_emit_kernel(const uint32_t *__restr
         for (int j = 0; j < 8; ++j) { uint32_t c = warp_cnt[j]; if (j < wid) before += c; all += c; }
         if (ok && write) {
             const uint32_t o = s_run + before + __popc(m & ((1u << lane) - 1));
-            out_keys[o] = ((uint64_t)row << ep.gbits) | col;
-            out_vals[o] = v;
+            out_keys[o] = ((uint64_t)row << 32) | col;
+            out_vals[o] = v | (ok == 1 ? BORDERLINE : 0u);
+            out_ani[o] = ani;
+            if (ok == 1) atomicAdd(n_border, 1ULL);
         }
         __syncthreads();
         if (threadIdx.x == 0) s_run += all;
@@ -852,9 +908,113 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *__restrict_
     if (threadIdx.x == 0) *total = s_total;
 }
 
+// Accumulator -> unordered list of compact entries (key = row << gbits | col, value = count).
+//   world == 1: entries that can still pass (count >= min_kmers, ani test not failed) -> destination 0
+//   world  > 1: every non-zero partial count, once for each distinct owner of its two genomes
+// pass 0 counts per destination into dest_cnt[world]; pass 1 appends at dest_cur[d] (pre-set to the region starts).
+__global__ void __launch_bounds__(256) acc_emit_kernel(PairAcc A, uint64_t n_entries, const uint32_t *__restrict__ totals, EmitParams ep,
+                                                       int write, unsigned long long *__restrict__ dest_cur,
+                                                       uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+{
+    const int lane = threadIdx.x & 31;
+    // n_entries rounded up to whole warps by the loop condition: every lane of a warp takes part in the ballots
+    for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ULL; i0 < n_entries; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + lane;
+        uint32_t v = 0, row = 0, col = 0;
+        if (i < n_entries) {
+            if (A.dense) { v = A.dense[i]; if (v) tri_decode(i, row, col); }
+            else { const uint64_t k = A.tkeys[i]; if (k != SLOT_EMPTY) { v = A.tvals[i]; row = (uint32_t)(k >> 32); col = (uint32_t)k; } }
+        }
+        uint32_t d1 = 0xffffffffu, d2 = 0xffffffffu;
+        if (v) {
+            if (ep.world == 1) {
+                float ani;
+                if (v >= ep.min_kmers && ani_test(v, totals[row], totals[col], ep, ani)) d1 = 0;
+            } else {
+                d1 = row % ep.world; d2 = col % ep.world;
+                if (d2 == d1) d2 = 0xffffffffu;
+            }
+        }
+        for (uint32_t d = 0; d < ep.world; ++d) {
+            const bool mine = d1 == d || d2 == d;
+            const unsigned m = __ballot_sync(0xffffffffu, mine);
+            if (!m) continue;
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&dest_cur[d], (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (mine && write) {
+                const unsigned long long o = base + __popc(m & ((1u << lane) - 1));
+                out_keys[o] = ((uint64_t)row << ep.gbits) | col;
+                out_vals[o] = v;
+            }
+        }
+    }
+}
+
 __global__ void fill_u64_kernel(uint64_t *p, uint64_t n, uint64_t v)
 {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// Sorted compact entries (equal keys adjacent: the partial counts of one pair from several ranks / passes) -> final
+// list.  The head of every run sums the run, applies the thresholds and, if it passes, is written in order.
+// pass 0: passing heads per block; pass 1: write (block_cnt holds exclusive offsets).  mine_only: keep only pairs whose
+// row this rank owns (the list reported to rank 0).
+__global__ void __launch_bounds__(256) finalize_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n,
+                                                       uint64_t per_block, const uint32_t *__restrict__ totals, EmitParams ep, int write,
+                                                       int mine_only, uint32_t *__restrict__ block_cnt, uint64_t *__restrict__ out_keys,
+                                                       uint32_t *__restrict__ out_vals, float *__restrict__ out_ani,
+                                                       unsigned long long *__restrict__ n_border)
+{
+    __shared__ uint32_t warp_cnt[8];
+    __shared__ uint32_t s_run;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t lo = blockIdx.x * per_block, hi = min(n, lo + per_block);
+    const uint64_t cmask = (1ULL << ep.gbits) - 1;
+    if (threadIdx.x == 0) s_run = write ? block_cnt[blockIdx.x] : 0;
+    __syncthreads();
+    for (uint64_t base = lo; base < hi; base += 256) {
+        const uint64_t t = base + threadIdx.x;
+        int ok = 0;
+        uint32_t sum = 0, row = 0, col = 0;
+        float ani = 0;
+        if (t < hi) {
+            const uint64_t k = keys[t];
+            if (k != KEY_SENTINEL && (t == 0 || keys[t - 1] != k)) {
+                uint64_t s = 0;
+                for (uint64_t j = t; j < n && keys[j] == k; ++j) s += vals[j];
+                sum = (uint32_t)s;
+                row = (uint32_t)(k >> ep.gbits); col = (uint32_t)(k & cmask);
+                if (sum >= ep.min_kmers && sum > 0 && (!mine_only || row % ep.world == ep.rank))
+                    ok = ani_test(sum, totals[row], totals[col], ep, ani);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok != 0);
+        if (lane == 0) warp_cnt[wid] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { uint32_t c = warp_cnt[j]; if (j < wid) before += c; all += c; }
+        if (ok && write) {
+            const uint32_t o = s_run + before + __popc(m & ((1u << lane) - 1));
+            out_keys[o] = ((uint64_t)row << 32) | col;
+            out_vals[o] = sum | (ok == 1 ? BORDERLINE : 0u);
+            out_ani[o] = ani;
+            if (ok == 1) atomicAdd(n_border, 1ULL);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += all;
+        __syncthreads();
+    }
+    if (!write && threadIdx.x == 0) block_cnt[blockIdx.x] = s_run;
+}
+
+// final key (row << 32 | col) -> compact sort key (row << gbits | col)
+__global__ void compact_keys_kernel(const uint64_t *__restrict__ in, uint64_t n, int gbits, uint64_t *__restrict__ out)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = ((in[i] >> 32) << gbits) | (uint32_t)in[i];
 }
 
 int grid_for(uint64_t n, int threads = 256, int max_blocks = 148 * 16)
@@ -862,25 +1022,158 @@ int grid_for(uint64_t n, int threads = 256, int max_blocks = 148 * 16)
     return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + threads - 1) / threads, (uint64_t)max_blocks));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct PoolScope {                       // buffers allocated inside live in the stream-ordered pool, not in the call's arena
+    bool saved;
+    PoolScope() : saved(vb_tls_pool_alloc) { vb_tls_pool_alloc = true; }
+    ~PoolScope() { vb_tls_pool_alloc = saved; }
+};
+
+void comm_check(int rc, const char *what)
+{
+    if (rc != 0) throw vb_error(VB_ERR_INTERNAL, std::string("collective failed: ") + what);
+}
+
+// exclusive scan on the device, n <= 2^20 (see the kernels above)
+void dev_exscan(vb_ctx *ctx, cudaStream_t st, const uint32_t *in, uint32_t n, uint32_t *out, uint32_t *out2, uint32_t *scratch /* 1025 */)
+{
+    const uint32_t chunks = (n + 1023) / 1024;
+    if (chunks > 1024) throw vb_error(VB_ERR_INTERNAL, "dev_exscan: too many counters");
+    exscan_chunks_kernel<<<chunks, 1024, 0, st>>>(in, n, out, scratch);
+    VB_LAUNCH_CHECK(ctx);
+    exscan_totals_kernel<<<1, 1024, 0, st>>>(scratch, chunks, out + n);
+    VB_LAUNCH_CHECK(ctx);
+    exscan_add_kernel<<<chunks, 1024, 0, st>>>(out, n, scratch, out2);
+    VB_LAUNCH_CHECK(ctx);
+}
+
+struct Accumulator {
+    PairAcc acc = {nullptr, nullptr, nullptr, 0, nullptr};
+    DevBuf<uint32_t> dense, tvals;
+    DevBuf<uint64_t> tkeys;
+    uint64_t cap = 0;                    // dense: N(N-1)/2 entries; hashed: slots
+    bool is_dense() const { return acc.dense != nullptr; }
+};
+
+void acc_alloc_hashed(vb_ctx *ctx, cudaStream_t st, Accumulator &a, uint64_t cap, unsigned long long *status)
+{
+    if (cap > (1ULL << 34)) throw vb_error(VB_ERR_MEM, "pair table would exceed 2^34 slots");
+    PoolScope pool;
+    a.tkeys.alloc(cap);
+    a.tvals.alloc(cap);
+    VB_CUDA(cudaMemsetAsync(a.tkeys.p, 0xff, a.tkeys.bytes(), st));       // SLOT_EMPTY
+    VB_CUDA(cudaMemsetAsync(a.tvals.p, 0, a.tvals.bytes(), st));
+    a.cap = cap;
+    a.acc = {nullptr, a.tkeys.p, a.tvals.p, cap - 1, status};
+    (void)ctx;
+}
+
+// grow the hashed table to new_cap slots, keeping its contents
+void acc_grow(vb_ctx *ctx, cudaStream_t st, Accumulator &a, uint64_t new_cap)
+{
+    Accumulator b;
+    acc_alloc_hashed(ctx, st, b, new_cap, a.acc.status);
+    rehash_kernel<<<grid_for(a.cap), 256, 0, st>>>(a.tkeys.p, a.tvals.p, a.cap, b.acc);
+    VB_LAUNCH_CHECK(ctx);
+    a.tkeys = std::move(b.tkeys); a.tvals = std::move(b.tvals);
+    a.cap = b.cap; a.acc = b.acc;
+}
+
+struct FinalList {                       // the device-side result of a prefilter call
+    uint64_t n = 0;
+    DevBuf<uint64_t> keys;               // row << 32 | col, sorted
+    DevBuf<uint32_t> vals;               // common | BORDERLINE
+    DevBuf<float> ani;
+};
+
+// sorted compact entries -> FinalList (ordered compaction in two passes)
+void finalize_sorted(vb_ctx *ctx, cudaStream_t st, const uint64_t *skeys, const uint32_t *svals, uint64_t n, const uint32_t *totals,
+                     const EmitParams &em, bool mine_only, unsigned long long *d_scalar, unsigned long long *d_border, FinalList &out, bool pool)
+{
+    out.n = 0;
+    if (!n) return;
+    const uint32_t n_blocks = (uint32_t)std::min<uint64_t>(4096, (n + 255) / 256);
+    const uint64_t per_block = ((n + n_blocks - 1) / n_blocks + 255) / 256 * 256;
+    DevBuf<uint32_t> block_cnt(4096);
+    finalize_kernel<<<n_blocks, 256, 0, st>>>(skeys, svals, n, per_block, totals, em, 0, mine_only ? 1 : 0, block_cnt.p, nullptr, nullptr, nullptr, d_border);
+    VB_LAUNCH_CHECK(ctx);
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(block_cnt.p, n_blocks, d_scalar);
+    VB_LAUNCH_CHECK(ctx);
+    unsigned long long n_out = 0;
+    VB_CUDA(cudaMemcpyAsync(&n_out, d_scalar, sizeof(n_out), cudaMemcpyDeviceToHost, st));
+    VB_CUDA(cudaStreamSynchronize(st));
+    out.n = n_out;
+    if (!n_out) return;
+    {
+        const bool saved = vb_tls_pool_alloc;
+        vb_tls_pool_alloc = pool;
+        try { out.keys.alloc(n_out); out.vals.alloc(n_out); out.ani.alloc(n_out); } catch (...) { vb_tls_pool_alloc = saved; throw; }
+        vb_tls_pool_alloc = saved;
+    }
+    finalize_kernel<<<n_blocks, 256, 0, st>>>(skeys, svals, n, per_block, totals, em, 1, mine_only ? 1 : 0, block_cnt.p, out.keys.p, out.vals.p, out.ani.p, d_border);
+    VB_LAUNCH_CHECK(ctx);
+}
+
+// unordered compact entries (n real ones in buffers of n_pad) -> sorted; returns pointers into a/b
+struct SortBufs { DevBuf<uint64_t> ka, kb; DevBuf<uint32_t> va, vb; };
+void sort_entries(vb_ctx *ctx, cudaStream_t st, SortBufs &sb, uint64_t n, uint64_t n_pad, int key_bits, rsort::Workspace &ws,
+                  const uint64_t *&skeys, const uint32_t *&svals)
+{
+    if (n_pad > n) {
+        fill_u64_kernel<<<grid_for(n_pad - n), 256, 0, st>>>(sb.ka.p + n, n_pad - n, KEY_SENTINEL);
+        VB_LAUNCH_CHECK(ctx);
+    }
+    const bool in_b = rsort::sort_kv<8>(ctx, sb.ka.p, sb.va.p, sb.kb.p, sb.vb.p, n_pad, key_bits, ws);
+    skeys = in_b ? sb.kb.p : sb.ka.p;
+    svals = in_b ? sb.vb.p : sb.va.p;
+}
+
 }  // namespace
 
 vb_pairs *vb_pairs_alloc(uint64_t n, uint32_t n_genomes);
 
-// shard_count > 1: partial result of one k-mer shard -- no thresholds, ani = 0, total_kmers = this shard's part
-void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, uint32_t shard_index,
-                       uint32_t shard_count, vb_pairs **out_pairs)
+void vb_drop_dev_pairs(vb_ctx *ctx)
 {
-    const bool partial = shard_count > 1;
-    if (shard_count == 0 || shard_index >= shard_count) throw vb_error(VB_ERR_ARG, "bad k-mer shard");
+    if (!ctx->dev_pairs) return;
+    cudaStream_t saved = vb_tls_stream;
+    vb_tls_stream = (cudaStream_t)ctx->stream;
+    delete ctx->dev_pairs;
+    ctx->dev_pairs = nullptr;
+    vb_tls_stream = saved;
+}
+
+void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilter_params *p, vb_pairs **out_pairs)
+{
+    const vb_genomes *g = job.g;
+    const vb_comm *comm = job.comm;
+    const uint32_t world = comm ? (uint32_t)comm->world : 1u, rank = comm ? (uint32_t)comm->rank : 0u;
+    const bool partial = job.shard_count > 1;                   // vb_prefilter_partial: raw counts of one k-mer shard
+    if (job.shard_count == 0 || job.shard_index >= job.shard_count) throw vb_error(VB_ERR_ARG, "bad k-mer shard");
     if (p->k < 10 || p->k > 31) throw vb_error(VB_ERR_ARG, "k must be in [10, 31]");
     if (!(p->kmers_fraction > 0)) throw vb_error(VB_ERR_ARG, "kmers_fraction must be > 0");
+    if (world > 1 && (partial || p->max_seqs > 0)) throw vb_error(VB_ERR_ARG, "k-mer shards / --max-seqs are not available in the multi-GPU pipeline");
+    if (world > 1024) throw vb_error(VB_ERR_ARG, "more than 1024 ranks");
     cudaStream_t st = (cudaStream_t)ctx->stream;
     VB_CUDA(cudaSetDevice(ctx->device));
-    const uint32_t n = g->count();
-    EventTimer t_all(st), t_up(st), t_ext(st), t_sort(st), t_seg(st), t_emit(st);
+    ctx->clear_timings("prefilter.");
+    vb_drop_dev_pairs(ctx);
+    const uint32_t n_local = g->count();
+    const uint32_t n = job.n_total ? job.n_total : n_local;    // genomes of the whole set
+    if ((uint64_t)job.gid_base + n_local > n) throw vb_error(VB_ERR_ARG, "genome block outside the set");
+    EventTimer t_all(st), t_up(st);
+    double ms_ext = 0, ms_part = 0, ms_group = 0, ms_exch = 0;
+    // stage timers are read at the end of the call (reading one waits for its stop event)
+    std::vector<std::pair<std::unique_ptr<EventTimer>, double *>> laps;
+    auto lap_start = [&](double &acc_ms) -> EventTimer * {
+        laps.emplace_back(std::make_unique<EventTimer>(st), &acc_ms);
+        laps.back().first->start();
+        return laps.back().first.get();
+    };
 
     t_all.start();
-    DevBuf<uint32_t> counters(3 * (size_t)std::max<uint32_t>(n, 1));        // valid | dup | totals
+    DevBuf<uint32_t> counters(3 * (size_t)std::max<uint32_t>(n, 1) + 1);       // valid | dup | totals (+ 1: overflow flag of all ranks)
     uint32_t *valid_cnt = counters.p, *dup_cnt = counters.p + n, *totals = counters.p + 2 * (size_t)n;
     VB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
     ExtractParams ep;
@@ -890,24 +1183,44 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     ep.use_filter = p->kmers_fraction < 1.0;
     ep.max_thr = (uint64_t)((double)UINT64_MAX * (0.0 + p->kmers_fraction));
     ep.c = (uint64_t)std::ceil((double)p->k / 4);
-    ep.shard_index = shard_index;
-    ep.shard_count = shard_count;
-    DevBuf<unsigned long long> scalars(8);
+    ep.gid_base = job.gid_base;
+    // status words: [0] table overflow, [1] keys in the hashed table, [2] bubbles found, [3] scratch counter,
+    // [4] screen: tuples that found their slot marked, [5] screen: slots marked twice, [6] collect cursor, [7] scratch
+    DevBuf<unsigned long long> scalars(16);
     VB_CUDA(cudaMemsetAsync(scalars.p, 0, scalars.bytes(), st));
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
-    const bool use_lsd = getenv("VB_PREFILTER_LSD") != nullptr;            // A/B switch: the round-1 LSD radix path
 
-    // ---- singleton screen set-up (MSD path), before the genomes are fetched: when they have to be uploaded, the
-    // screen pass over each chunk of genomes is enqueued while the next chunk is still on the PCIe bus
-    // seen table: >= 4 slots per expected k-mer, at most 2^28 slots (64 MB, stays in the 126 MB L2); for inputs
-    // beyond ~2^27 k-mers the collision rate would let most singletons through, so the screen is switched off
+    // ---- plan: passes and level-1 buckets, from sizes every rank knows
+    const double frac = std::min(1.0, p->kmers_fraction);
+    const double est_local = (double)vb_store_slots(g, VB_STORE_PAD) * frac / job.shard_count;
+    const double est_all = std::max(est_local, job.est_kmers_all * frac / job.shard_count);
+    const char *pe = getenv("VB_PREFILTER_PASSES");
+    // one pass groups at most 2^20 buckets of ~1 280 tuples (over all ranks) and must fit the device: 36 B per tuple
+    const double per_pass_cap = std::min(1.0e9, 0.5 * (double)ctx->mem_total / 36.0 * world);
+    uint32_t passes = pe ? (uint32_t)std::max(1, atoi(pe)) : (uint32_t)std::ceil(est_all / per_pass_cap);
+    passes = std::max(1u, std::min(passes, 4096u));
+    const double est_pass = est_all / passes;
+
+    // singleton screen (one rank, small inputs): >= 4 slots per expected k-mer, at most 2^28 slots (64 MB, L2-resident)
     const char *seen_env = getenv("VB_PREFILTER_SEEN");                    // "0": off, "N": force 2^N slots
-    const double est_all = (double)vb_store_slots(g, VB_STORE_PAD) * std::min(1.0, p->kmers_fraction) / shard_count;
     int seen_bits = 20;
-    while ((double)(1ULL << seen_bits) < 4.0 * est_all && seen_bits < 28) ++seen_bits;
-    bool use_seen = !use_lsd && est_all <= (double)(1ULL << 27);
-    if (seen_env && !use_lsd) { int v = atoi(seen_env); use_seen = v > 0; if (v >= 10 && v <= 34) seen_bits = v; }
+    while ((double)(1ULL << seen_bits) < 4.0 * est_pass && seen_bits < 28) ++seen_bits;
+    bool use_seen = world == 1 && est_pass <= (double)(1ULL << 27);
+    if (seen_env && world == 1) { int v = atoi(seen_env); use_seen = v > 0; if (v >= 10 && v <= 34) seen_bits = v; }
+
+    uint32_t Bper, B1;
+    {
+        const double est_keep = use_seen ? 0.5 * est_pass : est_pass;       // the screen drops about half of the tuples
+        int bits = 0;
+        while (est_keep / (double)(1ULL << bits) > BUCKET_TARGET && bits < 2 * MAX_BUCKET_BITS) ++bits;
+        uint32_t want = 1u << std::min(MAX_BUCKET_BITS, (bits + 1) / 2);     // parents over all ranks
+        Bper = 1;
+        while (Bper * 2 * world <= std::max(want, world) && Bper * 2 * world <= (1u << MAX_BUCKET_BITS)) Bper *= 2;
+        B1 = Bper * world;
+    }
+    const uint32_t n_fine = B1 << FINE_BITS;
+
     // The slot axis is walked in chunks (kernel-side offsets inside a chunk stay small; inputs beyond 2^32 base
     // slots just take more launches).  VB_PREFILTER_CHUNK (slots, test hook) forces many small chunks.
     const uint64_t chunk_env = getenv("VB_PREFILTER_CHUNK") ? strtoull(getenv("VB_PREFILTER_CHUNK"), nullptr, 10) : 0;
@@ -922,6 +1235,8 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
         VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
         seen = {seen_words.p, (1ULL << seen_bits) - 1};
     }
+    ep.shard_count = job.shard_count * passes;
+    ep.shard_index = job.shard_index * passes;                  // pass 0
     auto screen_range = [&](const DevGenomes &d, uint64_t lo_all, uint64_t hi_all) {
         for (uint64_t lo = lo_all; lo < hi_all; lo += chunk) {
             const uint64_t hi = std::min(hi_all, lo + chunk);
@@ -930,6 +1245,8 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
             VB_LAUNCH_CHECK(ctx);
         }
     };
+    // when the genomes have to be uploaded, the screen pass (of pass 0) over each chunk of genomes is enqueued while the
+    // next chunk is still on the PCIe bus
     bool screened = false;
     const vb_chunk_fn hook = [&](const DevGenomes &d, uint64_t lo, uint64_t hi) {
         if (use_seen) { screen_range(d, lo, hi); screened = true; }
@@ -939,82 +1256,72 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
     t_up.stop();
     const uint64_t n_slots = dg.total_slots;
 
+    // ---- the accumulator of all passes
     const unsigned long long max_pairs = (unsigned long long)n * (n > 0 ? n - 1 : 0) / 2;
-    unsigned long long n_inc = max_pairs;
     const bool force_hash = getenv("VB_PREFILTER_HASH") != nullptr;   // test hook: exercise the large-N layout
-    const bool count_first = force_hash || max_pairs > (1ULL << 26);   // large N: hashed pair table sized by a counting pass
-    DevBuf<uint64_t> tkeys;
-    DevBuf<uint32_t> tvals, dense;
-    DevBuf<int> overflow(1);
-    uint64_t cap = 0;
-    PairAcc acc = {nullptr, nullptr, nullptr, 0, overflow.p};
-    auto alloc_table = [&]() {
-        VB_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), st));
-        if (!count_first) {                                  // dense triangular counters
-            dense.alloc(std::max<unsigned long long>(max_pairs, 1));
-            VB_CUDA(cudaMemsetAsync(dense.p, 0, dense.bytes(), st));
-            acc.dense = dense.p;
-            cap = max_pairs;
-            return;
-        }
-        unsigned long long distinct_bound = std::min(n_inc, max_pairs);
-        cap = 1024;
-        while (cap < 2 * distinct_bound) cap <<= 1;
-        if (cap > (1ULL << 32)) throw vb_error(VB_ERR_MEM, "pair table would exceed 2^32 slots; split the input (--batch-size)");
-        tkeys.alloc(cap);
-        tvals.alloc(cap);
-        VB_CUDA(cudaMemsetAsync(tkeys.p, 0xff, tkeys.bytes(), st));       // SLOT_EMPTY
-        VB_CUDA(cudaMemsetAsync(tvals.p, 0, tvals.bytes(), st));
-        acc.tkeys = tkeys.p; acc.tvals = tvals.p; acc.cap_mask = cap - 1;
-    };
-    auto read_n_inc = [&]() {
-        VB_CUDA(cudaMemcpyAsync(&n_inc, scalars.p, sizeof(n_inc), cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaStreamSynchronize(st));
-    };
+    const bool want_dense = !force_hash && max_pairs <= (1ULL << 26);
+    const uint64_t cap_env = getenv("VB_PREFILTER_TABLE") ? strtoull(getenv("VB_PREFILTER_TABLE"), nullptr, 10) : 0;   // test hook: initial slots
+    uint64_t cap_hint = 1024;
+    if (cap_env) { while (cap_hint < cap_env) cap_hint <<= 1; }
+    else {
+        const double guess = std::min((double)max_pairs * 2.0, std::max(1048576.0, est_all / world / 4.0));
+        while ((double)cap_hint < guess) cap_hint <<= 1;
+    }
     rsort::Workspace ws;
-    unsigned long long n_survivors = 0;
-
-    if (use_lsd) {
-        // ---- k1 + k2 + k3, LSD flavour: full stable sort of (k-mer, genome) tuples, then a run scan
-        t_ext.start();
-        const uint64_t n_pad = ((n_slots + rsort::TILE - 1) / rsort::TILE) * rsort::TILE;
-        DevBuf<uint64_t> keys_a(n_pad), keys_b(n_pad);
-        DevBuf<uint32_t> vals_a(n_pad), vals_b(n_pad);
-        extract_kernel<<<grid_for(n_pad), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, n_slots, n_pad, ep, keys_a.p,
-                                                       vals_a.p, valid_cnt);
-        VB_LAUNCH_CHECK(ctx);
-        t_ext.stop();
-        t_sort.start();                                     // bit 2k+shift is set only in the sentinel: it sorts last
-        const int key_bits = 2 * p->k + ep.shift + 1;
-        bool in_b = rsort::sort_kv<8>(ctx, keys_a.p, vals_a.p, keys_b.p, vals_b.p, n_pad, key_bits, ws);
-        const uint64_t *skeys = in_b ? keys_b.p : keys_a.p;
-        const uint32_t *svals = in_b ? vals_b.p : vals_a.p;
-        t_sort.stop();
-        t_seg.start();
-        if (count_first) {
-            segment_count_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, scalars.p);
-            VB_LAUNCH_CHECK(ctx);
-            read_n_inc();
+    static std::mutex attr_mutex;
+    static bool attr_done_dev[64] = {false};                 // the opt-in is per device (one process may hold several contexts)
+    const size_t part_smem = PART_TILE * 12 + 4 * (1 << MAX_BUCKET_BITS) * sizeof(uint32_t);
+    {
+        std::lock_guard<std::mutex> lock(attr_mutex);
+        bool &attr_done = attr_done_dev[ctx->device & 63];
+        if (!attr_done) {
+            VB_CUDA(cudaFuncSetAttribute(part_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            VB_CUDA(cudaFuncSetAttribute(part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            VB_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
+            attr_done = true;
         }
-        alloc_table();
-        segment_pairs_kernel<<<grid_for(n_pad), 256, 0, st>>>(skeys, svals, n_pad, dup_cnt, acc);
-        VB_LAUNCH_CHECK(ctx);
+    }
+
+    unsigned long long n_survivors_all = 0, n_tuples_grouped = 0, n_bubbles = 0;
+    Accumulator A;
+    for (int attempt = 0;; ++attempt) {
+    // (a retry re-runs all passes into a larger table: an insert that found no slot is lost, so nothing can be salvaged)
+    if (attempt > 0) {
+        VB_CUDA(cudaMemsetAsync(counters.p, 0, counters.bytes(), st));
+        VB_CUDA(cudaMemsetAsync(scalars.p, 0, scalars.bytes(), st));
+        if (use_seen) VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
+        screened = false;
+        n_survivors_all = 0; n_tuples_grouped = 0; n_bubbles = 0;
+    }
+    if (want_dense) {
+        if (!A.dense.p) { PoolScope pool; A.dense.alloc(std::max<unsigned long long>(max_pairs, 1)); }
+        VB_CUDA(cudaMemsetAsync(A.dense.p, 0, A.dense.bytes(), st));
+        A.acc = {A.dense.p, nullptr, nullptr, 0, scalars.p};
+        A.cap = max_pairs;
     } else {
-        // ---- k1 + k2 + k3, MSD flavour: hash once, screen out singletons, hash-bucket partition, shared-memory grouping
-        t_ext.start();
-        const int fine_bits = est_all > (double)BUCKET_TARGET * (double)(1u << FINE_BITS_SMALL) ? FINE_BITS_LARGE : FINE_BITS_SMALL;
-        DevBuf<uint32_t> fine_hist(1u << fine_bits);
+        A.tkeys.release(); A.tvals.release();
+        acc_alloc_hashed(ctx, st, A, cap_hint, scalars.p);
+    }
+
+    for (uint32_t pass = 0; pass < passes; ++pass) {
+        ep.shard_index = job.shard_index * passes + pass;
+        // ---- extract: hash once, (optionally) screen out singletons, compact list + fine histogram
+        EventTimer *t_ext = lap_start(ms_ext);
+        DevBuf<uint32_t> fine_hist(n_fine);
         VB_CUDA(cudaMemsetAsync(fine_hist.p, 0, fine_hist.bytes(), st));
         unsigned long long *d_cursor = scalars.p + 6;
-        // small inputs: room for every slot's tuple, no counting pass.  Large inputs: count the survivors first.
-        const bool exact_alloc = n_slots >= (1ULL << 31) || 12.0 * (double)n_slots > 0.125 * (double)ctx->mem_total ||
-                                 getenv("VB_PREFILTER_EXACT") != nullptr;
+        if (use_seen && pass > 0) VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
+        // small inputs: room for every slot's tuple, no counting pass.  Large inputs / several passes: count first.
+        const bool exact_alloc = passes > 1 || job.shard_count > 1 || n_slots >= (1ULL << 31) ||
+                                 12.0 * (double)n_slots > 0.125 * (double)ctx->mem_total || getenv("VB_PREFILTER_EXACT") != nullptr;
         auto for_chunks = [&](auto &&launch) {
             for (uint64_t lo = 0; lo < n_slots; lo += chunk) launch(lo, std::min(n_slots, lo + chunk));
         };
-        bool counted_valid = false;
+        bool counted_valid = pass > 0;                           // valid k-mers per genome are counted by the first full scan of every pass' shard
+        // (every pass sees only its own k-mers, so each pass counts the valid k-mers of its shard; they add up)
+        counted_valid = false;
         if (use_seen) {
-            if (!screened) screen_range(dg, 0, n_slots);         // (already enqueued chunk by chunk when the genomes were uploaded)
+            if (!(screened && pass == 0)) screen_range(dg, 0, n_slots);   // (pass 0: already enqueued chunk by chunk during the upload)
             counted_valid = true;
         }
         uint64_t list_cap = n_slots + 64;
@@ -1029,7 +1336,7 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
             } else {
                 for_chunks([&](uint64_t lo, uint64_t hi) {
                     collect_kernel<true><<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen,
-                                                                              valid_cnt, d_cursor, 0, nullptr, nullptr, nullptr, fine_bits);
+                                                                              valid_cnt, d_cursor, 0, nullptr, nullptr, nullptr, B1);
                     VB_LAUNCH_CHECK(ctx);
                 });
                 counted_valid = true;
@@ -1039,180 +1346,451 @@ void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_para
                 list_cap = cnt[0] + 64;
             }
         }
-        if (list_cap >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 k-mer tuples in one prefilter call: split the input or shard the k-mers over more GPUs");
+        if (list_cap >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 k-mer tuples in one prefilter pass: raise VB_PREFILTER_PASSES or use more GPUs");
         DevBuf<uint64_t> keys0(list_cap);                    // compact list of surviving (hash, genome) tuples
         DevBuf<uint32_t> vals0(list_cap);
         for_chunks([&](uint64_t lo, uint64_t hi) {
             if (counted_valid)
                 collect_kernel<false><<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen, valid_cnt,
-                                                                           d_cursor, 1, keys0.p, vals0.p, fine_hist.p, fine_bits);
+                                                                           d_cursor, 1, keys0.p, vals0.p, fine_hist.p, B1);
             else
                 collect_kernel<true><<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen, valid_cnt,
-                                                                          d_cursor, 1, keys0.p, vals0.p, fine_hist.p, fine_bits);
+                                                                          d_cursor, 1, keys0.p, vals0.p, fine_hist.p, B1);
             VB_LAUNCH_CHECK(ctx);
         });
-        VB_CUDA(cudaMemcpyAsync(&n_survivors, d_cursor, sizeof(n_survivors), cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaStreamSynchronize(st));                  // the bucket plan and the grids below depend on the count
-        const uint64_t n_keep = n_survivors;
-        MsdPlan pl;
-        {
-            int bits = 0;
-            while ((double)n_keep / (double)(1ULL << bits) > BUCKET_TARGET && bits < fine_bits) ++bits;
-            pl.b1 = (bits + 1) / 2; pl.b2 = bits - pl.b1;
-            pl.B1 = 1u << pl.b1; pl.B2 = 1u << pl.b2; pl.NB = pl.B1 * pl.B2;
-        }
-        DevBuf<uint32_t> hist(pl.NB), off(pl.NB + 1), cursor1(pl.B1), cursor2(pl.NB), tile_start(pl.B1 + 1), big_list(pl.NB + 1);
-        DevBuf<uint32_t> n_big(1);
-        VB_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), st));
-        VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
-        coarsen_kernel<<<(1u << fine_bits) / 256, 256, 0, st>>>(fine_hist.p, fine_bits, pl.b1 + pl.b2, hist.p);
+        // level-1 histogram (tuples per parent, all ranks' parents) -> offsets of the level-1 / send buffer
+        DevBuf<uint32_t> hist1(B1), off1(B1 + 1), cursor1(B1), scan_tmp(1025);
+        coarsen_kernel<<<(B1 + 255) / 256, 256, 0, st>>>(fine_hist.p, 1, 0, 0, B1, hist1.p);
         VB_LAUNCH_CHECK(ctx);
-        scan_kernel<<<1, 1024, 0, st>>>(hist.p, pl, off.p, cursor1.p, cursor2.p, tile_start.p);
-        VB_LAUNCH_CHECK(ctx);
-        t_ext.stop();
-        t_sort.start();
-        DevBuf<uint64_t> keys1(n_keep + 64), keys2(pl.b2 ? n_keep + 64 : 1);
-        DevBuf<uint32_t> vals1(n_keep + 64), vals2(pl.b2 ? n_keep + 64 : 1);
-        const size_t part_smem = PART_TILE * 12 + 4 * (1 << MAX_BUCKET_BITS) * sizeof(uint32_t);
-        static bool attr_done_dev[64] = {false};             // the opt-in is per device (one process may hold several contexts)
-        bool &attr_done = attr_done_dev[ctx->device & 63];
-        if (!attr_done) {
-            VB_CUDA(cudaFuncSetAttribute(part_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
-            VB_CUDA(cudaFuncSetAttribute(part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
-            VB_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
-            attr_done = true;
-        }
+        dev_exscan(ctx, st, hist1.p, B1, off1.p, cursor1.p, scan_tmp.p);
+        // every rank's offsets, gathered (one rank: just its own), and the survivor count: one synchronisation
+        std::vector<uint32_t> h_off1_all((size_t)world * (B1 + 1));
+        DevBuf<uint32_t> off1_all(world > 1 ? (size_t)world * (B1 + 1) : 1);
+        if (world > 1) {
+            comm_check(comm->all_gather(comm->user, off1.p, off1_all.p, sizeof(uint32_t) * (B1 + 1)), "all_gather(level-1 offsets)");
+            VB_CUDA(cudaMemcpyAsync(h_off1_all.data(), off1_all.p, sizeof(uint32_t) * h_off1_all.size(), cudaMemcpyDeviceToHost, st));
+        } else
+            VB_CUDA(cudaMemcpyAsync(h_off1_all.data(), off1.p, sizeof(uint32_t) * (B1 + 1), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        const uint32_t *my_off1 = h_off1_all.data() + (size_t)rank * (B1 + 1);
+        const uint64_t n_keep = my_off1[B1];
+        n_survivors_all += n_keep;
+        t_ext->stop();
+
+        // ---- level 1: tuples -> parents (the send buffer of all-to-all #1)
+        EventTimer *t_part = lap_start(ms_part);
+        DevBuf<uint64_t> keys1(n_keep + 64);
+        DevBuf<uint32_t> vals1(n_keep + 64);
         const uint32_t tiles1 = (uint32_t)((n_keep + PART_TILE - 1) / PART_TILE);
-        uint64_t *fkeys = keys1.p;
-        uint32_t *fvals = vals1.p;
         if (tiles1) {
-            part_kernel<1><<<std::min<uint32_t>(tiles1, 148 * 8), PART_THREADS, part_smem, st>>>(
-                n_keep, pl, keys0.p, vals0.p, off.p, tile_start.p, tiles1, cursor1.p, keys1.p, vals1.p);
+            part_kernel<1><<<std::min<uint32_t>(tiles1, n_sm * 8), PART_THREADS, part_smem, st>>>(
+                n_keep, B1, 0, keys0.p, vals0.p, nullptr, 0, tiles1, cursor1.p, keys1.p, vals1.p);
             VB_LAUNCH_CHECK(ctx);
         }
-        if (pl.b2) {
-            part_kernel<2><<<std::min<uint32_t>(tiles1 + pl.B1, 148 * 8), PART_THREADS, part_smem, st>>>(
-                n_keep, pl, keys1.p, vals1.p, off.p, tile_start.p, 0, cursor2.p, keys2.p, vals2.p);
-            VB_LAUNCH_CHECK(ctx);
-            fkeys = keys2.p; fvals = vals2.p;
+        t_part->stop();
+
+        // ---- all-to-all #1 (several ranks): every parent's tuples travel to the rank that owns the parent
+        const uint64_t *rkeys = keys1.p;
+        const uint32_t *rvals = vals1.p;
+        DevBuf<uint64_t> keysR;
+        DevBuf<uint32_t> valsR, fineR;
+        const uint32_t *fine_src = fine_hist.p + ((size_t)rank * Bper << FINE_BITS);
+        uint32_t fine_n_src = 1;
+        std::vector<Segment> segs;
+        uint64_t n_recv = n_keep;
+        if (world > 1) {
+            EventTimer *t_x = lap_start(ms_exch);
+            std::vector<uint64_t> sc(world), rc(world);
+            n_recv = 0;
+            for (uint32_t d = 0; d < world; ++d) {
+                sc[d] = my_off1[(d + 1) * Bper] - my_off1[d * Bper];
+                const uint32_t *o = h_off1_all.data() + (size_t)d * (B1 + 1);
+                rc[d] = o[(rank + 1) * Bper] - o[rank * Bper];
+                n_recv += rc[d];
+            }
+            if (n_recv >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 k-mer tuples arrive at one rank in one pass: raise VB_PREFILTER_PASSES");
+            keysR.alloc(n_recv + 64); valsR.alloc(n_recv + 64);
+            comm_check(comm->all_to_all(comm->user, keys1.p, sc.data(), keysR.p, rc.data(), 8), "all_to_all(tuple hashes)");
+            comm_check(comm->all_to_all(comm->user, vals1.p, sc.data(), valsR.p, rc.data(), 4), "all_to_all(tuple genomes)");
+            // the fine histograms of my parents, from every rank
+            fineR.alloc((size_t)world * (Bper << FINE_BITS));
+            std::vector<uint64_t> fc(world, (uint64_t)Bper << FINE_BITS);
+            comm_check(comm->all_to_all(comm->user, fine_hist.p, fc.data(), fineR.p, fc.data(), 4), "all_to_all(bucket histograms)");
+            fine_src = fineR.p; fine_n_src = world;
+            rkeys = keysR.p; rvals = valsR.p;
+            uint64_t at = 0;
+            for (uint32_t s = 0; s < world; ++s) {                       // segments: (source rank, parent)
+                const uint32_t *o = h_off1_all.data() + (size_t)s * (B1 + 1);
+                for (uint32_t j = 0; j < Bper; ++j) {
+                    const uint32_t len = o[rank * Bper + j + 1] - o[rank * Bper + j];
+                    if (len) segs.push_back({(uint32_t)at, len, j, 0});
+                    at += len;
+                }
+            }
+            t_x->stop();
+        } else {
+            for (uint32_t j = 0; j < B1; ++j) {
+                const uint32_t len = my_off1[j + 1] - my_off1[j];
+                if (len) segs.push_back({my_off1[j], len, j, 0});
+            }
         }
-        t_sort.stop();
-        t_seg.start();
-        const int bgrid = (int)std::min<uint32_t>(pl.NB, 148 * 12);
-        if (count_first) {
-            bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(fkeys, fvals, off.p, pl.NB, 1, dup_cnt, acc, big_list.p, n_big.p,
-                                                                  scalars.p);
-            VB_LAUNCH_CHECK(ctx);
-            big_bucket_kernel<<<64, 1024, 0, st>>>(fkeys, fvals, off.p, big_list.p, n_big.p, 1, dup_cnt, acc, scalars.p);
-            VB_LAUNCH_CHECK(ctx);
-            read_n_inc();
-            VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
-        }
-        alloc_table();
-        bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(fkeys, fvals, off.p, pl.NB, 0, dup_cnt, acc, big_list.p, n_big.p,
-                                                              scalars.p);
+        n_tuples_grouped += n_recv;
+        uint32_t tiles2 = 0;
+        for (auto &sg : segs) { sg.tile_start = tiles2; tiles2 += (sg.len + PART_TILE - 1) / PART_TILE; }
+
+        // ---- level 2: parents -> final buckets
+        t_part = lap_start(ms_part);
+        int b2 = 0;
+        while ((double)n_recv / (double)((uint64_t)Bper << b2) > BUCKET_TARGET && b2 < MAX_BUCKET_BITS) ++b2;
+        const uint32_t NB = Bper << b2;
+        DevBuf<uint32_t> hist(NB), off(NB + 1), cursor2(NB), big_list(NB + 1), n_big(1);
+        DevBuf<Segment> d_segs(std::max<size_t>(segs.size(), 1));
+        VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
+        if (!segs.empty()) VB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st));
+        coarsen_kernel<<<(NB + 255) / 256, 256, 0, st>>>(fine_src, fine_n_src, (uint64_t)Bper << FINE_BITS, b2, NB, hist.p);
         VB_LAUNCH_CHECK(ctx);
-        big_bucket_kernel<<<64, 1024, 0, st>>>(fkeys, fvals, off.p, big_list.p, n_big.p, 0, dup_cnt, acc, scalars.p);
+        dev_exscan(ctx, st, hist.p, NB, off.p, cursor2.p, scan_tmp.p);
+        DevBuf<uint64_t> keys2(n_recv + 64);
+        DevBuf<uint32_t> vals2(n_recv + 64);
+        if (tiles2) {
+            part_kernel<2><<<std::min<uint32_t>(tiles2, n_sm * 8), PART_THREADS, part_smem, st>>>(
+                n_recv, B1, b2, rkeys, rvals, d_segs.p, (uint32_t)segs.size(), tiles2, cursor2.p, keys2.p, vals2.p);
+            VB_LAUNCH_CHECK(ctx);
+        }
+        t_part->stop();
+
+        // ---- group: shared-memory chains per bucket, oversized buckets, bubbles
+        EventTimer *t_grp = lap_start(ms_group);
+        const uint32_t huge_cap = 1u << 16;
+        DevBuf<HugeRun> huge_list(huge_cap);
+        VB_CUDA(cudaMemsetAsync(scalars.p + 2, 0, sizeof(unsigned long long), st));
+        const int bgrid = (int)std::min<uint32_t>(NB, n_sm * 12);
+        bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(keys2.p, vals2.p, off.p, NB, dup_cnt, A.acc, big_list.p, n_big.p);
         VB_LAUNCH_CHECK(ctx);
+        big_bucket_kernel<<<64, 1024, 0, st>>>(keys2.p, vals2.p, off.p, big_list.p, n_big.p, dup_cnt, A.acc, huge_list.p, huge_cap, scalars.p + 2);
+        VB_LAUNCH_CHECK(ctx);
+        unsigned long long h_status[3] = {0, 0, 0};
+        VB_CUDA(cudaMemcpyAsync(h_status, scalars.p, sizeof(h_status), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        if (h_status[2] > huge_cap) throw vb_error(VB_ERR_INTERNAL, "more than 65536 bubble k-mers in one pass");
+        if (h_status[2] > 0) {
+            // bubbles: compact the member sets, collapse identical ones, expand each set once with its multiplicity
+            const uint32_t nh = (uint32_t)h_status[2];
+            n_bubbles += nh;
+            DevBuf<uint32_t> members(n_recv + 64);
+            DevBuf<HugeInfo> d_info(nh);
+            bubble_prepare_kernel<<<std::min<uint32_t>(nh, n_sm * 2), 1024, 0, st>>>(vals2.p, huge_list.p, nh, members.p, d_info.p, dup_cnt);
+            VB_LAUNCH_CHECK(ctx);
+            std::vector<HugeInfo> info(nh);
+            VB_CUDA(cudaMemcpyAsync(info.data(), d_info.p, sizeof(HugeInfo) * nh, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+            std::vector<uint32_t> order(nh), rep(nh);
+            for (uint32_t i = 0; i < nh; ++i) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                if (info[a].m != info[b].m) return info[a].m < info[b].m;
+                if (info[a].sig1 != info[b].sig1) return info[a].sig1 < info[b].sig1;
+                if (info[a].sig2 != info[b].sig2) return info[a].sig2 < info[b].sig2;
+                return a < b;
+            });
+            for (uint32_t i = 0; i < nh; ++i) {
+                const uint32_t a = order[i];
+                rep[a] = a;
+                if (i > 0) {
+                    const uint32_t b = order[i - 1];
+                    if (info[a].m == info[b].m && info[a].sig1 == info[b].sig1 && info[a].sig2 == info[b].sig2) rep[a] = rep[b];
+                }
+            }
+            const bool no_collapse = getenv("VB_PREFILTER_NO_COLLAPSE") != nullptr;              // test hook
+            if (no_collapse) for (uint32_t i = 0; i < nh; ++i) rep[i] = i;
+            DevBuf<uint32_t> d_rep(nh), d_differ(nh);
+            std::vector<uint32_t> differ(nh, 0);
+            VB_CUDA(cudaMemcpyAsync(d_rep.p, rep.data(), sizeof(uint32_t) * nh, cudaMemcpyHostToDevice, st));
+            VB_CUDA(cudaMemsetAsync(d_differ.p, 0, sizeof(uint32_t) * nh, st));
+            bubble_equal_kernel<<<dim3(8, std::min<uint32_t>(nh, 32768)), 256, 0, st>>>(members.p, d_info.p, d_rep.p, nh, d_differ.p);
+            VB_LAUNCH_CHECK(ctx);
+            VB_CUDA(cudaMemcpyAsync(differ.data(), d_differ.p, sizeof(uint32_t) * nh, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+            std::vector<uint32_t> weight(nh, 0);
+            for (uint32_t i = 0; i < nh; ++i) { if (differ[i]) rep[i] = i; weight[rep[i]]++; }   // (a signature collision: expand on its own)
+            std::vector<BubbleJob> jobs;
+            uint64_t tiles = 0, new_pairs = 0;
+            for (uint32_t i = 0; i < nh; ++i) {
+                if (!weight[i] || info[i].m < 2) continue;
+                const uint64_t T = (info[i].m + 127) / 128;
+                if (tiles + T * (T + 1) / 2 >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "bubble k-mers too large for one pass");
+                jobs.push_back({info[i].beg, info[i].m, weight[i], (uint32_t)tiles});
+                tiles += T * (T + 1) / 2;
+                new_pairs += (uint64_t)info[i].m * (info[i].m - 1) / 2;
+            }
+            if (!A.is_dense()) {                              // make room: every pair of a bubble may be new
+                uint64_t need = 1024;
+                while (need < 2 * (h_status[1] + new_pairs)) need <<= 1;
+                if (need > A.cap) acc_grow(ctx, st, A, need);
+            }
+            if (!jobs.empty()) {
+                DevBuf<BubbleJob> d_jobs(jobs.size());
+                VB_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(BubbleJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+                bubble_pairs_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)n_sm * 16), 256, 0, st>>>(members.p, d_jobs.p, (uint32_t)jobs.size(),
+                                                                                                              (uint32_t)tiles, A.acc);
+                VB_LAUNCH_CHECK(ctx);
+                VB_CUDA(cudaStreamSynchronize(st));           // d_jobs / members are released below
+            }
+        }
+        // the table is grown between passes while it is more than a quarter full (never inside a pass)
+        if (!A.is_dense() && pass + 1 < passes && h_status[1] > A.cap / 4) acc_grow(ctx, st, A, A.cap * 4);
+        VB_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 3 * sizeof(unsigned long long), st));     // screen / collect counters of the next pass
+        t_grp->stop();
     }
+
+    // ---- totals (all ranks: all-reduce) and the overflow flag of all ranks
     totals_kernel<<<(n + 255) / 256 + 1, 256, 0, st>>>(valid_cnt, dup_cnt, n, totals);
     VB_LAUNCH_CHECK(ctx);
-    t_seg.stop();
+    unsigned long long h_over[2] = {0, 0};
+    if (world > 1) {
+        VB_CUDA(cudaMemcpyAsync(totals + n, scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));     // low word of the flag
+        comm_check(comm->all_reduce_sum_u32(comm->user, totals, (uint64_t)n + 1), "all_reduce(total k-mers)");
+        uint32_t any = 0;
+        VB_CUDA(cudaMemcpyAsync(&any, totals + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        h_over[0] = any;
+    } else {
+        VB_CUDA(cudaMemcpyAsync(h_over, scalars.p, sizeof(h_over), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (!h_over[0]) break;
+    if (attempt >= 6) throw vb_error(VB_ERR_MEM, "pair table overflow");
+    cap_hint = A.cap * 8;
+    }   // attempts
 
-    // ---- k4
+    // ---- finish
+    EventTimer t_emit(st);
     t_emit.start();
     EmitParams em;
     em.min_kmers = partial ? 1u : (uint32_t)std::max(p->min_kmers, 0);
-    em.min_ident_slack = partial ? -1e300 : p->min_ident - 1e-7;
+    em.min_ident = partial ? -1.0 : std::max(p->min_ident, 0.0);
     em.k = p->k;
     em.gbits = 1;
     while ((1ULL << em.gbits) < n) em.gbits++;
-    unsigned long long n_emit = 0;
-    int h_overflow = 0;
-    std::vector<uint64_t> h_keys;
-    std::vector<uint32_t> h_vals;
-    if (acc.dense) {
+    em.world = world; em.rank = rank;
+    FinalList fin;                       // pairs that involve this rank's genomes (one rank: all pairs)
+    const bool keep_dev = job.keep_dev && !partial && p->max_seqs <= 0;
+    if (A.is_dense() && world == 1) {
         // dense layout: ordered compaction, the output is born sorted by (row, col)
         const uint32_t n_blocks = (uint32_t)std::min<uint64_t>(4096, (max_pairs + 255) / 256 + 1);
         const uint64_t per_block = ((max_pairs + n_blocks - 1) / n_blocks + 255) / 256 * 256;
         DevBuf<uint32_t> block_cnt(4096);
-        dense_emit_kernel<<<n_blocks, 256, 0, st>>>(dense.p, max_pairs, per_block, totals, em, 0, block_cnt.p, nullptr, nullptr);
+        dense_emit_kernel<<<n_blocks, 256, 0, st>>>(A.dense.p, max_pairs, per_block, totals, em, 0, block_cnt.p, nullptr, nullptr, nullptr, scalars.p + 8);
         VB_LAUNCH_CHECK(ctx);
-        scan_blocks_kernel<<<1, 1024, 0, st>>>(block_cnt.p, n_blocks, scalars.p + 1);
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(block_cnt.p, n_blocks, scalars.p + 7);
         VB_LAUNCH_CHECK(ctx);
-        VB_CUDA(cudaMemcpyAsync(&n_emit, scalars.p + 1, sizeof(n_emit), cudaMemcpyDeviceToHost, st));
+        unsigned long long n_emit = 0;
+        VB_CUDA(cudaMemcpyAsync(&n_emit, scalars.p + 7, sizeof(n_emit), cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaStreamSynchronize(st));
-        h_keys.resize(n_emit); h_vals.resize(n_emit);
+        fin.n = n_emit;
         if (n_emit) {
-            DevBuf<uint64_t> ek(n_emit);
-            DevBuf<uint32_t> ev(n_emit);
-            dense_emit_kernel<<<n_blocks, 256, 0, st>>>(dense.p, max_pairs, per_block, totals, em, 1, block_cnt.p, ek.p, ev.p);
+            { const bool saved = vb_tls_pool_alloc; vb_tls_pool_alloc = keep_dev;
+              try { fin.keys.alloc(n_emit); fin.vals.alloc(n_emit); fin.ani.alloc(n_emit); } catch (...) { vb_tls_pool_alloc = saved; throw; }
+              vb_tls_pool_alloc = saved; }
+            dense_emit_kernel<<<n_blocks, 256, 0, st>>>(A.dense.p, max_pairs, per_block, totals, em, 1, block_cnt.p, fin.keys.p, fin.vals.p, fin.ani.p, scalars.p + 8);
             VB_LAUNCH_CHECK(ctx);
-            VB_CUDA(cudaMemcpyAsync(h_keys.data(), ek.p, sizeof(uint64_t) * n_emit, cudaMemcpyDeviceToHost, st));
-            VB_CUDA(cudaMemcpyAsync(h_vals.data(), ev.p, sizeof(uint32_t) * n_emit, cudaMemcpyDeviceToHost, st));
-            VB_CUDA(cudaStreamSynchronize(st));
         }
     } else {
-        emit_kernel<<<grid_for(cap), 256, 0, st>>>(tkeys.p, tvals.p, cap, totals, em, 0, scalars.p + 1, nullptr, nullptr);
+        // accumulator -> per-destination lists of compact entries (count, then write)
+        DevBuf<unsigned long long> dest_cur(world);
+        VB_CUDA(cudaMemsetAsync(dest_cur.p, 0, sizeof(unsigned long long) * world, st));
+        const uint64_t n_entries = A.cap;
+        acc_emit_kernel<<<grid_for(n_entries), 256, 0, st>>>(A.acc, n_entries, totals, em, 0, dest_cur.p, nullptr, nullptr);
         VB_LAUNCH_CHECK(ctx);
-        VB_CUDA(cudaMemcpyAsync(&n_emit, scalars.p + 1, sizeof(n_emit), cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaMemcpyAsync(&h_overflow, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaStreamSynchronize(st));
-        if (h_overflow) throw vb_error(VB_ERR_INTERNAL, "pair table overflow");
-        const uint64_t e_pad = ((n_emit + rsort::TILE - 1) / rsort::TILE) * rsort::TILE;
-        h_keys.resize(n_emit); h_vals.resize(n_emit);
-        if (n_emit) {
-            DevBuf<uint64_t> ek_a(e_pad), ek_b(e_pad);
-            DevBuf<uint32_t> ev_a(e_pad), ev_b(e_pad);
-            fill_u64_kernel<<<grid_for(e_pad), 256, 0, st>>>(ek_a.p, e_pad, KEY_SENTINEL);
-            VB_LAUNCH_CHECK(ctx);
-            emit_kernel<<<grid_for(cap), 256, 0, st>>>(tkeys.p, tvals.p, cap, totals, em, 1, scalars.p + 2, ek_a.p, ev_a.p);
-            VB_LAUNCH_CHECK(ctx);
-            bool eb = rsort::sort_kv<8>(ctx, ek_a.p, ev_a.p, ek_b.p, ev_b.p, e_pad, 2 * em.gbits + 1, ws);
-            VB_CUDA(cudaMemcpyAsync(h_keys.data(), eb ? ek_b.p : ek_a.p, sizeof(uint64_t) * n_emit, cudaMemcpyDeviceToHost, st));
-            VB_CUDA(cudaMemcpyAsync(h_vals.data(), eb ? ev_b.p : ev_a.p, sizeof(uint32_t) * n_emit, cudaMemcpyDeviceToHost, st));
+        std::vector<unsigned long long> sc(world), all_counts((size_t)world * world, 0);
+        if (world > 1) {
+            DevBuf<unsigned long long> d_all((size_t)world * world);
+            comm_check(comm->all_gather(comm->user, dest_cur.p, d_all.p, sizeof(unsigned long long) * world), "all_gather(pair counts)");
+            VB_CUDA(cudaMemcpyAsync(all_counts.data(), d_all.p, sizeof(unsigned long long) * all_counts.size(), cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+        } else {
+            VB_CUDA(cudaMemcpyAsync(all_counts.data(), dest_cur.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             VB_CUDA(cudaStreamSynchronize(st));
         }
+        uint64_t n_send = 0, n_recv = 0;
+        std::vector<unsigned long long> starts(world);
+        std::vector<uint64_t> scv(world), rcv(world);
+        for (uint32_t d = 0; d < world; ++d) {
+            scv[d] = all_counts[(size_t)rank * world + d]; starts[d] = n_send; n_send += scv[d];
+            rcv[d] = all_counts[(size_t)d * world + rank]; n_recv += rcv[d];
+        }
+        if (n_recv >= (1ULL << 32) - rsort::TILE || n_send >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 partial pair counts at one rank");
+        const uint64_t n_pad = (n_recv + rsort::TILE - 1) / rsort::TILE * rsort::TILE;
+        SortBufs sb;
+        DevBuf<uint64_t> sendk(world > 1 ? n_send + 1 : 1);
+        DevBuf<uint32_t> sendv(world > 1 ? n_send + 1 : 1);
+        sb.ka.alloc(n_pad + 1); sb.kb.alloc(n_pad + 1); sb.va.alloc(n_pad + 1); sb.vb.alloc(n_pad + 1);
+        VB_CUDA(cudaMemcpyAsync(dest_cur.p, starts.data(), sizeof(unsigned long long) * world, cudaMemcpyHostToDevice, st));
+        acc_emit_kernel<<<grid_for(n_entries), 256, 0, st>>>(A.acc, n_entries, totals, em, 1, dest_cur.p, world > 1 ? sendk.p : sb.ka.p,
+                                                             world > 1 ? sendv.p : sb.va.p);
+        VB_LAUNCH_CHECK(ctx);
+        if (world > 1) {
+            EventTimer *t_x = lap_start(ms_exch);
+            comm_check(comm->all_to_all(comm->user, sendk.p, scv.data(), sb.ka.p, rcv.data(), 8), "all_to_all(pair keys)");
+            comm_check(comm->all_to_all(comm->user, sendv.p, scv.data(), sb.va.p, rcv.data(), 4), "all_to_all(pair counts)");
+            t_x->stop();
+        }
+        const uint64_t *skeys = nullptr;
+        const uint32_t *svals = nullptr;
+        if (n_pad) sort_entries(ctx, st, sb, n_recv, n_pad, 2 * em.gbits, ws, skeys, svals);
+        finalize_sorted(ctx, st, skeys, svals, n_pad, totals, em, false, scalars.p + 7, scalars.p + 8, fin, keep_dev);
     }
+    A.dense.release(); A.tkeys.release(); A.tvals.release();
+
+    // ---- what goes to the host: one rank: everything; several ranks: the pairs whose row this rank owns, gathered on rank 0
+    std::vector<uint64_t> h_keys;
+    std::vector<uint32_t> h_vals;
     std::vector<uint32_t> h_tot(n);
     if (n) VB_CUDA(cudaMemcpyAsync(h_tot.data(), totals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (world == 1) {
+        h_keys.resize(fin.n); h_vals.resize(fin.n);
+        if (fin.n) {
+            VB_CUDA(cudaMemcpyAsync(h_keys.data(), fin.keys.p, sizeof(uint64_t) * fin.n, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(h_vals.data(), fin.vals.p, sizeof(uint32_t) * fin.n, cudaMemcpyDeviceToHost, st));
+        }
+    } else {
+        // row-owned subset (still sorted) -> rank 0, which merges the ranks' runs with one more sort
+        FinalList mine;
+        {
+            const uint64_t n_in = fin.n, n_pad = (n_in + rsort::TILE - 1) / rsort::TILE * rsort::TILE;
+            SortBufs sb;
+            sb.ka.alloc(n_pad + 1); sb.va.alloc(n_pad + 1);
+            if (n_in) {
+                compact_keys_kernel<<<grid_for(n_in), 256, 0, st>>>(fin.keys.p, n_in, em.gbits, sb.ka.p);
+                VB_LAUNCH_CHECK(ctx);
+                VB_CUDA(cudaMemcpyAsync(sb.va.p, fin.vals.p, sizeof(uint32_t) * n_in, cudaMemcpyDeviceToDevice, st));
+            }
+            EmitParams raw = em;
+            raw.min_kmers = 0; raw.min_ident = -1.0;             // already thresholded: only select the rows this rank owns
+            finalize_sorted(ctx, st, sb.ka.p, sb.va.p, n_in, totals, raw, true, scalars.p + 7, scalars.p + 9, mine, false);
+        }
+        DevBuf<unsigned long long> d_cnt(1), d_all(world);
+        const unsigned long long my_n = mine.n;
+        VB_CUDA(cudaMemcpyAsync(d_cnt.p, &my_n, sizeof(my_n), cudaMemcpyHostToDevice, st));
+        comm_check(comm->all_gather(comm->user, d_cnt.p, d_all.p, sizeof(unsigned long long)), "all_gather(result sizes)");
+        std::vector<unsigned long long> cnts(world);
+        VB_CUDA(cudaMemcpyAsync(cnts.data(), d_all.p, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        uint64_t total = 0;
+        std::vector<uint64_t> scv(world, 0), rcv(world, 0);
+        scv[0] = mine.n;
+        if (rank == 0) for (uint32_t s = 0; s < world; ++s) { rcv[s] = cnts[s]; total += cnts[s]; }
+        if (total >= (1ULL << 32) - rsort::TILE) throw vb_error(VB_ERR_ARG, "more than 2^32 candidate pairs");
+        const uint64_t n_pad = (total + rsort::TILE - 1) / rsort::TILE * rsort::TILE;
+        SortBufs sb;
+        sb.ka.alloc(n_pad + 1); sb.kb.alloc(n_pad + 1); sb.va.alloc(n_pad + 1); sb.vb.alloc(n_pad + 1);
+        DevBuf<uint64_t> ck(mine.n + 1);
+        if (mine.n) { compact_keys_kernel<<<grid_for(mine.n), 256, 0, st>>>(mine.keys.p, mine.n, em.gbits, ck.p); VB_LAUNCH_CHECK(ctx); }
+        DevBuf<uint32_t> dummy(1);
+        comm_check(comm->all_to_all(comm->user, ck.p, scv.data(), sb.ka.p, rcv.data(), 8), "all_to_all(result keys)");
+        comm_check(comm->all_to_all(comm->user, mine.n ? mine.vals.p : dummy.p, scv.data(), sb.va.p, rcv.data(), 4), "all_to_all(result counts)");
+        if (rank == 0 && total) {
+            const uint64_t *skeys = nullptr;
+            const uint32_t *svals = nullptr;
+            sort_entries(ctx, st, sb, total, n_pad, 2 * em.gbits, ws, skeys, svals);
+            h_keys.resize(total); h_vals.resize(total);
+            VB_CUDA(cudaMemcpyAsync(h_keys.data(), skeys, sizeof(uint64_t) * total, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(h_vals.data(), svals, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+            const uint64_t cmask = (1ULL << em.gbits) - 1;      // compact -> (row << 32 | col)
+            for (auto &k : h_keys) k = ((k >> em.gbits) << 32) | (k & cmask);
+        }
+    }
+    unsigned long long n_border_dev = 0;
+    VB_CUDA(cudaMemcpyAsync(&n_border_dev, scalars.p + 8, sizeof(n_border_dev), cudaMemcpyDeviceToHost, st));
     t_emit.stop();
     t_all.stop();
     VB_CUDA(cudaStreamSynchronize(st));
+    if (world > 1 && n_border_dev && fin.n) {
+        // a pair within 1e-9 of the ani threshold (practically never): decide it exactly on the host and rebuild this rank's list
+        std::vector<uint64_t> fk(fin.n);
+        std::vector<uint32_t> fv(fin.n);
+        std::vector<float> fa(fin.n);
+        VB_CUDA(cudaMemcpyAsync(fk.data(), fin.keys.p, sizeof(uint64_t) * fin.n, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaMemcpyAsync(fv.data(), fin.vals.p, sizeof(uint32_t) * fin.n, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaMemcpyAsync(fa.data(), fin.ani.p, sizeof(float) * fin.n, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        uint64_t w = 0;
+        for (uint64_t i = 0; i < fin.n; ++i) {
+            if (fv[i] & BORDERLINE) {
+                const uint32_t r = (uint32_t)(fk[i] >> 32), c = (uint32_t)fk[i];
+                if (!(vb_ani_shorter(fv[i] & ~BORDERLINE, h_tot[r], h_tot[c], p->k) >= p->min_ident)) continue;
+            }
+            fk[w] = fk[i]; fa[w] = fa[i]; ++w;
+        }
+        VB_CUDA(cudaMemcpyAsync(fin.keys.p, fk.data(), sizeof(uint64_t) * w, cudaMemcpyHostToDevice, st));
+        VB_CUDA(cudaMemcpyAsync(fin.ani.p, fa.data(), sizeof(float) * w, cudaMemcpyHostToDevice, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        fin.n = w;
+    }
 
-    // ---- host: exact IEEE-double metric (params.cpp:28-32) and the two -min filters (sparse_filters.h:49-61)
+    // ---- host: the exact IEEE-double metric (params.cpp:28-32) for the output, the borderline cases re-decided exactly
     const auto hp0 = std::chrono::steady_clock::now();
-    std::vector<uint32_t> o_row, o_col, o_common;
-    std::vector<double> o_ani;
-    o_row.reserve(n_emit); o_col.reserve(n_emit); o_common.reserve(n_emit); o_ani.reserve(n_emit);
-    const uint64_t cmask = (1ULL << em.gbits) - 1;
-    for (uint64_t i = 0; i < n_emit; ++i) {
-        const uint32_t r = (uint32_t)(h_keys[i] >> em.gbits), c = (uint32_t)(h_keys[i] & cmask);
-        const double a = partial ? 0.0 : vb_ani_shorter(h_vals[i], h_tot[r], h_tot[c], p->k);
-        if (partial || a >= p->min_ident) { o_row.push_back(r); o_col.push_back(c); o_common.push_back(h_vals[i]); o_ani.push_back(a); }
+    const uint64_t n_emit = h_keys.size();
+    vb_pairs *res = vb_pairs_alloc(n_emit, n);
+    std::vector<uint8_t> drop;
+    bool any_border = false;
+    for (uint64_t i = 0; i < n_emit && !any_border; ++i) any_border = (h_vals[i] & BORDERLINE) != 0;
+    vb_parallel_for(n_emit, 16384, 16, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            const uint32_t r = (uint32_t)(h_keys[i] >> 32), c = (uint32_t)h_keys[i], v = h_vals[i] & ~BORDERLINE;
+            res->row[i] = r; res->col[i] = c; res->common[i] = v;
+            res->ani[i] = partial ? 0.0 : vb_ani_shorter(v, h_tot[r], h_tot[c], p->k);
+        }
+    });
+    bool list_changed = false;
+    if (any_border && !partial) {
+        uint64_t w = 0;
+        for (uint64_t i = 0; i < n_emit; ++i) {
+            if ((h_vals[i] & BORDERLINE) && !(res->ani[i] >= p->min_ident)) { list_changed = true; continue; }
+            res->row[w] = res->row[i]; res->col[w] = res->col[i]; res->common[w] = res->common[i]; res->ani[w] = res->ani[i]; ++w;
+        }
+        res->n_pairs = w;
     }
     // --max-seqs: the per-row sampler needs complete counts, so a k-mer shard leaves it to vb_pairs_merge
-    if (!partial && p->max_seqs > 0) vb_sample_rows(n, (uint32_t)p->max_seqs, o_row, o_col, o_common, o_ani);
-    vb_pairs *res = vb_pairs_alloc(o_row.size(), n);
-    for (uint64_t o = 0; o < o_row.size(); ++o) {
-        res->row[o] = o_row[o]; res->col[o] = o_col[o]; res->common[o] = o_common[o]; res->ani[o] = o_ani[o];
+    if (!partial && p->max_seqs > 0) {
+        std::vector<uint32_t> o_row(res->row, res->row + res->n_pairs), o_col(res->col, res->col + res->n_pairs),
+            o_common(res->common, res->common + res->n_pairs);
+        std::vector<double> o_ani(res->ani, res->ani + res->n_pairs);
+        vb_sample_rows(n, (uint32_t)p->max_seqs, o_row, o_col, o_common, o_ani);
+        vb_pairs *r2 = vb_pairs_alloc(o_row.size(), n);
+        for (uint64_t o = 0; o < o_row.size(); ++o) { r2->row[o] = o_row[o]; r2->col[o] = o_col[o]; r2->common[o] = o_common[o]; r2->ani[o] = o_ani[o]; }
+        vb_pairs_free(res);
+        res = r2;
     }
     for (uint32_t i = 0; i < n; ++i) res->total_kmers[i] = h_tot[i];
     res->k = p->k;
     res->kmers_fraction = p->kmers_fraction;
     *out_pairs = res;
+    // the device copy for the align stage (several ranks: this rank's share, whatever rank 0 reports)
+    if (keep_dev && !(list_changed && world == 1)) {
+        auto *dp = new DevPairs();
+        dp->uid = vb_pairs_uid(res);
+        dp->n = fin.n;
+        dp->keys = std::move(fin.keys);
+        dp->ani = std::move(fin.ani);
+        ctx->dev_pairs = dp;
+    }
     ctx->set_timing("prefilter.host_post_ms",
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hp0).count());
 
+    for (auto &l : laps) *l.second += l.first->ms();
     ctx->set_timing("prefilter.total_ms", t_all.ms());
     ctx->set_timing("prefilter.upload_pack_ms", t_up.ms());
-    ctx->set_timing("prefilter.extract_ms", t_ext.ms());
-    ctx->set_timing("prefilter.sort_ms", t_sort.ms());
-    ctx->set_timing("prefilter.segment_ms", t_seg.ms());
+    ctx->set_timing("prefilter.extract_ms", ms_ext);
+    ctx->set_timing("prefilter.sort_ms", ms_part);
+    ctx->set_timing("prefilter.segment_ms", ms_group);
+    ctx->set_timing("prefilter.exchange_ms", ms_exch);
     ctx->set_timing("prefilter.emit_ms", t_emit.ms());
+    ctx->set_timing("prefilter.passes", (double)passes);
     ctx->set_timing("prefilter.tuples", (double)dg.total_slots);
-    ctx->set_timing("prefilter.survivors", (double)n_survivors);
-    ctx->set_timing("prefilter.pair_increments", (double)n_inc);
-    ctx->set_timing("prefilter.table_slots", (double)cap);
-    ctx->set_timing("prefilter.candidates", (double)n_emit);
+    ctx->set_timing("prefilter.survivors", (double)n_survivors_all);
+    ctx->set_timing("prefilter.grouped", (double)n_tuples_grouped);
+    ctx->set_timing("prefilter.bubbles", (double)n_bubbles);
+    ctx->set_timing("prefilter.table_slots", (double)A.cap);
+    ctx->set_timing("prefilter.candidates", (double)res->n_pairs);
 }

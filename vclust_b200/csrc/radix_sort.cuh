@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(BLOCK) hist_kernel(const uint64_t *__restrict_
 }
 
 // exclusive scan of each digit row over tiles (one block per digit), row totals to digit_total
-__global__ void __launch_bounds__(BLOCK) scan_rows_kernel(uint32_t *__restrict__ tile_hist, uint32_t n_tiles,
+static __global__ void __launch_bounds__(BLOCK) scan_rows_kernel(uint32_t *__restrict__ tile_hist, uint32_t n_tiles,
                                                           uint32_t *__restrict__ digit_total)
 {
     __shared__ uint32_t warp_sum[WARPS];

@@ -16,7 +16,7 @@ void vb_pairs_free_impl(vb_pairs *p);
 void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char *ani_path, const char *ids_path,
                        const char *const *columns, int n_columns, const double out_filters[5]);
 
-void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad);
+void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, uint64_t force_slots = 0);
 void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g);
 void vb_unpin_genomes(const vb_genomes *g);
 
@@ -49,22 +49,33 @@ static void vb_enter(vb_ctx *ctx)
     ctx->arena->reset((cudaStream_t)ctx->stream);
 }
 
-// LZ-ANI order: length descending, then name ascending (stable) -- seq_reservoir.cpp:229-236
-static std::vector<uint32_t> vb_lz_order(const vb_genomes *g)
+void vb_enter_call(vb_ctx *ctx) { vb_enter(ctx); }
+
+// LZ-ANI order: length descending, then name ascending (stable) -- seq_reservoir.cpp:229-236.  Computed once per set.
+const std::vector<uint32_t> &vb_lz_order(const vb_genomes *g)
 {
-    std::vector<uint32_t> order(g->count());
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        uint32_t la = (uint32_t)g->length(a) - 2u, lb = (uint32_t)g->length(b) - 2u;   // len - 2*no_parts, unsigned (sic)
-        if (la != lb) return la > lb;
-        return g->names[a] < g->names[b];
-    });
-    return order;
+    if (g->lz_order.size() != g->count() || g->lz_rank.size() != g->count()) {
+        std::vector<uint32_t> order(g->count());
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            uint32_t la = (uint32_t)g->length(a) - 2u, lb = (uint32_t)g->length(b) - 2u;   // len - 2*no_parts, unsigned (sic)
+            if (la != lb) return la > lb;
+            return g->names[a] < g->names[b];
+        });
+        std::vector<uint32_t> rank(g->count());
+        for (uint32_t i = 0; i < g->count(); ++i) rank[order[i]] = i;
+        g->lz_order.swap(order);
+        g->lz_rank.swap(rank);
+    }
+    return g->lz_order;
 }
+const std::vector<uint32_t> &vb_lz_rank(const vb_genomes *g) { vb_lz_order(g); return g->lz_rank; }
 
 static vb_align_out *vb_align_out_alloc(uint64_t total, uint32_t n)
 {
+    if (total >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 directed pairs in one call");
     auto *res = (vb_align_out *)calloc(1, sizeof(vb_align_out));
+    if (!res) throw vb_error(VB_ERR_MEM, "out of host memory");
     res->n = total;
     res->n_genomes = n;
     res->ref = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint64_t>(total, 1));
@@ -73,8 +84,14 @@ static vb_align_out *vb_align_out_alloc(uint64_t total, uint32_t n)
     res->sym_in_literals = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
     res->no_components = (int32_t *)calloc(std::max<uint64_t>(total, 1), sizeof(int32_t));
     res->order = (uint32_t *)malloc(sizeof(uint32_t) * std::max<uint32_t>(n, 1));
+    if (!res->ref || !res->qry || !res->sym_in_matches || !res->sym_in_literals || !res->no_components || !res->order) {
+        vb_align_out_free(res);
+        throw vb_error(VB_ERR_MEM, "out of host memory for " + std::to_string(total) + " directed pairs");
+    }
     return res;
 }
+
+vb_align_out *vb_align_out_alloc_impl(uint64_t total, uint32_t n) { return vb_align_out_alloc(total, n); }
 
 extern "C" {
 
@@ -95,7 +112,9 @@ int vb_device_count(void)
 
 const char *vb_last_error(void) { return g_last_error.c_str(); }
 
-int vb_ctx_create(int device, vb_ctx **out)
+int vb_ctx_create(int device, vb_ctx **out) { return vb_ctx_create_on_stream(device, nullptr, out); }
+
+int vb_ctx_create_on_stream(int device, void *cuda_stream, vb_ctx **out)
 {
     VB_GUARD_BEGIN
     if (!out) throw vb_error(VB_ERR_ARG, "vb_ctx_create: null out pointer");
@@ -105,9 +124,12 @@ int vb_ctx_create(int device, vb_ctx **out)
     VB_CUDA(cudaSetDevice(device));
     auto *ctx = new vb_ctx();
     ctx->device = device;
-    cudaStream_t st;
-    VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    ctx->stream = (void *)st;
+    if (cuda_stream) { ctx->stream = cuda_stream; ctx->owns_stream = false; }
+    else {
+        cudaStream_t st;
+        VB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->stream = (void *)st;
+    }
     cudaStream_t cs;
     VB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     ctx->copy_stream = (void *)cs;
@@ -134,13 +156,14 @@ void vb_ctx_destroy(vb_ctx *ctx)
     cudaSetDevice(ctx->device);
     vb_tls_stream = (cudaStream_t)ctx->stream;
     vb_tls_arena = nullptr;
+    vb_drop_dev_pairs(ctx);
     vb_evict_impl(ctx, nullptr);
     cudaStreamSynchronize((cudaStream_t)ctx->stream);
     if (ctx->arena) { ctx->arena->destroy(); delete ctx->arena; }
     for (auto &e : ctx->events) if (e) cudaEventDestroy((cudaEvent_t)e);
     for (auto &e : ctx->copy_events) if (e) cudaEventDestroy((cudaEvent_t)e);
     if (ctx->copy_stream) { cudaStreamSynchronize((cudaStream_t)ctx->copy_stream); cudaStreamDestroy((cudaStream_t)ctx->copy_stream); }
-    if (ctx->stream) cudaStreamDestroy((cudaStream_t)ctx->stream);
+    if (ctx->stream && ctx->owns_stream) cudaStreamDestroy((cudaStream_t)ctx->stream);
     delete ctx;
 }
 
@@ -213,81 +236,37 @@ int vb_genomes_from_memory(const char *const *names, const char *const *seqs, co
     VB_GUARD_END
 }
 
+int vb_genomes_skeleton(const char *const *names, const uint64_t *lens, uint32_t n, vb_genomes **out)
+{
+    VB_GUARD_BEGIN
+    if (!out || (n && (!names || !lens))) throw vb_error(VB_ERR_ARG, "vb_genomes_skeleton: bad arguments");
+    auto *g = new vb_genomes();
+    g->skeleton = true;
+    g->names.reserve(n);
+    g->offset.assign(1, 0);
+    for (uint32_t i = 0; i < n; ++i) { g->names.emplace_back(names[i]); g->offset.push_back(g->offset.back() + lens[i]); }
+    *out = g;
+    VB_GUARD_END
+}
+
 uint32_t vb_genomes_count(const vb_genomes *g) { return g ? g->count() : 0; }
 const char *vb_genomes_name(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->names[i].c_str() : ""; }
 uint64_t vb_genomes_length(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->length(i) : 0; }
-uint64_t vb_genomes_total_bases(const vb_genomes *g) { return g ? g->bases.size() : 0; }
-const char *vb_genomes_sequence(const vb_genomes *g, uint32_t i) { return (g && i < g->count()) ? g->bases.data() + g->offset[i] : nullptr; }
+uint64_t vb_genomes_total_bases(const vb_genomes *g) { return g ? g->offset.back() : 0; }
+const char *vb_genomes_sequence(const vb_genomes *g, uint32_t i) { return (g && !g->skeleton && i < g->count()) ? g->bases.data() + g->offset[i] : nullptr; }
 void vb_genomes_free(vb_genomes *g) { if (g) { vb_unpin_genomes(g); delete g; } }
-
-// Sum partial (row, col, common) lists that are each sorted by (row, col), apply the thresholds exactly
-// (sparse_filters.h:49-61) and --max-seqs.  lists[s] = {row, col, common, n}.
-struct PartialList { const uint32_t *row, *col, *common; uint64_t n; };
-static vb_pairs *merge_sorted_partials(const std::vector<PartialList> &lists, const uint32_t *total_kmers, uint32_t n_genomes,
-                                       const vb_prefilter_params *p)
-{
-    std::vector<uint64_t> at(lists.size(), 0);
-    std::vector<uint32_t> r, c, v;
-    std::vector<double> a;
-    auto key = [&](size_t s) { return ((uint64_t)lists[s].row[at[s]] << 32) | lists[s].col[at[s]]; };
-    for (;;) {
-        uint64_t best = ~0ULL;
-        for (size_t s = 0; s < lists.size(); ++s) if (at[s] < lists[s].n) best = std::min(best, key(s));
-        if (best == ~0ULL) break;
-        uint64_t sum = 0;
-        for (size_t s = 0; s < lists.size(); ++s)
-            while (at[s] < lists[s].n && key(s) == best) sum += lists[s].common[at[s]++];
-        const uint32_t rr = (uint32_t)(best >> 32), cc = (uint32_t)best;
-        if (rr >= n_genomes || cc >= n_genomes) throw vb_error(VB_ERR_ARG, "pair id out of range");
-        if (sum > 0 && sum >= (uint64_t)std::max(p->min_kmers, 0)) {
-            const double ani = vb_ani_shorter((uint32_t)sum, total_kmers[rr], total_kmers[cc], p->k);
-            if (ani >= p->min_ident) { r.push_back(rr); c.push_back(cc); v.push_back((uint32_t)sum); a.push_back(ani); }
-        }
-    }
-    if (p->max_seqs > 0) vb_sample_rows(n_genomes, (uint32_t)p->max_seqs, r, c, v, a);
-    vb_pairs *res = vb_pairs_alloc(r.size(), n_genomes);
-    for (size_t i = 0; i < r.size(); ++i) { res->row[i] = r[i]; res->col[i] = c[i]; res->common[i] = v[i]; res->ani[i] = a[i]; }
-    for (uint32_t i = 0; i < n_genomes; ++i) res->total_kmers[i] = total_kmers[i];
-    res->k = p->k;
-    res->kmers_fraction = p->kmers_fraction;
-    return res;
-}
 
 int vb_prefilter(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, vb_pairs **out)
 {
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter: bad arguments");
-    // One pass holds at most ~10^9 k-mer tuples (2^20 shared-memory buckets of ~1 280 tuples; 2^32 list entries).  Larger
-    // inputs are processed in P passes over disjoint shards of the k-mer hash space -- the same split that spreads one
-    // data set over several GPUs, run back to back on one -- and the partial counts are summed on the host.  This is what
-    // vclust's --batch-size is for (the reference builds partial databases and runs all2all-parts); the output does not
-    // depend on it.  VB_PREFILTER_PASSES (test hook) forces P.
-    const char *pe = getenv("VB_PREFILTER_PASSES");
-    const double est = (double)vb_store_slots(g, 0) * std::min(1.0, std::max(p->kmers_fraction, 0.0));
-    uint32_t passes = pe ? (uint32_t)std::max(1, atoi(pe)) : (uint32_t)std::ceil(est / 1.0e9);
-    passes = std::max(1u, std::min(passes, 1024u));
-    if (passes == 1) {
-        vb_enter(ctx);
-        vb_prefilter_impl(ctx, g, p, 0, 1, out);
-    } else {
-        std::vector<vb_pairs *> parts;
-        auto release = [&]() { for (auto *q : parts) vb_pairs_free_impl(q); parts.clear(); };
-        try {
-            std::vector<uint32_t> totals(g->count(), 0);
-            std::vector<PartialList> lists;
-            for (uint32_t s = 0; s < passes; ++s) {
-                vb_pairs *part = nullptr;
-                vb_enter(ctx);
-                vb_prefilter_impl(ctx, g, p, s, passes, &part);
-                parts.push_back(part);
-                lists.push_back({part->row, part->col, part->common, part->n_pairs});
-                for (uint32_t i = 0; i < g->count(); ++i) totals[i] += part->total_kmers[i];
-            }
-            *out = merge_sorted_partials(lists, totals.data(), g->count(), p);
-            ctx->set_timing("prefilter.passes", (double)passes);
-        } catch (...) { release(); throw; }
-        release();
-    }
+    // Inputs beyond what one pass holds (~10^9 k-mer tuples) run in several passes over disjoint slices of the k-mer hash
+    // space into one accumulator (prefilter.cu) -- what vclust's --batch-size is for (the reference builds partial
+    // databases and runs all2all-parts); the output does not depend on it.
+    vb_enter(ctx);
+    vb_prefilter_job job;
+    job.g = g;
+    vb_prefilter_run(ctx, job, p, out);
     VB_GUARD_END
 }
 
@@ -297,7 +276,12 @@ int vb_prefilter_partial(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_pa
     VB_GUARD_BEGIN
     if (!ctx || !g || !p || !out) throw vb_error(VB_ERR_ARG, "vb_prefilter_partial: bad arguments");
     vb_enter(ctx);
-    vb_prefilter_impl(ctx, g, p, shard_index, shard_count, out);
+    vb_prefilter_job job;
+    job.g = g;
+    job.shard_index = shard_index;
+    job.shard_count = shard_count;
+    job.keep_dev = false;
+    vb_prefilter_run(ctx, job, p, out);
     VB_GUARD_END
 }
 
@@ -485,13 +469,74 @@ int vb_align_regions(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, co
     VB_GUARD_END
 }
 
+// device result of vb_align_fast -> vb_align_out (keys are ref << gbits | query in LZ-ANI ids, already sorted)
+static vb_align_out *align_out_from_fast(vb_ctx *ctx, const vb_genomes *g, const AlignFastOut &fo)
+{
+    cudaStream_t st = (cudaStream_t)ctx->stream;
+    std::vector<uint64_t> keys(fo.n);
+    std::vector<int32_t> stats(3 * fo.n);
+    if (fo.n) {
+        VB_CUDA(cudaMemcpyAsync(keys.data(), fo.keys.p, sizeof(uint64_t) * fo.n, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaMemcpyAsync(stats.data(), fo.stats.p, sizeof(int32_t) * 3 * fo.n, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+    }
+    vb_align_out *res = vb_align_out_alloc(fo.n, g->count());
+    const std::vector<uint32_t> &order = vb_lz_order(g);
+    std::copy(order.begin(), order.end(), res->order);
+    const uint64_t qmask = (1ULL << fo.gbits) - 1;
+    vb_parallel_for(fo.n, 65536, 8, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            res->ref[i] = (uint32_t)(keys[i] >> fo.gbits); res->qry[i] = (uint32_t)(keys[i] & qmask);
+            res->sym_in_matches[i] = stats[3 * i]; res->sym_in_literals[i] = stats[3 * i + 1]; res->no_components[i] = stats[3 * i + 2];
+        }
+    });
+    return res;
+}
+
 static void vb_align_common(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, const vb_align_params *p, vb_align_out **out,
                             vb_regions **regions)
 {
     {
     vb_enter(ctx);
+    ctx->clear_timings("align.");
     const auto h0 = std::chrono::steady_clock::now();
     const uint32_t n = g->count();
+    if (!regions && out && !getenv("VB_ALIGN_HOST_LIST")) {
+        // fast path: the directed pair list, its order and the schedule are built on the device -- from the candidate list
+        // the preceding vb_prefilter left there, else from an upload of (row, col, ani)
+        cudaStream_t st = (cudaStream_t)ctx->stream;
+        const DevGenomes &dg = vb_get_dev_genomes(ctx, g, (uint32_t)p->mrd + 128);
+        const uint64_t np = pairs ? pairs->n_pairs : 0;
+        const uint64_t *d_keys = nullptr;
+        const float *d_ani = nullptr;
+        DevBuf<uint64_t> up_keys;
+        DevBuf<float> up_ani;
+        std::vector<uint64_t> h_keys;
+        std::vector<float> h_ani;
+        if (pairs && ctx->dev_pairs && ctx->dev_pairs->uid == vb_pairs_uid(pairs) && ctx->dev_pairs->n == np) {
+            d_keys = ctx->dev_pairs->keys.p; d_ani = ctx->dev_pairs->ani.p;
+        } else if (pairs && np) {
+            h_keys.resize(np); h_ani.resize(np);
+            for (uint64_t i = 0; i < np; ++i) {
+                if (pairs->row[i] >= n || pairs->col[i] >= n) throw vb_error(VB_ERR_ARG, "vb_align: pair id out of range");
+                h_keys[i] = ((uint64_t)pairs->row[i] << 32) | pairs->col[i];
+                h_ani[i] = pairs->ani ? (float)pairs->ani[i] : 0.9f;
+            }
+            up_keys.alloc(np); up_ani.alloc(np);
+            VB_CUDA(cudaMemcpyAsync(up_keys.p, h_keys.data(), sizeof(uint64_t) * np, cudaMemcpyHostToDevice, st));
+            VB_CUDA(cudaMemcpyAsync(up_ani.p, h_ani.data(), sizeof(float) * np, cudaMemcpyHostToDevice, st));
+            d_keys = up_keys.p; d_ani = up_ani.p;
+        }
+        AlignFastOut fo;
+        if (vb_align_fast(ctx, g, dg, p, d_keys, d_ani, np, pairs == nullptr && n >= 2, 1, 0, fo)) {
+            const auto h1 = std::chrono::steady_clock::now();
+            *out = align_out_from_fast(ctx, g, fo);
+            ctx->set_timing("align.host_post_ms", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h1).count());
+            ctx->set_timing("align.api_prep_ms", 0.0);
+            return;
+        }
+        vb_enter(ctx);                     // the references do not fit in one batch: host-built list, batches of references
+    }
     // which genomes are references?  (every genome that occurs in a pair: the list is symmetrised)  The reference side
     // of the work is launched now; the pair list is built on the host while the GPU indexes the references.
     std::vector<uint8_t> is_ref(n, pairs ? 0 : 1);

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -59,12 +61,30 @@ struct vb_genomes {
     std::vector<uint64_t> offset;   // n+1 offsets into bases
     vb_bytes bases;                 // concatenated ASCII
     vb_fasta_flavor flavor = VB_FASTA_KMERDB;
+    // One vb_genomes may be used by one thread at a time (the lazily filled caches below are not synchronised across
+    // concurrent calls on the SAME set; different sets / contexts are independent).
     mutable bool pinned = false;    // bases page-locked with cudaHostRegister (done lazily by the second upload)
     mutable int uploads = 0;
+    bool skeleton = false;          // names + lengths only (vb_genomes_skeleton): `bases` is empty
     uint64_t uid = vb_next_uid();   // distinguishes a new set that re-uses the address of a freed one (device-copy cache)
+    // LZ-ANI order (seq_reservoir.cpp:215-251): computed once per set (a string sort of all names), used by every vb_align
+    mutable std::vector<uint32_t> lz_order, lz_rank;
     uint32_t count() const { return (uint32_t)names.size(); }
     uint64_t length(uint32_t i) const { return offset[i + 1] - offset[i]; }
 };
+const std::vector<uint32_t> &vb_lz_order(const vb_genomes *g);     // order[i] = input id of the genome with LZ-ANI id i
+const std::vector<uint32_t> &vb_lz_rank(const vb_genomes *g);      // rank[input id] = LZ-ANI id
+
+// fn(lo, hi) over [0, n) on up to `max_threads` host threads (inline when the range is small)
+void vb_parallel_for(uint64_t n, uint64_t min_per_thread, unsigned max_threads, const std::function<void(uint64_t, uint64_t)> &fn);
+
+// vb_pairs as allocated by the library: the public struct plus an identity, so that a context can recognise the list
+// its last prefilter call produced and use the copy it kept on the device
+struct vb_pairs_box {
+    vb_pairs pub;
+    uint64_t uid;
+};
+inline uint64_t vb_pairs_uid(const vb_pairs *p) { return p ? ((const vb_pairs_box *)p)->uid : 0; }
 
 // ---- text formats (host_format.cpp) ---------------------------------------------------------------------------
 int vb_fmt_fixed6(double v, char *out);                 // kmer-db conversion.h:167-219 Double2PChar(v, 6)
@@ -79,6 +99,7 @@ void vb_sample_rows(uint32_t n_genomes, uint32_t max_items, std::vector<uint32_t
 struct vb_timing { std::string key; double ms; };
 
 struct DevGenomes;
+struct DevPairs;
 struct vb_arena;
 struct vb_resident {                 // a genome set kept packed in HBM across calls (vb_genomes_make_resident)
     const vb_genomes *g;
@@ -90,6 +111,7 @@ struct vb_resident {                 // a genome set kept packed in HBM across c
 struct vb_ctx {
     int device = 0;
     void *stream = nullptr;          // cudaStream_t
+    bool owns_stream = true;         // false: the caller's stream (vb_ctx_create_on_stream)
     void *events[8] = {nullptr};     // cudaEvent_t, vb_ctx_mark / vb_ctx_elapsed_ms
     void *copy_stream = nullptr;     // cudaStream_t: chunked H2D of a genome upload, overlapped with the kernels on `stream`
     void *copy_events[9] = {nullptr};
@@ -98,15 +120,36 @@ struct vb_ctx {
     uint64_t mem_total = 0;          // device memory, queried once (cudaMemGetInfo is slow and synchronising)
     std::vector<vb_resident> resident;
     vb_resident last = {nullptr, 0, 0, nullptr};   // the most recent upload that was not made resident (implicit cache)
+    DevPairs *dev_pairs = nullptr;   // candidate list of the last vb_prefilter, kept on the device for vb_align
     std::vector<vb_timing> timings;
     void set_timing(const std::string &k, double ms) {
         for (auto &t : timings) if (t.key == k) { t.ms = ms; return; }
         timings.push_back({k, ms});
     }
+    void add_timing(const std::string &k, double ms) {
+        for (auto &t : timings) if (t.key == k) { t.ms += ms; return; }
+        timings.push_back({k, ms});
+    }
+    void clear_timings(const std::string &prefix) {            // at the start of every top-level call of that stage
+        timings.erase(std::remove_if(timings.begin(), timings.end(), [&](const vb_timing &t) { return t.key.compare(0, prefix.size(), prefix) == 0; }),
+                      timings.end());
+    }
 };
 
-void vb_prefilter_impl(vb_ctx *ctx, const vb_genomes *g, const vb_prefilter_params *p, uint32_t shard_index,
-                       uint32_t shard_count, vb_pairs **out);
+// The prefilter pipeline (prefilter.cu).  One rank of `comm` (nullptr: the whole job) works on the genomes of `g`, whose
+// global ids start at gid_base; n_total / total_slots_all describe the whole set.  shard_index / shard_count: the legacy
+// k-mer shard of vb_prefilter_partial (no thresholds).  keep_dev: leave the final candidate list on the device
+// (ctx->dev_pairs) for the align stage.
+struct vb_prefilter_job {
+    const vb_genomes *g = nullptr;
+    uint32_t gid_base = 0, n_total = 0;
+    double est_kmers_all = 0;            // k-mers of the whole set (all ranks), for the pass / bucket plan
+    const vb_comm *comm = nullptr;
+    uint32_t shard_index = 0, shard_count = 1;
+    bool keep_dev = true;
+};
+void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilter_params *p, vb_pairs **out);
+void vb_drop_dev_pairs(vb_ctx *ctx);
 // vb_align in two steps: _begin uploads the genomes and launches the reference texts + anchor tables of the genomes
 // flagged in is_ref[n_genomes] (asynchronously); _run takes the directed pairs (every reference must have been
 // flagged) and returns the statistics; _end releases the device buffers (LIFO after everything _run allocated).

@@ -1,29 +1,218 @@
-"""One genome set over N GPUs of one node (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
+"""One genome set over the GPUs of one node: one process per GPU, ``torch.distributed`` for the plumbing (NCCL on GPUs,
+gloo in the CPU tests), ``libvclust_b200.so`` for everything else.
 
-Plan, no tuple exchange and exactly one all-to-all on the data path:
-  1. every rank holds all genomes; rank r counts only the k-mers of hash shard r (vb_prefilter_partial)
-     -> partial (row, col, common) triples + partial total-kmers;
-  2. total-kmers: all-reduce(SUM);
-  3. ONE all-to-all: every partial triple goes to the owners of both of its genomes (owner(g) = g % N);
-  4. every owner sums the partial counts, applies the two -min filters exactly (vb_pairs_merge) and now knows, for each
-     of its genomes, the complete candidate list -> the directed parses (ref = own genome, query) are local and each
-     reference index is built on exactly one GPU (vb_align_pairs);
-  5. results (ref, qry, 3 ints) and the candidate pairs (reported by the owner of `row`) are gathered on rank 0.
+Data path (the library side is csrc/shard.cu + csrc/prefilter.cu + csrc/align.cu):
 
-The collectives live in ``exchange_and_align``; the compute steps are passed in as callables so that the host logic can
-be tested on CPU with gloo (tests/test_distributed.py feeds it oracle-computed partial counts).
+  setup     the genomes are block-partitioned by cumulative length; every rank packs its block on its GPU and the packed
+            align-stage records are ALL-GATHERED, so every GPU can read every genome afterwards
+  extract   k-mers of the LOCAL genomes -> (hash, genome) tuples, partitioned by hash range
+  exchange  all-to-all #1: every tuple travels to the rank that owns its hash range
+  count     grouping + pair counting on the owner's range -> partial common-k-mer counts per genome pair
+  reduce    all-reduce of total-kmers; all-to-all #2: partial counts travel to the owners of both genomes
+            (owner(g) = g mod world), which sum them and apply the -min filters: each owner then holds the complete
+            candidate list of its genomes
+  align     every owner parses (reference = own genome, query) for its pairs; results are gathered on rank 0
+
+The library owns all device buffers and runs all kernels on ONE stream that this module creates; the collectives are
+handed to it as C callbacks (``TorchComm``) and are issued on that same stream, so kernels and collectives are ordered by
+the stream and the host never waits in between except where it needs a count.
+
+``exchange_and_align`` / ``prefilter_align_sharded`` below are the older host-staged variant (k-mer shards of replicated
+genomes, numpy exchange); it is kept for ``--max-seqs``, which the native pipeline does not cover.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+import ctypes as C
+from typing import Callable, Optional, Sequence, Tuple
 
 import numpy as np
+
+from . import _lib
 
 
 def owner(g, world: int):
     return g % world
 
 
+def block_partition(lengths: Sequence[int], world: int):
+    """Contiguous blocks of genomes with (nearly) equal numbers of bases: [(first, count)] per rank."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(lengths)])
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    cuts.append(len(lengths))
+    cuts = np.maximum.accumulate(np.minimum(cuts, len(lengths)))
+    return [(int(cuts[r]), int(cuts[r + 1] - cuts[r])) for r in range(world)]
+
+
+def _wrap(ptr: int, nbytes: int, device):
+    """A uint8 torch tensor over `nbytes` bytes of memory the library owns (device memory on a GPU, host memory in the
+    gloo tests)."""
+    import torch
+    if nbytes == 0 or not ptr:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    if device.type == "cuda":
+        class _Mem:
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+        return torch.as_tensor(m, device=device)
+    return torch.frombuffer((C.c_uint8 * int(nbytes)).from_address(int(ptr)), dtype=torch.uint8)
+
+
+class TorchComm:
+    """vb_comm over torch.distributed.  All three callbacks work on memory owned by the caller (the library) and are
+    enqueued on the current torch stream; they return 0 or, after stashing the exception in ``self.error``, 1."""
+
+    def __init__(self, dist, device, group=None):
+        import torch
+        self.dist, self.device, self.group = dist, torch.device(device), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        # device memory but a CPU-only backend (several ranks sharing one GPU in the tests): stage through the host
+        self.staged = self.device.type == "cuda" and dist.get_backend(group) == "gloo"
+        self.error: Optional[BaseException] = None
+        self.bytes_sent = 0          # payload this rank handed to all-to-all / all-gather (diagnostics)
+        self.calls = 0
+        self._a2a = _lib.A2A_FN(self._all_to_all)
+        self._gather = _lib.GATHER_FN(self._all_gather)
+        self._reduce = _lib.REDUCE_FN(self._all_reduce)
+        self.struct = _lib.Comm(self.rank, self.world, None, self._a2a, self._gather, self._reduce)
+
+    def _guard(self, fn):
+        try:
+            fn()
+            return 0
+        except BaseException as e:      # noqa: BLE001 -- nothing may propagate through the C frames
+            self.error = e
+            return 1
+
+    def _all_to_all(self, user, send, send_counts, recv, recv_counts, width):
+        def run():
+            w = self.world
+            sc = [int(send_counts[i]) * int(width) for i in range(w)]
+            rc = [int(recv_counts[i]) * int(width) for i in range(w)]
+            s = _wrap(send, sum(sc), self.device)
+            r = _wrap(recv, sum(rc), self.device)
+            if self.staged:
+                import torch
+                self.stream_sync()
+                hr = torch.empty(sum(rc), dtype=torch.uint8)
+                self.dist.all_to_all_single(hr, s.cpu(), output_split_sizes=rc, input_split_sizes=sc, group=self.group)
+                r.copy_(hr)
+            else:
+                self.dist.all_to_all_single(r, s, output_split_sizes=rc, input_split_sizes=sc, group=self.group)
+            self.bytes_sent += sum(sc) - sc[self.rank]
+            self.calls += 1
+        return self._guard(run)
+
+    def _all_gather(self, user, send, recv, nbytes):
+        def run():
+            s = _wrap(send, int(nbytes), self.device)
+            r = _wrap(recv, int(nbytes) * self.world, self.device)
+            if self.staged:
+                import torch
+                self.stream_sync()
+                hr = torch.empty(int(nbytes) * self.world, dtype=torch.uint8)
+                self.dist.all_gather(list(hr.chunk(self.world)), s.cpu(), group=self.group)
+                r.copy_(hr)
+            elif self.device.type == "cuda":
+                self.dist.all_gather_into_tensor(r, s, group=self.group)
+            else:
+                self.dist.all_gather(list(r.chunk(self.world)), s, group=self.group)
+            self.bytes_sent += int(nbytes) * (self.world - 1)
+            self.calls += 1
+        return self._guard(run)
+
+    def _all_reduce(self, user, buf, n):
+        def run():
+            import torch
+            t = _wrap(buf, 4 * int(n), self.device).view(torch.int32)     # two's complement: the sum is exact mod 2^32
+            if self.staged:
+                self.stream_sync()
+                h = t.cpu()
+                self.dist.all_reduce(h, op=self.dist.ReduceOp.SUM, group=self.group)
+                t.copy_(h)
+            else:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.calls += 1
+        return self._guard(run)
+
+    def stream_sync(self):
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def check(self, rc: int):
+        if rc != 0:
+            err, self.error = self.error, None
+            if err is not None:
+                raise err
+            _lib.check(rc)
+
+
+class ShardedRun:
+    """The multi-GPU pipeline on one rank.
+
+    names / lengths: ALL genomes of the set (every rank knows them); local_seqs: the sequences of this rank's block
+    ``block = block_partition(lengths, world)[rank]`` (ASCII, bytes or uint8 arrays)."""
+
+    def __init__(self, dist, device_index: int, names: Sequence[str], lengths: Sequence[int], local_seqs: Sequence, mrd: int = 40,
+                 group=None):
+        import torch
+
+        from . import api
+        self.dist = dist
+        self.device = torch.device("cuda", device_index)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.comm = TorchComm(dist, self.device, group)
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.first, count = block_partition(lengths, self.world)[self.rank]
+        if len(local_seqs) != count:
+            raise ValueError("rank %d holds %d genomes, its block has %d" % (self.rank, len(local_seqs), count))
+        self.ctx = api.Context(device_index, stream=self.stream.cuda_stream)
+        self.meta = api.Genomes.skeleton(names, lengths)
+        self.local = api.Genomes.from_memory(list(names[self.first:self.first + count]), local_seqs)
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        with torch.cuda.stream(self.stream):
+            self.comm.check(self._L.vb_shard_create(self.ctx._h, C.byref(self.comm.struct), self.meta._h, self.local._h,
+                                                    self.first, int(mrd), C.byref(self._h)))
+
+    def prefilter(self, k=25, min_kmers=20, min_ident=0.7, kmers_fraction=1.0):
+        """Collective.  Rank 0 gets the complete candidate list (api.PairList), the others an empty one."""
+        import torch
+
+        from . import api
+        p = _lib.PrefilterParams(k, min_kmers, min_ident, kmers_fraction, 0, 0)
+        out = C.POINTER(_lib.Pairs)()
+        with torch.cuda.stream(self.stream):
+            self.comm.check(self._L.vb_shard_prefilter(self._h, C.byref(p), C.byref(out)))
+        return api.PairList(out)
+
+    def align(self, params=None):
+        """Collective, after prefilter().  Rank 0 gets the complete api.AlignResult, the others an empty one."""
+        import torch
+
+        from . import api
+        params = params or api.align_params()
+        out = C.POINTER(_lib.AlignOut)()
+        with torch.cuda.stream(self.stream):
+            self.comm.check(self._L.vb_shard_align(self._h, C.byref(params), C.byref(out)))
+        return api.AlignResult(out)
+
+    def close(self):
+        if self._h:
+            self._L.vb_shard_destroy(self._h)
+            self._h = C.c_void_p()
+        self.local.close()
+        self.meta.close()
+        self.ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# host-staged variant (kept for --max-seqs)
+# ----------------------------------------------------------------------------------------------------------------
 def _a2a_variable(dist, send_chunks, device, width: int):
     """all-to-all of int64 rows with per-destination sizes; returns the concatenation of what was received."""
     import torch
@@ -60,7 +249,7 @@ def _gather_rows(dist, rows: np.ndarray, device, width: int, dst: int = 0):
 
 def exchange_and_align(dist, device, partial: Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray],
                        merge_fn: Callable, align_fn: Callable, sampled: bool = False):
-    """Steps 2-5.  partial = (rows, cols, common, partial_totals) of this rank's k-mer shard.
+    """Host-staged exchange.  partial = (rows, cols, common, partial_totals) of this rank's k-mer shard.
     merge_fn(rows, cols, common, totals) -> (rows, cols, common, ani) kept pairs (thresholds applied, sorted).
     align_fn(ref, qry) -> (n, 3) int32.
     sampled: merge_fn applies --max-seqs, i.e. returns ROWS of the filter (entries on both sides of the diagonal).  An
@@ -124,15 +313,12 @@ def exchange_and_align(dist, device, partial: Tuple[np.ndarray, np.ndarray, np.n
 
 def prefilter_align_sharded(ctx, genomes_kmerdb, genomes_lzani, dist, device, k=25, min_kmers=20, min_ident=0.7,
                             kmers_fraction=1.0, lz_params=None, max_seqs=0, passes=0) -> Optional[dict]:
-    """The GPU instantiation: vb_prefilter_partial -> exchange -> vb_pairs_merge -> vb_align_pairs.
-    genomes_kmerdb / genomes_lzani: the same input loaded with the two FASTA flavours (they may be the same object
-    when the input has no corner cases, e.g. synthetic data)."""
+    """Host-staged variant on GPUs: vb_prefilter_partial -> exchange -> vb_pairs_merge -> vb_align_pairs.  Every rank
+    holds all genomes (the same input loaded with the two FASTA flavours; they may be the same object when the input has
+    no corner cases) and counts the k-mers of hash shard `rank`."""
     from . import api
     rank, world = dist.get_rank(), dist.get_world_size()
-    # one pass holds ~10^9 k-mer tuples: a rank whose hash shard is larger splits it further and runs the sub-shards back to
-    # back (c5: 3 x 10^10 k-mers over 8 GPUs = 4 passes per rank); their partial counts simply join the rank's list
-    if passes <= 0:
-        passes = max(1, int(np.ceil(genomes_kmerdb.total_bases * min(1.0, kmers_fraction) / world / 1.0e9)))
+    passes = max(1, passes)
     rows, cols, common, totals = [], [], [], None
     for s in range(passes):
         part = api.prefilter_partial(ctx, genomes_kmerdb, rank * passes + s, world * passes, k=k, kmers_fraction=kmers_fraction)
