@@ -611,7 +611,7 @@ def test_c3_full_size_vs_reference_binaries(tmp_path):
     del seqs
     api.prefilter([fa], tmp_path / "fltr.txt", True)
     api.align([fa], tmp_path / "ani.tsv", True, filter_file=tmp_path / "fltr.txt", out_format=api.ALIGN_OUTFMT["complete"])
-    assert (tmp_path / "fltr.txt").read_bytes().count(b":") == 95000 + 1
+    assert (tmp_path / "fltr.txt").read_bytes().count(b":") == 95000 + 2
     _ref_vs_files(tmp_path, fa, tmp_path / "fltr.txt", tmp_path / "ani.tsv")
 
 
@@ -625,7 +625,7 @@ def test_c3_s200_slice_vs_reference_binaries(tmp_path):
     synth.write_fasta(fa, names, seqs)
     api.prefilter([fa], tmp_path / "fltr.txt", True)
     api.align([fa], tmp_path / "ani.tsv", True, filter_file=tmp_path / "fltr.txt", out_format=api.ALIGN_OUTFMT["complete"])
-    assert (tmp_path / "fltr.txt").read_bytes().count(b":") == 199000 + 1
+    assert (tmp_path / "fltr.txt").read_bytes().count(b":") == 199000 + 2
     _ref_vs_files(tmp_path, fa, tmp_path / "fltr.txt", tmp_path / "ani.tsv")
 
 

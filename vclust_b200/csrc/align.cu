@@ -163,35 +163,123 @@ __global__ void __launch_bounds__(256) build_ref_text_kernel(const uint4 *__rest
 // hit.  Half the inserts and half the table for the same candidate set.
 // slot (32 bit) = fingerprint << pos_bits | forward position; fingerprint = top 32 - pos_bits bits of the hash
 // ---------------------------------------------------------------------------------------------------------------
-// One block per reference, no global atomics and no table clear: the table is built partition by partition (IDX_PS slots =
-// 128 KB) in SHARED memory and every partition leaves with one coalesced store.  Linear probing never wraps: an entry
-// that reaches the end of its partition is carried into the next one (kept in a per-block list in global memory; rare
-// unless the genome is a long repeat), and the table ends with ht_tail >= #entries spare slots, so the carries of the
-// last home partition always find room.  Any insertion order gives a table the lookup reads the same way (it takes
-// the maximum over the whole probe chain).  Every reference position is hashed once per home partition; the hash is two
-// 32-bit multiplies.
-constexpr uint32_t IDX_PS = 32768;
-constexpr int IDX_THREADS = 1024;
+// One block per reference (blocks fetch references from a shared counter), no global atomics and no table clear: the
+// table is built partition by partition (IDX_PS slots = 32 KB) in SHARED memory and every partition leaves with one
+// coalesced store; five blocks are resident per SM, so the phases of different references overlap.
+//   1. every position is hashed ONCE (a thread takes IDX_CHUNK consecutive positions from one pair of 128-bit loads):
+//      (home slot, entry) goes to a per-block scratch list, a shared-memory histogram counts the entries per partition;
+//   2. the list is counting-sorted by partition (second scratch list; both are L2-resident);
+//   3. partition by partition: clear, insert the carried and the own entries (shared-memory CAS, all lanes busy), store.
+// Linear probing never wraps: an entry that reaches the end of its partition is carried into the next one (rare unless
+// the genome is a long repeat), and the table ends with ht_tail >= #entries spare slots, so the carries of the last home
+// partition always find room.  Any insertion order gives a table the lookup reads the same way (it takes the maximum
+// over the whole probe chain).
+constexpr uint32_t IDX_PS = 8192;
+constexpr int IDX_THREADS = 256;
+constexpr int IDX_CHUNK = 8;
+constexpr uint32_t IDX_MAXP = 1024;                  // histogram bins; longer tables put several partitions into one bin
 
-__global__ void __launch_bounds__(IDX_THREADS, 1) build_ref_index_kernel(const RefDesc *__restrict__ refs, uint32_t n_refs, int mal,
+struct Window { uint64_t lo, hi, nv; };             // >= 40 symbols starting at a position that is a multiple of 8
+__device__ __forceinline__ Window load_window(const uint4 *__restrict__ rec, uint32_t p0)
+{
+    const uint4 a = __ldg(rec + (p0 >> 5)), b = __ldg(rec + (p0 >> 5) + 1);
+    const unsigned sh = p0 & 31;
+    Window w;
+    w.lo = (((uint64_t)b.x << 32) | a.x) >> sh; w.hi = (((uint64_t)b.y << 32) | a.y) >> sh; w.nv = (((uint64_t)b.z << 32) | a.z) >> sh;
+    return w;
+}
+// hash of the mal-mer at offset j of the window; false when it holds an N
+__device__ __forceinline__ bool window_hash(const Window &w, int j, int mal, uint32_t nmask, uint64_t &h)
+{
+    if ((uint32_t)(w.nv >> j) & nmask) return false;
+    const uint64_t code = (uint64_t)((uint32_t)(w.lo >> j) & nmask) | ((uint64_t)((uint32_t)(w.hi >> j) & nmask) << 32);
+    h = anchor_hash(canonical_kmer(code, mal), mal);
+    return true;
+}
+
+__global__ void __launch_bounds__(IDX_THREADS, 5) build_ref_index_kernel(const RefDesc *__restrict__ refs, uint32_t n_refs, int mal,
                                                                         const uint4 *__restrict__ ref_rec, uint32_t *__restrict__ ht,
                                                                         const uint8_t *__restrict__ is_ref, uint32_t *__restrict__ carry_all,
-                                                                        uint32_t carry_stride)
+                                                                        uint32_t carry_stride, uint2 *__restrict__ ent_all, uint32_t ent_stride,
+                                                                        unsigned int *__restrict__ next_ref)
 {
-    extern __shared__ uint32_t tab[];                   // IDX_PS
-    __shared__ uint32_t s_carry_n[2];
+    __shared__ uint32_t tab[IDX_PS];
+    __shared__ uint32_t s_off[IDX_MAXP + 1], s_cur[IDX_MAXP];
+    __shared__ uint32_t s_carry_n[2], s_ref, s_wtot[IDX_THREADS / 32];
     const uint32_t nmask = (1u << mal) - 1;
-    uint32_t *carry[2] = {carry_all + (size_t)blockIdx.x * 2 * carry_stride, carry_all + (size_t)blockIdx.x * 2 * carry_stride + carry_stride};
-    for (uint32_t r = blockIdx.x; r < n_refs; r += gridDim.x) {
+    uint32_t *const carry0 = carry_all + (size_t)blockIdx.x * 2 * carry_stride;
+    auto carry = [&](int which) { return carry0 + (which ? carry_stride : 0u); };
+    uint2 *entA = ent_all + (size_t)blockIdx.x * 2 * ent_stride, *entB = entA + ent_stride;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ref = atomicAdd(next_ref, 1u);
+        __syncthreads();
+        const uint32_t r = s_ref;
+        if (r >= n_refs) return;
         if (is_ref && !is_ref[r]) continue;
         const RefDesc d = refs[r];
         const uint4 *rec = ref_rec + d.rec_off;
         uint32_t *out = ht + d.ht_off;
         const uint32_t n_pos = d.len >= (uint32_t)mal ? d.len - mal + 1 : 0;
+        const uint32_t n_chunks = (n_pos + IDX_CHUNK - 1) / IDX_CHUNK;
         const uint32_t total = d.ht_cap + d.ht_tail;
+        const uint32_t n_home_parts = (d.ht_cap + IDX_PS - 1) / IDX_PS;
+        const uint32_t G = (n_home_parts + IDX_MAXP - 1) / IDX_MAXP;        // partitions per histogram bin (1 unless the genome is > 2 Mb)
+        const uint32_t n_bins = (n_home_parts + G - 1) / G;
         if (threadIdx.x < 2) s_carry_n[threadIdx.x] = 0;
+        for (uint32_t i = threadIdx.x; i <= n_bins; i += IDX_THREADS) s_off[i] = 0;
         __syncthreads();
-        int cur = 0;                                    // carry[cur]: entries carried INTO this partition
+        // ---- 1. hash every position once; count the entries of every bin (s_off[bin + 1])
+        for (uint32_t c = threadIdx.x; c < n_chunks; c += IDX_THREADS) {
+            const uint32_t p0 = c * IDX_CHUNK;
+            const Window w = load_window(rec, p0);
+            uint2 e[IDX_CHUNK];
+#pragma unroll
+            for (int j = 0; j < IDX_CHUNK; ++j) {
+                uint64_t h;
+                e[j] = make_uint2(0xffffffffu, 0u);
+                if (p0 + j < n_pos && window_hash(w, j, mal, nmask, h)) {
+                    e[j] = make_uint2(ht_slot(h, d.ht_cap), ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | (p0 + j));
+                    atomicAdd(&s_off[e[j].x / (IDX_PS * G) + 1], 1u);
+                }
+            }
+            uint4 *o = (uint4 *)(entA + p0);             // 8 entries = 64 bytes
+#pragma unroll
+            for (int j = 0; j < IDX_CHUNK; j += 2) o[j / 2] = make_uint4(e[j].x, e[j].y, e[j + 1].x, e[j + 1].y);
+        }
+        __syncthreads();
+        // ---- 2. exclusive scan of the bin counts (n_bins <= 1024 = 4 per thread), then the counting sort
+        {
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            uint32_t v[4], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const uint32_t i = threadIdx.x * 4 + j; v[j] = i < n_bins ? s_off[i + 1] : 0u; sum += v[j]; }
+            uint32_t x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_wtot[wid] = x;
+            __syncthreads();
+            uint32_t base = 0;
+            for (int k = 0; k < wid; ++k) base += s_wtot[k];
+            uint32_t run = base + x - sum;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i = threadIdx.x * 4 + j;
+                if (i < n_bins) { s_cur[i] = run; s_off[i] = run; }
+                run += v[j];
+                if (i + 1 == n_bins) s_off[n_bins] = run;
+            }
+        }
+        __syncthreads();
+        const uint32_t n_ent = n_chunks * IDX_CHUNK;
+        for (uint32_t i = threadIdx.x; i < n_ent; i += IDX_THREADS) {
+            const uint2 e = entA[i];
+            if (e.x != 0xffffffffu) entB[atomicAdd(&s_cur[e.x / (IDX_PS * G)], 1u)] = e;
+        }
+        __syncthreads();
+        // ---- 3. the partitions
+        int cur = 0;                                    // carry(cur): entries carried INTO this partition
         for (uint32_t pbase = 0; pbase < total; pbase += IDX_PS, cur ^= 1) {
             const uint32_t plen = min(IDX_PS, total - pbase);
             const uint32_t n_in = s_carry_n[cur];
@@ -201,18 +289,16 @@ __global__ void __launch_bounds__(IDX_THREADS, 1) build_ref_index_kernel(const R
             auto insert = [&](uint32_t s, uint32_t val) {
                 for (; s < plen; ++s)
                     if (atomicCAS(&tab[s], HT_EMPTY, val) == HT_EMPTY) return;
-                carry[cur ^ 1][atomicAdd(&s_carry_n[cur ^ 1], 1u)] = val;           // (at most n_pos entries exist in all)
+                carry(cur ^ 1)[atomicAdd(&s_carry_n[cur ^ 1], 1u)] = val;          // (at most n_pos entries exist in all)
             };
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < n_in; i += IDX_THREADS) insert(0, carry[cur][i]);
+            for (uint32_t i = threadIdx.x; i < n_in; i += IDX_THREADS) insert(0, carry(cur)[i]);
             if (pbase < d.ht_cap) {
-                for (uint32_t p = threadIdx.x; p < n_pos; p += IDX_THREADS) {
-                    const W3 w = fetch3(rec, p);
-                    if (w.nv & nmask) continue;
-                    const uint64_t h = anchor_hash(canonical_kmer(kmer_code(w, mal), mal), mal);
-                    const uint32_t home = ht_slot(h, d.ht_cap);
-                    if (home < pbase || home - pbase >= plen) continue;
-                    insert(home - pbase, ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | p);
+                const uint32_t bin = (pbase / IDX_PS) / G;
+                const uint32_t lo = s_off[bin], hi = s_off[bin + 1];
+                for (uint32_t i = lo + threadIdx.x; i < hi; i += IDX_THREADS) {
+                    const uint2 e = entB[i];
+                    if (G == 1 || e.x - pbase < plen) insert(e.x - pbase, e.y);   // (a shared bin: only this partition's entries)
                 }
             }
             __syncthreads();
@@ -1014,6 +1100,8 @@ struct RefBatch {
     DevBuf<RefDesc> d_refs;
     DevBuf<uint4> ref_rec;
     DevBuf<uint32_t> ht, carry;
+    DevBuf<uint2> ent;
+    DevBuf<unsigned int> next_ref;
 };
 
 static uint64_t ref_table_slots(uint64_t len)
@@ -1048,26 +1136,15 @@ static void ref_batch_add(RefBatch &b, const vb_genomes *g, uint32_t gid, int mr
     b.max_len = std::max<uint64_t>(b.max_len, len);
 }
 
-static void index_kernel_opt_in(vb_ctx *ctx)
-{
-    static std::mutex m;
-    static bool done[64] = {false};
-    std::lock_guard<std::mutex> lock(m);
-    if (done[ctx->device & 63]) return;
-    VB_CUDA(cudaFuncSetAttribute(build_ref_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IDX_PS * sizeof(uint32_t))));
-    done[ctx->device & 63] = true;
-}
-
 // allocate, upload the descriptors, build texts and anchor tables (all asynchronous).  is_ref (device, optional): one
 // flag per descriptor; references whose flag is 0 are skipped.
 static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, const vb_align_params *ap, cudaStream_t st,
                              const uint8_t *d_is_ref = nullptr)
 {
-    index_kernel_opt_in(ctx);
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
     const uint32_t n_refs = (uint32_t)b.refs.size();
-    const uint32_t iblocks = std::min<uint32_t>(n_refs, (uint32_t)n_sm);
+    const uint32_t iblocks = std::min<uint32_t>(n_refs, (uint32_t)n_sm * 5);
     const uint32_t carry_stride = (uint32_t)((b.max_len + 1 + 1023) / 1024 * 1024);
     if (!b.d_refs.p) {
         b.d_refs.alloc(n_refs);
@@ -1076,11 +1153,15 @@ static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, con
         VB_CUDA(cudaMemcpyAsync(b.d_refs.p, b.refs.data(), sizeof(RefDesc) * n_refs, cudaMemcpyHostToDevice, st));
     }
     b.carry.alloc((size_t)iblocks * 2 * carry_stride);
+    const uint32_t ent_stride = carry_stride + 2 * IDX_CHUNK;          // multiple of 8 entries: every chunk store is 16-byte aligned
+    b.ent.alloc((size_t)iblocks * 2 * ent_stride);
+    b.next_ref.alloc(1);
+    VB_CUDA(cudaMemsetAsync(b.next_ref.p, 0, sizeof(unsigned int), st));
     dim3 grid_b(16, (unsigned)std::min<size_t>(n_refs, 32768));
     build_ref_text_kernel<<<grid_b, 256, 0, st>>>(dg.rec.p, dg.gofs.p, b.d_refs.p, n_refs, ap->mrd, b.ref_rec.p, d_is_ref);
     VB_LAUNCH_CHECK(ctx);
-    build_ref_index_kernel<<<iblocks, IDX_THREADS, IDX_PS * sizeof(uint32_t), st>>>(b.d_refs.p, n_refs, ap->mal, b.ref_rec.p, b.ht.p, d_is_ref,
-                                                                                   b.carry.p, carry_stride);
+    build_ref_index_kernel<<<iblocks, IDX_THREADS, 0, st>>>(b.d_refs.p, n_refs, ap->mal, b.ref_rec.p, b.ht.p, d_is_ref, b.carry.p, carry_stride,
+                                                            b.ent.p, ent_stride, b.next_ref.p);
     VB_LAUNCH_CHECK(ctx);
 }
 
@@ -1465,10 +1546,10 @@ bool vb_align_fast(vb_ctx *ctx, const vb_genomes *meta, const DevGenomes &store,
     t_par.stop();
     // the sorted keys must outlive this scope: keep whichever buffer holds them
     out.keys = (skeys == ka.p) ? std::move(ka) : std::move(kb);
-    unsigned long long n_dir = 0;
-    VB_CUDA(cudaMemcpyAsync(&n_dir, counts.p, sizeof(n_dir), cudaMemcpyDeviceToHost, st));
     t_all.stop();
     const double host_prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    unsigned long long n_dir = 0;
+    VB_CUDA(cudaMemcpyAsync(&n_dir, counts.p, sizeof(n_dir), cudaMemcpyDeviceToHost, st));
     VB_CUDA(cudaStreamSynchronize(st));
     out.n = n_dir;
     ctx->set_timing("align.total_ms", t_all.ms());

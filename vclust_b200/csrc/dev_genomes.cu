@@ -336,3 +336,17 @@ void vb_arena::destroy()
     for (auto &s : slabs) cudaFree(s.base);
     slabs.clear();
 }
+
+void *vb_pinned(vb_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->pin_cap) return ctx->pin_buf;
+    if (ctx->pin_buf) { cudaFreeHost(ctx->pin_buf); ctx->pin_buf = nullptr; ctx->pin_cap = 0; }
+    const size_t want = std::max(bytes + bytes / 4, (size_t)1 << 20);
+    void *q = nullptr;
+    if (cudaHostAlloc(&q, want, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        throw vb_error(VB_ERR_MEM, "cudaHostAlloc of " + std::to_string(want) + " bytes failed");
+    }
+    ctx->pin_buf = q; ctx->pin_cap = want;
+    return q;
+}

@@ -1642,15 +1642,22 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     A.dense.release(); A.tkeys.release(); A.tvals.release();
 
     // ---- what goes to the host: one rank: everything; several ranks: the pairs whose row this rank owns, gathered on rank 0
-    std::vector<uint64_t> h_keys;
-    std::vector<uint32_t> h_vals;
-    std::vector<uint32_t> h_tot(n);
-    if (n) VB_CUDA(cudaMemcpyAsync(h_tot.data(), totals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    // (read-backs go through the context's page-locked staging buffer: pageable targets would make every copy synchronous)
+    uint64_t n_host = 0;                 // pairs that go to the host
+    char *pin = nullptr;
+    uint64_t *h_keys = nullptr;
+    uint32_t *h_vals = nullptr, *h_tot = nullptr;
+    auto stage = [&](uint64_t n_out) {
+        n_host = n_out;
+        pin = (char *)vb_pinned(ctx, 12 * n_out + 4 * (size_t)n + 64);
+        h_keys = (uint64_t *)pin; h_vals = (uint32_t *)(pin + 8 * n_out); h_tot = (uint32_t *)(pin + 12 * n_out);
+        if (n) VB_CUDA(cudaMemcpyAsync(h_tot, totals, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    };
     if (world == 1) {
-        h_keys.resize(fin.n); h_vals.resize(fin.n);
+        stage(fin.n);
         if (fin.n) {
-            VB_CUDA(cudaMemcpyAsync(h_keys.data(), fin.keys.p, sizeof(uint64_t) * fin.n, cudaMemcpyDeviceToHost, st));
-            VB_CUDA(cudaMemcpyAsync(h_vals.data(), fin.vals.p, sizeof(uint32_t) * fin.n, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(h_keys, fin.keys.p, sizeof(uint64_t) * fin.n, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(h_vals, fin.vals.p, sizeof(uint32_t) * fin.n, cudaMemcpyDeviceToHost, st));
         }
     } else {
         // row-owned subset (still sorted) -> rank 0, which merges the ranks' runs with one more sort
@@ -1688,23 +1695,28 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         DevBuf<uint32_t> dummy(1);
         comm_check(comm->all_to_all(comm->user, ck.p, scv.data(), sb.ka.p, rcv.data(), 8), "all_to_all(result keys)");
         comm_check(comm->all_to_all(comm->user, mine.n ? mine.vals.p : dummy.p, scv.data(), sb.va.p, rcv.data(), 4), "all_to_all(result counts)");
+        stage(rank == 0 ? total : 0);
         if (rank == 0 && total) {
             const uint64_t *skeys = nullptr;
             const uint32_t *svals = nullptr;
             sort_entries(ctx, st, sb, total, n_pad, 2 * em.gbits, ws, skeys, svals);
-            h_keys.resize(total); h_vals.resize(total);
-            VB_CUDA(cudaMemcpyAsync(h_keys.data(), skeys, sizeof(uint64_t) * total, cudaMemcpyDeviceToHost, st));
-            VB_CUDA(cudaMemcpyAsync(h_vals.data(), svals, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(h_keys, skeys, sizeof(uint64_t) * total, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(h_vals, svals, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, st));
             VB_CUDA(cudaStreamSynchronize(st));
             const uint64_t cmask = (1ULL << em.gbits) - 1;      // compact -> (row << 32 | col)
-            for (auto &k : h_keys) k = ((k >> em.gbits) << 32) | (k & cmask);
+            const int gb = em.gbits;
+            uint64_t *hk = h_keys;
+            vb_parallel_for(total, 1 << 18, 16, [&](uint64_t lo, uint64_t hi) {
+                for (uint64_t i = lo; i < hi; ++i) hk[i] = ((hk[i] >> gb) << 32) | (hk[i] & cmask);
+            });
         }
     }
-    unsigned long long n_border_dev = 0;
-    VB_CUDA(cudaMemcpyAsync(&n_border_dev, scalars.p + 8, sizeof(n_border_dev), cudaMemcpyDeviceToHost, st));
+    unsigned long long *n_border_pin = (unsigned long long *)(pin + 12 * n_host + 4 * (size_t)n + 8 - (12 * n_host + 4 * (size_t)n) % 8);
+    VB_CUDA(cudaMemcpyAsync(n_border_pin, scalars.p + 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     t_emit.stop();
     t_all.stop();
     VB_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long n_border_dev = *n_border_pin;
     if (world > 1 && n_border_dev && fin.n) {
         // a pair within 1e-9 of the ani threshold (practically never): decide it exactly on the host and rebuild this rank's list
         std::vector<uint64_t> fk(fin.n);
@@ -1730,7 +1742,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
 
     // ---- host: the exact IEEE-double metric (params.cpp:28-32) for the output, the borderline cases re-decided exactly
     const auto hp0 = std::chrono::steady_clock::now();
-    const uint64_t n_emit = h_keys.size();
+    const uint64_t n_emit = n_host;
     vb_pairs *res = vb_pairs_alloc(n_emit, n);
     std::vector<uint8_t> drop;
     bool any_border = false;

@@ -160,6 +160,7 @@ void vb_ctx_destroy(vb_ctx *ctx)
     vb_evict_impl(ctx, nullptr);
     cudaStreamSynchronize((cudaStream_t)ctx->stream);
     if (ctx->arena) { ctx->arena->destroy(); delete ctx->arena; }
+    if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
     for (auto &e : ctx->events) if (e) cudaEventDestroy((cudaEvent_t)e);
     for (auto &e : ctx->copy_events) if (e) cudaEventDestroy((cudaEvent_t)e);
     if (ctx->copy_stream) { cudaStreamSynchronize((cudaStream_t)ctx->copy_stream); cudaStreamDestroy((cudaStream_t)ctx->copy_stream); }
@@ -473,14 +474,15 @@ int vb_align_regions(vb_ctx *ctx, const vb_genomes *g, const vb_pairs *pairs, co
 static vb_align_out *align_out_from_fast(vb_ctx *ctx, const vb_genomes *g, const AlignFastOut &fo)
 {
     cudaStream_t st = (cudaStream_t)ctx->stream;
-    std::vector<uint64_t> keys(fo.n);
-    std::vector<int32_t> stats(3 * fo.n);
+    char *pin = (char *)vb_pinned(ctx, 20 * fo.n + 16);
+    const uint64_t *keys = (const uint64_t *)pin;
+    const int32_t *stats = (const int32_t *)(pin + 8 * fo.n);
     if (fo.n) {
-        VB_CUDA(cudaMemcpyAsync(keys.data(), fo.keys.p, sizeof(uint64_t) * fo.n, cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaMemcpyAsync(stats.data(), fo.stats.p, sizeof(int32_t) * 3 * fo.n, cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaStreamSynchronize(st));
+        VB_CUDA(cudaMemcpyAsync(pin, fo.keys.p, sizeof(uint64_t) * fo.n, cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaMemcpyAsync(pin + 8 * fo.n, fo.stats.p, sizeof(int32_t) * 3 * fo.n, cudaMemcpyDeviceToHost, st));
     }
-    vb_align_out *res = vb_align_out_alloc(fo.n, g->count());
+    vb_align_out *res = vb_align_out_alloc(fo.n, g->count());     // (host allocation overlaps the transfer)
+    VB_CUDA(cudaStreamSynchronize(st));
     const std::vector<uint32_t> &order = vb_lz_order(g);
     std::copy(order.begin(), order.end(), res->order);
     const uint64_t qmask = (1ULL << fo.gbits) - 1;

@@ -121,6 +121,8 @@ struct vb_ctx {
     std::vector<vb_resident> resident;
     vb_resident last = {nullptr, 0, 0, nullptr};   // the most recent upload that was not made resident (implicit cache)
     DevPairs *dev_pairs = nullptr;   // candidate list of the last vb_prefilter, kept on the device for vb_align
+    void *pin_buf = nullptr;         // page-locked staging buffer for result read-backs (grown on demand, kept)
+    size_t pin_cap = 0;
     std::vector<vb_timing> timings;
     void set_timing(const std::string &k, double ms) {
         for (auto &t : timings) if (t.key == k) { t.ms = ms; return; }
@@ -150,6 +152,8 @@ struct vb_prefilter_job {
 };
 void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilter_params *p, vb_pairs **out);
 void vb_drop_dev_pairs(vb_ctx *ctx);
+// page-locked host memory of at least `bytes` bytes, owned by the context, valid until the next call of vb_pinned
+void *vb_pinned(vb_ctx *ctx, size_t bytes);
 // vb_align in two steps: _begin uploads the genomes and launches the reference texts + anchor tables of the genomes
 // flagged in is_ref[n_genomes] (asynchronously); _run takes the directed pairs (every reference must have been
 // flagged) and returns the statistics; _end releases the device buffers (LIFO after everything _run allocated).

@@ -155,10 +155,11 @@ class ShardedRun:
     """The multi-GPU pipeline on one rank.
 
     names / lengths: ALL genomes of the set (every rank knows them); local_seqs: the sequences of this rank's block
-    ``block = block_partition(lengths, world)[rank]`` (ASCII, bytes or uint8 arrays)."""
+    (ASCII, bytes or uint8 arrays).  blocks: [(first, count)] per rank, contiguous and in rank order; default
+    ``block_partition(lengths, world)`` (equal numbers of bases)."""
 
     def __init__(self, dist, device_index: int, names: Sequence[str], lengths: Sequence[int], local_seqs: Sequence, mrd: int = 40,
-                 group=None):
+                 group=None, blocks=None):
         import torch
 
         from . import api
@@ -167,17 +168,30 @@ class ShardedRun:
         self.stream = torch.cuda.Stream(device=self.device)
         self.comm = TorchComm(dist, self.device, group)
         self.rank, self.world = self.comm.rank, self.comm.world
-        self.first, count = block_partition(lengths, self.world)[self.rank]
+        self.first, count = (blocks or block_partition(lengths, self.world))[self.rank]
         if len(local_seqs) != count:
             raise ValueError("rank %d holds %d genomes, its block has %d" % (self.rank, len(local_seqs), count))
+        self.mrd = int(mrd)
         self.ctx = api.Context(device_index, stream=self.stream.cuda_stream)
         self.meta = api.Genomes.skeleton(names, lengths)
         self.local = api.Genomes.from_memory(list(names[self.first:self.first + count]), local_seqs)
         self._L = _lib.load()
         self._h = C.c_void_p()
+        self.load()
+
+    def load(self):
+        """Collective: (re-)upload and pack this rank's block, all-gather the packed records (the host-buffer leg of the
+        end-to-end measurement; the constructor calls it once)."""
+        import torch
+        self.unload()
         with torch.cuda.stream(self.stream):
             self.comm.check(self._L.vb_shard_create(self.ctx._h, C.byref(self.comm.struct), self.meta._h, self.local._h,
-                                                    self.first, int(mrd), C.byref(self._h)))
+                                                    self.first, self.mrd, C.byref(self._h)))
+
+    def unload(self):
+        if self._h:
+            self._L.vb_shard_destroy(self._h)
+            self._h = C.c_void_p()
 
     def prefilter(self, k=25, min_kmers=20, min_ident=0.7, kmers_fraction=1.0):
         """Collective.  Rank 0 gets the complete candidate list (api.PairList), the others an empty one."""
@@ -202,9 +216,7 @@ class ShardedRun:
         return api.AlignResult(out)
 
     def close(self):
-        if self._h:
-            self._L.vb_shard_destroy(self._h)
-            self._h = C.c_void_p()
+        self.unload()
         self.local.close()
         self.meta.close()
         self.ctx.close()

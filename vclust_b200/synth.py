@@ -71,6 +71,51 @@ def make_genomes(n: int, length: int | tuple[int, int] = 40_000, family: int = 2
     return names, seqs
 
 
+def family_blocks(n: int, family: int, world: int):
+    """Whole families per rank (equal numbers of families): [(first genome, genome count)]; used where every rank
+    generates only its own block (c4, c5 on 8 GPUs) -- make_family_block."""
+    n_fam = (n + family - 1) // family
+    cuts = [n_fam * r // world for r in range(world + 1)]
+    return [(min(cuts[r] * family, n), min(cuts[r + 1] * family, n) - min(cuts[r] * family, n)) for r in range(world)]
+
+
+def make_family_block(first: int, count: int, n: int, length=40_000, family: int = 20, seed: int = BASE_SEED, max_div: float = 0.12,
+                      indel: int = 500, n_frac: float = 0.0, lower_frac: float = 0.0, core: tuple | None = None):
+    """Genomes [first, first + count) of a set of n (first a multiple of `family`), every FAMILY seeded on its own
+    (``default_rng([seed, family index])``), so that any rank can generate any block without generating the rest.
+    (A different random stream than make_genomes: sets made by the two functions differ.)
+    core = (n_core, every): n_core "core" 25-mers; genome g carries core (g mod n_core) when g mod every < n_core ... i.e.
+    each core k-mer is planted in n / every genomes (50 cores in 20 000 of 10^6 genomes each)."""
+    assert first % family == 0
+    names, seqs = [], []
+    cores = None
+    if core:
+        crng = np.random.default_rng([seed, 0x7fffffff])
+        cores = [_ACGT[crng.integers(0, 4, size=25)] for _ in range(core[0])]
+    g = first
+    while g < min(first + count, n):
+        rng = np.random.default_rng([seed, g // family])
+        if isinstance(length, tuple):
+            L = int(np.exp(rng.uniform(np.log(length[0]), np.log(length[1]))))
+        else:
+            L = int(length)
+        root = _ACGT[rng.integers(0, 4, size=L)]
+        for _ in range(min(family, n - g)):
+            sq = _member(rng, root, max_div, indel)
+            if n_frac and rng.random() < n_frac and sq.size > 1000:
+                p = int(rng.integers(0, sq.size - 100))
+                sq[p:p + 100] = ord("N")
+            if lower_frac and rng.random() < lower_frac and sq.size > 1000:
+                p = int(rng.integers(0, sq.size - 500))
+                sq[p:p + 500] |= 0x20
+            if cores is not None and g % core[1] < core[0] and sq.size > 2000:
+                sq[1000:1025] = cores[g % core[1]]
+            names.append("g%07d" % g)
+            seqs.append(sq)
+            g += 1
+    return names, seqs
+
+
 def fasta_bytes(names, seqs, width: int = 80) -> bytes:
     out = bytearray()
     for name, s in zip(names, seqs):
@@ -103,4 +148,9 @@ CONFIGS = {
     "n30k": dict(n=30_000, length=40_000, family=20, seed=BASE_SEED + 7),
     "c4": dict(n=100_000, length=(5_000, 200_000), family=200, seed=BASE_SEED + 4, n_frac=0.01, lower_frac=0.01),
     "c5": dict(n=1_000_000, length=30_000, family=20, seed=BASE_SEED + 5),
+}
+# the 8-GPU configurations, generated block by block with make_family_block (c5: 50 core 25-mers, each in 20 000 genomes)
+BLOCK_CONFIGS = {
+    "c4": dict(n=100_000, length=(5_000, 200_000), family=200, seed=BASE_SEED + 4, n_frac=0.01, lower_frac=0.01),
+    "c5": dict(n=1_000_000, length=30_000, family=20, seed=BASE_SEED + 5, core=(50, 50)),
 }
