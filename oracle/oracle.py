@@ -36,6 +36,9 @@ def build(force: bool = False) -> Path:
 def build_ref() -> bool:
     """Build the unmodified reference binaries into oracle/_ref (no-op when the sources are absent)."""
     subprocess.run(["bash", str(HERE / "build_ref.sh")], check=True)
+    if ref_available():
+        from . import make_dropin        # the reference's vclust.py + test.py with the GPU patch applied (tests/test_dropin.py)
+        make_dropin.make()
     return ref_available()
 
 

@@ -322,18 +322,24 @@ __global__ void __launch_bounds__(256) seen_popc_kernel(const uint32_t *__restri
 // ---------------------------------------------------------------------------------------------------------------
 // histograms and scans
 // ---------------------------------------------------------------------------------------------------------------
-// out[i] = sum over the `n_src` source histograms (stride src_stride) of the 2^(FINE_BITS - bits) fine bins of coarse bin i;
-// n_out coarse bins = parents << bits
+// Level-2 bucket of a tuple inside its parent: sub = (fine bin * B2) >> FINE_BITS, B2 <= 2^FINE_BITS buckets per parent (any
+// number, so that the mean bucket size can be set exactly).  Coarse histogram: out[parent * B2 + sub] = sum over the
+// `n_src` source histograms (stride src_stride) of the fine bins that map to sub.
+__device__ __forceinline__ uint32_t sub_of(uint64_t h, uint32_t B1, uint32_t B2)
+{
+    return ((frac_of(h, B1) >> (32 - FINE_BITS)) * B2) >> FINE_BITS;
+}
 __global__ void __launch_bounds__(256) coarsen_kernel(const uint32_t *__restrict__ fine, uint32_t n_src, uint64_t src_stride,
-                                                      int bits, uint32_t n_out, uint32_t *__restrict__ out)
+                                                      uint32_t B2, uint32_t n_out, uint32_t *__restrict__ out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
-    const uint32_t w = 1u << (FINE_BITS - bits);
+    const uint32_t parent = i / B2, sub = i % B2;
+    const uint32_t f_lo = ((sub << FINE_BITS) + B2 - 1) / B2, f_hi = (((sub + 1) << FINE_BITS) + B2 - 1) / B2;
     uint32_t s = 0;
     for (uint32_t src = 0; src < n_src; ++src) {
-        const uint32_t *f = fine + src * src_stride + (uint64_t)i * w;
-        for (uint32_t j = 0; j < w; ++j) s += f[j];
+        const uint32_t *f = fine + src * src_stride + ((uint64_t)parent << FINE_BITS);
+        for (uint32_t j = f_lo; j < f_hi; ++j) s += f[j];
     }
     out[i] = s;
 }
@@ -405,11 +411,11 @@ struct Segment {
 };
 
 // Partition one tile of tuples into buckets.  LEVEL 1: tuples come from the compact survivor list, bucket = parent.
-// LEVEL 2: tuples come from a segment of one parent, bucket = top b2 bits of the position inside the parent's range.
+// LEVEL 2: tuples come from a segment of one parent, bucket = sub_of() = the position inside the parent's range, scaled to B2.
 // Inside the block the tile is first grouped by bucket in shared memory, so that every bucket receives one contiguous
 // run per tile.  cursor[] holds the next free slot of every destination bucket.
 template <int LEVEL>
-__global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, uint32_t B1, int b2, const uint64_t *__restrict__ in_keys,
+__global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, uint32_t B1, uint32_t B2, const uint64_t *__restrict__ in_keys,
                                                             const uint32_t *__restrict__ in_vals, const Segment *__restrict__ segs,
                                                             uint32_t n_segs, uint32_t n_tiles,
                                                             uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys,
@@ -423,11 +429,11 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, ui
     uint32_t *s_start = s_cnt + MAXB;
     uint32_t *s_fill = s_start + MAXB;
     uint32_t *s_gbase = s_fill + MAXB;
-    __shared__ uint32_t s_total, s_seg;
-    const uint32_t NBK = (LEVEL == 1) ? B1 : (1u << b2);
+    __shared__ uint32_t s_total, s_seg, s_wtot[PART_THREADS / 32];
+    const uint32_t NBK = (LEVEL == 1) ? B1 : B2;
     auto bucket_of = [&](uint64_t h) -> uint32_t {
         if (LEVEL == 1) return parent_of(h, B1);
-        return b2 ? (frac_of(h, B1) >> (32 - b2)) : 0u;
+        return sub_of(h, B1, B2);
     };
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -446,10 +452,26 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, ui
             const Segment sg = segs[s_seg];
             src_lo = (uint64_t)sg.beg + (uint64_t)(tile - sg.tile_start) * PART_TILE;
             src_hi = min(src_lo + PART_TILE, (uint64_t)sg.beg + sg.len);
-            cur_base = sg.parent << b2;
+            cur_base = sg.parent * B2;
         } else {
             src_lo = (uint64_t)tile * PART_TILE;
             src_hi = min(src_lo + PART_TILE, n_in);
+        }
+        // the tile this block takes next: pull its lines into L2 now (the loads below wait for DRAM otherwise: they were
+        // 45 % of this kernel's stalls)
+        if (LEVEL == 1) {
+            const uint64_t nxt = ((uint64_t)tile + gridDim.x) * PART_TILE;
+            if (nxt < n_in && threadIdx.x < PART_TILE / 16) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_keys + nxt + threadIdx.x * 16));
+                if ((threadIdx.x & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_vals + nxt + threadIdx.x * 16));
+            }
+        } else if (tile + gridDim.x < n_tiles && threadIdx.x < PART_TILE / 16) {
+            // (level 2: the next tile of this block usually lies in the same or the following segment, gridDim tiles ahead)
+            const uint64_t nxt = src_lo + (uint64_t)gridDim.x * PART_TILE;
+            if (nxt + PART_TILE <= n_in) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_keys + nxt + threadIdx.x * 16));
+                if ((threadIdx.x & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_vals + nxt + threadIdx.x * 16));
+            }
         }
         uint64_t key[PART_ITEMS];
         uint32_t val[PART_ITEMS];
@@ -466,18 +488,23 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, ui
             }
         }
         __syncthreads();
-        // exclusive scan of s_cnt (NBK <= 1024) + one global reservation per non-empty bucket
-        if (threadIdx.x < 32) {
-            uint32_t carry = 0;
-            for (uint32_t base = 0; base < NBK; base += 32) {
-                uint32_t b = base + threadIdx.x;
-                uint32_t v = b < NBK ? s_cnt[b] : 0, x = v;
+        // exclusive scan of s_cnt (NBK <= 1024 = 2 per thread; every warp takes part) + one global reservation per bucket
+        {
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            const uint32_t b0 = 2 * threadIdx.x;
+            const uint32_t v0 = b0 < NBK ? s_cnt[b0] : 0u, v1 = b0 + 1 < NBK ? s_cnt[b0 + 1] : 0u;
+            uint32_t x = v0 + v1;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (threadIdx.x >= o) x += y; }
-                if (b < NBK) s_start[b] = carry + x - v;
-                carry += __shfl_sync(0xffffffffu, x, 31);
-            }
-            if (threadIdx.x == 0) s_total = carry;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_wtot[wid] = x;
+            __syncthreads();
+            uint32_t base = 0;
+#pragma unroll
+            for (int k = 0; k < PART_THREADS / 32; ++k) { const uint32_t t = s_wtot[k]; if (k < wid) base += t; }
+            const uint32_t pre = base + x - (v0 + v1);
+            if (b0 < NBK) s_start[b0] = pre;
+            if (b0 + 1 < NBK) s_start[b0 + 1] = pre + v0;
+            if (threadIdx.x == PART_THREADS - 1) s_total = base + x;
         }
         __syncthreads();
         for (uint32_t b = threadIdx.x; b < NBK; b += PART_THREADS) {
@@ -513,10 +540,10 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, ui
 //          fire-and-forget atomic, and an ordered scan of the array yields the pairs already sorted by (row, col);
 //   hashed (larger N): open addressing, uint64 key (row << 32 | col) + uint32 count.  Sized by a guess, grown between
 //          passes when it fills up; an insert that finds no slot sets *overflow and the whole call is redone larger.
+struct PairSlot { uint64_t key; uint32_t val; uint32_t pad; };      // key and counter share a 32-byte sector: one DRAM access per increment
 struct PairAcc {
     uint32_t *dense;        // non-null selects the dense layout
-    uint64_t *tkeys;
-    uint32_t *tvals;
+    PairSlot *slots;
     uint64_t cap_mask;
     unsigned long long *status;     // [0] overflow flag, [1] keys inserted so far
 };
@@ -527,13 +554,13 @@ __device__ __forceinline__ uint32_t table_add(const PairAcc &A, uint64_t key, ui
 {
     uint64_t h = fmix64(key) & A.cap_mask;
     for (uint32_t probes = 0; probes < MAX_PROBES; ++probes) {
-        uint64_t cur = A.tkeys[h];
+        uint64_t cur = A.slots[h].key;
         uint32_t fresh = 0;
         if (cur == SLOT_EMPTY) {
-            cur = atomicCAS((unsigned long long *)&A.tkeys[h], (unsigned long long)SLOT_EMPTY, (unsigned long long)key);
+            cur = atomicCAS((unsigned long long *)&A.slots[h].key, (unsigned long long)SLOT_EMPTY, (unsigned long long)key);
             if (cur == SLOT_EMPTY) { cur = key; fresh = 1; }
         }
-        if (cur == key) { atomicAdd(&A.tvals[h], inc); return fresh; }
+        if (cur == key) { atomicAdd(&A.slots[h].val, inc); return fresh; }
         h = (h + 1) & A.cap_mask;
     }
     A.status[0] = 1;
@@ -555,29 +582,48 @@ __device__ __forceinline__ void flush_fresh(const PairAcc &A, uint32_t fresh)
 }
 
 // move every entry of an old table into a new (larger) one
-__global__ void __launch_bounds__(256) rehash_kernel(const uint64_t *__restrict__ okeys, const uint32_t *__restrict__ ovals, uint64_t ocap, PairAcc A)
+__global__ void __launch_bounds__(256) rehash_kernel(const PairSlot *__restrict__ old, uint64_t ocap, PairAcc A)
 {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ocap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t k = okeys[i];
-        if (k != SLOT_EMPTY) table_add(A, k, ovals[i]);
+        const PairSlot e = old[i];
+        if (e.key != SLOT_EMPTY) table_add(A, e.key, e.val);
     }
 }
 
-// shared-memory layout of bucket_kernel (dynamic, 44 KB -> 5 blocks per SM)
-constexpr uint32_t CHAIN_END = 0x7fffu;        // prev[]: low 15 bits = previous tuple with the same k-mer
-constexpr uint32_t CHAIN_DUP = 0x8000u;        // prev[]: this tuple repeats a genome that is already in its chain
+// all slots empty: key = ~0, count 0
+__global__ void __launch_bounds__(256) table_clear_kernel(PairSlot *__restrict__ slots, uint64_t cap)
+{
+    uint4 *p = (uint4 *)slots;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+}
+
+// shared-memory layout of bucket_kernel (dynamic, 52 KB -> 4 blocks per SM).  The hashes are only needed while the tuples
+// are grouped; their space then holds the group-sorted member list and the scans.
+constexpr uint32_t MEMBER_DUP = 0x8000u;       // member[]: this tuple repeats a genome that is already in its group
 struct BucketSmem {
-    uint64_t keys[BUCKET_CAP];                 // h of every tuple
+    union {
+        uint64_t keys[BUCKET_CAP + 1];         // h of every tuple (grouping)
+        struct {
+            uint32_t poff[BUCKET_CAP + 1];     // pairs of all groups before tuple i's group (non-zero width only at representatives)
+            uint16_t off[BUCKET_CAP];          // first member of the group whose representative is tuple i
+            uint16_t member[BUCKET_CAP];       // tuple indices, group by group
+        } g;
+    } u;
     uint32_t gids[BUCKET_CAP];
-    uint32_t table[BUCKET_SLOTS];              // slot -> the most recently inserted tuple with the slot's key
-    uint16_t prev[BUCKET_CAP];
+    uint32_t table[BUCKET_SLOTS];              // slot -> representative (first inserted tuple) of the slot's k-mer
+    uint32_t cnt[BUCKET_CAP];                  // members of the group whose representative is tuple i
+    uint16_t rep[BUCKET_CAP];                  // representative of tuple i's group
+    uint32_t warp_tot[2][8];
+    uint32_t total_pairs;
 };
 
-// One block per final bucket.  Equal k-mers are linked into chains through a shared-memory hash table: a tuple finds the
-// slot of its key and swaps itself in as the slot's newest member, keeping the previous one as its predecessor.  A
-// tuple's chain is then exactly the set of tuples with the same k-mer inserted before it, so walking it enumerates every
-// unordered pair of the group once -- no sort, no regrouping.  A tuple whose genome already occurs in its chain is a
-// within-genome duplicate (counted in dup_cnt, skipped by everybody else).
+// One block per final bucket.  Equal k-mers are grouped through a shared-memory hash table (the first tuple of a k-mer
+// becomes the group's representative), a counting sort lays every group out contiguously, a tuple whose genome already
+// occurs earlier in its group is a within-genome duplicate (counted in dup_cnt, skipped afterwards), and the pairs of ALL
+// groups are then enumerated as one flat index space split evenly over the threads -- every lane does the same amount
+// of work whatever the group sizes (walking per-tuple chains instead left most lanes of a warp idle: 5.3 G warp
+// instructions at c3, 40 % of them in the pair loop).
 __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                      const uint32_t *__restrict__ off, uint32_t n_buckets,
                                                      uint32_t *__restrict__ dup_cnt, PairAcc A,
@@ -585,7 +631,7 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
 {
     extern __shared__ unsigned char smem_raw[];
     BucketSmem &S = *(BucketSmem *)smem_raw;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t fresh = 0;
     for (uint32_t bkt = blockIdx.x; bkt < n_buckets; bkt += gridDim.x) {
         const uint32_t beg = off[bkt], size = off[bkt + 1] - beg;
@@ -595,55 +641,113 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
             continue;
         }
         for (int s = tid; s < BUCKET_SLOTS; s += 256) S.table[s] = 0xffffffffu;
-        for (uint32_t i = tid; i < size; i += 256) { S.keys[i] = keys[beg + i]; S.gids[i] = vals[beg + i]; }
+        for (uint32_t i = tid; i < size; i += 256) { S.u.keys[i] = keys[beg + i]; S.gids[i] = vals[beg + i]; S.cnt[i] = 0; }
+        {   // the bucket this block takes next: pull its lines into L2 while this one is grouped
+            const uint32_t nxt = bkt + gridDim.x;
+            if (nxt < n_buckets) {
+                const uint32_t nb = off[nxt], ns = min(off[nxt + 1] - nb, (uint32_t)BUCKET_CAP);
+                for (uint32_t i = tid * 16; i < ns; i += 256 * 16) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(keys + nb + i));
+                    if ((i & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + nb + i));
+                }
+            }
+        }
         __syncthreads();
-        // ---- insert: chain every tuple to the earlier tuples with the same key
+        // ---- 1. group: every tuple learns its representative, representatives count their members
         for (uint32_t i = tid; i < size; i += 256) {
-            const uint64_t k = S.keys[i];
+            const uint64_t k = S.u.keys[i];
             uint32_t s = (uint32_t)k & (BUCKET_SLOTS - 1);                    // low bits: independent of the bucket bits
-            uint32_t pv = CHAIN_END;
+            uint32_t r;
             for (;;) {
                 uint32_t cur = S.table[s];
                 if (cur == 0xffffffffu) {
                     cur = atomicCAS(&S.table[s], 0xffffffffu, i);
-                    if (cur == 0xffffffffu) break;                            // first tuple with this key
+                    if (cur == 0xffffffffu) { r = i; break; }                 // first tuple with this key
                 }
-                if (S.keys[cur] == k) { pv = atomicExch(&S.table[s], i); break; }
+                if (S.u.keys[cur] == k) { r = cur; break; }
                 s = (s + 1) & (BUCKET_SLOTS - 1);
             }
-            S.prev[i] = (uint16_t)pv;
+            S.rep[i] = (uint16_t)r;
+            atomicAdd(&S.cnt[r], 1u);
         }
         __syncthreads();
-        // ---- duplicates: same genome earlier in the chain
-        uint32_t dup_mask = 0;                                                // bit t: this thread's t-th tuple is a duplicate
-        int t = 0;
-        for (uint32_t i = tid; i < size; i += 256, ++t) {                     // size <= BUCKET_CAP = 8 * 256
+        // ---- 2. exclusive scans over the tuples (8 per thread): members -> off, pairs m (m - 1) / 2 -> poff
+        {
+            uint32_t c[8], sum_c = 0, sum_p = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t i = tid * 8 + j;
+                c[j] = i < size ? S.cnt[i] : 0u;
+                sum_c += c[j]; sum_p += c[j] * (c[j] - 1) / 2;               // (c == 0: 0 * 0xffffffff / 2 = 0)
+            }
+            uint32_t xc = sum_c, xp = sum_p;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t yc = __shfl_up_sync(0xffffffffu, xc, o), yp = __shfl_up_sync(0xffffffffu, xp, o);
+                if (lane >= o) { xc += yc; xp += yp; }
+            }
+            if (lane == 31) { S.warp_tot[0][wid] = xc; S.warp_tot[1][wid] = xp; }
+            __syncthreads();                                                  // (also: nobody reads the hashes any more)
+            uint32_t bc = 0, bp = 0, tp = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const uint32_t t0 = S.warp_tot[0][k], t1 = S.warp_tot[1][k]; if (k < wid) { bc += t0; bp += t1; } tp += t1; }
+            uint32_t rc = bc + xc - sum_c, rp = bp + xp - sum_p;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t i = tid * 8 + j;
+                if (i < size) { S.u.g.off[i] = (uint16_t)rc; S.u.g.poff[i] = rp; }
+                rc += c[j]; rp += c[j] * (c[j] - 1) / 2;
+            }
+            if (tid == 0) { S.u.g.poff[size] = tp; S.total_pairs = tp; }
+        }
+        __syncthreads();
+        // ---- 3. counting sort: the members of every group, contiguous
+        for (uint32_t i = tid; i < size; i += 256) {
+            const uint32_t r = S.rep[i];
+            S.u.g.member[S.u.g.off[r] + atomicSub(&S.cnt[r], 1u) - 1] = (uint16_t)i;
+        }
+        __syncthreads();
+        const uint32_t P = S.total_pairs;
+        if (P == 0) continue;                                                 // all singletons (uniform: every thread read the same word)
+        // ---- 4. duplicates: the same genome earlier in the group's member list
+        for (uint32_t x = tid; x < size; x += 256) {
+            const uint32_t i = S.u.g.member[x] & (MEMBER_DUP - 1);
+            const uint32_t start = S.u.g.off[S.rep[i]];
+            if (start == x) continue;
             const uint32_t g = S.gids[i];
-            uint32_t j = S.prev[i];                                           // no flags are set during this phase
-            while (j != CHAIN_END) {
-                if (S.gids[j] == g) {
-                    dup_mask |= 1u << t;
+            for (uint32_t y = start; y < x; ++y)
+                if (S.gids[S.u.g.member[y] & (MEMBER_DUP - 1)] == g) {
+                    S.u.g.member[x] = (uint16_t)(i | MEMBER_DUP);
                     atomicAdd(&dup_cnt[g], 1u);
                     break;
                 }
-                j = S.prev[j];
-            }
         }
-        __syncthreads();                                                      // all chain walks done: now flag the duplicates
-        t = 0;
-        for (uint32_t i = tid; i < size; i += 256, ++t)
-            if ((dup_mask >> t) & 1u) S.prev[i] = (uint16_t)(S.prev[i] | CHAIN_DUP);
         __syncthreads();
-        // ---- pair increments: every non-duplicate tuple with every non-duplicate tuple before it in its chain
-        for (uint32_t i = tid; i < size; i += 256) {
-            const uint32_t pi = S.prev[i];
-            if (pi & CHAIN_DUP) continue;
-            const uint32_t g = S.gids[i];
-            uint32_t j = pi;
-            while (j != CHAIN_END) {
-                const uint32_t pj = S.prev[j];
-                if (!(pj & CHAIN_DUP)) fresh += pair_add(A, g, S.gids[j]);
-                j = pj & CHAIN_END;
+        // ---- 5. pair increments: the pairs (a, b), b < a, of all groups as one index space, an equal share per thread
+        {
+            const uint32_t chunk = (P + 255) / 256;
+            uint32_t p0 = tid * chunk;
+            const uint32_t p1 = min(P, p0 + chunk);
+            if (p0 < p1) {
+                uint32_t lo = 0, hi = size;                                   // the last tuple index with poff <= p0: a representative
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.u.g.poff[mid] <= p0) lo = mid + 1; else hi = mid; }
+                uint32_t r = lo - 1;
+                uint32_t q = p0 - S.u.g.poff[r];
+                uint32_t pc = S.u.g.poff[r + 1] - S.u.g.poff[r];
+                uint32_t start = S.u.g.off[r];
+                uint32_t a = (uint32_t)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
+                while (a * (a - 1) / 2 > q) --a;
+                while ((a + 1) * a / 2 <= q) ++a;
+                uint32_t b = q - a * (a - 1) / 2;
+                for (; p0 < p1; ++p0) {
+                    const uint32_t xa = S.u.g.member[start + a], xb = S.u.g.member[start + b];
+                    if (!((xa | xb) & MEMBER_DUP)) fresh += pair_add(A, S.gids[xa], S.gids[xb]);
+                    if (++q == pc) {                                          // next group with pairs
+                        if (p0 + 1 == p1) break;
+                        do { ++r; pc = S.u.g.poff[r + 1] - S.u.g.poff[r]; } while (pc == 0);
+                        start = S.u.g.off[r]; q = 0; a = 1; b = 0;
+                    } else if (++b == a) { ++a; b = 0; }
+                }
             }
         }
         __syncthreads();
@@ -923,7 +1027,7 @@ __global__ void __launch_bounds__(256) acc_emit_kernel(PairAcc A, uint64_t n_ent
         uint32_t v = 0, row = 0, col = 0;
         if (i < n_entries) {
             if (A.dense) { v = A.dense[i]; if (v) tri_decode(i, row, col); }
-            else { const uint64_t k = A.tkeys[i]; if (k != SLOT_EMPTY) { v = A.tvals[i]; row = (uint32_t)(k >> 32); col = (uint32_t)k; } }
+            else { const PairSlot e = A.slots[i]; if (e.key != SLOT_EMPTY) { v = e.val; row = (uint32_t)(e.key >> 32); col = (uint32_t)e.key; } }
         }
         uint32_t d1 = 0xffffffffu, d2 = 0xffffffffu;
         if (v) {
@@ -1050,24 +1154,22 @@ void dev_exscan(vb_ctx *ctx, cudaStream_t st, const uint32_t *in, uint32_t n, ui
 }
 
 struct Accumulator {
-    PairAcc acc = {nullptr, nullptr, nullptr, 0, nullptr};
-    DevBuf<uint32_t> dense, tvals;
-    DevBuf<uint64_t> tkeys;
+    PairAcc acc = {nullptr, nullptr, 0, nullptr};
+    DevBuf<uint32_t> dense;
+    DevBuf<PairSlot> slots;
     uint64_t cap = 0;                    // dense: N(N-1)/2 entries; hashed: slots
     bool is_dense() const { return acc.dense != nullptr; }
 };
 
 void acc_alloc_hashed(vb_ctx *ctx, cudaStream_t st, Accumulator &a, uint64_t cap, unsigned long long *status)
 {
-    if (cap > (1ULL << 34)) throw vb_error(VB_ERR_MEM, "pair table would exceed 2^34 slots");
+    if (cap > (1ULL << 33)) throw vb_error(VB_ERR_MEM, "pair table would exceed 2^33 slots");
     PoolScope pool;
-    a.tkeys.alloc(cap);
-    a.tvals.alloc(cap);
-    VB_CUDA(cudaMemsetAsync(a.tkeys.p, 0xff, a.tkeys.bytes(), st));       // SLOT_EMPTY
-    VB_CUDA(cudaMemsetAsync(a.tvals.p, 0, a.tvals.bytes(), st));
+    a.slots.alloc(cap);
+    table_clear_kernel<<<(int)std::min<uint64_t>((cap + 255) / 256, 148 * 16), 256, 0, st>>>(a.slots.p, cap);
+    VB_LAUNCH_CHECK(ctx);
     a.cap = cap;
-    a.acc = {nullptr, a.tkeys.p, a.tvals.p, cap - 1, status};
-    (void)ctx;
+    a.acc = {nullptr, a.slots.p, cap - 1, status};
 }
 
 // grow the hashed table to new_cap slots, keeping its contents
@@ -1075,9 +1177,9 @@ void acc_grow(vb_ctx *ctx, cudaStream_t st, Accumulator &a, uint64_t new_cap)
 {
     Accumulator b;
     acc_alloc_hashed(ctx, st, b, new_cap, a.acc.status);
-    rehash_kernel<<<grid_for(a.cap), 256, 0, st>>>(a.tkeys.p, a.tvals.p, a.cap, b.acc);
+    rehash_kernel<<<grid_for(a.cap), 256, 0, st>>>(a.slots.p, a.cap, b.acc);
     VB_LAUNCH_CHECK(ctx);
-    a.tkeys = std::move(b.tkeys); a.tvals = std::move(b.tvals);
+    a.slots = std::move(b.slots);
     a.cap = b.cap; a.acc = b.acc;
 }
 
@@ -1263,7 +1365,11 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     const uint64_t cap_env = getenv("VB_PREFILTER_TABLE") ? strtoull(getenv("VB_PREFILTER_TABLE"), nullptr, 10) : 0;   // test hook: initial slots
     uint64_t cap_hint = 1024;
     if (cap_env) { while (cap_hint < cap_env) cap_hint <<= 1; }
-    else {
+    else if (ctx->pair_hint_uid == g->uid && ctx->pair_hint_n == n && ctx->pair_hint_k == p->k && ctx->pair_hint_entries > 0) {
+        // the same genome set again: size the table for the number of distinct pairs the last call saw (load <= 0.4), so
+        // that it is as cache-friendly as it can be; a wrong guess costs a grow or, at worst, a redo
+        while ((double)cap_hint < 2.5 * (double)ctx->pair_hint_entries) cap_hint <<= 1;
+    } else {
         const double guess = std::min((double)max_pairs * 2.0, std::max(1048576.0, est_all / world / 4.0));
         while ((double)cap_hint < guess) cap_hint <<= 1;
     }
@@ -1296,10 +1402,10 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     if (want_dense) {
         if (!A.dense.p) { PoolScope pool; A.dense.alloc(std::max<unsigned long long>(max_pairs, 1)); }
         VB_CUDA(cudaMemsetAsync(A.dense.p, 0, A.dense.bytes(), st));
-        A.acc = {A.dense.p, nullptr, nullptr, 0, scalars.p};
+        A.acc = {A.dense.p, nullptr, 0, scalars.p};
         A.cap = max_pairs;
     } else {
-        A.tkeys.release(); A.tvals.release();
+        A.slots.release();
         acc_alloc_hashed(ctx, st, A, cap_hint, scalars.p);
     }
 
@@ -1360,7 +1466,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         });
         // level-1 histogram (tuples per parent, all ranks' parents) -> offsets of the level-1 / send buffer
         DevBuf<uint32_t> hist1(B1), off1(B1 + 1), cursor1(B1), scan_tmp(1025);
-        coarsen_kernel<<<(B1 + 255) / 256, 256, 0, st>>>(fine_hist.p, 1, 0, 0, B1, hist1.p);
+        coarsen_kernel<<<(B1 + 255) / 256, 256, 0, st>>>(fine_hist.p, 1, 0, 1, B1, hist1.p);
         VB_LAUNCH_CHECK(ctx);
         dev_exscan(ctx, st, hist1.p, B1, off1.p, cursor1.p, scan_tmp.p);
         // every rank's offsets, gathered (one rank: just its own), and the survivor count: one synchronisation
@@ -1384,7 +1490,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         const uint32_t tiles1 = (uint32_t)((n_keep + PART_TILE - 1) / PART_TILE);
         if (tiles1) {
             part_kernel<1><<<std::min<uint32_t>(tiles1, n_sm * 8), PART_THREADS, part_smem, st>>>(
-                n_keep, B1, 0, keys0.p, vals0.p, nullptr, 0, tiles1, cursor1.p, keys1.p, vals1.p);
+                n_keep, B1, 1, keys0.p, vals0.p, nullptr, 0, tiles1, cursor1.p, keys1.p, vals1.p);
             VB_LAUNCH_CHECK(ctx);
         }
         t_part->stop();
@@ -1440,21 +1546,20 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
 
         // ---- level 2: parents -> final buckets
         t_part = lap_start(ms_part);
-        int b2 = 0;
-        while ((double)n_recv / (double)((uint64_t)Bper << b2) > BUCKET_TARGET && b2 < MAX_BUCKET_BITS) ++b2;
-        const uint32_t NB = Bper << b2;
+        const uint32_t B2 = (uint32_t)std::min<uint64_t>(1u << MAX_BUCKET_BITS, std::max<uint64_t>(1, (n_recv / Bper + BUCKET_TARGET - 1) / BUCKET_TARGET));
+        const uint32_t NB = Bper * B2;
         DevBuf<uint32_t> hist(NB), off(NB + 1), cursor2(NB), big_list(NB + 1), n_big(1);
         DevBuf<Segment> d_segs(std::max<size_t>(segs.size(), 1));
         VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
         if (!segs.empty()) VB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st));
-        coarsen_kernel<<<(NB + 255) / 256, 256, 0, st>>>(fine_src, fine_n_src, (uint64_t)Bper << FINE_BITS, b2, NB, hist.p);
+        coarsen_kernel<<<(NB + 255) / 256, 256, 0, st>>>(fine_src, fine_n_src, (uint64_t)Bper << FINE_BITS, B2, NB, hist.p);
         VB_LAUNCH_CHECK(ctx);
         dev_exscan(ctx, st, hist.p, NB, off.p, cursor2.p, scan_tmp.p);
         DevBuf<uint64_t> keys2(n_recv + 64);
         DevBuf<uint32_t> vals2(n_recv + 64);
         if (tiles2) {
             part_kernel<2><<<std::min<uint32_t>(tiles2, n_sm * 8), PART_THREADS, part_smem, st>>>(
-                n_recv, B1, b2, rkeys, rvals, d_segs.p, (uint32_t)segs.size(), tiles2, cursor2.p, keys2.p, vals2.p);
+                n_recv, B1, B2, rkeys, rvals, d_segs.p, (uint32_t)segs.size(), tiles2, cursor2.p, keys2.p, vals2.p);
             VB_LAUNCH_CHECK(ctx);
         }
         t_part->stop();
@@ -1536,8 +1641,8 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
                 VB_CUDA(cudaStreamSynchronize(st));           // d_jobs / members are released below
             }
         }
-        // the table is grown between passes while it is more than a quarter full (never inside a pass)
-        if (!A.is_dense() && pass + 1 < passes && h_status[1] > A.cap / 4) acc_grow(ctx, st, A, A.cap * 4);
+        // the table is grown between passes when it is more than half full (never inside a pass)
+        if (!A.is_dense() && pass + 1 < passes && h_status[1] > A.cap / 2) acc_grow(ctx, st, A, A.cap * 4);
         VB_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 3 * sizeof(unsigned long long), st));     // screen / collect counters of the next pass
         t_grp->stop();
     }
@@ -1547,6 +1652,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     VB_LAUNCH_CHECK(ctx);
     unsigned long long h_over[2] = {0, 0};
     if (world > 1) {
+        VB_CUDA(cudaMemcpyAsync(h_over + 1, scalars.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaMemcpyAsync(totals + n, scalars.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));     // low word of the flag
         comm_check(comm->all_reduce_sum_u32(comm->user, totals, (uint64_t)n + 1), "all_reduce(total k-mers)");
         uint32_t any = 0;
@@ -1557,7 +1663,11 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         VB_CUDA(cudaMemcpyAsync(h_over, scalars.p, sizeof(h_over), cudaMemcpyDeviceToHost, st));
         VB_CUDA(cudaStreamSynchronize(st));
     }
-    if (!h_over[0]) break;
+    if (!h_over[0]) {
+        ctx->pair_hint_uid = g->uid; ctx->pair_hint_n = n; ctx->pair_hint_k = p->k;
+        ctx->pair_hint_entries = A.is_dense() ? 0 : h_over[1];
+        break;
+    }
     if (attempt >= 6) throw vb_error(VB_ERR_MEM, "pair table overflow");
     cap_hint = A.cap * 8;
     }   // attempts
@@ -1639,7 +1749,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         if (n_pad) sort_entries(ctx, st, sb, n_recv, n_pad, 2 * em.gbits, ws, skeys, svals);
         finalize_sorted(ctx, st, skeys, svals, n_pad, totals, em, false, scalars.p + 7, scalars.p + 8, fin, keep_dev);
     }
-    A.dense.release(); A.tkeys.release(); A.tvals.release();
+    A.dense.release(); A.slots.release();
 
     // ---- what goes to the host: one rank: everything; several ranks: the pairs whose row this rank owns, gathered on rank 0
     // (read-backs go through the context's page-locked staging buffer: pageable targets would make every copy synchronous)

@@ -199,8 +199,9 @@ int vb_shard_align(vb_shard *sh, const vb_align_params *p, vb_align_out **out)
     comm_check(cm.all_to_all(cm.user, fo.n ? fo.stats.p : dummy_s.p, scv.data(), st_all.p, rcv.data(), 12), "all_to_all(result statistics)");
     vb_align_out *res = nullptr;
     if (rank == 0) {
-        std::vector<uint64_t> keys(total);
-        std::vector<int32_t> stats(3 * total);
+        char *pin = (char *)vb_pinned(ctx, 20 * total + 16);
+        const uint64_t *keys = (const uint64_t *)pin;
+        const int32_t *stats = (const int32_t *)(pin + 8 * total);
         if (total) {
             rsort::Workspace ws;
             iota_kernel<<<grid_for(n_pad), 256, 0, st>>>(va.p, n_pad);
@@ -209,12 +210,12 @@ int vb_shard_align(vb_shard *sh, const vb_align_params *p, vb_align_out **out)
             const bool in_b = rsort::sort_kv<8>(ctx, ka.p, va.p, kb.p, vbuf.p, n_pad, 2 * fo.gbits, ws);
             gather3_kernel<<<grid_for(total), 256, 0, st>>>(st_all.p, in_b ? vbuf.p : va.p, total, st_sorted.p);
             VB_LAUNCH_CHECK(ctx);
-            VB_CUDA(cudaMemcpyAsync(keys.data(), in_b ? kb.p : ka.p, sizeof(uint64_t) * total, cudaMemcpyDeviceToHost, st));
-            VB_CUDA(cudaMemcpyAsync(stats.data(), st_sorted.p, sizeof(int32_t) * 3 * total, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(pin, in_b ? kb.p : ka.p, sizeof(uint64_t) * total, cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaMemcpyAsync(pin + 8 * total, st_sorted.p, sizeof(int32_t) * 3 * total, cudaMemcpyDeviceToHost, st));
         }
         t_g.stop();
+        res = vb_align_out_alloc_impl(total, n);            // (host allocation overlaps the transfer)
         VB_CUDA(cudaStreamSynchronize(st));
-        res = vb_align_out_alloc_impl(total, n);
         const std::vector<uint32_t> &order = vb_lz_order(sh->meta);
         std::copy(order.begin(), order.end(), res->order);
         const uint64_t qmask = (1ULL << fo.gbits) - 1;

@@ -121,6 +121,9 @@ struct vb_ctx {
     std::vector<vb_resident> resident;
     vb_resident last = {nullptr, 0, 0, nullptr};   // the most recent upload that was not made resident (implicit cache)
     DevPairs *dev_pairs = nullptr;   // candidate list of the last vb_prefilter, kept on the device for vb_align
+    uint64_t pair_hint_uid = 0, pair_hint_entries = 0;    // distinct pairs the last hashed-table prefilter of set `uid` produced
+    uint32_t pair_hint_n = 0;
+    int pair_hint_k = 0;
     void *pin_buf = nullptr;         // page-locked staging buffer for result read-backs (grown on demand, kept)
     size_t pin_cap = 0;
     std::vector<vb_timing> timings;
