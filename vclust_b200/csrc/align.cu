@@ -36,8 +36,8 @@ struct LzParams { int mal, msl, mrd, mqd, reg, aw, am, ar; };
 struct RefDesc {
     uint64_t rec_off;    // record offset of the text in ref_rec (one uint4 per 32 symbols)
     uint64_t ht_off;     // slot offset of the anchor table
-    uint32_t ht_cap;     // home slots (range reduction by multiply-shift); the table has ht_tail more slots behind them, so
-    uint32_t ht_tail;    // that a probe chain never wraps: ht_tail >= number of entries
+    uint32_t ht_cap;     // home slots (range reduction by multiply-shift); the table has ht_tail more slots behind them that
+    uint32_t ht_tail;    // take the overflow of the last home slots (a chain wraps to slot 0 only beyond them)
     uint32_t pos_bits;   // a slot is fingerprint << pos_bits | position, 2^pos_bits > n
     uint32_t n;          // text length: 2*len + 3*mrd
     uint32_t len;        // genome length
@@ -170,10 +170,10 @@ __global__ void __launch_bounds__(256) build_ref_text_kernel(const uint4 *__rest
 //      (home slot, entry) goes to a per-block scratch list, a shared-memory histogram counts the entries per partition;
 //   2. the list is counting-sorted by partition (second scratch list; both are L2-resident);
 //   3. partition by partition: clear, insert the carried and the own entries (shared-memory CAS, all lanes busy), store.
-// Linear probing never wraps: an entry that reaches the end of its partition is carried into the next one (rare unless
-// the genome is a long repeat), and the table ends with ht_tail >= #entries spare slots, so the carries of the last home
-// partition always find room.  Any insertion order gives a table the lookup reads the same way (it takes the maximum
-// over the whole probe chain).
+// An entry that reaches the end of its partition is carried into the next one (rare unless the genome is a long repeat);
+// the table ends with ht_tail spare slots for the carries of the last home partition, and what is still carried at the
+// very end wraps around: the first partitions are then read back, topped up and stored again.  Any insertion order
+// gives a table the lookup reads the same way (it takes the maximum over the whole probe chain).
 constexpr uint32_t IDX_PS = 8192;
 constexpr int IDX_THREADS = 256;
 constexpr int IDX_CHUNK = 8;
@@ -304,6 +304,28 @@ __global__ void __launch_bounds__(IDX_THREADS, 5) build_ref_index_kernel(const R
             __syncthreads();
             uint4 *o4 = (uint4 *)(out + pbase);         // tables start 16-byte aligned, partition sizes are multiples of 1024
             const uint4 *t4 = (const uint4 *)tab;
+            for (uint32_t i = threadIdx.x; i < plen / 4; i += IDX_THREADS) o4[i] = t4[i];
+            __syncthreads();
+        }
+        // entries still carried at the end of the table (a genome that is mostly one repeat) wrap around to its start:
+        // the finished partitions are read back, topped up and stored again until nothing is left to carry
+        for (uint32_t pbase = 0; s_carry_n[cur] != 0; pbase = pbase + IDX_PS < total ? pbase + IDX_PS : 0u, cur ^= 1) {
+            const uint32_t plen = min(IDX_PS, total - pbase);
+            const uint32_t n_in = s_carry_n[cur];
+            uint4 *o4 = (uint4 *)(out + pbase);
+            uint4 *t4 = (uint4 *)tab;
+            for (uint32_t i = threadIdx.x; i < plen / 4; i += IDX_THREADS) t4[i] = o4[i];
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry_n[cur ^ 1] = 0;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n_in; i += IDX_THREADS) {
+                const uint32_t val = carry(cur)[i];
+                uint32_t s = 0;
+                for (; s < plen; ++s)
+                    if (atomicCAS(&tab[s], HT_EMPTY, val) == HT_EMPTY) break;
+                if (s == plen) carry(cur ^ 1)[atomicAdd(&s_carry_n[cur ^ 1], 1u)] = val;
+            }
+            __syncthreads();
             for (uint32_t i = threadIdx.x; i < plen / 4; i += IDX_THREADS) o4[i] = t4[i];
             __syncthreads();
         }
@@ -533,8 +555,10 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, ui
     const int rc0 = len + 2 * P.mrd;
     int my_len = 0, my_pos = 0x7fffffff;
     for (uint32_t step = 0;; step += 32) {
-        const uint32_t at = slot0 + step + lane;            // chains never wrap: the table has spare slots behind its home range,
-        uint32_t s = at < ttotal ? __ldg(tab + at) : HT_EMPTY;  // and it ends with an empty one
+        uint32_t at = slot0 + step + lane;                  // chains wrap only at the very end of the table (spare slots behind
+        if (at >= ttotal) at -= ttotal;                     // the home range take the ordinary overflows)
+        if (at >= ttotal) at -= ttotal;
+        uint32_t s = __ldg(tab + at);
         unsigned empties = __ballot_sync(0xffffffffu, s == HT_EMPTY);
         bool in_chain = empties == 0 || lane < (__ffs(empties) - 1);
         if (in_chain && (s >> pos_bits) == fp) {
@@ -546,7 +570,7 @@ __device__ void anchor_search(const uint32_t *__restrict__ tab, uint32_t cap, ui
                 if (ml >= P.mal && (ml > my_len || (ml == my_len && pos < my_pos))) { my_len = ml; my_pos = pos; }
             }
         }
-        if (empties) break;                                 // an empty slot ends the chain
+        if (empties || step + 32 >= ttotal) break;          // an empty slot ends the chain; else the whole table was seen
     }
     int mx = __reduce_max_sync(0xffffffffu, my_len);
     if (mx == 0) return;
@@ -774,7 +798,7 @@ __device__ void parse_pair(const Text &Q, const Text &R, const uint32_t *__restr
         while (pr_live) {                                 // resolve the probe: any entry with this fingerprint in the chain?
             if (pr_s == HT_EMPTY) break;
             if ((pr_s >> pos_bits) == pr_fp) { flag = true; break; }
-            ++pr_slot;                                    // (the table ends with an empty slot: no bound check)
+            pr_slot = (pr_slot + 1 == ttotal) ? 0u : pr_slot + 1;
             pr_s = __ldg(tab + pr_slot);
         }
         unsigned fb = __ballot_sync(0xffffffffu, flag);
@@ -1111,7 +1135,9 @@ static uint64_t ref_table_slots(uint64_t len)
     return std::max<uint64_t>(1024, ((uint64_t)quarter_slots * (len + 1) / 4 + 1023) / 1024 * 1024);
 }
 
-static uint64_t ref_table_tail(uint64_t len) { return (len + 1 + 1023) / 1024 * 1024; }   // >= entries + 1: chains never wrap
+// spare slots behind the home range: probe chains run into them instead of wrapping; only a chain that is still not
+// finished at the very end of the table (a genome that is mostly one repeat) continues at slot 0
+static uint64_t ref_table_tail(uint64_t len) { (void)len; return 1024; }
 
 static uint64_t ref_bytes(uint64_t len, int mrd)
 {

@@ -624,10 +624,10 @@ struct BucketSmem {
 // groups are then enumerated as one flat index space split evenly over the threads -- every lane does the same amount
 // of work whatever the group sizes (walking per-tuple chains instead left most lanes of a warp idle: 5.3 G warp
 // instructions at c3, 40 % of them in the pair loop).
-__global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                                     const uint32_t *__restrict__ off, uint32_t n_buckets,
-                                                     uint32_t *__restrict__ dup_cnt, PairAcc A,
-                                                     uint32_t *__restrict__ big_list, uint32_t *__restrict__ n_big)
+__global__ void __launch_bounds__(256) bucket_flat_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                          const uint32_t *__restrict__ off, uint32_t n_buckets,
+                                                          uint32_t *__restrict__ dup_cnt, PairAcc A,
+                                                          uint32_t *__restrict__ big_list, uint32_t *__restrict__ n_big)
 {
     extern __shared__ unsigned char smem_raw[];
     BucketSmem &S = *(BucketSmem *)smem_raw;
@@ -748,6 +748,97 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint64_t *__restrict_
                         start = S.u.g.off[r]; q = 0; a = 1; b = 0;
                     } else if (++b == a) { ++a; b = 0; }
                 }
+            }
+        }
+        __syncthreads();
+    }
+    if (!A.dense) flush_fresh(A, fresh);
+}
+
+// The same grouping with per-tuple CHAINS instead of group arrays: a tuple finds the slot of its key and swaps itself in
+// as the slot's newest member, keeping the previous one as its predecessor; its chain is then exactly the set of tuples
+// with the same k-mer inserted before it, so walking it enumerates every unordered pair of the group once.  Fewer
+// phases (three block-wide barriers fewer) but the walks leave lanes idle when group sizes differ inside a warp: faster
+// for small families (c2, c3: 8.4 vs 13.2 ms), no faster for families of hundreds; vb_prefilter_run picks the flat kernel
+// for large groups on the hashed table (VB_PREFILTER_BUCKET=chain|flat forces one).
+constexpr uint32_t CHAIN_END = 0xffffu;
+struct ChainSmem {
+    uint64_t keys[BUCKET_CAP];                 // h of every tuple
+    uint32_t gids[BUCKET_CAP];
+    uint32_t table[BUCKET_SLOTS];              // slot -> the most recently inserted tuple with the slot's key
+    uint16_t prev[BUCKET_CAP];                 // the previous tuple with the same k-mer
+    uint32_t dup[BUCKET_CAP / 32];             // bit i: tuple i repeats a genome that is already in its chain
+};
+
+__global__ void __launch_bounds__(256) bucket_chain_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                           const uint32_t *__restrict__ off, uint32_t n_buckets,
+                                                           uint32_t *__restrict__ dup_cnt, PairAcc A,
+                                                           uint32_t *__restrict__ big_list, uint32_t *__restrict__ n_big)
+{
+    extern __shared__ unsigned char smem_raw[];
+    ChainSmem &S = *(ChainSmem *)smem_raw;
+    const int tid = threadIdx.x;
+    uint32_t fresh = 0;
+    for (uint32_t bkt = blockIdx.x; bkt < n_buckets; bkt += gridDim.x) {
+        const uint32_t beg = off[bkt], size = off[bkt + 1] - beg;
+        if (size < 2) continue;                                              // uniform for the block
+        if (size > BUCKET_CAP) {                                             // too big for shared memory: generic path
+            if (tid == 0) big_list[atomicAdd(n_big, 1u)] = bkt;
+            continue;
+        }
+        for (int s = tid; s < BUCKET_SLOTS; s += 256) S.table[s] = 0xffffffffu;
+        if (tid < BUCKET_CAP / 32) S.dup[tid] = 0;
+        for (uint32_t i = tid; i < size; i += 256) { S.keys[i] = keys[beg + i]; S.gids[i] = vals[beg + i]; }
+        {   // the bucket this block takes next: pull its lines into L2 while this one is grouped
+            const uint32_t nxt = bkt + gridDim.x;
+            if (nxt < n_buckets) {
+                const uint32_t nb = off[nxt], ns = min(off[nxt + 1] - nb, (uint32_t)BUCKET_CAP);
+                for (uint32_t i = tid * 16; i < ns; i += 256 * 16) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(keys + nb + i));
+                    if ((i & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals + nb + i));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- insert: chain every tuple to the earlier tuples with the same key
+        for (uint32_t i = tid; i < size; i += 256) {
+            const uint64_t k = S.keys[i];
+            uint32_t s = (uint32_t)k & (BUCKET_SLOTS - 1);                    // low bits: independent of the bucket bits
+            uint32_t pv = CHAIN_END;
+            for (;;) {
+                uint32_t cur = S.table[s];
+                if (cur == 0xffffffffu) {
+                    cur = atomicCAS(&S.table[s], 0xffffffffu, i);
+                    if (cur == 0xffffffffu) break;                            // first tuple with this key
+                }
+                if (S.keys[cur] == k) { pv = atomicExch(&S.table[s], i); break; }
+                s = (s + 1) & (BUCKET_SLOTS - 1);
+            }
+            S.prev[i] = (uint16_t)pv;
+        }
+        __syncthreads();
+        // ---- duplicates: same genome earlier in the chain (flagged in a bit mask, read by the next phase)
+        for (uint32_t i = tid; i < size; i += 256) {
+            const uint32_t g = S.gids[i];
+            uint32_t j = S.prev[i];
+            while (j != CHAIN_END) {
+                if (S.gids[j] == g) {
+                    atomicOr(&S.dup[i >> 5], 1u << (i & 31));
+                    atomicAdd(&dup_cnt[g], 1u);
+                    break;
+                }
+                j = S.prev[j];
+            }
+        }
+        __syncthreads();
+        // ---- pair increments: every non-duplicate tuple with every non-duplicate tuple before it in its chain
+        for (uint32_t i = tid; i < size; i += 256) {
+            uint32_t j = S.prev[i];
+            if (j == CHAIN_END || ((S.dup[i >> 5] >> (i & 31)) & 1u)) continue;
+            const uint32_t g = S.gids[i];
+            while (j != CHAIN_END) {
+                if (!((S.dup[j >> 5] >> (j & 31)) & 1u)) fresh += pair_add(A, g, S.gids[j]);
+                j = S.prev[j];
             }
         }
         __syncthreads();
@@ -1383,11 +1474,19 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         if (!attr_done) {
             VB_CUDA(cudaFuncSetAttribute(part_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
             VB_CUDA(cudaFuncSetAttribute(part_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
-            VB_CUDA(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
+            VB_CUDA(cudaFuncSetAttribute(bucket_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BucketSmem)));
+            VB_CUDA(cudaFuncSetAttribute(bucket_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem)));
             attr_done = true;
         }
     }
 
+    // grouping kernel: chains for small families, flat pair enumeration for large ones (see bucket_chain_kernel)
+    // The flat kernel pays when groups are large AND every increment is a dependent look-up in the hashed table (a thread
+    // that walks a chain of 200 serialises 200 global round trips); known from the previous call on the same set: more
+    // than 32 distinct pairs per genome.  c3 (families of 20, dense counters): chains 8.4 ms, flat 13.2 ms.
+    const char *bk_env = getenv("VB_PREFILTER_BUCKET");
+    const bool hint_ok = ctx->pair_hint_uid == g->uid && ctx->pair_hint_n == n && ctx->pair_hint_k == p->k;
+    const bool flat_buckets = bk_env ? strcmp(bk_env, "flat") == 0 : (hint_ok && ctx->pair_hint_entries > 32ULL * n);
     unsigned long long n_survivors_all = 0, n_tuples_grouped = 0, n_bubbles = 0;
     Accumulator A;
     for (int attempt = 0;; ++attempt) {
@@ -1570,7 +1669,10 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         DevBuf<HugeRun> huge_list(huge_cap);
         VB_CUDA(cudaMemsetAsync(scalars.p + 2, 0, sizeof(unsigned long long), st));
         const int bgrid = (int)std::min<uint32_t>(NB, n_sm * 12);
-        bucket_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(keys2.p, vals2.p, off.p, NB, dup_cnt, A.acc, big_list.p, n_big.p);
+        if (flat_buckets)
+            bucket_flat_kernel<<<bgrid, 256, sizeof(BucketSmem), st>>>(keys2.p, vals2.p, off.p, NB, dup_cnt, A.acc, big_list.p, n_big.p);
+        else
+            bucket_chain_kernel<<<bgrid, 256, sizeof(ChainSmem), st>>>(keys2.p, vals2.p, off.p, NB, dup_cnt, A.acc, big_list.p, n_big.p);
         VB_LAUNCH_CHECK(ctx);
         big_bucket_kernel<<<64, 1024, 0, st>>>(keys2.p, vals2.p, off.p, big_list.p, n_big.p, dup_cnt, A.acc, huge_list.p, huge_cap, scalars.p + 2);
         VB_LAUNCH_CHECK(ctx);
