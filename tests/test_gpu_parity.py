@@ -464,11 +464,16 @@ def _bubble_set():
     return ["b%05d" % i for i in range(len(seqs))], seqs
 
 
-@pytest.mark.parametrize("env", [{}, {"VB_PREFILTER_HASH": "1"}, {"VB_PREFILTER_NO_COLLAPSE": "1", "VB_PREFILTER_PASSES": "2"}])
-def test_prefilter_bubbles_vs_kmerdb(ctx, tmp_path, monkeypatch, env):
+@pytest.mark.parametrize("env,min_kmers,min_ident", [
+    ({}, 230, 0.5),                                                     # dense counters: bubbles expanded at once
+    ({"VB_PREFILTER_HASH": "1"}, 230, 0.5),                             # hashed table: bubbles deferred, added when the thresholds are applied
+    ({"VB_PREFILTER_HASH": "1", "VB_PREFILTER_PASSES": "3"}, 100, 0.97),   # ... and pairs of "heavy" genomes (bubble weight >= min-kmers) expanded
+    ({"VB_PREFILTER_NO_COLLAPSE": "1", "VB_PREFILTER_PASSES": "2"}, 230, 0.5),
+])
+def test_prefilter_bubbles_vs_kmerdb(ctx, tmp_path, monkeypatch, env, min_kmers, min_ident):
     """k-mers shared by more than 8 000 genomes against the unmodified kmer-db (which defers them as "bubbles"): the
-    filter file must be byte-identical.  --min-kmers above the size of the cores keeps the file small while every kept
-    pair still needs the bubble counts to be right."""
+    filter file must be byte-identical.  --min-kmers above the size of the cores (or a high --min-ident) keeps the file
+    small while every kept pair still needs the bubble counts to be right."""
     if not oracle.ref_available():
         pytest.skip("oracle/_ref binaries not present")
     for k, v in env.items():
@@ -476,8 +481,8 @@ def test_prefilter_bubbles_vs_kmerdb(ctx, tmp_path, monkeypatch, env):
     names, seqs = _bubble_set()
     fa = tmp_path / "bubbles.fna"
     synth.write_fasta(fa, names, seqs)
-    api.prefilter([fa], tmp_path / "fltr.txt", True, kmer_size=21, min_kmers=230, min_ident=0.5)
-    oracle.ref_prefilter([fa], tmp_path / "ref.txt", tmp_path / "p", k=21, min_kmers=230, min_ident=0.5)
+    api.prefilter([fa], tmp_path / "fltr.txt", True, kmer_size=21, min_kmers=min_kmers, min_ident=min_ident)
+    oracle.ref_prefilter([fa], tmp_path / "ref.txt", tmp_path / "p", k=21, min_kmers=min_kmers, min_ident=min_ident)
     got = (tmp_path / "fltr.txt").read_bytes()
     assert got == (tmp_path / "ref.txt").read_bytes()
     assert got.count(b":") > 8000            # families of 5 -> ~17 000 pairs

@@ -1002,6 +1002,66 @@ __global__ void __launch_bounds__(256) bubble_pairs_kernel(const uint32_t *__res
     if (!A.dense) flush_fresh(A, fresh);
 }
 
+// ---- deferred bubbles (hashed accumulator) ---------------------------------------------------------------------------
+// Expanding a k-mer shared by 20 000 genomes costs 2 x 10^8 table entries -- nearly all of them pairs that share nothing
+// else and can never reach --min-kmers.  kmer-db applies its bubbles per row when the matrix is compacted
+// (array.h:392-446); the analogue here: the member sets are kept (BubSet), every rank learns all of them, and
+//   * a pair of two "heavy" genomes (total bubble weight W >= min_kmers each: such a pair could pass on bubbles alone) gets
+//     its bubble counts by expansion, restricted to the heavy members of each set;
+//   * every other pair can only pass if it also shares an ordinary k-mer, i.e. if it is in some rank's table anyway: the
+//     finalize kernel adds  sum of w over the sets that contain both genomes  (intersection of two short presence lists)
+//     to the summed partial counts before it applies the thresholds.
+struct BubSet { uint32_t off, m, w; };          // members [off, off + m) of the bubble store, multiplicity w
+
+__global__ void __launch_bounds__(256) bub_count_kernel(const uint32_t *__restrict__ members, const BubSet *__restrict__ sets, uint32_t n_sets,
+                                                        uint32_t *__restrict__ cnt, uint32_t *__restrict__ W)
+{
+    for (uint32_t b = blockIdx.x; b < n_sets; b += gridDim.x) {
+        const BubSet st = sets[b];
+        for (uint32_t i = threadIdx.x; i < st.m; i += blockDim.x) {
+            const uint32_t g = members[st.off + i];
+            atomicAdd(&cnt[g], 1u);
+            atomicAdd(&W[g], st.w);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) bub_fill_kernel(const uint32_t *__restrict__ members, const BubSet *__restrict__ sets, uint32_t n_sets,
+                                                       const uint32_t *__restrict__ off, uint32_t *__restrict__ fill, uint32_t *__restrict__ pres)
+{
+    for (uint32_t b = blockIdx.x; b < n_sets; b += gridDim.x) {
+        const BubSet st = sets[b];
+        for (uint32_t i = threadIdx.x; i < st.m; i += blockDim.x) {
+            const uint32_t g = members[st.off + i];
+            pres[off[g] + atomicAdd(&fill[g], 1u)] = b;
+        }
+    }
+}
+// the heavy members (W >= thr) of sets [first, first + n_own), compacted in order into out at the set's own offset
+__global__ void __launch_bounds__(1024) bub_filter_kernel(const uint32_t *__restrict__ members, const BubSet *__restrict__ sets, uint32_t first,
+                                                          uint32_t n_own, const uint32_t *__restrict__ W, uint32_t thr,
+                                                          uint32_t *__restrict__ out, uint32_t *__restrict__ m_out)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_total, s_run;
+    for (uint32_t q = blockIdx.x; q < n_own; q += gridDim.x) {
+        const BubSet st = sets[first + q];
+        if (threadIdx.x == 0) s_run = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < st.m; base += 1024) {
+            const uint32_t i = base + threadIdx.x;
+            uint32_t g = 0, keep = 0;
+            if (i < st.m) { g = members[st.off + i]; keep = W[g] >= thr ? 1u : 0u; }
+            const uint32_t pre = block_exscan_1024(keep, warp_tot, &s_total);
+            if (keep) out[st.off + s_run + pre] = g;
+            __syncthreads();
+            if (threadIdx.x == 0) s_run += s_total;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) m_out[q] = s_run;
+        __syncthreads();
+    }
+}
+
 __global__ void totals_kernel(const uint32_t *__restrict__ valid_cnt, const uint32_t *__restrict__ dup_cnt, uint32_t n,
                               uint32_t *__restrict__ totals)
 {
@@ -1018,7 +1078,27 @@ struct EmitParams {
     int k;
     int gbits;
     uint32_t world, rank;       // multi-GPU: owner(g) = g % world
+    // deferred bubbles (null: none): presence lists per genome (CSR over set ids), the sets, total bubble weight per genome
+    const uint32_t *pres_off, *pres, *bub_W;
+    const BubSet *bub_sets;
+    uint32_t heavy_thr;
 };
+
+// what the bubbles add to the pair (r, c): nothing for two heavy genomes (their pairs were expanded), else the weights of
+// the sets that contain both
+__device__ __forceinline__ uint32_t bubble_common(const EmitParams &ep, uint32_t r, uint32_t c)
+{
+    if (!ep.pres_off) return 0;
+    if (ep.bub_W[r] >= ep.heavy_thr && ep.bub_W[c] >= ep.heavy_thr) return 0;
+    const uint32_t a0 = ep.pres_off[r], a1 = ep.pres_off[r + 1], b0 = ep.pres_off[c], b1 = ep.pres_off[c + 1];
+    uint32_t sum = 0;
+    for (uint32_t x = a0; x < a1; ++x) {
+        const uint32_t id = ep.pres[x];
+        for (uint32_t y = b0; y < b1; ++y)
+            if (ep.pres[y] == id) { sum += ep.bub_sets[id].w; break; }
+    }
+    return sum;
+}
 constexpr double ANI_MARGIN = 1e-9;         // |device ani - host ani| is ~1e-16; anything closer to the threshold is re-checked on the host
 constexpr uint32_t BORDERLINE = 0x80000000u;
 
@@ -1124,7 +1204,7 @@ __global__ void __launch_bounds__(256) acc_emit_kernel(PairAcc A, uint64_t n_ent
         if (v) {
             if (ep.world == 1) {
                 float ani;
-                if (v >= ep.min_kmers && ani_test(v, totals[row], totals[col], ep, ani)) d1 = 0;
+                if (ep.pres_off || (v >= ep.min_kmers && ani_test(v, totals[row], totals[col], ep, ani))) d1 = 0;
             } else {
                 d1 = row % ep.world; d2 = col % ep.world;
                 if (d2 == d1) d2 = 0xffffffffu;
@@ -1179,8 +1259,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const uint64_t *__restric
             if (k != KEY_SENTINEL && (t == 0 || keys[t - 1] != k)) {
                 uint64_t s = 0;
                 for (uint64_t j = t; j < n && keys[j] == k; ++j) s += vals[j];
-                sum = (uint32_t)s;
                 row = (uint32_t)(k >> ep.gbits); col = (uint32_t)(k & cmask);
+                sum = (uint32_t)s + bubble_common(ep, row, col);
                 if (sum >= ep.min_kmers && sum > 0 && (!mine_only || row % ep.world == ep.rank))
                     ok = ani_test(sum, totals[row], totals[col], ep, ani);
             }
@@ -1489,6 +1569,13 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     const bool flat_buckets = bk_env ? strcmp(bk_env, "flat") == 0 : (hint_ok && ctx->pair_hint_entries > 32ULL * n);
     unsigned long long n_survivors_all = 0, n_tuples_grouped = 0, n_bubbles = 0;
     Accumulator A;
+    // deferred bubbles (hashed accumulator): member sets of all passes, kept until the thresholds are applied
+    DevBuf<uint32_t> bub_members;            // the store: concatenated member lists
+    uint64_t bub_used = 0;
+    std::vector<BubSet> bub_sets;            // this rank's sets (offsets into bub_members)
+    DevBuf<uint32_t> bub_all_members, bub_pres_off, bub_pres, bub_W;   // after the passes: all ranks' sets, presence lists
+    DevBuf<BubSet> bub_all_sets;
+    bool bub_active = false;
     for (int attempt = 0;; ++attempt) {
     // (a retry re-runs all passes into a larger table: an insert that found no slot is lost, so nothing can be salvaged)
     if (attempt > 0) {
@@ -1497,6 +1584,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         if (use_seen) VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
         screened = false;
         n_survivors_all = 0; n_tuples_grouped = 0; n_bubbles = 0;
+        bub_used = 0; bub_sets.clear(); bub_active = false;
     }
     if (want_dense) {
         if (!A.dense.p) { PoolScope pool; A.dense.alloc(std::max<unsigned long long>(max_pairs, 1)); }
@@ -1720,21 +1808,33 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
             std::vector<uint32_t> weight(nh, 0);
             for (uint32_t i = 0; i < nh; ++i) { if (differ[i]) rep[i] = i; weight[rep[i]]++; }   // (a signature collision: expand on its own)
             std::vector<BubbleJob> jobs;
-            uint64_t tiles = 0, new_pairs = 0;
+            uint64_t tiles = 0;
             for (uint32_t i = 0; i < nh; ++i) {
                 if (!weight[i] || info[i].m < 2) continue;
                 const uint64_t T = (info[i].m + 127) / 128;
-                if (tiles + T * (T + 1) / 2 >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "bubble k-mers too large for one pass");
+                if (A.is_dense() && tiles + T * (T + 1) / 2 >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "bubble k-mers too large for one pass");
                 jobs.push_back({info[i].beg, info[i].m, weight[i], (uint32_t)tiles});
                 tiles += T * (T + 1) / 2;
-                new_pairs += (uint64_t)info[i].m * (info[i].m - 1) / 2;
             }
-            if (!A.is_dense()) {                              // make room: every pair of a bubble may be new
-                uint64_t need = 1024;
-                while (need < 2 * (h_status[1] + new_pairs)) need <<= 1;
-                if (need > A.cap) acc_grow(ctx, st, A, need);
-            }
-            if (!jobs.empty()) {
+            if (!A.is_dense()) {
+                // hashed accumulator: the sets are kept, their pairs are resolved when the thresholds are applied (see BubSet)
+                uint64_t need = bub_used;
+                for (auto &jb : jobs) need += jb.m;
+                if (need > bub_members.n) {
+                    PoolScope pool;
+                    DevBuf<uint32_t> bigger(std::max<uint64_t>(need, 2 * bub_members.n) + 1024);
+                    if (bub_used) VB_CUDA(cudaMemcpyAsync(bigger.p, bub_members.p, sizeof(uint32_t) * bub_used, cudaMemcpyDeviceToDevice, st));
+                    VB_CUDA(cudaStreamSynchronize(st));
+                    bub_members = std::move(bigger);
+                }
+                for (auto &jb : jobs) {
+                    VB_CUDA(cudaMemcpyAsync(bub_members.p + bub_used, members.p + jb.beg, sizeof(uint32_t) * jb.m, cudaMemcpyDeviceToDevice, st));
+                    bub_sets.push_back({(uint32_t)bub_used, jb.m, jb.weight});
+                    bub_used += jb.m;
+                }
+                if (bub_used >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 bubble members on one rank");
+                VB_CUDA(cudaStreamSynchronize(st));           // members is released below
+            } else if (!jobs.empty()) {
                 DevBuf<BubbleJob> d_jobs(jobs.size());
                 VB_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(BubbleJob) * jobs.size(), cudaMemcpyHostToDevice, st));
                 bubble_pairs_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)n_sm * 16), 256, 0, st>>>(members.p, d_jobs.p, (uint32_t)jobs.size(),
@@ -1747,6 +1847,108 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         if (!A.is_dense() && pass + 1 < passes && h_status[1] > A.cap / 2) acc_grow(ctx, st, A, A.cap * 4);
         VB_CUDA(cudaMemsetAsync(scalars.p + 4, 0, 3 * sizeof(unsigned long long), st));     // screen / collect counters of the next pass
         t_grp->stop();
+    }
+
+    // ---- deferred bubbles: every rank learns all sets; presence lists; pairs of heavy genomes expanded (see BubSet)
+    if (!A.is_dense()) {
+        unsigned long long mine[2] = {bub_sets.size(), bub_used};
+        std::vector<unsigned long long> cnts(2 * (size_t)world, 0);
+        cnts[0] = mine[0]; cnts[1] = mine[1];
+        if (world > 1) {
+            DevBuf<unsigned long long> d_mine(2), d_cnts(2 * (size_t)world);
+            VB_CUDA(cudaMemcpyAsync(d_mine.p, mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+            comm_check(comm->all_gather(comm->user, d_mine.p, d_cnts.p, sizeof(mine)), "all_gather(bubble counts)");
+            VB_CUDA(cudaMemcpyAsync(cnts.data(), d_cnts.p, sizeof(unsigned long long) * cnts.size(), cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+        }
+        uint64_t max_sets = 0, max_mem = 0, all_sets = 0;
+        for (uint32_t r = 0; r < world; ++r) { max_sets = std::max<uint64_t>(max_sets, cnts[2 * r]); max_mem = std::max<uint64_t>(max_mem, cnts[2 * r + 1]); all_sets += cnts[2 * r]; }
+        if (all_sets) {
+            bub_active = true;
+            if ((uint64_t)world * max_mem >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 bubble members");
+            PoolScope pool;
+            // members of all ranks, rank r's at r * max_mem; set descriptors rebuilt on the host with global offsets
+            std::vector<BubSet> sets_all;
+            uint32_t my_first = 0;
+            bub_all_members.alloc((uint64_t)world * max_mem + 1);
+            if (world > 1) {
+                DevBuf<uint32_t> pad_mem(max_mem + 1), desc_send(3 * max_sets + 3), desc_all((uint64_t)world * (3 * max_sets + 3));
+                VB_CUDA(cudaMemsetAsync(pad_mem.p, 0, pad_mem.bytes(), st));
+                if (bub_used) VB_CUDA(cudaMemcpyAsync(pad_mem.p, bub_members.p, sizeof(uint32_t) * bub_used, cudaMemcpyDeviceToDevice, st));
+                std::vector<uint32_t> h_desc(3 * max_sets + 3, 0);
+                for (size_t i = 0; i < bub_sets.size(); ++i) { h_desc[3 * i] = bub_sets[i].off; h_desc[3 * i + 1] = bub_sets[i].m; h_desc[3 * i + 2] = bub_sets[i].w; }
+                VB_CUDA(cudaMemcpyAsync(desc_send.p, h_desc.data(), sizeof(uint32_t) * h_desc.size(), cudaMemcpyHostToDevice, st));
+                comm_check(comm->all_gather(comm->user, pad_mem.p, bub_all_members.p, sizeof(uint32_t) * max_mem), "all_gather(bubble members)");
+                comm_check(comm->all_gather(comm->user, desc_send.p, desc_all.p, sizeof(uint32_t) * (3 * max_sets + 3)), "all_gather(bubble sets)");
+                std::vector<uint32_t> h_all((size_t)world * (3 * max_sets + 3));
+                VB_CUDA(cudaMemcpyAsync(h_all.data(), desc_all.p, sizeof(uint32_t) * h_all.size(), cudaMemcpyDeviceToHost, st));
+                VB_CUDA(cudaStreamSynchronize(st));
+                for (uint32_t r = 0; r < world; ++r) {
+                    if (r == rank) my_first = (uint32_t)sets_all.size();
+                    const uint32_t *d = h_all.data() + (size_t)r * (3 * max_sets + 3);
+                    for (uint64_t i = 0; i < cnts[2 * r]; ++i) sets_all.push_back({d[3 * i] + (uint32_t)(r * max_mem), d[3 * i + 1], d[3 * i + 2]});
+                }
+            } else {
+                VB_CUDA(cudaMemcpyAsync(bub_all_members.p, bub_members.p, sizeof(uint32_t) * bub_used, cudaMemcpyDeviceToDevice, st));
+                sets_all = bub_sets;
+            }
+            const uint32_t ns = (uint32_t)sets_all.size();
+            bub_all_sets.alloc(ns);
+            VB_CUDA(cudaMemcpyAsync(bub_all_sets.p, sets_all.data(), sizeof(BubSet) * ns, cudaMemcpyHostToDevice, st));
+            // presence lists: sets per genome (CSR) and the genomes' total bubble weights
+            if ((uint64_t)n + 1 > (1u << 20)) throw vb_error(VB_ERR_ARG, "bubble k-mers with more than 2^20 genomes are not supported");
+            bub_pres_off.alloc((size_t)n + 2);
+            bub_W.alloc(std::max<uint32_t>(n, 1));
+            DevBuf<uint32_t> cnt(std::max<uint32_t>(n, 1)), fill(std::max<uint32_t>(n, 1)), scan_tmp2(1025);
+            VB_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+            VB_CUDA(cudaMemsetAsync(fill.p, 0, fill.bytes(), st));
+            VB_CUDA(cudaMemsetAsync(bub_W.p, 0, bub_W.bytes(), st));
+            const int sgrid = (int)std::min<uint32_t>(ns, (uint32_t)n_sm * 8);
+            bub_count_kernel<<<sgrid, 256, 0, st>>>(bub_all_members.p, bub_all_sets.p, ns, cnt.p, bub_W.p);
+            VB_LAUNCH_CHECK(ctx);
+            dev_exscan(ctx, st, cnt.p, n, bub_pres_off.p, nullptr, scan_tmp2.p);
+            uint32_t total_pres = 0;
+            VB_CUDA(cudaMemcpyAsync(&total_pres, bub_pres_off.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+            bub_pres.alloc((size_t)total_pres + 1);
+            bub_fill_kernel<<<sgrid, 256, 0, st>>>(bub_all_members.p, bub_all_sets.p, ns, bub_pres_off.p, fill.p, bub_pres.p);
+            VB_LAUNCH_CHECK(ctx);
+            // pairs of two heavy genomes: expansion of this rank's own sets, restricted to their heavy members
+            const uint32_t heavy_thr = partial ? 1u : (uint32_t)std::max(p->min_kmers, 1);
+            const uint32_t n_own = (uint32_t)bub_sets.size();
+            if (n_own) {
+                DevBuf<uint32_t> heavy_members((uint64_t)world * max_mem + 1), m_out(n_own);
+                bub_filter_kernel<<<std::min<uint32_t>(n_own, (uint32_t)n_sm * 2), 1024, 0, st>>>(bub_all_members.p, bub_all_sets.p, my_first, n_own, bub_W.p,
+                                                                                               heavy_thr, heavy_members.p, m_out.p);
+                VB_LAUNCH_CHECK(ctx);
+                std::vector<uint32_t> h_m(n_own);
+                unsigned long long entries_now = 0;
+                VB_CUDA(cudaMemcpyAsync(h_m.data(), m_out.p, sizeof(uint32_t) * n_own, cudaMemcpyDeviceToHost, st));
+                VB_CUDA(cudaMemcpyAsync(&entries_now, scalars.p + 1, sizeof(entries_now), cudaMemcpyDeviceToHost, st));
+                VB_CUDA(cudaStreamSynchronize(st));
+                std::vector<BubbleJob> jobs;
+                uint64_t tiles = 0, new_pairs = 0;
+                for (uint32_t q = 0; q < n_own; ++q) {
+                    if (h_m[q] < 2) continue;
+                    const uint64_t T = (h_m[q] + 127) / 128;
+                    if (tiles + T * (T + 1) / 2 >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "bubble k-mers too large to expand");
+                    jobs.push_back({sets_all[my_first + q].off, h_m[q], sets_all[my_first + q].w, (uint32_t)tiles});
+                    tiles += T * (T + 1) / 2;
+                    new_pairs += (uint64_t)h_m[q] * (h_m[q] - 1) / 2;
+                }
+                if (!jobs.empty()) {
+                    uint64_t need = 1024;                        // make room: every pair may be new
+                    while (need < 2 * (entries_now + new_pairs)) need <<= 1;
+                    if (need > A.cap) acc_grow(ctx, st, A, need);
+                    DevBuf<BubbleJob> d_jobs(jobs.size());
+                    VB_CUDA(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(BubbleJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+                    bubble_pairs_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)n_sm * 16), 256, 0, st>>>(heavy_members.p, d_jobs.p, (uint32_t)jobs.size(),
+                                                                                                                  (uint32_t)tiles, A.acc);
+                    VB_LAUNCH_CHECK(ctx);
+                    VB_CUDA(cudaStreamSynchronize(st));
+                }
+            }
+        }
     }
 
     // ---- totals (all ranks: all-reduce) and the overflow flag of all ranks
@@ -1784,6 +1986,9 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     em.gbits = 1;
     while ((1ULL << em.gbits) < n) em.gbits++;
     em.world = world; em.rank = rank;
+    em.pres_off = bub_active ? bub_pres_off.p : nullptr;
+    em.pres = bub_pres.p; em.bub_W = bub_W.p; em.bub_sets = bub_all_sets.p;
+    em.heavy_thr = partial ? 1u : (uint32_t)std::max(p->min_kmers, 1);
     FinalList fin;                       // pairs that involve this rank's genomes (one rank: all pairs)
     const bool keep_dev = job.keep_dev && !partial && p->max_seqs <= 0;
     if (A.is_dense() && world == 1) {
@@ -1885,6 +2090,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
             }
             EmitParams raw = em;
             raw.min_kmers = 0; raw.min_ident = -1.0;             // already thresholded: only select the rows this rank owns
+            raw.pres_off = nullptr;
             finalize_sorted(ctx, st, sb.ka.p, sb.va.p, n_in, totals, raw, true, scalars.p + 7, scalars.p + 9, mine, false);
         }
         DevBuf<unsigned long long> d_cnt(1), d_all(world);
