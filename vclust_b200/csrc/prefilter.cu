@@ -1189,7 +1189,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *__restrict_
 // pass 0 counts per destination into dest_cnt[world]; pass 1 appends at dest_cur[d] (pre-set to the region starts).
 __global__ void __launch_bounds__(256) acc_emit_kernel(PairAcc A, uint64_t n_entries, const uint32_t *__restrict__ totals, EmitParams ep,
                                                        int write, unsigned long long *__restrict__ dest_cur,
-                                                       uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals)
+                                                       uint64_t *__restrict__ out_keys, uint32_t *__restrict__ out_vals, uint4 *__restrict__ out_rec)
 {
     const int lane = threadIdx.x & 31;
     // n_entries rounded up to whole warps by the loop condition: every lane of a warp takes part in the ballots
@@ -1220,8 +1220,9 @@ __global__ void __launch_bounds__(256) acc_emit_kernel(PairAcc A, uint64_t n_ent
             base = __shfl_sync(0xffffffffu, base, leader);
             if (mine && write) {
                 const unsigned long long o = base + __popc(m & ((1u << lane) - 1));
-                out_keys[o] = ((uint64_t)row << ep.gbits) | col;
-                out_vals[o] = v;
+                const uint64_t ck = ((uint64_t)row << ep.gbits) | col;
+                if (out_rec) out_rec[o] = make_uint4((uint32_t)ck, (uint32_t)(ck >> 32), v, 0u);      // one 16-byte record: one all-to-all
+                else { out_keys[o] = ck; out_vals[o] = v; }
             }
         }
     }
@@ -1283,6 +1284,23 @@ __global__ void __launch_bounds__(256) finalize_kernel(const uint64_t *__restric
         __syncthreads();
     }
     if (!write && threadIdx.x == 0) block_cnt[blockIdx.x] = s_run;
+}
+
+// 16-byte exchange records {key, value} <-> the sort's key / value arrays (small exchanges travel as ONE all-to-all)
+__global__ void unpack_rec_kernel(const uint4 *__restrict__ rec, uint64_t n, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 r = rec[i];
+        keys[i] = ((uint64_t)r.y << 32) | r.x; vals[i] = r.z;
+    }
+}
+// final list (row << 32 | col, value) -> records with the compact sort key (row << gbits | col)
+__global__ void pack_final_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, int gbits, uint4 *__restrict__ rec)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t ck = ((keys[i] >> 32) << gbits) | (uint32_t)keys[i];
+        rec[i] = make_uint4((uint32_t)ck, (uint32_t)(ck >> 32), vals[i], 0u);
+    }
 }
 
 // final key (row << 32 | col) -> compact sort key (row << gbits | col)
@@ -1670,50 +1688,90 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         n_survivors_all += n_keep;
         t_ext->stop();
 
-        // ---- level 1: tuples -> parents (the send buffer of all-to-all #1)
+        // ---- level 1: tuples -> parents; ordered by parent, the level-1 buffer is the send buffer of all-to-all #1 (several
+        // ranks): every parent's tuples travel to the rank that owns the parent.
         EventTimer *t_part = lap_start(ms_part);
+        const uint32_t tiles1 = (uint32_t)((n_keep + PART_TILE - 1) / PART_TILE);
+        const uint64_t fine_slice = (uint64_t)Bper << FINE_BITS;                 // fine-histogram entries per destination rank
+        std::vector<uint64_t> sc(world, 0), rc(world, 0), recv_of(world, 0);     // tuples I send to / receive from d; all tuples d receives
+        for (uint32_t d = 0; d < world; ++d) {
+            sc[d] = my_off1[(d + 1) * Bper] - my_off1[d * Bper];
+            for (uint32_t s2 = 0; s2 < world; ++s2) {
+                const uint32_t *o = h_off1_all.data() + (size_t)s2 * (B1 + 1);
+                const uint64_t c = o[(d + 1) * Bper] - o[d * Bper];
+                recv_of[d] += c;
+                if (d == rank) rc[s2] = c;
+            }
+        }
+        uint64_t n_recv = world > 1 ? recv_of[rank] : n_keep;
+        if (n_recv >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 k-mer tuples arrive at one rank in one pass: raise VB_PREFILTER_PASSES");
         DevBuf<uint64_t> keys1(n_keep + 64);
         DevBuf<uint32_t> vals1(n_keep + 64);
-        const uint32_t tiles1 = (uint32_t)((n_keep + PART_TILE - 1) / PART_TILE);
         if (tiles1) {
             part_kernel<1><<<std::min<uint32_t>(tiles1, n_sm * 8), PART_THREADS, part_smem, st>>>(
                 n_keep, B1, 1, keys0.p, vals0.p, nullptr, 0, tiles1, cursor1.p, keys1.p, vals1.p);
             VB_LAUNCH_CHECK(ctx);
         }
         t_part->stop();
+        // Two ways to move the tuples: NCCL all-to-alls, or -- when the ranks' receive buffers are mapped into each other's
+        // address space (vb_peer_xbuf, CUDA IPC) -- one peer copy per destination straight out of the level-1 buffer (a
+        // destination's parents are contiguous there) over NVLink, with a one-word all-reduce as the barrier behind them.
+        // Layout of a receive buffer: [keys of all segments][vals of all segments] ... [fine histograms: world slices] at the end.
+        bool use_peer = world > 1 && job.xbuf != nullptr;
+        uint64_t fine_at = 0;
+        if (use_peer) {
+            fine_at = (job.xbuf->cap - 4 * fine_slice * world) / 16 * 16;
+            for (uint32_t d = 0; d < world; ++d)
+                if (4 * fine_slice * world + 64 > job.xbuf->cap || 12 * recv_of[d] + 64 > fine_at) use_peer = false;   // (every rank decides alike)
+        }
+        auto vals_base = [&](uint64_t n_all) { return (8 * n_all + 15) / 16 * 16; };       // byte offset of the vals region in a receive buffer
 
-        // ---- all-to-all #1 (several ranks): every parent's tuples travel to the rank that owns the parent
         const uint64_t *rkeys = keys1.p;
         const uint32_t *rvals = vals1.p;
         DevBuf<uint64_t> keysR;
-        DevBuf<uint32_t> valsR, fineR;
+        DevBuf<uint32_t> valsR, fineR, d_flag(1);
         const uint32_t *fine_src = fine_hist.p + ((size_t)rank * Bper << FINE_BITS);
         uint32_t fine_n_src = 1;
         std::vector<Segment> segs;
-        uint64_t n_recv = n_keep;
         if (world > 1) {
             EventTimer *t_x = lap_start(ms_exch);
-            std::vector<uint64_t> sc(world), rc(world);
-            n_recv = 0;
-            for (uint32_t d = 0; d < world; ++d) {
-                sc[d] = my_off1[(d + 1) * Bper] - my_off1[d * Bper];
-                const uint32_t *o = h_off1_all.data() + (size_t)d * (B1 + 1);
-                rc[d] = o[(rank + 1) * Bper] - o[rank * Bper];
-                n_recv += rc[d];
+            if (use_peer) {
+                // destinations in a rotated order, so that the ranks do not all write to the same peer at the same time
+                for (uint32_t t = 0; t < world; ++t) {
+                    const uint32_t d = (rank + 1 + t) % world;
+                    uint64_t before = 0;                                        // tuples of the ranks before me in d's buffer
+                    for (uint32_t s2 = 0; s2 < rank; ++s2) {
+                        const uint32_t *o = h_off1_all.data() + (size_t)s2 * (B1 + 1);
+                        before += o[(d + 1) * Bper] - o[d * Bper];
+                    }
+                    char *base = (char *)job.xbuf->peer[d];
+                    if (sc[d]) {
+                        VB_CUDA(cudaMemcpyAsync(base + 8 * before, keys1.p + my_off1[d * Bper], 8 * sc[d], cudaMemcpyDeviceToDevice, st));
+                        VB_CUDA(cudaMemcpyAsync(base + vals_base(recv_of[d]) + 4 * before, vals1.p + my_off1[d * Bper], 4 * sc[d], cudaMemcpyDeviceToDevice, st));
+                    }
+                    VB_CUDA(cudaMemcpyAsync(base + fine_at + 4 * fine_slice * rank, fine_hist.p + fine_slice * d, 4 * fine_slice, cudaMemcpyDeviceToDevice, st));
+                }
+                // the all-reduce returns once every rank's copies are behind it
+                VB_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(uint32_t), st));
+                comm_check(comm->all_reduce_sum_u32(comm->user, d_flag.p, 1), "all_reduce(exchange barrier)");
+                rkeys = (const uint64_t *)job.xbuf->local;
+                rvals = (const uint32_t *)((const char *)job.xbuf->local + vals_base(n_recv));
+                fine_src = (const uint32_t *)((const char *)job.xbuf->local + fine_at);
+            } else {
+                keysR.alloc(n_recv + 64); valsR.alloc(n_recv + 64);
+                comm_check(comm->all_to_all(comm->user, keys1.p, sc.data(), keysR.p, rc.data(), 8), "all_to_all(tuple hashes)");
+                comm_check(comm->all_to_all(comm->user, vals1.p, sc.data(), valsR.p, rc.data(), 4), "all_to_all(tuple genomes)");
+                // the fine histograms of my parents, from every rank
+                fineR.alloc((size_t)world * fine_slice);
+                std::vector<uint64_t> fc(world, fine_slice);
+                comm_check(comm->all_to_all(comm->user, fine_hist.p, fc.data(), fineR.p, fc.data(), 4), "all_to_all(bucket histograms)");
+                fine_src = fineR.p;
+                rkeys = keysR.p; rvals = valsR.p;
             }
-            if (n_recv >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 k-mer tuples arrive at one rank in one pass: raise VB_PREFILTER_PASSES");
-            keysR.alloc(n_recv + 64); valsR.alloc(n_recv + 64);
-            comm_check(comm->all_to_all(comm->user, keys1.p, sc.data(), keysR.p, rc.data(), 8), "all_to_all(tuple hashes)");
-            comm_check(comm->all_to_all(comm->user, vals1.p, sc.data(), valsR.p, rc.data(), 4), "all_to_all(tuple genomes)");
-            // the fine histograms of my parents, from every rank
-            fineR.alloc((size_t)world * (Bper << FINE_BITS));
-            std::vector<uint64_t> fc(world, (uint64_t)Bper << FINE_BITS);
-            comm_check(comm->all_to_all(comm->user, fine_hist.p, fc.data(), fineR.p, fc.data(), 4), "all_to_all(bucket histograms)");
-            fine_src = fineR.p; fine_n_src = world;
-            rkeys = keysR.p; rvals = valsR.p;
+            fine_n_src = world;
             uint64_t at = 0;
-            for (uint32_t s = 0; s < world; ++s) {                       // segments: (source rank, parent)
-                const uint32_t *o = h_off1_all.data() + (size_t)s * (B1 + 1);
+            for (uint32_t s2 = 0; s2 < world; ++s2) {                     // segments: (source rank, parent)
+                const uint32_t *o = h_off1_all.data() + (size_t)s2 * (B1 + 1);
                 for (uint32_t j = 0; j < Bper; ++j) {
                     const uint32_t len = o[rank * Bper + j + 1] - o[rank * Bper + j];
                     if (len) segs.push_back({(uint32_t)at, len, j, 0});
@@ -2016,7 +2074,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         DevBuf<unsigned long long> dest_cur(world);
         VB_CUDA(cudaMemsetAsync(dest_cur.p, 0, sizeof(unsigned long long) * world, st));
         const uint64_t n_entries = A.cap;
-        acc_emit_kernel<<<grid_for(n_entries), 256, 0, st>>>(A.acc, n_entries, totals, em, 0, dest_cur.p, nullptr, nullptr);
+        acc_emit_kernel<<<grid_for(n_entries), 256, 0, st>>>(A.acc, n_entries, totals, em, 0, dest_cur.p, nullptr, nullptr, nullptr);
         VB_LAUNCH_CHECK(ctx);
         std::vector<unsigned long long> sc(world), all_counts((size_t)world * world, 0);
         if (world > 1) {
@@ -2038,17 +2096,16 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         if (n_recv >= (1ULL << 32) - rsort::TILE || n_send >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 partial pair counts at one rank");
         const uint64_t n_pad = (n_recv + rsort::TILE - 1) / rsort::TILE * rsort::TILE;
         SortBufs sb;
-        DevBuf<uint64_t> sendk(world > 1 ? n_send + 1 : 1);
-        DevBuf<uint32_t> sendv(world > 1 ? n_send + 1 : 1);
+        DevBuf<uint4> send_rec(world > 1 ? n_send + 1 : 1), recv_rec(world > 1 ? n_recv + 1 : 1);
         sb.ka.alloc(n_pad + 1); sb.kb.alloc(n_pad + 1); sb.va.alloc(n_pad + 1); sb.vb.alloc(n_pad + 1);
         VB_CUDA(cudaMemcpyAsync(dest_cur.p, starts.data(), sizeof(unsigned long long) * world, cudaMemcpyHostToDevice, st));
-        acc_emit_kernel<<<grid_for(n_entries), 256, 0, st>>>(A.acc, n_entries, totals, em, 1, dest_cur.p, world > 1 ? sendk.p : sb.ka.p,
-                                                             world > 1 ? sendv.p : sb.va.p);
+        acc_emit_kernel<<<grid_for(n_entries), 256, 0, st>>>(A.acc, n_entries, totals, em, 1, dest_cur.p, sb.ka.p, sb.va.p,
+                                                             world > 1 ? send_rec.p : nullptr);
         VB_LAUNCH_CHECK(ctx);
         if (world > 1) {
             EventTimer *t_x = lap_start(ms_exch);
-            comm_check(comm->all_to_all(comm->user, sendk.p, scv.data(), sb.ka.p, rcv.data(), 8), "all_to_all(pair keys)");
-            comm_check(comm->all_to_all(comm->user, sendv.p, scv.data(), sb.va.p, rcv.data(), 4), "all_to_all(pair counts)");
+            comm_check(comm->all_to_all(comm->user, send_rec.p, scv.data(), recv_rec.p, rcv.data(), 16), "all_to_all(partial pair counts)");
+            if (n_recv) { unpack_rec_kernel<<<grid_for(n_recv), 256, 0, st>>>(recv_rec.p, n_recv, sb.ka.p, sb.va.p); VB_LAUNCH_CHECK(ctx); }
             t_x->stop();
         }
         const uint64_t *skeys = nullptr;
@@ -2108,11 +2165,10 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         const uint64_t n_pad = (total + rsort::TILE - 1) / rsort::TILE * rsort::TILE;
         SortBufs sb;
         sb.ka.alloc(n_pad + 1); sb.kb.alloc(n_pad + 1); sb.va.alloc(n_pad + 1); sb.vb.alloc(n_pad + 1);
-        DevBuf<uint64_t> ck(mine.n + 1);
-        if (mine.n) { compact_keys_kernel<<<grid_for(mine.n), 256, 0, st>>>(mine.keys.p, mine.n, em.gbits, ck.p); VB_LAUNCH_CHECK(ctx); }
-        DevBuf<uint32_t> dummy(1);
-        comm_check(comm->all_to_all(comm->user, ck.p, scv.data(), sb.ka.p, rcv.data(), 8), "all_to_all(result keys)");
-        comm_check(comm->all_to_all(comm->user, mine.n ? mine.vals.p : dummy.p, scv.data(), sb.va.p, rcv.data(), 4), "all_to_all(result counts)");
+        DevBuf<uint4> send_rec(mine.n + 1), recv_rec(total + 1);
+        if (mine.n) { pack_final_kernel<<<grid_for(mine.n), 256, 0, st>>>(mine.keys.p, mine.vals.p, mine.n, em.gbits, send_rec.p); VB_LAUNCH_CHECK(ctx); }
+        comm_check(comm->all_to_all(comm->user, send_rec.p, scv.data(), recv_rec.p, rcv.data(), 16), "all_to_all(result pairs)");
+        if (total) { unpack_rec_kernel<<<grid_for(total), 256, 0, st>>>(recv_rec.p, total, sb.ka.p, sb.va.p); VB_LAUNCH_CHECK(ctx); }
         stage(rank == 0 ? total : 0);
         if (rank == 0 && total) {
             const uint64_t *skeys = nullptr;
@@ -2215,6 +2271,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     ctx->set_timing("prefilter.sort_ms", ms_part);
     ctx->set_timing("prefilter.segment_ms", ms_group);
     ctx->set_timing("prefilter.exchange_ms", ms_exch);
+    ctx->set_timing("prefilter.peer_stores", world > 1 && job.xbuf ? 1.0 : 0.0);
     ctx->set_timing("prefilter.emit_ms", t_emit.ms());
     ctx->set_timing("prefilter.passes", (double)passes);
     ctx->set_timing("prefilter.tuples", (double)dg.total_slots);

@@ -24,6 +24,13 @@ struct vb_shard {
     uint64_t block_slots = 0;            // slots of every rank's (padded) local store
     DevGenomes all;                      // rec / gofs / glen of ALL genomes (rec all-gathered); no seq2 / inv_kdb / tile map
     double est_kmers_all = 0;
+    vb_peer_xbuf xbuf;                   // all-to-all #1 as direct peer stores (empty: NCCL all-to-all)
+    ~vb_shard()
+    {
+        for (size_t r = 0; r < xbuf.peer.size(); ++r)
+            if (xbuf.peer[r] && xbuf.peer[r] != xbuf.local) cudaIpcCloseMemHandle(xbuf.peer[r]);
+        if (xbuf.local) cudaFree(xbuf.local);
+    }
 };
 
 namespace {
@@ -47,6 +54,21 @@ __global__ void gather3_kernel(const int32_t *__restrict__ in, const uint32_t *_
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t j = perm[i];
         out[3 * i] = in[3 * j]; out[3 * i + 1] = in[3 * j + 1]; out[3 * i + 2] = in[3 * j + 2];
+    }
+}
+
+// align results as 24-byte records {key, 3 ints, pad}: one all-to-all instead of two
+struct ResRec { uint64_t key; int32_t st[3]; uint32_t pad; };
+__global__ void pack_res_kernel(const uint64_t *__restrict__ keys, const int32_t *__restrict__ stats, uint64_t n, ResRec *__restrict__ rec)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        rec[i] = {keys[i], {stats[3 * i], stats[3 * i + 1], stats[3 * i + 2]}, 0u};
+}
+__global__ void unpack_res_kernel(const ResRec *__restrict__ rec, uint64_t n, uint64_t *__restrict__ keys, int32_t *__restrict__ stats)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const ResRec r = rec[i];
+        keys[i] = r.key; stats[3 * i] = r.st[0]; stats[3 * i + 1] = r.st[1]; stats[3 * i + 2] = r.st[2];
     }
 }
 
@@ -141,6 +163,54 @@ int vb_shard_create(vb_ctx *ctx, const vb_comm *comm, const vb_genomes *meta, co
     }
     VB_CUDA(cudaStreamSynchronize(st));
     ctx->set_timing("shard.block_slots", (double)max_slots);
+    // Receive buffers for the tuple exchange, exported to all ranks (CUDA IPC): one pass moves at most ~10^9 tuples in all
+    // (the prefilter's pass planner), 12 bytes each, plus the bucket histograms.  Every rank tries; the path is used only
+    // if it works everywhere (VB_SHARD_NO_PEER=1 forces the NCCL all-to-all).
+    if (world > 1) {
+        const double per_rank = std::min(total_len, 1.0e9) / world;
+        const uint64_t cap = ((uint64_t)(12.0 * 1.4 * per_rank) + (64ull << 20) + 4095) / 4096 * 4096;
+        uint32_t ok = getenv("VB_SHARD_NO_PEER") ? 0u : 1u;
+        cudaIpcMemHandle_t mine_h;
+        memset(&mine_h, 0, sizeof(mine_h));
+        if (ok && cudaMalloc(&sh->xbuf.local, cap) != cudaSuccess) { cudaGetLastError(); sh->xbuf.local = nullptr; ok = 0; }
+        if (ok && cudaIpcGetMemHandle(&mine_h, sh->xbuf.local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        DevBuf<uint32_t> d_h(17), d_all(17 * (size_t)world);
+        uint32_t send[17];
+        memcpy(send, &mine_h, 64);
+        send[16] = ok;
+        std::vector<uint32_t> all(17 * (size_t)world);
+        VB_CUDA(cudaMemcpyAsync(d_h.p, send, sizeof(send), cudaMemcpyHostToDevice, st));
+        comm_check(comm->all_gather(comm->user, d_h.p, d_all.p, sizeof(send)), "all_gather(IPC handles)");
+        VB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(uint32_t) * all.size(), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        bool everyone = true;
+        for (uint32_t r = 0; r < world; ++r) everyone = everyone && all[17 * r + 16] == 1;
+        sh->xbuf.peer.assign(world, nullptr);
+        if (everyone) {
+            for (uint32_t r = 0; r < world && ok; ++r) {
+                if (r == (uint32_t)comm->rank) { sh->xbuf.peer[r] = sh->xbuf.local; continue; }
+                cudaIpcMemHandle_t h;
+                memcpy(&h, &all[17 * r], 64);
+                if (cudaIpcOpenMemHandle(&sh->xbuf.peer[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); sh->xbuf.peer[r] = nullptr; ok = 0; }
+            }
+        } else ok = 0;
+        // did every rank map every buffer?
+        DevBuf<uint32_t> d_ok(1);
+        VB_CUDA(cudaMemcpyAsync(d_ok.p, &ok, sizeof(ok), cudaMemcpyHostToDevice, st));
+        comm_check(comm->all_reduce_sum_u32(comm->user, d_ok.p, 1), "all_reduce(peer mapping)");
+        uint32_t n_ok = 0;
+        VB_CUDA(cudaMemcpyAsync(&n_ok, d_ok.p, sizeof(n_ok), cudaMemcpyDeviceToHost, st));
+        VB_CUDA(cudaStreamSynchronize(st));
+        if (n_ok == world) sh->xbuf.cap = cap;
+        else {
+            for (uint32_t r = 0; r < world; ++r)
+                if (sh->xbuf.peer[r] && sh->xbuf.peer[r] != sh->xbuf.local) cudaIpcCloseMemHandle(sh->xbuf.peer[r]);
+            sh->xbuf.peer.clear();
+            if (sh->xbuf.local) { cudaFree(sh->xbuf.local); sh->xbuf.local = nullptr; }
+        }
+        ctx->set_timing("shard.peer_exchange", sh->xbuf.cap ? 1.0 : 0.0);
+    }
     *out = sh.release();
     VB_GUARD_END
 }
@@ -156,6 +226,7 @@ int vb_shard_prefilter(vb_shard *sh, const vb_prefilter_params *p, vb_pairs **ou
     job.n_total = sh->meta->count();
     job.est_kmers_all = sh->est_kmers_all;
     job.comm = &sh->comm;
+    job.xbuf = sh->xbuf.cap ? &sh->xbuf : nullptr;
     job.keep_dev = true;
     vb_prefilter_run(sh->ctx, job, p, out);
     VB_GUARD_END
@@ -192,11 +263,14 @@ int vb_shard_align(vb_shard *sh, const vb_align_params *p, vb_align_out **out)
     if (rank == 0) for (uint32_t s = 0; s < world; ++s) { rcv[s] = cnts[s]; total += cnts[s]; }
     if (total >= (1ULL << 32) - rsort::TILE) throw vb_error(VB_ERR_ARG, "more than 2^32 directed pairs");
     const uint64_t n_pad = (total + rsort::TILE - 1) / rsort::TILE * rsort::TILE;
-    DevBuf<uint64_t> ka(n_pad + 1), kb(n_pad + 1), dummy_k(1);
+    DevBuf<uint64_t> ka(n_pad + 1), kb(n_pad + 1);
     DevBuf<uint32_t> va(n_pad + 1), vbuf(n_pad + 1);
-    DevBuf<int32_t> st_all(3 * total + 3), st_sorted(3 * total + 3), dummy_s(3);
-    comm_check(cm.all_to_all(cm.user, fo.n ? fo.keys.p : dummy_k.p, scv.data(), ka.p, rcv.data(), 8), "all_to_all(result keys)");
-    comm_check(cm.all_to_all(cm.user, fo.n ? fo.stats.p : dummy_s.p, scv.data(), st_all.p, rcv.data(), 12), "all_to_all(result statistics)");
+    DevBuf<int32_t> st_all(3 * total + 3), st_sorted(3 * total + 3);
+    DevBuf<ResRec> send_rec(fo.n + 1), recv_rec(total + 1);
+    static_assert(sizeof(ResRec) == 24, "result record size");
+    if (fo.n) { pack_res_kernel<<<grid_for(fo.n), 256, 0, st>>>(fo.keys.p, fo.stats.p, fo.n, send_rec.p); VB_LAUNCH_CHECK(ctx); }
+    comm_check(cm.all_to_all(cm.user, send_rec.p, scv.data(), recv_rec.p, rcv.data(), 24), "all_to_all(results)");
+    if (total) { unpack_res_kernel<<<grid_for(total), 256, 0, st>>>(recv_rec.p, total, ka.p, st_all.p); VB_LAUNCH_CHECK(ctx); }
     vb_align_out *res = nullptr;
     if (rank == 0) {
         char *pin = (char *)vb_pinned(ctx, 20 * total + 16);

@@ -145,8 +145,17 @@ struct vb_ctx {
 // global ids start at gid_base; n_total / total_slots_all describe the whole set.  shard_index / shard_count: the legacy
 // k-mer shard of vb_prefilter_partial (no thresholds).  keep_dev: leave the final candidate list on the device
 // (ctx->dev_pairs) for the align stage.
+// Receive buffers of all-to-all #1, one per rank, mapped into every rank's address space (CUDA IPC): the level-1
+// partition kernel of a rank stores its tuples straight into the buffers of their owners over NVLink (shard.cu).
+struct vb_peer_xbuf {
+    void *local = nullptr;               // this rank's buffer (cudaMalloc)
+    uint64_t cap = 0;                    // bytes, the same on every rank
+    std::vector<void *> peer;            // peer[r]: rank r's buffer as seen from this process (peer[rank] == local)
+};
+
 struct vb_prefilter_job {
     const vb_genomes *g = nullptr;
+    const vb_peer_xbuf *xbuf = nullptr;  // several ranks: direct peer stores instead of the tuple all-to-all
     uint32_t gid_base = 0, n_total = 0;
     double est_kmers_all = 0;            // k-mers of the whole set (all ranks), for the pass / bucket plan
     const vb_comm *comm = nullptr;
