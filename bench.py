@@ -31,6 +31,8 @@ sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 
 PRE = dict(k=25, min_kmers=20, min_ident=0.7, kmers_fraction=1.0)
+# the prefilter's kernels and their launches per step (one GPU, dense pair counters): for roofline.traffic
+PREFILTER_KERNELS = {"collect_kernel": 1, "part_kernel<1>": 1, "part_kernel<2>": 1, "bucket_chain_kernel": 1, "dense_emit_kernel": 2}
 CONFIG_NAME = "c3"
 DTYPE = "u8/int32 (2-bit bases, integer counts; f64 only for the final ratios)"
 
@@ -150,14 +152,17 @@ def cpu_baseline(names, seqs, n_sample: int, threads: int):
             "prefilter_s": t_pre, "align_s": t_al, "build": REF_NOTE}
 
 
-def ncu_value(kernel: str, metrics):
-    """Sum of `metrics` for `kernel` from the committed `ncu --set full` summary of this same bench command
-    (profiles/r02_kernels_ncu_full.txt, written by profiles/ncu_summary.py); None when absent."""
-    for name in ("r02_kernels_ncu_full.txt", "r01_kernels_ncu_full.txt"):
-        f = ROOT / "profiles" / name
-        if f.exists():
-            break
-    else:
+def ncu_value(kernel, metrics):
+    """Sum of `metrics` for `kernel` (a name prefix, or a dict {prefix: launches per step}) from the committed
+    `ncu --set full` summary of this same bench command (profiles/r02_kernels_ncu_full.txt, written by
+    profiles/ncu_summary.py; per-launch values); None when absent."""
+    if isinstance(kernel, dict):
+        vals = [(ncu_value(k, metrics), n) for k, n in kernel.items()]
+        if any(v is None for v, _ in vals):
+            return None
+        return float(sum(v * n for v, n in vals))
+    f = ROOT / "profiles" / ("r02_kernels_ncu_full_%s.txt" % CONFIG_NAME)
+    if not f.exists():
         return None
     total, inside, seen = 0.0, False, False
     for ln in f.read_text().splitlines():
@@ -305,7 +310,7 @@ def build_line(args, world, step_ms, e2e_ms, pairs_total, directed, lens, infos,
         # the path's HBM-bound stage and the north-star metric: the whole prefilter (its kernels + collectives), per GPU
         "roofline": {"kernel": "prefilter: collect + partition x2 + bucket grouping + emit (all kernels of the stage)", "bound": "hbm",
                      "achieved": pre_rate, "peak": peak, "unit": "GB/s", "frac": pre_rate / peak,
-                     "traffic": ncu_value("prefilter_stage", ["dram__bytes_read.sum", "dram__bytes_write.sum"]),
+                     "traffic": (lambda t: None if t is None else t / world)(ncu_value(dict(PREFILTER_KERNELS, **({"screen_kernel": 1} if CONFIG_NAME == "c2" else {})), ["dram__bytes_read.sum", "dram__bytes_write.sum"])),
                      "algorithmic_bytes": pre_bytes / world, "stage_ms": pre_kernel_ms, "peak_source": peak_src,
                      "note": "algorithmic bytes = 24.25 B/base + 12 B/pair + 4 B/genome (SURVEY 8(d)), per GPU; duration = CUDA events around the stage's kernels"},
         "timed_region_s": region_s,
@@ -500,7 +505,8 @@ def main_sharded(args, rank: int, world: int, local_rank: int):
     # max over ranks, per step (every rank's step i is bracketed by the same barriers)
     t = torch.tensor([ev_ms, wall_ms, e_wall], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    agg = torch.tensor([float(launches), float(sent)], dtype=torch.float64, device="cuda")
+    peer = float(np.mean([i["pre"].get("peer_bytes", 0.0) for i in infos]))
+    agg = torch.tensor([float(launches), float(sent), peer], dtype=torch.float64, device="cuda")
     dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     # per-rank stage times (for the report: slowest rank per stage)
     keys_p = ["extract_ms", "sort_ms", "segment_ms", "exchange_ms", "emit_ms", "total_ms"]
@@ -529,8 +535,9 @@ def main_sharded(args, rank: int, world: int, local_rank: int):
                  "config": {"parallelism": "genomes block-partitioned over %d GPUs; k-mer tuples all-to-all by hash range; partial pair counts "
                                            "all-to-all to the genome owners; owner-local parses; results gathered on rank 0" % world,
                             "e2e_note": "every step: each rank uploads and packs its block (ASCII from host memory), the packed records are all-gathered, then the step"},
-                 "comm": {"backend": "nccl", "ranks": world, "collectives_per_step_per_rank": calls,
-                          "bytes_sent_per_step_all_ranks": float(agg[1]), "exchange_ms_prefilter_max_rank": mx[keys_p.index("exchange_ms")],
+                 "comm": {"backend": "nccl + CUDA-IPC peer copies (tuple exchange)" if float(agg[2]) > 0 else "nccl", "ranks": world,
+                          "collectives_per_step_per_rank": calls, "nccl_bytes_sent_per_step_all_ranks": float(agg[1]),
+                          "nvlink_peer_copy_bytes_per_step_all_ranks": float(agg[2]), "exchange_ms_prefilter_max_rank": mx[keys_p.index("exchange_ms")],
                           "gather_ms_align_max_rank": mx[len(keys_p) + keys_a.index("gather_ms")]},
                  "balance": {"parse_ms_min_rank": mn[len(keys_p) + keys_a.index("parse_ms")],
                              "parse_ms_max_rank": mx[len(keys_p) + keys_a.index("parse_ms")],

@@ -76,7 +76,7 @@ class Context:
     def timings(self, prefix: str) -> dict:
         keys = {
             "prefilter": ["total_ms", "upload_pack_ms", "extract_ms", "sort_ms", "segment_ms", "exchange_ms", "emit_ms", "host_post_ms",
-                          "passes", "tuples", "survivors", "grouped", "bubbles", "table_slots", "candidates"],
+                          "passes", "tuples", "survivors", "grouped", "bubbles", "table_slots", "candidates", "peer_bytes"],
             "align": ["total_ms", "upload_pack_ms", "list_ms", "index_ms", "parse_ms", "gather_ms", "api_prep_ms", "host_prep_ms",
                       "host_post_ms", "batches", "pairs"],
         }[prefix]

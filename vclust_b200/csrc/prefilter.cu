@@ -1455,6 +1455,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     if ((uint64_t)job.gid_base + n_local > n) throw vb_error(VB_ERR_ARG, "genome block outside the set");
     EventTimer t_all(st), t_up(st);
     double ms_ext = 0, ms_part = 0, ms_group = 0, ms_exch = 0;
+    double peer_bytes = 0;                   // bytes this rank copied into other ranks' receive buffers (NVLink)
     // stage timers are read at the end of the call (reading one waits for its stop event)
     std::vector<std::pair<std::unique_ptr<EventTimer>, double *>> laps;
     auto lap_start = [&](double &acc_ms) -> EventTimer * {
@@ -1745,6 +1746,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
                         before += o[(d + 1) * Bper] - o[d * Bper];
                     }
                     char *base = (char *)job.xbuf->peer[d];
+                    if (d != rank) peer_bytes += 12.0 * (double)sc[d] + 4.0 * (double)fine_slice;
                     if (sc[d]) {
                         VB_CUDA(cudaMemcpyAsync(base + 8 * before, keys1.p + my_off1[d * Bper], 8 * sc[d], cudaMemcpyDeviceToDevice, st));
                         VB_CUDA(cudaMemcpyAsync(base + vals_base(recv_of[d]) + 4 * before, vals1.p + my_off1[d * Bper], 4 * sc[d], cudaMemcpyDeviceToDevice, st));
@@ -2221,7 +2223,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     std::vector<uint8_t> drop;
     bool any_border = false;
     for (uint64_t i = 0; i < n_emit && !any_border; ++i) any_border = (h_vals[i] & BORDERLINE) != 0;
-    vb_parallel_for(n_emit, 16384, 16, [&](uint64_t lo, uint64_t hi) {
+    vb_parallel_for(n_emit, 4096, 32, [&](uint64_t lo, uint64_t hi) {
         for (uint64_t i = lo; i < hi; ++i) {
             const uint32_t r = (uint32_t)(h_keys[i] >> 32), c = (uint32_t)h_keys[i], v = h_vals[i] & ~BORDERLINE;
             res->row[i] = r; res->col[i] = c; res->common[i] = v;
@@ -2271,7 +2273,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     ctx->set_timing("prefilter.sort_ms", ms_part);
     ctx->set_timing("prefilter.segment_ms", ms_group);
     ctx->set_timing("prefilter.exchange_ms", ms_exch);
-    ctx->set_timing("prefilter.peer_stores", world > 1 && job.xbuf ? 1.0 : 0.0);
+    ctx->set_timing("prefilter.peer_bytes", peer_bytes);
     ctx->set_timing("prefilter.emit_ms", t_emit.ms());
     ctx->set_timing("prefilter.passes", (double)passes);
     ctx->set_timing("prefilter.tuples", (double)dg.total_slots);

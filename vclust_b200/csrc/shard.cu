@@ -24,14 +24,17 @@ struct vb_shard {
     uint64_t block_slots = 0;            // slots of every rank's (padded) local store
     DevGenomes all;                      // rec / gofs / glen of ALL genomes (rec all-gathered); no seq2 / inv_kdb / tile map
     double est_kmers_all = 0;
-    vb_peer_xbuf xbuf;                   // all-to-all #1 as direct peer stores (empty: NCCL all-to-all)
-    ~vb_shard()
-    {
-        for (size_t r = 0; r < xbuf.peer.size(); ++r)
-            if (xbuf.peer[r] && xbuf.peer[r] != xbuf.local) cudaIpcCloseMemHandle(xbuf.peer[r]);
-        if (xbuf.local) cudaFree(xbuf.local);
-    }
+    const vb_peer_xbuf *xbuf = nullptr;  // all-to-all #1 as peer copies (null: NCCL all-to-all); owned by the context
 };
+
+void vb_peer_xbuf_free(vb_peer_xbuf *x)
+{
+    if (!x) return;
+    for (size_t r = 0; r < x->peer.size(); ++r)
+        if (x->peer[r] && x->peer[r] != x->local) cudaIpcCloseMemHandle(x->peer[r]);
+    if (x->local) cudaFree(x->local);
+    delete x;
+}
 
 namespace {
 
@@ -169,47 +172,49 @@ int vb_shard_create(vb_ctx *ctx, const vb_comm *comm, const vb_genomes *meta, co
     if (world > 1) {
         const double per_rank = std::min(total_len, 1.0e9) / world;
         const uint64_t cap = ((uint64_t)(12.0 * 1.4 * per_rank) + (64ull << 20) + 4095) / 4096 * 4096;
-        uint32_t ok = getenv("VB_SHARD_NO_PEER") ? 0u : 1u;
-        cudaIpcMemHandle_t mine_h;
-        memset(&mine_h, 0, sizeof(mine_h));
-        if (ok && cudaMalloc(&sh->xbuf.local, cap) != cudaSuccess) { cudaGetLastError(); sh->xbuf.local = nullptr; ok = 0; }
-        if (ok && cudaIpcGetMemHandle(&mine_h, sh->xbuf.local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-        DevBuf<uint32_t> d_h(17), d_all(17 * (size_t)world);
-        uint32_t send[17];
-        memcpy(send, &mine_h, 64);
-        send[16] = ok;
-        std::vector<uint32_t> all(17 * (size_t)world);
-        VB_CUDA(cudaMemcpyAsync(d_h.p, send, sizeof(send), cudaMemcpyHostToDevice, st));
-        comm_check(comm->all_gather(comm->user, d_h.p, d_all.p, sizeof(send)), "all_gather(IPC handles)");
-        VB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(uint32_t) * all.size(), cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaStreamSynchronize(st));
-        bool everyone = true;
-        for (uint32_t r = 0; r < world; ++r) everyone = everyone && all[17 * r + 16] == 1;
-        sh->xbuf.peer.assign(world, nullptr);
-        if (everyone) {
-            for (uint32_t r = 0; r < world && ok; ++r) {
-                if (r == (uint32_t)comm->rank) { sh->xbuf.peer[r] = sh->xbuf.local; continue; }
-                cudaIpcMemHandle_t h;
-                memcpy(&h, &all[17 * r], 64);
-                if (cudaIpcOpenMemHandle(&sh->xbuf.peer[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); sh->xbuf.peer[r] = nullptr; ok = 0; }
-            }
-        } else ok = 0;
-        // did every rank map every buffer?
-        DevBuf<uint32_t> d_ok(1);
-        VB_CUDA(cudaMemcpyAsync(d_ok.p, &ok, sizeof(ok), cudaMemcpyHostToDevice, st));
-        comm_check(comm->all_reduce_sum_u32(comm->user, d_ok.p, 1), "all_reduce(peer mapping)");
-        uint32_t n_ok = 0;
-        VB_CUDA(cudaMemcpyAsync(&n_ok, d_ok.p, sizeof(n_ok), cudaMemcpyDeviceToHost, st));
-        VB_CUDA(cudaStreamSynchronize(st));
-        if (n_ok == world) sh->xbuf.cap = cap;
-        else {
-            for (uint32_t r = 0; r < world; ++r)
-                if (sh->xbuf.peer[r] && sh->xbuf.peer[r] != sh->xbuf.local) cudaIpcCloseMemHandle(sh->xbuf.peer[r]);
-            sh->xbuf.peer.clear();
-            if (sh->xbuf.local) { cudaFree(sh->xbuf.local); sh->xbuf.local = nullptr; }
+        // (mapping costs ~0.2 s: the buffers are kept by the context and reused while they are large enough -- every rank
+        // sees the same sizes, so every rank decides alike)
+        if (ctx->xbuf && (ctx->xbuf->cap < cap || ctx->xbuf->peer.size() != world)) { vb_peer_xbuf_free(ctx->xbuf); ctx->xbuf = nullptr; }
+        if (!ctx->xbuf && !getenv("VB_SHARD_NO_PEER")) {
+            auto *x = new vb_peer_xbuf();
+            uint32_t ok = 1u;
+            cudaIpcMemHandle_t mine_h;
+            memset(&mine_h, 0, sizeof(mine_h));
+            if (cudaMalloc(&x->local, cap) != cudaSuccess) { cudaGetLastError(); x->local = nullptr; ok = 0; }
+            if (ok && cudaIpcGetMemHandle(&mine_h, x->local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+            DevBuf<uint32_t> d_h(17), d_all(17 * (size_t)world);
+            uint32_t send[17];
+            memcpy(send, &mine_h, 64);
+            send[16] = ok;
+            std::vector<uint32_t> all(17 * (size_t)world);
+            VB_CUDA(cudaMemcpyAsync(d_h.p, send, sizeof(send), cudaMemcpyHostToDevice, st));
+            comm_check(comm->all_gather(comm->user, d_h.p, d_all.p, sizeof(send)), "all_gather(IPC handles)");
+            VB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(uint32_t) * all.size(), cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+            bool everyone = true;
+            for (uint32_t r = 0; r < world; ++r) everyone = everyone && all[17 * r + 16] == 1;
+            x->peer.assign(world, nullptr);
+            if (everyone) {
+                for (uint32_t r = 0; r < world && ok; ++r) {
+                    if (r == (uint32_t)comm->rank) { x->peer[r] = x->local; continue; }
+                    cudaIpcMemHandle_t h;
+                    memcpy(&h, &all[17 * r], 64);
+                    if (cudaIpcOpenMemHandle(&x->peer[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); x->peer[r] = nullptr; ok = 0; }
+                }
+            } else ok = 0;
+            // did every rank map every buffer?
+            DevBuf<uint32_t> d_ok(1);
+            VB_CUDA(cudaMemcpyAsync(d_ok.p, &ok, sizeof(ok), cudaMemcpyHostToDevice, st));
+            comm_check(comm->all_reduce_sum_u32(comm->user, d_ok.p, 1), "all_reduce(peer mapping)");
+            uint32_t n_ok = 0;
+            VB_CUDA(cudaMemcpyAsync(&n_ok, d_ok.p, sizeof(n_ok), cudaMemcpyDeviceToHost, st));
+            VB_CUDA(cudaStreamSynchronize(st));
+            if (n_ok == world) { x->cap = cap; ctx->xbuf = x; }
+            else vb_peer_xbuf_free(x);
         }
-        ctx->set_timing("shard.peer_exchange", sh->xbuf.cap ? 1.0 : 0.0);
+        sh->xbuf = getenv("VB_SHARD_NO_PEER") ? nullptr : ctx->xbuf;
+        ctx->set_timing("shard.peer_exchange", sh->xbuf ? 1.0 : 0.0);
     }
     *out = sh.release();
     VB_GUARD_END
@@ -226,7 +231,7 @@ int vb_shard_prefilter(vb_shard *sh, const vb_prefilter_params *p, vb_pairs **ou
     job.n_total = sh->meta->count();
     job.est_kmers_all = sh->est_kmers_all;
     job.comm = &sh->comm;
-    job.xbuf = sh->xbuf.cap ? &sh->xbuf : nullptr;
+    job.xbuf = sh->xbuf;
     job.keep_dev = true;
     vb_prefilter_run(sh->ctx, job, p, out);
     VB_GUARD_END

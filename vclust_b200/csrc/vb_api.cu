@@ -17,6 +17,7 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
                        const char *const *columns, int n_columns, const double out_filters[5]);
 
 void vb_make_resident_impl(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, uint64_t force_slots = 0);
+void vb_peer_xbuf_free(vb_peer_xbuf *x);
 void vb_evict_impl(vb_ctx *ctx, const vb_genomes *g);
 void vb_unpin_genomes(const vb_genomes *g);
 
@@ -161,6 +162,7 @@ void vb_ctx_destroy(vb_ctx *ctx)
     cudaStreamSynchronize((cudaStream_t)ctx->stream);
     if (ctx->arena) { ctx->arena->destroy(); delete ctx->arena; }
     if (ctx->pin_buf) cudaFreeHost(ctx->pin_buf);
+    if (ctx->xbuf) vb_peer_xbuf_free(ctx->xbuf);
     for (auto &e : ctx->events) if (e) cudaEventDestroy((cudaEvent_t)e);
     for (auto &e : ctx->copy_events) if (e) cudaEventDestroy((cudaEvent_t)e);
     if (ctx->copy_stream) { cudaStreamSynchronize((cudaStream_t)ctx->copy_stream); cudaStreamDestroy((cudaStream_t)ctx->copy_stream); }

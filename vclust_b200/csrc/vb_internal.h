@@ -108,6 +108,14 @@ struct vb_resident {                 // a genome set kept packed in HBM across c
     DevGenomes *dev;
 };
 
+// Receive buffers of all-to-all #1, one per rank, mapped into every rank's address space (CUDA IPC): the level-1
+// partition kernel of a rank stores its tuples straight into the buffers of their owners over NVLink (shard.cu).
+struct vb_peer_xbuf {
+    void *local = nullptr;               // this rank's buffer (cudaMalloc)
+    uint64_t cap = 0;                    // bytes, the same on every rank
+    std::vector<void *> peer;            // peer[r]: rank r's buffer as seen from this process (peer[rank] == local)
+};
+
 struct vb_ctx {
     int device = 0;
     void *stream = nullptr;          // cudaStream_t
@@ -124,6 +132,7 @@ struct vb_ctx {
     uint64_t pair_hint_uid = 0, pair_hint_entries = 0;    // distinct pairs the last hashed-table prefilter of set `uid` produced
     uint32_t pair_hint_n = 0;
     int pair_hint_k = 0;
+    struct vb_peer_xbuf *xbuf = nullptr;   // exchange buffers mapped between the ranks (kept across vb_shard_create calls)
     void *pin_buf = nullptr;         // page-locked staging buffer for result read-backs (grown on demand, kept)
     size_t pin_cap = 0;
     std::vector<vb_timing> timings;
@@ -145,14 +154,6 @@ struct vb_ctx {
 // global ids start at gid_base; n_total / total_slots_all describe the whole set.  shard_index / shard_count: the legacy
 // k-mer shard of vb_prefilter_partial (no thresholds).  keep_dev: leave the final candidate list on the device
 // (ctx->dev_pairs) for the align stage.
-// Receive buffers of all-to-all #1, one per rank, mapped into every rank's address space (CUDA IPC): the level-1
-// partition kernel of a rank stores its tuples straight into the buffers of their owners over NVLink (shard.cu).
-struct vb_peer_xbuf {
-    void *local = nullptr;               // this rank's buffer (cudaMalloc)
-    uint64_t cap = 0;                    // bytes, the same on every rank
-    std::vector<void *> peer;            // peer[r]: rank r's buffer as seen from this process (peer[rank] == local)
-};
-
 struct vb_prefilter_job {
     const vb_genomes *g = nullptr;
     const vb_peer_xbuf *xbuf = nullptr;  // several ranks: direct peer stores instead of the tuple all-to-all
