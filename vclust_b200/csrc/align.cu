@@ -1042,23 +1042,73 @@ __global__ void __launch_bounds__(256) cost_hist_kernel(const uint32_t *__restri
 // in the heavy list (classes in descending order); counts[1] = number of heavy pairs, counts[2] = the cut
 __global__ void __launch_bounds__(1024) lpt_cut_kernel(uint32_t *__restrict__ hist, unsigned long long *__restrict__ counts, int heavy_div)
 {
-    __shared__ uint32_t h[COST_CLASSES];
-    for (int c = threadIdx.x; c < COST_CLASSES; c += 1024) h[c] = hist[c];
+    // suffix sums over the 4 096 classes (4 per thread, descending class order), then the cut is found in parallel
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t s_total;
+    __shared__ int s_cut;
+    const int t = threadIdx.x;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[j] = hist[COST_CLASSES - 1 - (4 * t + j)]; sum += v[j]; }     // v[j]: class COST_CLASSES-1-(4t+j)
+    const int lane = t & 31, w = t >> 5;
+    uint32_t x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_tot[w] = x;
+    if (t == 0) s_cut = COST_CLASSES;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long n = counts[0];
-        const unsigned long long n_heavy_want = n / heavy_div;
-        int cut = COST_CLASSES;
-        unsigned long long acc = 0;
-        if (n >= 64) {
-            while (cut > 0 && acc < n_heavy_want) acc += h[--cut];
-            if (acc > n / 2 && heavy_div > 2) { acc -= h[cut]; ++cut; }       // one huge class: do not reorder half the list
-        }
-        unsigned long long run = 0;
-        for (int c = COST_CLASSES - 1; c >= cut; --c) { const uint32_t t = h[c]; hist[c] = (uint32_t)run; run += t; }
-        counts[1] = run;
-        counts[2] = (unsigned long long)cut;
+    if (w == 0) {
+        uint32_t tt = warp_tot[lane], z = tt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+        warp_tot[lane] = z - tt;
+        if (lane == 31) s_total = z;
     }
+    __syncthreads();
+    uint32_t before = warp_tot[w] + x - sum;          // pairs in classes ABOVE class COST_CLASSES-1-4t
+    const unsigned long long n = counts[0];
+    const unsigned long long want = n / heavy_div;
+    // the cut: the highest class c such that the pairs in classes >= c reach `want` (none when n < 64)
+    uint32_t run = before;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = COST_CLASSES - 1 - (4 * t + j);
+        if (n >= 64 && run < want && run + v[j] >= want) s_cut = c;      // exactly one (thread, j) satisfies this when want > 0
+        run += v[j];
+    }
+    __syncthreads();
+    int cut = s_cut;
+    if (n >= 64 && want == 0) cut = COST_CLASSES;
+    // one huge class: do not reorder half the list
+    __shared__ uint32_t s_acc;
+    if (t == 0) s_acc = 0;
+    __syncthreads();
+    run = before;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = COST_CLASSES - 1 - (4 * t + j);
+        if (c == cut) s_acc = run + v[j];
+        run += v[j];
+    }
+    __syncthreads();
+    if (cut < COST_CLASSES && (unsigned long long)s_acc > n / 2 && heavy_div > 2) ++cut;
+    // starts of the heavy classes in the heavy list (descending class order): pairs in the classes above
+    run = before;
+    unsigned long long heavy_total = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = COST_CLASSES - 1 - (4 * t + j);
+        if (c >= cut) { hist[c] = run; heavy_total = run + v[j]; }
+        run += v[j];
+    }
+    // the number of heavy pairs = pairs in classes >= cut: written by the thread that owns class `cut` (or 0)
+    if (cut >= COST_CLASSES) { if (t == 0) { counts[1] = 0; counts[2] = (unsigned long long)cut; } }
+    else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (COST_CLASSES - 1 - (4 * t + j) == cut) { counts[1] = heavy_total; counts[2] = (unsigned long long)cut; }
+    }
+    (void)s_total;
 }
 
 __global__ void __launch_bounds__(256) heavy_fill_kernel(const uint32_t *__restrict__ cost, const unsigned long long *__restrict__ counts,

@@ -332,16 +332,18 @@ __device__ __forceinline__ uint32_t sub_of(uint64_t h, uint32_t B1, uint32_t B2)
 __global__ void __launch_bounds__(256) coarsen_kernel(const uint32_t *__restrict__ fine, uint32_t n_src, uint64_t src_stride,
                                                       uint32_t B2, uint32_t n_out, uint32_t *__restrict__ out)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per coarse bin (a bin of the level-1 histogram sums 1 024 fine bins per source)
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n_out) return;
     const uint32_t parent = i / B2, sub = i % B2;
     const uint32_t f_lo = ((sub << FINE_BITS) + B2 - 1) / B2, f_hi = (((sub + 1) << FINE_BITS) + B2 - 1) / B2;
     uint32_t s = 0;
     for (uint32_t src = 0; src < n_src; ++src) {
         const uint32_t *f = fine + src * src_stride + ((uint64_t)parent << FINE_BITS);
-        for (uint32_t j = f_lo; j < f_hi; ++j) s += f[j];
+        for (uint32_t j = f_lo + lane; j < f_hi; j += 32) s += f[j];
     }
-    out[i] = s;
+    s = __reduce_add_sync(0xffffffffu, s);
+    if (lane == 0) out[i] = s;
 }
 
 // exclusive scan of one value per thread over a 1024-thread block; returns the prefix, *total gets the sum
@@ -456,22 +458,6 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, ui
         } else {
             src_lo = (uint64_t)tile * PART_TILE;
             src_hi = min(src_lo + PART_TILE, n_in);
-        }
-        // the tile this block takes next: pull its lines into L2 now (the loads below wait for DRAM otherwise: they were
-        // 45 % of this kernel's stalls)
-        if (LEVEL == 1) {
-            const uint64_t nxt = ((uint64_t)tile + gridDim.x) * PART_TILE;
-            if (nxt < n_in && threadIdx.x < PART_TILE / 16) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_keys + nxt + threadIdx.x * 16));
-                if ((threadIdx.x & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_vals + nxt + threadIdx.x * 16));
-            }
-        } else if (tile + gridDim.x < n_tiles && threadIdx.x < PART_TILE / 16) {
-            // (level 2: the next tile of this block usually lies in the same or the following segment, gridDim tiles ahead)
-            const uint64_t nxt = src_lo + (uint64_t)gridDim.x * PART_TILE;
-            if (nxt + PART_TILE <= n_in) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_keys + nxt + threadIdx.x * 16));
-                if ((threadIdx.x & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_vals + nxt + threadIdx.x * 16));
-            }
         }
         uint64_t key[PART_ITEMS];
         uint32_t val[PART_ITEMS];
@@ -1672,7 +1658,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         });
         // level-1 histogram (tuples per parent, all ranks' parents) -> offsets of the level-1 / send buffer
         DevBuf<uint32_t> hist1(B1), off1(B1 + 1), cursor1(B1), scan_tmp(1025);
-        coarsen_kernel<<<(B1 + 255) / 256, 256, 0, st>>>(fine_hist.p, 1, 0, 1, B1, hist1.p);
+        coarsen_kernel<<<(B1 * 32 + 255) / 256, 256, 0, st>>>(fine_hist.p, 1, 0, 1, B1, hist1.p);
         VB_LAUNCH_CHECK(ctx);
         dev_exscan(ctx, st, hist1.p, B1, off1.p, cursor1.p, scan_tmp.p);
         // every rank's offsets, gathered (one rank: just its own), and the survivor count: one synchronisation
@@ -1799,7 +1785,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         DevBuf<Segment> d_segs(std::max<size_t>(segs.size(), 1));
         VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
         if (!segs.empty()) VB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st));
-        coarsen_kernel<<<(NB + 255) / 256, 256, 0, st>>>(fine_src, fine_n_src, (uint64_t)Bper << FINE_BITS, B2, NB, hist.p);
+        coarsen_kernel<<<(int)(((uint64_t)NB * 32 + 255) / 256), 256, 0, st>>>(fine_src, fine_n_src, (uint64_t)Bper << FINE_BITS, B2, NB, hist.p);
         VB_LAUNCH_CHECK(ctx);
         dev_exscan(ctx, st, hist.p, NB, off.p, cursor2.p, scan_tmp.p);
         DevBuf<uint64_t> keys2(n_recv + 64);
