@@ -127,6 +127,22 @@ def test_fasta_ingest_fuzz_against_record_rules(lib, tmp_path):
         assert len(g) == 2 and g.sequence(0) == joined and g.sequence(1) == joined, (trial, data)
 
 
+def test_fasta_ingest_big_file_read_by_several_threads(lib, tmp_path):
+    """Files of 64 MB and more are read by several threads on disjoint ranges (host_fasta.cpp read_whole): the records
+    must be the ones a single read gives, and a second file appended to the same store must start where the first ended."""
+    from vclust_b200 import synth
+    names, seqs = synth.make_genomes(n=1700, length=40_000, seed=5, family=10)
+    big, small = tmp_path / "big.fna", tmp_path / "small.fna"
+    synth.write_fasta(big, names, seqs)
+    assert big.stat().st_size >= 64 << 20
+    small.write_bytes(b">tail one\nACGT\nAC\n")
+    for flavor in (api.FASTA_KMERDB, api.FASTA_LZANI):
+        g = api.Genomes.load([big, small], True, flavor)
+        assert len(g) == len(names) + 1 and g.names()[:-1] == names and g.name(len(names)) == "tail"
+        assert all(g.sequence(i) == bytes(seqs[i]) for i in range(0, len(names), 13)) and g.sequence(len(names)) == b"ACGTAC"
+        g.close()
+
+
 def test_filter_roundtrip_and_format(lib, golden, tmp_path):
     p = golden / "example" / "multifasta.fna.gz"
     g = api.Genomes.load([p], True, api.FASTA_LZANI)

@@ -9,6 +9,7 @@ files; instead of spawning kmer-db / lz-ani they call libvclust_b200.so through 
 from __future__ import annotations
 
 import ctypes as C
+import time
 from pathlib import Path
 from typing import Iterable, Sequence
 
@@ -428,34 +429,51 @@ def prefilter(input_paths: Sequence, output_path, is_multisample_fasta: bool, km
               kmers_fraction: float = 1.0, min_kmers: int = 20, min_ident: float = 0.7, max_seqs: int = 0,
               batch_size: int = 0, device: int = 0) -> dict:
     """`vclust prefilter` body: cmd_kmerdb_build + cmd_kmerdb_all2all + cmd_kmerdb_distance (vclust.py:915-1055)."""
+    t = [time.perf_counter()]
+    lap = lambda: t.append(time.perf_counter())
     with Context(device) as ctx:
+        lap()
         g = Genomes.load(input_paths, is_multisample_fasta, FASTA_KMERDB)
+        lap()
         pairs = prefilter_genomes(ctx, g, kmer_size, min_kmers, min_ident, kmers_fraction, max_seqs, batch_size)
+        lap()
         write_filter(g, pairs, output_path)
+        lap()
         info = ctx.timings("prefilter")
         info["pairs"] = pairs.n_pairs
         pairs.close()
         g.close()
-        return info
+    lap()
+    info["wall_s"] = dict(zip(("context", "read_fasta", "prefilter", "write_filter", "close"), np.diff(t).round(4).tolist()))
+    return info
 
 
 def align(input_paths: Sequence, output_path, is_multisample_fasta: bool, out_format: Sequence[str] | None = None,
           filter_file=None, filter_threshold: float = 0.0, out_filters: dict | None = None, mal=11, msl=7, mrd=40,
           mqd=40, reg=35, aw=15, am=7, ar=3, device: int = 0, out_aln=None) -> dict:
     """`vclust align` body: cmd_lzani (vclust.py:1058-1181); out_aln = --out-aln (lz-ani --out-alignment)."""
+    t = [time.perf_counter()]
+    lap = lambda: t.append(time.perf_counter())
     with Context(device) as ctx:
+        lap()
         g = Genomes.load(input_paths, is_multisample_fasta, FASTA_LZANI, sep_len=mrd)
+        lap()
         pairs = read_filter(filter_file, filter_threshold, g) if filter_file else None
+        lap()
         if out_aln:
             res, regions = align_genomes_regions(ctx, g, pairs, align_params(mal, msl, mrd, mqd, reg, aw, am, ar))
             write_aln(g, regions, out_aln, out_filters)
             regions.close()
         else:
             res = align_genomes(ctx, g, pairs, align_params(mal, msl, mrd, mqd, reg, aw, am, ar))
+        lap()
         write_ani(g, res, output_path, None, out_format or ALIGN_OUTFMT["standard"], out_filters)
+        lap()
         info = ctx.timings("align")
         res.close()
         if pairs is not None:
             pairs.close()
         g.close()
-        return info
+    lap()
+    info["wall_s"] = dict(zip(("context", "read_fasta", "read_filter", "align", "write_ani", "close"), np.diff(t).round(4).tolist()))
+    return info

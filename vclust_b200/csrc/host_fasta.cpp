@@ -3,9 +3,11 @@
 //   kmer-db : genome_input_file.h:80-136 (whole-file read, gzip by magic), :287-338 (record splitting),
 //             loader_ex.cpp:150-257 (directory mode: one sample per file, named by file name)
 //   lz-ani  : seq_reservoir.cpp:90-153 (directory mode), :156-210 (multi-FASTA), file_wrapper.h:917-950 (getline)
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <filesystem>
@@ -44,7 +46,24 @@ size_t read_whole(const char *path, vb_bytes &out)
     std::error_code ec;
     const auto fsize = std::filesystem::file_size(path, ec);
     rewind(fp);
-    if (!ec && fsize > 0) {
+    if (!ec && fsize >= (64u << 20)) {
+        // a big regular file: the copy out of the page cache and the first-touch faults of the destination are the
+        // whole cost of ingest, so several threads pread() disjoint ranges straight into the store
+        out.resize(start + (size_t)fsize);
+        char *dst = out.data() + start;
+        const int fd = fileno(fp);
+        std::atomic<bool> short_read{false};
+        vb_parallel_for((uint64_t)fsize, 32u << 20, 8, [&](uint64_t lo, uint64_t hi) {
+            while (lo < hi) {
+                const ssize_t n = pread(fd, dst + lo, (size_t)std::min<uint64_t>(hi - lo, 1u << 30), (off_t)lo);
+                if (n <= 0) { short_read = true; return; }
+                lo += (uint64_t)n;
+            }
+        });
+        fclose(fp);
+        if (short_read) { out.resize(start); throw vb_error(VB_ERR_IO, std::string("Cannot read file: ") + path); }
+        return (size_t)fsize;
+    } else if (!ec && fsize > 0) {
         out.resize(start + (size_t)fsize);
         used = fread(out.data() + start, 1, (size_t)fsize, fp);
     } else {                                            // not a regular file (pipe ...): read until EOF
