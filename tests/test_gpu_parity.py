@@ -89,6 +89,11 @@ def test_prefilter_counts_vs_oracle(ctx, golden, k, f):
     {"VB_PREFILTER_HASH": "1", "VB_PREFILTER_TABLE": "4096", "VB_PREFILTER_PASSES": "4"},   # ... grown between passes while it fills up
     {"VB_PREFILTER_PASSES": "3"},                                    # > 10^9 k-mers: several passes over k-mer hash shards
     {"VB_PREFILTER_PASSES": "2", "VB_PREFILTER_HASH": "1", "VB_PREFILTER_SEEN": "0"},
+    {"VB_PREFILTER_BUCKET": "flat"},                                 # grouping kernel for large families (picked from the size hint)
+    {"VB_PREFILTER_BUCKET": "flat", "VB_PREFILTER_HASH": "1", "VB_PREFILTER_SEEN": "0"},
+    {"VB_PREFILTER_BUCKET": "chain", "VB_PREFILTER_HASH": "1", "VB_PREFILTER_SEEN": "0"},
+    {"VB_PREFILTER_L1BITS": "2"},                                    # lopsided fan-out: few parents, many sub-buckets
+    {"VB_PREFILTER_L1BITS": "9", "VB_PREFILTER_SEEN": "0"},         # ... and the reverse
 ])
 def test_prefilter_large_input_paths_vs_oracle(ctx, golden, monkeypatch, env):
     """The code paths that only very large inputs select by themselves, forced on a small input: same integers."""
@@ -107,10 +112,54 @@ def test_prefilter_large_input_paths_vs_oracle(ctx, golden, monkeypatch, env):
                {(int(r), int(c)): int(v) for r, c, v in zip(rows, cols, vals)}
 
 
-def test_chunked_pinned_upload_gives_the_same_result(ctx):
+@pytest.mark.parametrize("env", [{}, {"VB_PREFILTER_BUCKET": "flat"}, {"VB_PREFILTER_SEEN": "0"},
+                                 {"VB_PREFILTER_SEEN": "0", "VB_PREFILTER_BUCKET": "flat"}, {"VB_PREFILTER_HASH": "1", "VB_PREFILTER_SEEN": "0"}])
+def test_prefilter_kmers_repeated_inside_genomes(ctx, monkeypatch, env):
+    """A k-mer counts once per genome however often it occurs there (kmer-db sorts and de-duplicates a sample's k-mers):
+    families whose members carry a block several times, forward and reverse-complemented, with some copies mutated --
+    the grouping kernels must tell repeats of one genome from members of the group."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    seqs = []
+    for fam in range(12):
+        block = acgt[rng.integers(0, 4, size=400)]
+        backbone = acgt[rng.integers(0, 4, size=3000)]
+        for member in range(9):
+            parts = [backbone[:1000].copy()]
+            for rep in range(int(rng.integers(1, 5))):                   # 1 to 4 copies of the block, some reversed, some mutated
+                b = block.copy()
+                if rng.random() < 0.5:
+                    b[rng.integers(0, b.size, size=3)] = acgt[rng.integers(0, 4, size=3)]
+                parts.append(comp[b[::-1]] if rng.random() < 0.4 else b)
+                parts.append(acgt[rng.integers(0, 4, size=int(rng.integers(0, 60)))])
+            parts.append(backbone[1000:].copy())
+            s = np.concatenate(parts)
+            s[rng.integers(0, s.size, size=member * 6)] = acgt[rng.integers(0, 4, size=member * 6)]
+            seqs.append(s.tobytes())
+    names = ["r%d" % i for i in range(len(seqs))]
+    for k in (25, 15):
+        sets = oracle.kmer_sets([[s] for s in seqs], k, 1.0)
+        rows, cols, vals = oracle.common_matrix(sets)
+        g = api.Genomes.from_memory(names, seqs)
+        pairs = api.prefilter_genomes(ctx, g, k=k, min_kmers=1, min_ident=0.0)
+        assert pairs.total_kmers.tolist() == [int(s.size) for s in sets]
+        assert {(int(r), int(c)): int(v) for r, c, v in zip(pairs.rows, pairs.cols, pairs.common)} == \
+               {(int(r), int(c)): int(v) for r, c, v in zip(rows, cols, vals)}
+        pairs.close(); g.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"VB_PREFILTER_SEEN": "0"}, {"VB_PREFILTER_SEEN": "0", "VB_PREFILTER_NO_EARLY": "1"}])
+def test_chunked_pinned_upload_gives_the_same_result(ctx, monkeypatch, env):
     """From the second upload of a host set on, the genomes travel in several chunks on a copy stream and the screen
-    pass of each chunk is enqueued while the next chunk is in flight (e2e path of bench.py): same pairs, same counts,
-    and the align stage finds the store the prefilter uploaded."""
+    pass of each chunk -- without a screen (large inputs): the whole extraction of each chunk -- is enqueued while the
+    next chunk is in flight (e2e path of bench.py): same pairs, same counts, and the align stage finds the store the
+    prefilter uploaded."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     names, seqs = synth.make_genomes(n=320, length=40_000, family=8, seed=5, n_frac=0.05, lower_frac=0.05)
     g = api.Genomes.from_memory(names, seqs)
     runs = []

@@ -166,9 +166,11 @@ __global__ void __launch_bounds__(256) build_ref_text_kernel(const uint4 *__rest
 // One block per reference (blocks fetch references from a shared counter), no global atomics and no table clear: the
 // table is built partition by partition (IDX_PS slots = 32 KB) in SHARED memory and every partition leaves with one
 // coalesced store; five blocks are resident per SM, so the phases of different references overlap.
-//   1. every position is hashed ONCE (a thread takes IDX_CHUNK consecutive positions from one pair of 128-bit loads):
-//      (home slot, entry) goes to a per-block scratch list, a shared-memory histogram counts the entries per partition;
-//   2. the list is counting-sorted by partition (second scratch list; both are L2-resident);
+//   1. every position is hashed (a thread takes IDX_CHUNK consecutive positions from one pair of 128-bit loads) and a
+//      shared-memory histogram counts the entries per partition;
+//   2. after a scan of the histogram the positions are hashed AGAIN and (home slot, entry) goes straight to its place
+//      in a per-block scratch list ordered by partition (the text is 10 KB and cached; parking the entries in a first
+//      list instead and sorting that cost 2 x 320 KB of DRAM traffic per 40 kb reference and exposed its latency);
 //   3. partition by partition: clear, insert the carried and the own entries (shared-memory CAS, all lanes busy), store.
 // An entry that reaches the end of its partition is carried into the next one (rare unless the genome is a long repeat);
 // the table ends with ht_tail spare slots for the carries of the last home partition, and what is still carried at the
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(IDX_THREADS, 5) build_ref_index_kernel(const R
     const uint32_t nmask = (1u << mal) - 1;
     uint32_t *const carry0 = carry_all + (size_t)blockIdx.x * 2 * carry_stride;
     auto carry = [&](int which) { return carry0 + (which ? carry_stride : 0u); };
-    uint2 *entA = ent_all + (size_t)blockIdx.x * 2 * ent_stride, *entB = entA + ent_stride;
+    uint2 *ent = ent_all + (size_t)blockIdx.x * ent_stride;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_ref = atomicAdd(next_ref, 1u);
@@ -229,23 +231,15 @@ __global__ void __launch_bounds__(IDX_THREADS, 5) build_ref_index_kernel(const R
         if (threadIdx.x < 2) s_carry_n[threadIdx.x] = 0;
         for (uint32_t i = threadIdx.x; i <= n_bins; i += IDX_THREADS) s_off[i] = 0;
         __syncthreads();
-        // ---- 1. hash every position once; count the entries of every bin (s_off[bin + 1])
+        // ---- 1. hash every position; count the entries of every bin (s_off[bin + 1])
         for (uint32_t c = threadIdx.x; c < n_chunks; c += IDX_THREADS) {
             const uint32_t p0 = c * IDX_CHUNK;
             const Window w = load_window(rec, p0);
-            uint2 e[IDX_CHUNK];
 #pragma unroll
             for (int j = 0; j < IDX_CHUNK; ++j) {
                 uint64_t h;
-                e[j] = make_uint2(0xffffffffu, 0u);
-                if (p0 + j < n_pos && window_hash(w, j, mal, nmask, h)) {
-                    e[j] = make_uint2(ht_slot(h, d.ht_cap), ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | (p0 + j));
-                    atomicAdd(&s_off[e[j].x / (IDX_PS * G) + 1], 1u);
-                }
+                if (p0 + j < n_pos && window_hash(w, j, mal, nmask, h)) atomicAdd(&s_off[ht_slot(h, d.ht_cap) / (IDX_PS * G) + 1], 1u);
             }
-            uint4 *o = (uint4 *)(entA + p0);             // 8 entries = 64 bytes
-#pragma unroll
-            for (int j = 0; j < IDX_CHUNK; j += 2) o[j / 2] = make_uint4(e[j].x, e[j].y, e[j + 1].x, e[j + 1].y);
         }
         __syncthreads();
         // ---- 2. exclusive scan of the bin counts (n_bins <= 1024 = 4 per thread), then the counting sort
@@ -272,10 +266,20 @@ __global__ void __launch_bounds__(IDX_THREADS, 5) build_ref_index_kernel(const R
             }
         }
         __syncthreads();
-        const uint32_t n_ent = n_chunks * IDX_CHUNK;
-        for (uint32_t i = threadIdx.x; i < n_ent; i += IDX_THREADS) {
-            const uint2 e = entA[i];
-            if (e.x != 0xffffffffu) entB[atomicAdd(&s_cur[e.x / (IDX_PS * G)], 1u)] = e;
+        // (home slot, entry) of every position, grouped by bin: hashed a second time rather than parked in a first scratch
+        // list -- the text is 10 KB and cached, the list was 320 KB written to and read back from DRAM
+        for (uint32_t c = threadIdx.x; c < n_chunks; c += IDX_THREADS) {
+            const uint32_t p0 = c * IDX_CHUNK;
+            const Window w = load_window(rec, p0);
+#pragma unroll
+            for (int j = 0; j < IDX_CHUNK; ++j) {
+                uint64_t h;
+                if (p0 + j < n_pos && window_hash(w, j, mal, nmask, h)) {
+                    const uint32_t home = ht_slot(h, d.ht_cap);
+                    ent[atomicAdd(&s_cur[home / (IDX_PS * G)], 1u)] =
+                        make_uint2(home, ((uint32_t)(h >> 32) >> d.pos_bits << d.pos_bits) | (p0 + j));
+                }
+            }
         }
         __syncthreads();
         // ---- 3. the partitions
@@ -296,9 +300,13 @@ __global__ void __launch_bounds__(IDX_THREADS, 5) build_ref_index_kernel(const R
             if (pbase < d.ht_cap) {
                 const uint32_t bin = (pbase / IDX_PS) / G;
                 const uint32_t lo = s_off[bin], hi = s_off[bin + 1];
-                for (uint32_t i = lo + threadIdx.x; i < hi; i += IDX_THREADS) {
-                    const uint2 e = entB[i];
-                    if (G == 1 || e.x - pbase < plen) insert(e.x - pbase, e.y);   // (a shared bin: only this partition's entries)
+                for (uint32_t i = lo + threadIdx.x; i < hi; i += 2 * IDX_THREADS) {          // two loads in flight per thread
+                    const uint32_t i1 = i + IDX_THREADS;
+                    const uint2 e0 = ent[i];
+                    uint2 e1 = make_uint2(0u, 0u);
+                    if (i1 < hi) e1 = ent[i1];
+                    if (G == 1 || e0.x - pbase < plen) insert(e0.x - pbase, e0.y);   // (a shared bin: only this partition's entries)
+                    if (i1 < hi && (G == 1 || e1.x - pbase < plen)) insert(e1.x - pbase, e1.y);
                 }
             }
             __syncthreads();
@@ -1229,8 +1237,8 @@ static void ref_batch_launch(vb_ctx *ctx, RefBatch &b, const DevGenomes &dg, con
         VB_CUDA(cudaMemcpyAsync(b.d_refs.p, b.refs.data(), sizeof(RefDesc) * n_refs, cudaMemcpyHostToDevice, st));
     }
     b.carry.alloc((size_t)iblocks * 2 * carry_stride);
-    const uint32_t ent_stride = carry_stride + 2 * IDX_CHUNK;          // multiple of 8 entries: every chunk store is 16-byte aligned
-    b.ent.alloc((size_t)iblocks * 2 * ent_stride);
+    const uint32_t ent_stride = carry_stride + 2 * IDX_CHUNK;
+    b.ent.alloc((size_t)iblocks * ent_stride);
     b.next_ref.alloc(1);
     VB_CUDA(cudaMemsetAsync(b.next_ref.p, 0, sizeof(unsigned int), st));
     dim3 grid_b(16, (unsigned)std::min<size_t>(n_refs, 32768));

@@ -201,6 +201,15 @@ static DevGenomes *upload_persistent(vb_ctx *ctx, const vb_genomes *g, uint32_t 
     return d;
 }
 
+// would vb_get_dev_genomes find a device copy (no upload, on_chunk not called)?
+bool vb_has_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad)
+{
+    if (min_pad < VB_STORE_PAD) min_pad = VB_STORE_PAD;
+    for (auto &r : ctx->resident)
+        if (r.g == g && r.uid == g->uid && r.min_pad >= min_pad) return true;
+    return ctx->last.dev && ctx->last.g == g && ctx->last.uid == g->uid && ctx->last.min_pad >= min_pad;
+}
+
 const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident,
                                      const vb_chunk_fn *on_chunk)
 {

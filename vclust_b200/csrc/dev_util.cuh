@@ -205,6 +205,7 @@ void vb_upload_genomes(vb_ctx *ctx, const vb_genomes *g, DevGenomes &out, uint32
 // Returns the packed copy of g: the resident one when vb_genomes_make_resident was called for it, else the copy the
 // previous call on this context uploaded (vclust prefilter followed by vclust align on the same set transfers the
 // genomes once), else uploads now and keeps the copy for the next call (vb_genomes_evict drops it).
+bool vb_has_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad);
 const DevGenomes &vb_get_dev_genomes(vb_ctx *ctx, const vb_genomes *g, uint32_t min_pad, bool *was_resident = nullptr,
                                      const vb_chunk_fn *on_chunk = nullptr);
 

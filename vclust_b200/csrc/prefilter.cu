@@ -419,7 +419,7 @@ struct Segment {
 template <int LEVEL>
 __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, uint32_t B1, uint32_t B2, const uint64_t *__restrict__ in_keys,
                                                             const uint32_t *__restrict__ in_vals, const Segment *__restrict__ segs,
-                                                            uint32_t n_segs, uint32_t n_tiles,
+                                                            const uint32_t *__restrict__ tile_seg, uint32_t n_tiles,
                                                             uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_keys,
                                                             uint32_t *__restrict__ out_vals)
 {
@@ -431,52 +431,53 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, ui
     uint32_t *s_start = s_cnt + MAXB;
     uint32_t *s_fill = s_start + MAXB;
     uint32_t *s_gbase = s_fill + MAXB;
-    __shared__ uint32_t s_total, s_seg, s_wtot[PART_THREADS / 32];
+    __shared__ uint32_t s_total, s_wtot[PART_THREADS / 32];
     const uint32_t NBK = (LEVEL == 1) ? B1 : B2;
     auto bucket_of = [&](uint64_t h) -> uint32_t {
         if (LEVEL == 1) return parent_of(h, B1);
         return sub_of(h, B1, B2);
     };
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t b = threadIdx.x; b < NBK; b += PART_THREADS) { s_cnt[b] = 0; s_fill[b] = 0; }
-        uint64_t src_lo = 0, src_hi = 0;
-        uint32_t cur_base = 0;
+    // The loads of a tile are issued one tile AHEAD, into the registers the previous tile has just vacated (its tuples sit
+    // in shared memory by then), so that they are in flight during the previous tile's write-out instead of stalling the
+    // histogram (42 % of the stall samples were these loads, plus the barrier behind them).
+    uint64_t key[PART_ITEMS];
+    uint32_t val[PART_ITEMS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // source range of a tile -> number of tuples in it, cursor base of its parent; issues the loads
+    auto fetch = [&](uint32_t tile, uint32_t &cnt, uint32_t &cur_base) {
+        uint64_t src_lo;
         if (LEVEL == 2) {
-            if (threadIdx.x == 0) {                                     // which segment does this tile belong to?
-                uint32_t lo = 0, hi = n_segs;
-                while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (segs[mid].tile_start <= tile) lo = mid; else hi = mid; }
-                s_seg = lo;
-            }
-        }
-        __syncthreads();
-        if (LEVEL == 2) {
-            const Segment sg = segs[s_seg];
-            src_lo = (uint64_t)sg.beg + (uint64_t)(tile - sg.tile_start) * PART_TILE;
-            src_hi = min(src_lo + PART_TILE, (uint64_t)sg.beg + sg.len);
+            const Segment sg = segs[tile_seg[tile]];                    // (host-built map: a search here was 13 % of the kernel's instructions)
+            const uint32_t done = (tile - sg.tile_start) * (uint32_t)PART_TILE;
+            src_lo = (uint64_t)sg.beg + done;
+            cnt = min((uint32_t)PART_TILE, sg.len - done);
             cur_base = sg.parent * B2;
         } else {
             src_lo = (uint64_t)tile * PART_TILE;
-            src_hi = min(src_lo + PART_TILE, n_in);
+            cnt = (uint32_t)min((uint64_t)PART_TILE, n_in - src_lo);
+            cur_base = 0;
         }
-        uint64_t key[PART_ITEMS];
-        uint32_t val[PART_ITEMS];
-        uint32_t bk[PART_ITEMS];
+        const uint64_t *kp = in_keys + src_lo + threadIdx.x;
+        const uint32_t *vp = in_vals + src_lo + threadIdx.x;
 #pragma unroll
-        for (int r = 0; r < PART_ITEMS; ++r) {
-            uint64_t p = src_lo + (uint64_t)r * PART_THREADS + threadIdx.x;
-            const bool ok = p < src_hi;
-            if (ok) { key[r] = in_keys[p]; val[r] = in_vals[p]; }
-            bk[r] = 0xffffffffu;
-            if (ok) {
-                bk[r] = bucket_of(key[r]);
-                atomicAdd(&s_cnt[bk[r]], 1u);
-            }
-        }
+        for (int r = 0; r < PART_ITEMS; ++r)
+            if ((uint32_t)(r * PART_THREADS) + threadIdx.x < cnt) { key[r] = kp[r * PART_THREADS]; val[r] = vp[r * PART_THREADS]; }
+    };
+
+    uint32_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;                                        // (uniform)
+    uint32_t cnt, cur_base;
+    fetch(tile, cnt, cur_base);
+    for (;;) {
+        for (uint32_t b = threadIdx.x; b < NBK; b += PART_THREADS) { s_cnt[b] = 0; s_fill[b] = 0; }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < PART_ITEMS; ++r)
+            if ((uint32_t)(r * PART_THREADS) + threadIdx.x < cnt) atomicAdd(&s_cnt[bucket_of(key[r])], 1u);
         __syncthreads();
         // exclusive scan of s_cnt (NBK <= 1024 = 2 per thread; every warp takes part) + one global reservation per bucket
         {
-            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
             const uint32_t b0 = 2 * threadIdx.x;
             const uint32_t v0 = b0 < NBK ? s_cnt[b0] : 0u, v1 = b0 + 1 < NBK ? s_cnt[b0 + 1] : 0u;
             uint32_t x = v0 + v1;
@@ -493,18 +494,32 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, ui
             if (threadIdx.x == PART_THREADS - 1) s_total = base + x;
         }
         __syncthreads();
-        for (uint32_t b = threadIdx.x; b < NBK; b += PART_THREADS) {
-            uint32_t c = s_cnt[b];
-            if (c) s_gbase[b] = atomicAdd(&cursor[cur_base + b], c);
+        // one global reservation per non-empty bucket; the answers are only needed for the write-out, so they stay in
+        // flight (in registers) while the tile is staged and the next one is requested
+        static_assert((1 << MAX_BUCKET_BITS) <= 2 * PART_THREADS, "two buckets per thread");
+        uint32_t gb0 = 0, gb1 = 0;
+        {
+            const uint32_t b0 = threadIdx.x, b1 = threadIdx.x + PART_THREADS;
+            const uint32_t c0 = b0 < NBK ? s_cnt[b0] : 0u, c1 = b1 < NBK ? s_cnt[b1] : 0u;
+            if (c0) gb0 = atomicAdd(&cursor[cur_base + b0], c0);
+            if (c1) gb1 = atomicAdd(&cursor[cur_base + b1], c1);
         }
 #pragma unroll
         for (int r = 0; r < PART_ITEMS; ++r) {
-            if (bk[r] != 0xffffffffu) {
-                uint32_t pos = s_start[bk[r]] + atomicAdd(&s_fill[bk[r]], 1u);
+            if ((uint32_t)(r * PART_THREADS) + threadIdx.x < cnt) {
+                const uint32_t b = bucket_of(key[r]);                   // (recomputed: cheaper than 8 registers held across the scan)
+                const uint32_t pos = s_start[b] + atomicAdd(&s_fill[b], 1u);
                 st_keys[pos] = key[r];
                 st_vals[pos] = val[r];
             }
         }
+        // the next tile's tuples start travelling now
+        const uint32_t next = tile + gridDim.x;
+        const bool more = next < n_tiles;                               // (uniform)
+        uint32_t cnt_next = 0, base_next = 0;
+        if (more) fetch(next, cnt_next, base_next);
+        s_gbase[threadIdx.x] = gb0;
+        s_gbase[threadIdx.x + PART_THREADS] = gb1;
         __syncthreads();
         const uint32_t total = s_total;
         for (uint32_t s = threadIdx.x; s < total; s += PART_THREADS) {
@@ -515,6 +530,8 @@ __global__ void __launch_bounds__(PART_THREADS, 3) part_kernel(uint64_t n_in, ui
             out_vals[dst] = st_vals[s];
         }
         __syncthreads();
+        if (!more) break;
+        tile = next; cnt = cnt_next; cur_base = base_next;
     }
 }
 
@@ -747,6 +764,11 @@ __global__ void __launch_bounds__(256) bucket_flat_kernel(const uint64_t *__rest
 // phases (three block-wide barriers fewer) but the walks leave lanes idle when group sizes differ inside a warp: faster
 // for small families (c2, c3: 8.4 vs 13.2 ms), no faster for families of hundreds; vb_prefilter_run picks the flat kernel
 // for large groups on the hashed table (VB_PREFILTER_BUCKET=chain|flat forces one).
+// (Tried and dropped in round 2: compacting the tuples that have a chain into a work list and walking them with lane refill
+// -- a lane whose chain ends takes the next tuple.  Same 8.4 ms at c3 with warp-private list slices, 9.4 ms with a shared
+// counter, 40.6 vs 36.9 ms at c3_s200: the kernel is not bound by idle lanes but by many small costs at c3 -- 5 G warp
+// instructions spread over load, insert, duplicate check and pair loop, 55 % of the issue slots used -- and by the L2
+// atomic rate, 1.1e11 increments/s, once families are large.  profiles/r02_ab_kernels.txt.)
 constexpr uint32_t CHAIN_END = 0xffffu;
 struct ChainSmem {
     uint64_t keys[BUCKET_CAP];                 // h of every tuple
@@ -1492,7 +1514,10 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         const double est_keep = use_seen ? 0.5 * est_pass : est_pass;       // the screen drops about half of the tuples
         int bits = 0;
         while (est_keep / (double)(1ULL << bits) > BUCKET_TARGET && bits < 2 * MAX_BUCKET_BITS) ++bits;
-        uint32_t want = 1u << std::min(MAX_BUCKET_BITS, (bits + 1) / 2);     // parents over all ranks
+        // parents over all ranks: the two levels get (about) the same fan-out -- a tile of 4 096 tuples then leaves runs of
+        // the same length in both; an odd bit goes to level 2, whose fan-out need not be a power of two
+        const char *l1_env = getenv("VB_PREFILTER_L1BITS");                  // test hook
+        uint32_t want = 1u << std::min(MAX_BUCKET_BITS, l1_env ? std::max(0, atoi(l1_env)) : bits / 2);
         Bper = 1;
         while (Bper * 2 * world <= std::max(want, world) && Bper * 2 * world <= (1u << MAX_BUCKET_BITS)) Bper *= 2;
         B1 = Bper * world;
@@ -1526,8 +1551,35 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
     // when the genomes have to be uploaded, the screen pass (of pass 0) over each chunk of genomes is enqueued while the
     // next chunk is still on the PCIe bus
     bool screened = false;
+    // Larger inputs have no screen; there the whole extraction of pass 0 rides on the upload instead: the tuples of every
+    // chunk of genomes are collected (into buffers sized for every slot, so no counting pass) while the next chunk is on
+    // the bus, and only the last chunk's extraction is left when the copy ends.
+    const uint64_t slots_pre = vb_store_slots(g, VB_STORE_PAD);
+    auto exact_alloc_for = [&](uint64_t slots) {
+        return passes > 1 || job.shard_count > 1 || slots >= (1ULL << 31) || 12.0 * (double)slots > 0.125 * (double)ctx->mem_total ||
+               getenv("VB_PREFILTER_EXACT") != nullptr;
+    };
+    const bool early_collect = !use_seen && !exact_alloc_for(slots_pre) && slots_pre <= chunk && !vb_has_dev_genomes(ctx, g, VB_STORE_PAD) &&
+                               getenv("VB_PREFILTER_NO_EARLY") == nullptr;                  // (test hook: extraction after the upload)
+    DevBuf<uint32_t> fine_early, vals_early;
+    DevBuf<uint64_t> keys_early;
+    bool collected_early = false;
+    if (early_collect) {
+        fine_early.alloc(n_fine);
+        VB_CUDA(cudaMemsetAsync(fine_early.p, 0, fine_early.bytes(), st));
+        keys_early.alloc(slots_pre + 64);
+        vals_early.alloc(slots_pre + 64);
+    }
     const vb_chunk_fn hook = [&](const DevGenomes &d, uint64_t lo, uint64_t hi) {
         if (use_seen) { screen_range(d, lo, hi); screened = true; }
+        else if (early_collect && hi > lo && d.total_slots == slots_pre) {
+            ep.shard_count = job.shard_count * passes;
+            ep.shard_index = job.shard_index * passes;
+            collect_kernel<true><<<grid_of(lo, hi, 8), 256, 0, st>>>(d.seq2.p, d.inv_kdb.p, d.tile_gid.p, lo, hi, ep, seen, valid_cnt,
+                                                                      scalars.p + 6, 1, keys_early.p, vals_early.p, fine_early.p, B1);
+            VB_LAUNCH_CHECK(ctx);
+            collected_early = true;
+        }
     };
     t_up.start();
     const DevGenomes &dg = vb_get_dev_genomes(ctx, g, VB_STORE_PAD, nullptr, &hook);
@@ -1605,13 +1657,17 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         ep.shard_index = job.shard_index * passes + pass;
         // ---- extract: hash once, (optionally) screen out singletons, compact list + fine histogram
         EventTimer *t_ext = lap_start(ms_ext);
-        DevBuf<uint32_t> fine_hist(n_fine);
-        VB_CUDA(cudaMemsetAsync(fine_hist.p, 0, fine_hist.bytes(), st));
+        const bool have_early = collected_early && attempt == 0 && pass == 0;    // this pass' tuples were collected during the upload
+        DevBuf<uint32_t> fine_hist;
+        if (have_early) fine_hist = std::move(fine_early);
+        else {
+            fine_hist.alloc(n_fine);
+            VB_CUDA(cudaMemsetAsync(fine_hist.p, 0, fine_hist.bytes(), st));
+        }
         unsigned long long *d_cursor = scalars.p + 6;
         if (use_seen && pass > 0) VB_CUDA(cudaMemsetAsync(seen_words.p, 0, seen_words.bytes(), st));
         // small inputs: room for every slot's tuple, no counting pass.  Large inputs / several passes: count first.
-        const bool exact_alloc = passes > 1 || job.shard_count > 1 || n_slots >= (1ULL << 31) ||
-                                 12.0 * (double)n_slots > 0.125 * (double)ctx->mem_total || getenv("VB_PREFILTER_EXACT") != nullptr;
+        const bool exact_alloc = !have_early && exact_alloc_for(n_slots);
         auto for_chunks = [&](auto &&launch) {
             for (uint64_t lo = 0; lo < n_slots; lo += chunk) launch(lo, std::min(n_slots, lo + chunk));
         };
@@ -1645,9 +1701,11 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
             }
         }
         if (list_cap >= (1ULL << 32)) throw vb_error(VB_ERR_ARG, "more than 2^32 k-mer tuples in one prefilter pass: raise VB_PREFILTER_PASSES or use more GPUs");
-        DevBuf<uint64_t> keys0(list_cap);                    // compact list of surviving (hash, genome) tuples
-        DevBuf<uint32_t> vals0(list_cap);
-        for_chunks([&](uint64_t lo, uint64_t hi) {
+        DevBuf<uint64_t> keys0;                              // compact list of surviving (hash, genome) tuples
+        DevBuf<uint32_t> vals0;
+        if (have_early) { keys0 = std::move(keys_early); vals0 = std::move(vals_early); }
+        else { keys0.alloc(list_cap); vals0.alloc(list_cap); }
+        if (!have_early) for_chunks([&](uint64_t lo, uint64_t hi) {
             if (counted_valid)
                 collect_kernel<false><<<grid_of(lo, hi, 8), 256, 0, st>>>(dg.seq2.p, dg.inv_kdb.p, dg.tile_gid.p, lo, hi, ep, seen, valid_cnt,
                                                                            d_cursor, 1, keys0.p, vals0.p, fine_hist.p, B1);
@@ -1696,7 +1754,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         DevBuf<uint32_t> vals1(n_keep + 64);
         if (tiles1) {
             part_kernel<1><<<std::min<uint32_t>(tiles1, n_sm * 8), PART_THREADS, part_smem, st>>>(
-                n_keep, B1, 1, keys0.p, vals0.p, nullptr, 0, tiles1, cursor1.p, keys1.p, vals1.p);
+                n_keep, B1, 1, keys0.p, vals0.p, nullptr, nullptr, tiles1, cursor1.p, keys1.p, vals1.p);
             VB_LAUNCH_CHECK(ctx);
         }
         t_part->stop();
@@ -1776,6 +1834,9 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         n_tuples_grouped += n_recv;
         uint32_t tiles2 = 0;
         for (auto &sg : segs) { sg.tile_start = tiles2; tiles2 += (sg.len + PART_TILE - 1) / PART_TILE; }
+        std::vector<uint32_t> tile_seg(tiles2);                               // tile -> its segment
+        for (size_t i = 0; i < segs.size(); ++i)
+            std::fill(tile_seg.begin() + segs[i].tile_start, tile_seg.begin() + (i + 1 < segs.size() ? segs[i + 1].tile_start : tiles2), (uint32_t)i);
 
         // ---- level 2: parents -> final buckets
         t_part = lap_start(ms_part);
@@ -1784,7 +1845,9 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         DevBuf<uint32_t> hist(NB), off(NB + 1), cursor2(NB), big_list(NB + 1), n_big(1);
         DevBuf<Segment> d_segs(std::max<size_t>(segs.size(), 1));
         VB_CUDA(cudaMemsetAsync(n_big.p, 0, sizeof(uint32_t), st));
+        DevBuf<uint32_t> d_tile_seg(std::max<size_t>(tile_seg.size(), 1));
         if (!segs.empty()) VB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st));
+        if (tiles2) VB_CUDA(cudaMemcpyAsync(d_tile_seg.p, tile_seg.data(), sizeof(uint32_t) * tiles2, cudaMemcpyHostToDevice, st));
         coarsen_kernel<<<(int)(((uint64_t)NB * 32 + 255) / 256), 256, 0, st>>>(fine_src, fine_n_src, (uint64_t)Bper << FINE_BITS, B2, NB, hist.p);
         VB_LAUNCH_CHECK(ctx);
         dev_exscan(ctx, st, hist.p, NB, off.p, cursor2.p, scan_tmp.p);
@@ -1792,7 +1855,7 @@ void vb_prefilter_run(vb_ctx *ctx, const vb_prefilter_job &job, const vb_prefilt
         DevBuf<uint32_t> vals2(n_recv + 64);
         if (tiles2) {
             part_kernel<2><<<std::min<uint32_t>(tiles2, n_sm * 8), PART_THREADS, part_smem, st>>>(
-                n_recv, B1, B2, rkeys, rvals, d_segs.p, (uint32_t)segs.size(), tiles2, cursor2.p, keys2.p, vals2.p);
+                n_recv, B1, B2, rkeys, rvals, d_segs.p, d_tile_seg.p, tiles2, cursor2.p, keys2.p, vals2.p);
             VB_LAUNCH_CHECK(ctx);
         }
         t_part->stop();
