@@ -226,7 +226,7 @@ def main_reference(args, rank: int, world: int):
             times.append(time.perf_counter() - t0)
         ms = 1000 * sum(times) / len(times)
         sample = "oracle port (plain C, 1 thread) on the first %d of %d genomes: %d candidate pairs per step" % (n_sample, len(names), pairs)
-        print(json.dumps(reference_line(args, pairs / (ms / 1000), ms, sample, 1, "port")))
+        emit(json.dumps(reference_line(args, pairs / (ms / 1000), ms, sample, 1, "port")))
         return
     threads = os.cpu_count() or 1
     total_passes = args.steps + args.warmup
@@ -253,7 +253,7 @@ def main_reference(args, rank: int, world: int):
             pairs = n_pairs
     ms = 1000 * sum(times) / len(times)
     sample = "first %d of %d genomes (whole families): %d candidate pairs per step, -t %d, file to file" % (n_sample, len(names), pairs, threads)
-    print(json.dumps(reference_line(args, pairs / (ms / 1000), ms, sample, threads, "reference")))
+    emit(json.dumps(reference_line(args, pairs / (ms / 1000), ms, sample, threads, "reference")))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -426,7 +426,7 @@ def main_single(args, local_rank: int):
                   "sample": "oracle port (plain C, 1 thread), first 100 of %d genomes: %d candidate pairs; prefilter %.2f s, "
                             "parse %.2f s" % (len(names), n_pairs, t_pre, t_al), "prefilter_s": t_pre, "align_s": t_al}
         out["cpu_baseline"] = cb
-    print(json.dumps(out))
+    emit(json.dumps(out))
     ctx.evict()
     g.close()
     ctx.close()
@@ -546,12 +546,31 @@ def main_sharded(args, rank: int, world: int, local_rank: int):
                              "directed_pairs_max_rank": mx[len(keys_p) + keys_a.index("pairs")]}}
         out = build_line(args, world, step_ms, e2e_ms, float(info["pairs"]), info["directed"], lens, infos, float(agg[0]), clocks, region_s,
                          h2d, d2h, extra)
-        print(json.dumps(out))
+        emit(json.dumps(out))
     run.close()
     dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line: str) -> None:
+    """The one JSON line of the contract, written to the process' ORIGINAL stdout."""
+    data = (line + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line + "\n")
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # stdout carries the JSON line and nothing else: whatever libraries print there (NCCL's version banner, under
+    # NCCL_DEBUG=VERSION, goes to stdout) is sent to stderr instead, and the line itself to a duplicate of the original fd
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
