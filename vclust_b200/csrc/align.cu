@@ -79,12 +79,6 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t k)
     return k;
 }
 
-__device__ __forceinline__ uint64_t reverse_digits(uint64_t x)
-{
-    x = __brevll(x);
-    return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
-}
-
 // home slot of a hash in a table of `cap` slots (low 32 bits; the fingerprint comes from the high 32)
 __device__ __forceinline__ uint32_t ht_slot(uint64_t h, uint32_t cap) { return __umulhi((uint32_t)h, cap); }
 
@@ -424,11 +418,10 @@ __device__ __forceinline__ uint32_t window_violations_15_7(uint64_t x)
     VB_FA(VB_Y(6), VB_Y(7), VB_Y(8), s2, c2)
     VB_FA(VB_Y(9), VB_Y(10), VB_Y(11), s3, c3)
     VB_FA(VB_Y(12), VB_Y(13), VB_Y(14), s4, c4)
-    uint32_t t0, d0, t1, d1, u0, d2;
+    uint32_t t0, d0, t1, d1, d2;
     VB_FA(s0, s1, s2, t0, d0)
     t1 = s3 ^ s4; d1 = s3 & s4;
-    u0 = t0 ^ t1; d2 = t0 & t1;                                    // u0 = bit 0 of the count (unused)
-    (void)u0;
+    d2 = t0 & t1;                                                  // (t0 ^ t1 = bit 0 of the count, unused)
     uint32_t e0, f0, e1, f1, e2, f2, f3;
     VB_FA(c0, c1, c2, e0, f0)
     VB_FA(c3, c4, d0, e1, f1)
@@ -1052,7 +1045,6 @@ __global__ void __launch_bounds__(1024) lpt_cut_kernel(uint32_t *__restrict__ hi
 {
     // suffix sums over the 4 096 classes (4 per thread, descending class order), then the cut is found in parallel
     __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t s_total;
     __shared__ int s_cut;
     const int t = threadIdx.x;
     uint32_t v[4], sum = 0;
@@ -1070,7 +1062,6 @@ __global__ void __launch_bounds__(1024) lpt_cut_kernel(uint32_t *__restrict__ hi
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
         warp_tot[lane] = z - tt;
-        if (lane == 31) s_total = z;
     }
     __syncthreads();
     uint32_t before = warp_tot[w] + x - sum;          // pairs in classes ABOVE class COST_CLASSES-1-4t
@@ -1116,7 +1107,6 @@ __global__ void __launch_bounds__(1024) lpt_cut_kernel(uint32_t *__restrict__ hi
         for (int j = 0; j < 4; ++j)
             if (COST_CLASSES - 1 - (4 * t + j) == cut) { counts[1] = heavy_total; counts[2] = (unsigned long long)cut; }
     }
-    (void)s_total;
 }
 
 __global__ void __launch_bounds__(256) heavy_fill_kernel(const uint32_t *__restrict__ cost, const unsigned long long *__restrict__ counts,

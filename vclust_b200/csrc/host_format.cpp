@@ -347,9 +347,9 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
         while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (res->qry[mid] < q) lo = mid + 1; else hi = mid; }
         return (lo < start[r + 1] && res->qry[lo] == q) ? (int64_t)lo : -1;
     };
-    // rows [a_lo, a_hi) formatted into `out`; big results are formatted by several host threads on disjoint row ranges
+    // rows [a_lo, a_hi) formatted into `dst`; big results are formatted by several host threads on disjoint row ranges
     // (equal numbers of directed pairs) and written in row order -- number formatting is the whole cost of this call
-    auto format_rows = [&](uint32_t a_lo, uint32_t a_hi, std::string &out) {
+    auto format_rows = [&](uint32_t a_lo, uint32_t a_hi, std::string &dst) {
     char num[64];
     for (uint32_t a = a_lo; a < a_hi; ++a) {
         for (uint64_t qi = start[a]; qi < start[a + 1]; ++qi) {
@@ -377,8 +377,8 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
                     switch (cols[c]) {
                     case C_RIDX: nn = put_u64(ids[i], num); break;
                     case C_QIDX: nn = put_u64(ids[!i], num); break;
-                    case C_REFERENCE: out += g->names[res->order[ids[i]]]; break;
-                    case C_QUERY: out += g->names[res->order[ids[!i]]]; break;
+                    case C_REFERENCE: dst += g->names[res->order[ids[i]]]; break;
+                    case C_QUERY: dst += g->names[res->order[ids[!i]]]; break;
                     case C_QCOV: nn = vb_fmt_real(cov[i], 6, num); break;
                     case C_RCOV: nn = vb_fmt_real(cov[!i], 6, num); break;
                     case C_GANI: nn = vb_fmt_real(gani[i], 6, num); break;
@@ -397,10 +397,10 @@ void vb_write_ani_impl(const vb_genomes *g, const vb_align_out *res, const char 
                         } else { num[0] = '0'; nn = 1; }
                         break;
                     }
-                    out.append(num, nn);
-                    out += (c + 1 < cols.size()) ? '\t' : '\n';
+                    dst.append(num, nn);
+                    dst += (c + 1 < cols.size()) ? '\t' : '\n';
                 }
-                if (cols.empty()) out += '\n';
+                if (cols.empty()) dst += '\n';
             }
         }
     }
