@@ -99,12 +99,17 @@ def _spec_lzani(data: bytes, dir_mode: bool):
     return [((n.split(b" ")[0] if b" " in n else n), s) for n, s in recs]
 
 
-def test_fasta_ingest_fuzz_against_record_rules(lib, tmp_path):
+@pytest.mark.parametrize("par", [None, (0, 2), (0, 8), (64, 3)])
+def test_fasta_ingest_fuzz_against_record_rules(lib, tmp_path, monkeypatch, par):
     """Random byte soup over the alphabet that matters (>, space, CR, LF, bases): the single-pass loader must give
-    exactly the records the two tools' rules give, in all four (flavor, mode) combinations."""
+    exactly the records the two tools' rules give, in all four (flavor, mode) combinations -- also when a multi-FASTA
+    is cut at line-start '>' bytes and parsed by several threads (forced here on tiny files: par = (from bytes, threads))."""
+    if par:
+        monkeypatch.setenv("VB_FASTA_PAR_MIN", str(par[0]))
+        monkeypatch.setenv("VB_FASTA_THREADS", str(par[1]))
     rng = np.random.default_rng(123)
     alphabet = np.frombuffer(b">> \r\n\n\n\nACGTNacgtUXY", dtype=np.uint8)
-    for trial in range(60):
+    for trial in range(60 if not par else 150):
         data = alphabet[rng.integers(0, alphabet.size, size=int(rng.integers(0, 400)))].tobytes()
         if trial % 3 == 0:
             data = b">s1 d\n" + data
@@ -113,11 +118,15 @@ def test_fasta_ingest_fuzz_against_record_rules(lib, tmp_path):
         want = _spec_kmerdb(data)
         g = api.Genomes.load([fa], True, api.FASTA_KMERDB)
         assert [(g.name(i).encode(), g.sequence(i)) for i in range(len(g))] == want, (trial, data)
+        g = api.Genomes.load([fa, fa], True, api.FASTA_KMERDB)             # second file: appended behind the first one's records
+        assert [(g.name(i).encode(), g.sequence(i)) for i in range(len(g))] == want + want, (trial, data)
         g = api.Genomes.load([fa], False, api.FASTA_KMERDB)
         assert len(g) == 1 and g.sequence(0) == b"N".join(s for _, s in want), (trial, data)
         want = _spec_lzani(data, False)
         g = api.Genomes.load([fa], True, api.FASTA_LZANI)
         assert [(g.name(i).encode(), g.sequence(i)) for i in range(len(g))] == want, (trial, data)
+        g = api.Genomes.load([fa, fa], True, api.FASTA_LZANI)
+        assert [(g.name(i).encode(), g.sequence(i)) for i in range(len(g))] == want + want, (trial, data)
         joined = b""
         for _, s in _spec_lzani(data, True):
             if joined:

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <filesystem>
+#include <thread>
+#include <vector>
 
 #include "vb_internal.h"
 
@@ -98,6 +100,8 @@ struct Sink {
     size_t file_start = 0, rec_start = 0;
     bool first_record = true;
     std::string rec_name;
+    std::vector<std::string> *names_out = nullptr;      // where kept records are listed (default: the genome set itself;
+    std::vector<uint64_t> *ends_out = nullptr;          // a chunk of a big file parsed by its own thread: local lists)
 
     // in place (multisample): the file's bytes already sit at bases[w ...); otherwise room for bytes + separators
     void start_file(size_t file_bytes, size_t max_records_hint, bool in_place)
@@ -122,8 +126,8 @@ struct Sink {
         if (!keep) { w = rec_start; return; }
         size_t sp = rec_name.find(' ');
         if (sp != std::string::npos) rec_name.resize(sp);
-        g->names.push_back(rec_name);
-        g->offset.push_back(w);
+        (names_out ? names_out : &g->names)->push_back(rec_name);
+        (ends_out ? ends_out : &g->offset)->push_back(w);
     }
     void end_file(const char *path)
     {
@@ -208,6 +212,84 @@ void split_lzani(const char *d, size_t n, bool dir_mode, Sink &s)
     close();
 }
 
+// A big multi-FASTA (already read into bases at [s.w, s.w + n)) parsed by several threads.  The file is cut at '>' bytes
+// that start a line -- a record start under both tools' rules, and the only place where a chunk can begin without
+// knowing what came before -- every thread compacts its chunk in place and lists its records, and the gaps between the
+// compacted chunks are then closed, again by all threads at once.
+void split_parallel(const char *d, size_t n, bool kmerdb, unsigned n_threads, Sink &s)
+{
+    struct Chunk { size_t lo, hi, w_end; std::vector<std::string> names; std::vector<uint64_t> ends; };
+    std::vector<Chunk> chunks(n_threads);
+    const char *end = d + n;
+    size_t prev = 0;
+    for (unsigned c = 0; c < n_threads; ++c) {
+        size_t hi = n;
+        if (c + 1 < n_threads) {
+            const char *p = d + std::max(prev, n * (size_t)(c + 1) / n_threads);
+            hi = n;
+            while (p < end && (p = (const char *)memchr(p, '>', (size_t)(end - p)))) {
+                if (p > d && p[-1] == '\n') { hi = (size_t)(p - d); break; }
+                ++p;
+            }
+        }
+        chunks[c].lo = prev; chunks[c].hi = hi;
+        prev = hi;
+    }
+    const size_t file_w = s.w;                          // the file's bytes start here (in-place mode)
+    char *base = s.base;
+    std::vector<std::thread> pool;
+    auto work = [&](unsigned c) {
+        Chunk &ch = chunks[c];
+        Sink ls{s.g, true, kmerdb, s.sep_len};
+        ls.base = base;
+        ls.w = ls.file_start = file_w + ch.lo;
+        ls.names_out = &ch.names; ls.ends_out = &ch.ends;
+        if (ch.hi > ch.lo) {
+            if (kmerdb) split_kmerdb(d + ch.lo, ch.hi - ch.lo, ls);
+            else split_lzani(d + ch.lo, ch.hi - ch.lo, false, ls);
+        }
+        ch.w_end = ls.w;
+    };
+    for (unsigned c = 1; c < n_threads; ++c) pool.emplace_back(work, c);
+    work(0);
+    for (auto &th : pool) th.join();
+    pool.clear();
+    // close the gaps between the compacted chunks, in place.  Chunk c moves left by shift[c] = the slack of the chunks
+    // before it -- far less than its length -- so its destination overlaps only the last shift[c-1] bytes of chunk c-1's
+    // compacted bytes: those tails are set aside first (a few MB), then all chunks move at the same time.
+    std::vector<size_t> dst(n_threads + 1, file_w);
+    for (unsigned c = 0; c < n_threads; ++c) dst[c + 1] = dst[c] + (chunks[c].w_end - (file_w + chunks[c].lo));
+    auto src_of = [&](unsigned c) { return file_w + chunks[c].lo; };
+    auto len_of = [&](unsigned c) { return dst[c + 1] - dst[c]; };
+    bool together = true;
+    for (unsigned c = 0; c + 1 < n_threads; ++c)
+        if (src_of(c) - dst[c] > len_of(c)) together = false;          // (degenerate: a chunk shorter than the slack before it)
+    if (together) {
+        std::vector<std::string> tails(n_threads);
+        for (unsigned c = 0; c + 1 < n_threads; ++c) {
+            const size_t ts = src_of(c) - dst[c];
+            tails[c].assign(base + src_of(c) + len_of(c) - ts, ts);
+        }
+        auto move = [&](unsigned c) {
+            const size_t ts = tails[c].size();
+            if (dst[c] != src_of(c)) memmove(base + dst[c], base + src_of(c), len_of(c) - ts);
+            if (ts) memcpy(base + dst[c] + len_of(c) - ts, tails[c].data(), ts);
+        };
+        for (unsigned c = 1; c < n_threads; ++c) pool.emplace_back(move, c);
+        move(0);
+        for (auto &th : pool) th.join();
+    } else {
+        for (unsigned c = 0; c < n_threads; ++c)
+            if (dst[c] != src_of(c)) memmove(base + dst[c], base + src_of(c), len_of(c));
+    }
+    for (unsigned c = 0; c < n_threads; ++c) {
+        const size_t shift = file_w + chunks[c].lo - dst[c];
+        for (auto &nm : chunks[c].names) s.g->names.push_back(std::move(nm));
+        for (uint64_t e : chunks[c].ends) s.g->offset.push_back(e - shift);
+    }
+    s.w = dst[n_threads];
+}
+
 }  // namespace
 
 vb_genomes *vb_genomes_load_impl(const char *const *paths, int n_paths, int multisample, vb_fasta_flavor flavor,
@@ -234,7 +316,13 @@ vb_genomes *vb_genomes_load_impl(const char *const *paths, int n_paths, int mult
                 for (const char *p = d, *e = d + n; (p = (const char *)memchr(p, '>', (size_t)(e - p))); ++p) ++hdrs;
                 s.start_file(n, hdrs, false);
             }
-            if (flavor == VB_FASTA_KMERDB) split_kmerdb(d, n, s);
+            // big multi-FASTA files are parsed by several threads (VB_FASTA_PAR_MIN: bytes from which on, test hook)
+            const size_t par_min = getenv("VB_FASTA_PAR_MIN") ? (size_t)strtoull(getenv("VB_FASTA_PAR_MIN"), nullptr, 10) : ((size_t)64 << 20);
+            const unsigned par_thr = getenv("VB_FASTA_THREADS") ? (unsigned)std::clamp(atoi(getenv("VB_FASTA_THREADS")), 1, 64) : 8u;
+            const unsigned n_thr = std::min({par_thr, std::max(1u, std::thread::hardware_concurrency()),
+                                             (unsigned)std::max<size_t>(1, n / std::max<size_t>(par_min / 4, 1))});
+            if (multisample && n >= par_min && n_thr > 1) split_parallel(d, n, flavor == VB_FASTA_KMERDB, n_thr, s);
+            else if (flavor == VB_FASTA_KMERDB) split_kmerdb(d, n, s);
             else split_lzani(d, n, !multisample, s);
             s.end_file(paths[i]);
         }

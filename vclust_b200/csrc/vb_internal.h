@@ -45,6 +45,7 @@ struct vb_bytes {
     }
     void resize(size_t m) { if (m > cap) reserve(std::max(m, cap + cap / 2)); n = m; }
     void append(const char *s, size_t len) { resize(n + len); if (len) memcpy(p + n - len, s, len); }
+    void swap(vb_bytes &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
     void shrink_to_fit()
     {
         if (n == cap || !p) return;
