@@ -109,8 +109,9 @@ struct vb_resident {                 // a genome set kept packed in HBM across c
     DevGenomes *dev;
 };
 
-// Receive buffers of all-to-all #1, one per rank, mapped into every rank's address space (CUDA IPC): the level-1
-// partition kernel of a rank stores its tuples straight into the buffers of their owners over NVLink (shard.cu).
+// Receive buffers of all-to-all #1, one per rank, mapped into every rank's address space (CUDA IPC, shard.cu): a rank
+// copies each destination's slice of its level-1 buffer straight into the owner's buffer over NVLink (one peer
+// cudaMemcpyAsync per destination; a fused store from the partition kernel was slower: tiny NVLink writes).
 struct vb_peer_xbuf {
     void *local = nullptr;               // this rank's buffer (cudaMalloc)
     uint64_t cap = 0;                    // bytes, the same on every rank
@@ -157,7 +158,7 @@ struct vb_ctx {
 // (ctx->dev_pairs) for the align stage.
 struct vb_prefilter_job {
     const vb_genomes *g = nullptr;
-    const vb_peer_xbuf *xbuf = nullptr;  // several ranks: direct peer stores instead of the tuple all-to-all
+    const vb_peer_xbuf *xbuf = nullptr;  // several ranks: peer copies into mapped receive buffers instead of the tuple all-to-all
     uint32_t gid_base = 0, n_total = 0;
     double est_kmers_all = 0;            // k-mers of the whole set (all ranks), for the pass / bucket plan
     const vb_comm *comm = nullptr;
