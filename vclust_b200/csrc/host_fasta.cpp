@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <filesystem>
 #include <thread>
 #include <vector>
@@ -250,10 +251,13 @@ void split_parallel(const char *d, size_t n, bool kmerdb, unsigned n_threads, Si
         }
         ch.w_end = ls.w;
     };
-    for (unsigned c = 1; c < n_threads; ++c) pool.emplace_back(work, c);
-    work(0);
+    std::vector<std::exception_ptr> failed(n_threads);          // (an exception must not leave a thread: std::terminate)
+    auto guarded = [&](unsigned c) { try { work(c); } catch (...) { failed[c] = std::current_exception(); } };
+    for (unsigned c = 1; c < n_threads; ++c) pool.emplace_back(guarded, c);
+    guarded(0);
     for (auto &th : pool) th.join();
     pool.clear();
+    for (auto &f : failed) if (f) std::rethrow_exception(f);
     // close the gaps between the compacted chunks, in place.  Chunk c moves left by shift[c] = the slack of the chunks
     // before it -- far less than its length -- so its destination overlaps only the last shift[c-1] bytes of chunk c-1's
     // compacted bytes: those tails are set aside first (a few MB), then all chunks move at the same time.
